@@ -1,0 +1,112 @@
+/* include/liinit_gpu.h -- C-ABI of the B200-native ICP measurement model of LI-Init.
+ *
+ * The reference has NO plugin / FFI boundary on this path: the code is inlined in
+ * main() over file-scope globals (/root/reference/src/laserMapping.cpp:102-125,
+ * 957-1134) and the only real API on it is the C++ class KD_TREE
+ * (include/ikd-Tree/ikd_Tree.h:165-187). This header is the cut SURVEY.md section 8(b)
+ * introduces; every entry point cites the reference lines it replaces.
+ *
+ * Conventions: extern "C"; opaque context; int return codes (0 = LIINIT_OK, <0 =
+ * error, message via liinit_last_error); no exceptions cross the ABI; the caller
+ * owns every host buffer, the library owns all device memory; single caller thread
+ * (the node's main thread, laserMapping.cpp:891-1238), internally asynchronous on
+ * one CUDA stream. Matrices are row-major doubles. Point arrays are float with a
+ * caller-given stride in floats: 3 (packed xyz), 4 (float4) or 12 (the 48-byte
+ * pcl::PointXYZINormal of include/common_lib.h:37 -- x,y,z are its first floats).
+ *
+ * There is NO CPU fallback: every compute entry point fails with
+ * LIINIT_ERR_CUDA when no sm_100-class device is usable.
+ */
+#ifndef LIINIT_GPU_H
+#define LIINIT_GPU_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LIINIT_OK 0
+#define LIINIT_ERR_INVALID (-1)   /* bad argument / call order */
+#define LIINIT_ERR_CUDA (-2)      /* CUDA runtime error (no device, launch failure, ...) */
+#define LIINIT_ERR_CAPACITY (-3)  /* map / scan / hash capacity exceeded */
+
+#define LIINIT_NUM_MATCH_POINTS 5 /* include/common_lib.h:28 */
+
+typedef struct liinit_ctx liinit_ctx;
+
+typedef struct liinit_config {
+    float filter_size_map;   /* mapping/filter_size_map (config/avia.yaml:23): map voxel ds; KD_TREE::set_downsample_param (laserMapping.cpp:923) */
+    int max_map_points;      /* capacity of the device map (live points); e.g. 50M for BASELINE config 4 */
+    int max_scan_points;     /* capacity per scan (replaces the fixed 100000 caps, laserMapping.cpp:108-109,117-119) */
+    int device_id;           /* CUDA device ordinal */
+    int brick_cells_log2;    /* voxels per brick edge = 1<<this; 0 -> default (2, i.e. brick edge = 4*ds) */
+    int hash_capacity_log2;  /* brick hash slots = 1<<this; 0 -> derived from max_map_points */
+    int knn_tile;            /* scan points per warp tile in the fused kernel: 8, 16 or 32; 0 -> default */
+    int reserved[8];
+} liinit_config;
+
+/* lifecycle ------------------------------------------------------------------ */
+int liinit_create(const liinit_config* cfg, liinit_ctx** out);
+int liinit_destroy(liinit_ctx* h);
+const char* liinit_last_error(const liinit_ctx* h);   /* h may be NULL: error of the last failed liinit_create */
+/* Run on an externally owned stream (cudaStream_t as void*); NULL -> the context's own stream. */
+int liinit_set_stream(liinit_ctx* h, void* cuda_stream);
+
+/* map (replaces KD_TREE, include/ikd-Tree/ikd_Tree.h:165-187) ------------------ */
+/* KD_TREE::Build (ikd_Tree.cpp:336-347; call site laserMapping.cpp:921-928): replaces the map, no downsampling. */
+int liinit_map_build(liinit_ctx* h, const float* xyz, int stride_floats, int n);
+/* KD_TREE::Add_Points(points, downsample_on) (ikd_Tree.cpp:381-456; call sites laserMapping.cpp:556-557).
+ * added: number of voxels whose content changed (downsample_on) / points appended. */
+int liinit_map_add_points(liinit_ctx* h, const float* xyz, int stride_floats, int n, int downsample_on, int* added);
+/* KD_TREE::validnum / size (ikd_Tree.cpp:71-88,120-137; laserMapping.cpp:932-933,1142): live points. */
+int liinit_map_validnum(liinit_ctx* h, int* n);
+int liinit_map_size(liinit_ctx* h, int* n);
+/* KD_TREE::flatten(Root_Node, out, NOT_RECORD) (ikd_Tree.cpp:1229-1255; laserMapping.cpp:251): live points, packed xyz. */
+int liinit_map_download(liinit_ctx* h, float* xyz, int cap_points, int* n);
+/* KD_TREE::Nearest_Search for n arbitrary world-frame queries (ikd_Tree.cpp:349-379), max_dist as at laserMapping.cpp:980:
+ * squared distance <= max_dist (sic). k must be 5. out_xyz [n*5*3], out_d2 [n*5] (-1 where missing), out_cnt [n]. */
+int liinit_map_nearest_search(liinit_ctx* h, const float* q_xyz, int stride_floats, int n, double max_dist,
+                              float* out_xyz, float* out_d2, int* out_cnt);
+
+/* per-scan hot path (replaces laserMapping.cpp:936-1080) ---------------------------- */
+/* feats_down_body (laserMapping.cpp:917-919): once per scan; resets selection flags / neighbour lists. */
+int liinit_scan_upload(liinit_ctx* h, const float* body_xyz, int stride_floats, int n);
+/* One ICP pass, laserMapping.cpp:959-1071 + the reduction of :1080.
+ *   rot_end, pos_end, R_LI (offset_R_L_I), T_LI (offset_T_L_I): the pose part of StatesGroup (common_lib.h:160-163).
+ *   imu_en: 12-column Jacobian (:1054-1062) else 6 columns (:1063-1066).
+ *   nearest_search_en: search pass (:978-985) or reuse of stored neighbours and flags (:989-994).
+ * Outputs (host): HtH[144] = Hsub^T Hsub (UNWEIGHTED; the reference's R_inv=1000 (:1050) is applied by the
+ * caller), Htr[12] = Hsub^T meas_vec with meas = -pd2 (:1070), m = effect_feat_num (:1012-1020).
+ * res_sq (optional, may be NULL) = sum of pd2^2 over the selected points. */
+int liinit_icp_iterate(liinit_ctx* h, const double rot_end[9], const double pos_end[3], const double R_LI[9],
+                       const double T_LI[3], int imu_en, int nearest_search_en, double HtH[144], double Htr[12], int* m,
+                       double* res_sq);
+/* Same pass, results left on the device for a collective: d_out = device pointer to 160 doubles
+ * [HtH 144 | Htr 12 | res_sq | m | pad 2], written on the context's stream; no host synchronisation. */
+int liinit_icp_iterate_device(liinit_ctx* h, const double rot_end[9], const double pos_end[3], const double R_LI[9],
+                              const double T_LI[3], int imu_en, int nearest_search_en, double* d_out160);
+/* laserCloudOri / corr_normvect after compaction (laserMapping.cpp:1013-1020; published at :625-636):
+ * ori_xyz [cap*3] body points, normvec [cap*4] = (nx,ny,nz,pd2), order preserved. */
+int liinit_scan_download_effect(liinit_ctx* h, float* ori_xyz, float* normvec, int cap_points, int* m);
+/* Per-point state of the last pass for parity tests (any pointer may be NULL): world [n*3] (feats_down_world),
+ * near_xyz [n*5*3] + near_cnt [n] (Nearest_Points), selected [n] (point_selected_surf), normvec [n*4]. */
+int liinit_scan_download_state(liinit_ctx* h, float* world_xyz, float* near_xyz, int* near_cnt, unsigned char* selected,
+                               float* normvec);
+/* map_incremental (laserMapping.cpp:516-559) with the final state; uses the neighbour lists retained on the
+ * device by the last search pass. ds = the node's double filter_size_map_min. n_add / n_no_downsample:
+ * sizes of PointToAdd / PointNoNeedDownsample. */
+int liinit_map_incremental(liinit_ctx* h, const double rot_end[9], const double pos_end[3], const double R_LI[9],
+                           const double T_LI[3], double ds, int flg_EKF_inited, int* n_add, int* n_no_downsample);
+
+/* instrumentation (the reference has none around this loop) ---- */
+/* Device time in milliseconds of the kernels of the last liinit_icp_iterate* call (CUDA events on the context's
+ * stream) and the number of kernel launches it made. */
+int liinit_last_pass_timing(liinit_ctx* h, float* kernel_ms, int* launches);
+/* Cumulative number of kernels launched by this context. */
+int liinit_launch_count(liinit_ctx* h, long long* launches);
+/* Map statistics: bricks in use, hash slots, pool points in use / capacity. */
+int liinit_map_stats(liinit_ctx* h, int* bricks, int* hash_slots, long long* pool_used, long long* pool_cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIINIT_GPU_H */

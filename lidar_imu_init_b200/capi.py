@@ -1,0 +1,223 @@
+"""ctypes binding of the C-ABI (include/liinit_gpu.h). Thin: one method per entry point.
+
+The CUDA library is REQUIRED: importing a handle without the built
+libliinit_gpu.so, or on a machine without a usable GPU, raises -- there is no
+CPU fallback on the product path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _build
+
+_LIB = None
+
+
+class LiInitError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"liinit error {code}: {msg}")
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [("filter_size_map", C.c_float), ("max_map_points", C.c_int), ("max_scan_points", C.c_int), ("device_id", C.c_int),
+                ("brick_cells_log2", C.c_int), ("hash_capacity_log2", C.c_int), ("knn_tile", C.c_int), ("reserved", C.c_int * 8)]
+
+
+_f32 = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+_f64 = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_i32 = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+
+SYMBOLS = [
+    "liinit_create", "liinit_destroy", "liinit_last_error", "liinit_set_stream", "liinit_map_build", "liinit_map_add_points",
+    "liinit_map_validnum", "liinit_map_size", "liinit_map_download", "liinit_map_nearest_search", "liinit_scan_upload",
+    "liinit_icp_iterate", "liinit_icp_iterate_device", "liinit_scan_download_effect", "liinit_scan_download_state",
+    "liinit_map_incremental", "liinit_last_pass_timing", "liinit_launch_count", "liinit_map_stats",
+]
+
+
+def lib_path() -> str:
+    return _build.GPU_LIB
+
+
+def load():
+    """dlopen the in-tree CUDA library (no compute). Raises if it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    p = lib_path()
+    if not os.path.exists(p):
+        raise FileNotFoundError(f"{p} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (nvcc) first. "
+                                "There is no CPU fallback.")
+    L = C.CDLL(p)
+    vp = C.c_void_p
+    L.liinit_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    L.liinit_destroy.argtypes = [vp]
+    L.liinit_last_error.restype = C.c_char_p
+    L.liinit_last_error.argtypes = [vp]
+    L.liinit_set_stream.argtypes = [vp, vp]
+    L.liinit_map_build.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.liinit_map_add_points.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    L.liinit_map_validnum.argtypes = [vp, C.POINTER(C.c_int)]
+    L.liinit_map_size.argtypes = [vp, C.POINTER(C.c_int)]
+    L.liinit_map_download.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int)]
+    L.liinit_map_nearest_search.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, vp, vp, vp]
+    L.liinit_scan_upload.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.liinit_icp_iterate.argtypes = [vp, _f64, _f64, _f64, _f64, C.c_int, C.c_int, _f64, _f64, C.POINTER(C.c_int), C.POINTER(C.c_double)]
+    L.liinit_icp_iterate_device.argtypes = [vp, _f64, _f64, _f64, _f64, C.c_int, C.c_int, vp]
+    L.liinit_scan_download_effect.argtypes = [vp, vp, vp, C.c_int, C.POINTER(C.c_int)]
+    L.liinit_scan_download_state.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.liinit_map_incremental.argtypes = [vp, _f64, _f64, _f64, _f64, C.c_double, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.liinit_last_pass_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+    L.liinit_launch_count.argtypes = [vp, C.POINTER(C.c_longlong)]
+    L.liinit_map_stats.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+    for s in SYMBOLS:
+        getattr(L, s).restype = getattr(L, s).restype if s == "liinit_last_error" else C.c_int
+    _LIB = L
+    return L
+
+
+def _pts(a):
+    """float32 C-contiguous [n, stride] with stride in (3, 4, 12)."""
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if a.ndim != 2 or a.shape[1] not in (3, 4, 12):
+        raise ValueError("points must be [n,3], [n,4] or [n,12] float32")
+    return a
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class LiInitGpu:
+    """One context = one GPU + one device-resident map + one resident scan."""
+
+    def __init__(self, filter_size_map=0.15, max_map_points=6_000_000, max_scan_points=300_000, device_id=0, brick_cells_log2=0,
+                 hash_capacity_log2=0, knn_tile=0):
+        self.L = load()
+        cfg = Config(filter_size_map, max_map_points, max_scan_points, device_id, brick_cells_log2, hash_capacity_log2, knn_tile)
+        h = C.c_void_p()
+        rc = self.L.liinit_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise LiInitError(rc, (self.L.liinit_last_error(None) or b"").decode())
+        self.h = h
+        self.scan_n = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.liinit_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise LiInitError(rc, (self.L.liinit_last_error(self.h) or b"").decode())
+
+    def set_stream(self, cuda_stream: int):
+        self._ck(self.L.liinit_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    # ---- map ----
+    def map_build(self, xyz):
+        a = _pts(xyz)
+        self._ck(self.L.liinit_map_build(self.h, _ptr(a), a.shape[1], a.shape[0]))
+
+    def map_add_points(self, xyz, downsample_on: bool) -> int:
+        a = _pts(xyz)
+        added = C.c_int(0)
+        if a.shape[0] == 0:
+            return 0
+        self._ck(self.L.liinit_map_add_points(self.h, _ptr(a), a.shape[1], a.shape[0], int(downsample_on), C.byref(added)))
+        return added.value
+
+    def map_validnum(self) -> int:
+        n = C.c_int(0)
+        self._ck(self.L.liinit_map_validnum(self.h, C.byref(n)))
+        return n.value
+
+    def map_download(self):
+        n = self.map_validnum()
+        out = np.zeros((max(n, 1), 3), np.float32)
+        m = C.c_int(0)
+        self._ck(self.L.liinit_map_download(self.h, _ptr(out), n, C.byref(m)))
+        return out[:min(n, m.value)]
+
+    def map_stats(self):
+        b, s, pu, pc = C.c_int(0), C.c_int(0), C.c_longlong(0), C.c_longlong(0)
+        self._ck(self.L.liinit_map_stats(self.h, C.byref(b), C.byref(s), C.byref(pu), C.byref(pc)))
+        return dict(bricks=b.value, hash_slots=s.value, pool_used=pu.value, pool_cap=pc.value)
+
+    def nearest_search(self, q, max_dist=5.0):
+        a = _pts(q)
+        n = a.shape[0]
+        xyz = np.zeros((n, 5, 3), np.float32)
+        d2 = np.zeros((n, 5), np.float32)
+        cnt = np.zeros(n, np.int32)
+        self._ck(self.L.liinit_map_nearest_search(self.h, _ptr(a), a.shape[1], n, max_dist, _ptr(xyz), _ptr(d2), _ptr(cnt)))
+        return xyz, d2, cnt
+
+    # ---- scan ----
+    def scan_upload(self, body):
+        a = _pts(body)
+        self._ck(self.L.liinit_scan_upload(self.h, _ptr(a), a.shape[1], a.shape[0]))
+        self.scan_n = a.shape[0]
+
+    def scan_upload_ptr(self, host_ptr: int, stride: int, n: int):
+        """Upload from a raw host pointer (e.g. pinned torch tensor)."""
+        self._ck(self.L.liinit_scan_upload(self.h, C.c_void_p(host_ptr), stride, n))
+        self.scan_n = n
+
+    def icp_iterate(self, rot_end, pos_end, R_LI, T_LI, imu_en: bool, search: bool):
+        HtH = np.zeros((12, 12))
+        Htr = np.zeros(12)
+        m = C.c_int(0)
+        rs = C.c_double(0)
+        self._ck(self.L.liinit_icp_iterate(self.h, np.ascontiguousarray(rot_end, np.float64).reshape(9), np.ascontiguousarray(pos_end, np.float64),
+                                           np.ascontiguousarray(R_LI, np.float64).reshape(9), np.ascontiguousarray(T_LI, np.float64),
+                                           int(imu_en), int(search), HtH.reshape(144), Htr, C.byref(m), C.byref(rs)))
+        return HtH, Htr, m.value, rs.value
+
+    def icp_iterate_device(self, rot_end, pos_end, R_LI, T_LI, imu_en: bool, search: bool, d_out_ptr: int):
+        self._ck(self.L.liinit_icp_iterate_device(self.h, np.ascontiguousarray(rot_end, np.float64).reshape(9), np.ascontiguousarray(pos_end, np.float64),
+                                                  np.ascontiguousarray(R_LI, np.float64).reshape(9), np.ascontiguousarray(T_LI, np.float64),
+                                                  int(imu_en), int(search), C.c_void_p(d_out_ptr)))
+
+    def scan_state(self):
+        n = self.scan_n
+        out = dict(world=np.zeros((n, 3), np.float32), near_xyz=np.zeros((n, 5, 3), np.float32), near_cnt=np.zeros(n, np.int32),
+                   selected=np.zeros(n, np.uint8), normvec=np.zeros((n, 4), np.float32))
+        self._ck(self.L.liinit_scan_download_state(self.h, _ptr(out["world"]), _ptr(out["near_xyz"]), _ptr(out["near_cnt"]),
+                                                   _ptr(out["selected"]), _ptr(out["normvec"])))
+        return out
+
+    def scan_effect(self):
+        n = self.scan_n
+        ori = np.zeros((n, 3), np.float32)
+        nv = np.zeros((n, 4), np.float32)
+        m = C.c_int(0)
+        self._ck(self.L.liinit_scan_download_effect(self.h, _ptr(ori), _ptr(nv), n, C.byref(m)))
+        return ori[:m.value], nv[:m.value]
+
+    def map_incremental(self, rot_end, pos_end, R_LI, T_LI, ds: float, flg_EKF_inited: bool = True):
+        na, nn = C.c_int(0), C.c_int(0)
+        self._ck(self.L.liinit_map_incremental(self.h, np.ascontiguousarray(rot_end, np.float64).reshape(9), np.ascontiguousarray(pos_end, np.float64),
+                                               np.ascontiguousarray(R_LI, np.float64).reshape(9), np.ascontiguousarray(T_LI, np.float64),
+                                               float(ds), int(flg_EKF_inited), C.byref(na), C.byref(nn)))
+        return na.value, nn.value
+
+    def last_pass_timing(self):
+        ms, nl = C.c_float(0), C.c_int(0)
+        self._ck(self.L.liinit_last_pass_timing(self.h, C.byref(ms), C.byref(nl)))
+        return ms.value, nl.value
+
+    def launch_count(self) -> int:
+        n = C.c_longlong(0)
+        self._ck(self.L.liinit_launch_count(self.h, C.byref(n)))
+        return n.value

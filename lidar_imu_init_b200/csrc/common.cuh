@@ -1,0 +1,117 @@
+// common.cuh -- device-side types and helpers shared by the map and ICP kernels.
+//
+// Map layout in HBM:
+//   * brick hash: open-addressing table of 16-byte entries {key(8) | first(4) | count(4)};
+//     a brick is a cube of (1<<bshift)^3 map voxels of edge ds = filter_size_map, i.e. the
+//     voxel grid of KD_TREE::Add_Points (ikd_Tree.cpp:389-394) grouped 4x4x4 by default.
+//   * aux[slot] = {cap, pending, fill, spare}: update-time bookkeeping, never read by searches.
+//   * pool: float4 points; every brick owns one contiguous, 128-byte aligned slab
+//     [first, first+cap) of which [first, first+count) are live. w carries the voxel-in-brick id.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define LI_FULL 0xffffffffu
+#define LI_EMPTY_KEY 0xffffffffffffffffull
+#define LI_CELL_LIMIT (1 << 20)   // |cell index| must stay below this (21-bit packing)
+
+struct MapDev {
+    uint4* ent;                    // hash entries
+    uint4* aux;                    // {cap, pending, fill, spare}
+    unsigned mask;                 // slots - 1
+    float4* pool;
+    unsigned long long pool_cap;   // points
+    unsigned long long* pool_top;  // bump allocator (points)
+    float ds;                      // filter_size_map as float (KD_TREE::downsample_size)
+    int bshift;                    // log2(voxels per brick edge)
+    int* touched_list;             // hash slots touched by the current update batch
+    int* counters;                 // [0]=touched_n [1]=err flags [2]=n_live [3]=n_bricks [4]=changed voxels [5]=dropped pts
+};
+
+enum { CNT_TOUCHED = 0, CNT_ERR = 1, CNT_LIVE = 2, CNT_BRICKS = 3, CNT_CHANGED = 4, CNT_DROPPED = 5, CNT_NADD = 6, CNT_NNOD = 7, CNT_COUNT = 16 };
+enum { ERR_HASH_FULL = 1, ERR_POOL_FULL = 2, ERR_RANGE = 4 };
+
+// Pose part of StatesGroup (common_lib.h:160-163), row-major doubles.
+struct PoseD {
+    double R[9];     // rot_end
+    double p[3];     // pos_end
+    double RLI[9];   // offset_R_L_I
+    double TLI[3];   // offset_T_L_I
+};
+
+__device__ __forceinline__ unsigned long long li_pack_key(int x, int y, int z) {
+    return ((unsigned long long)(unsigned)(x + LI_CELL_LIMIT) << 42) | ((unsigned long long)(unsigned)(y + LI_CELL_LIMIT) << 21) |
+           (unsigned long long)(unsigned)(z + LI_CELL_LIMIT);
+}
+
+__device__ __forceinline__ unsigned li_hash(unsigned long long k) {
+    k ^= k >> 33;
+    k *= 0xff51afd7ed558ccdull;
+    k ^= k >> 33;
+    k *= 0xc4ceb9fe1a85ec53ull;
+    k ^= k >> 33;
+    return (unsigned)k;
+}
+
+// Voxel index exactly as the reference computes it: floor(x / downsample_size) in float
+// (ikd_Tree.cpp:389). IEEE division, no reciprocal shortcut.
+__device__ __forceinline__ int li_cell(float x, float ds) { return (int)floorf(__fdiv_rn(x, ds)); }
+
+// fp32 squared distance with the reference's association and no FMA contraction
+// (KD_TREE::calc_dist, ikd_Tree.cpp:1273-1277): (dx*dx + dy*dy) + dz*dz.
+__device__ __forceinline__ float li_dist2(float ax, float ay, float az, float bx, float by, float bz) {
+    float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// Lookup only (searches). Returns true and (first,count) when the brick exists.
+__device__ __forceinline__ bool li_brick_find(const uint4* __restrict__ ent, unsigned mask, unsigned long long key,
+                                              unsigned& first, unsigned& count) {
+    unsigned h = li_hash(key) & mask;
+    for (unsigned i = 0; i <= mask; i++) {
+        uint4 e = __ldg(&ent[h]);
+        unsigned long long k = (unsigned long long)e.x | ((unsigned long long)e.y << 32);
+        if (k == key) {
+            first = e.z;
+            count = e.w;
+            return true;
+        }
+        if (k == LI_EMPTY_KEY) return false;
+        h = (h + 1) & mask;
+    }
+    return false;
+}
+
+// Find-or-create (updates). Returns the slot or -1 when the table is full.
+__device__ __forceinline__ int li_brick_find_or_insert(uint4* ent, unsigned mask, unsigned long long key, bool* created) {
+    unsigned h = li_hash(key) & mask;
+    for (unsigned i = 0; i <= mask; i++) {
+        unsigned long long* kp = reinterpret_cast<unsigned long long*>(&ent[h]);
+        unsigned long long k = *reinterpret_cast<volatile unsigned long long*>(kp);
+        if (k == key) return (int)h;
+        if (k == LI_EMPTY_KEY) {
+            unsigned long long old = atomicCAS(kp, LI_EMPTY_KEY, key);
+            if (old == LI_EMPTY_KEY) {
+                if (created) *created = true;
+                return (int)h;
+            }
+            if (old == key) return (int)h;
+        }
+        h = (h + 1) & mask;
+    }
+    return -1;
+}
+
+// pointBodyToWorld (laserMapping.cpp:209-220): double math without contraction, float store.
+__device__ __forceinline__ void li_body_to_world(const PoseD& P, float bx, float by, float bz, float& wx, float& wy, float& wz) {
+    double x = (double)bx, y = (double)by, z = (double)bz;
+    double t0 = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P.RLI[0], x), __dmul_rn(P.RLI[1], y)), __dmul_rn(P.RLI[2], z)), P.TLI[0]);
+    double t1 = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P.RLI[3], x), __dmul_rn(P.RLI[4], y)), __dmul_rn(P.RLI[5], z)), P.TLI[1]);
+    double t2 = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P.RLI[6], x), __dmul_rn(P.RLI[7], y)), __dmul_rn(P.RLI[8], z)), P.TLI[2]);
+    double g0 = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P.R[0], t0), __dmul_rn(P.R[1], t1)), __dmul_rn(P.R[2], t2)), P.p[0]);
+    double g1 = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P.R[3], t0), __dmul_rn(P.R[4], t1)), __dmul_rn(P.R[5], t2)), P.p[1]);
+    double g2 = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P.R[6], t0), __dmul_rn(P.R[7], t1)), __dmul_rn(P.R[8], t2)), P.p[2]);
+    wx = (float)g0;
+    wy = (float)g1;
+    wz = (float)g2;
+}

@@ -1,0 +1,686 @@
+// liinit_gpu.cu -- C-ABI implementation (include/liinit_gpu.h) over the sm_100a kernels.
+//
+// One context = one GPU, one stream, one device-resident map, one resident scan. No CPU fallback:
+// every entry point fails with LIINIT_ERR_CUDA if the CUDA runtime reports an error.
+#include "../../include/liinit_gpu.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "icp_kernels.cuh"
+#include "map_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Ctx {
+    liinit_config cfg;
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+
+    // map
+    MapDev M{};
+    unsigned hash_slots = 0;
+    int* d_counters = nullptr;
+    int* h_counters = nullptr;   // pinned
+    // staging
+    float* d_stage_raw = nullptr;   // strided host layout
+    size_t stage_raw_floats = 0;
+    float4* d_stage_pts = nullptr;  // repacked batch
+    int stage_pts_cap = 0;
+    int* d_slot_of = nullptr;
+    int* d_vslot_of = nullptr;
+    int* d_flag = nullptr;
+    VoxTmp V{};
+    // scan
+    ScanDev S{};
+    float4* d_body = nullptr;
+    float4* d_world = nullptr;
+    int* d_near_ids = nullptr;
+    unsigned char* d_selected = nullptr;
+    float4* d_normvec = nullptr;
+    int scan_n = 0;
+    bool have_neighbors = false;
+    // reduction
+    double* d_partials = nullptr;
+    unsigned* d_done = nullptr;
+    double* d_out = nullptr;    // 160
+    double* h_out = nullptr;    // pinned 160
+    int max_blocks = 0;
+    // knn query scratch
+    float* d_q_d2 = nullptr;
+    // stats
+    long long launches = 0;
+    float last_ms = 0.f;
+    int last_launches = 0;
+    int tile = 8;
+};
+
+#define CU(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t _e = (call);                                                                     \
+        if (_e != cudaSuccess) {                                                                     \
+            c->err = std::string(#call) + ": " + cudaGetErrorString(_e);                             \
+            return LIINIT_ERR_CUDA;                                                                  \
+        }                                                                                            \
+    } while (0)
+
+inline int nblk(long long n, int t) { return (int)((n + t - 1) / t); }
+
+int fail(Ctx* c, int code, const std::string& msg) {
+    c->err = msg;
+    return code;
+}
+
+// copy n points with a float stride from host to d_stage_pts[0..n) as float4
+int stage_points(Ctx* c, const float* xyz, int stride, int n) {
+    if (n > c->stage_pts_cap) return fail(c, LIINIT_ERR_CAPACITY, "batch exceeds staging capacity");
+    if (stride == 4) {
+        CU(cudaMemcpyAsync(c->d_stage_pts, xyz, (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
+        return LIINIT_OK;
+    }
+    if (stride != 3 && stride != 12) return fail(c, LIINIT_ERR_INVALID, "stride_floats must be 3, 4 or 12");
+    size_t nf = (size_t)n * stride;
+    if (nf > c->stage_raw_floats) return fail(c, LIINIT_ERR_CAPACITY, "batch exceeds raw staging capacity");
+    CU(cudaMemcpyAsync(c->d_stage_raw, xyz, nf * 4, cudaMemcpyHostToDevice, c->stream));
+    k_repack<<<nblk(n, 256), 256, 0, c->stream>>>(c->d_stage_raw, stride, n, c->d_stage_pts);
+    c->launches++;
+    CU(cudaGetLastError());
+    return LIINIT_OK;
+}
+
+int fetch_counters(Ctx* c) {
+    CU(cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(int) * CNT_COUNT, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return LIINIT_OK;
+}
+
+int check_map_err(Ctx* c) {
+    int e = c->h_counters[CNT_ERR];
+    if (e & ERR_HASH_FULL) return fail(c, LIINIT_ERR_CAPACITY, "brick hash table full (raise hash_capacity_log2 / max_map_points)");
+    if (e & ERR_POOL_FULL) return fail(c, LIINIT_ERR_CAPACITY, "map point pool full (raise max_map_points)");
+    return LIINIT_OK;
+}
+
+int reset_batch_counters(Ctx* c) {
+    // touched, changed, nadd, nnod reset; err, live, bricks, dropped persist
+    static const int zeros[CNT_COUNT] = {0};
+    CU(cudaMemcpyAsync(c->d_counters + CNT_TOUCHED, zeros, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_counters + CNT_CHANGED, zeros, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    return LIINIT_OK;
+}
+
+// plain insert of pts[0..n) (optionally only flag==want)
+int plain_insert(Ctx* c, const float4* pts, int n, const int* sel, int want) {
+    if (n <= 0) return LIINIT_OK;
+    int r = reset_batch_counters(c);
+    if (r) return r;
+    if (sel)
+        k_ins_count_sel<<<nblk(n, 256), 256, 0, c->stream>>>(c->M, pts, n, sel, want, c->d_slot_of);
+    else
+        k_ins_count<<<nblk(n, 256), 256, 0, c->stream>>>(c->M, pts, n, c->d_slot_of);
+    // number of touched bricks is unknown on the host: launch for the worst case (n warps), early exit inside
+    k_ins_reserve<<<nblk((long long)n * 32, 256), 256, 0, c->stream>>>(c->M);
+    k_ins_append<<<nblk(n, 256), 256, 0, c->stream>>>(c->M, pts, n, c->d_slot_of);
+    k_ins_commit<<<nblk(n, 256), 256, 0, c->stream>>>(c->M);
+    c->launches += 4;
+    CU(cudaGetLastError());
+    return LIINIT_OK;
+}
+
+int downsample_insert(Ctx* c, const float4* pts, int n, const int* sel, int want) {
+    if (n <= 0) return LIINIT_OK;
+    int r = reset_batch_counters(c);
+    if (r) return r;
+    k_vox_clear<<<nblk((long long)c->V.mask + 1, 256), 256, 0, c->stream>>>(c->V);
+    k_ds_vote<<<nblk(n, 256), 256, 0, c->stream>>>(c->M, c->V, pts, n, sel, want, c->d_vslot_of);
+    k_ds_reserve_votes<<<nblk(n, 256), 256, 0, c->stream>>>(c->M, c->V, pts, n, c->d_vslot_of, c->d_slot_of);
+    k_ins_reserve<<<nblk((long long)n * 32, 256), 256, 0, c->stream>>>(c->M);
+    k_ds_apply<<<nblk((long long)n * 32, 256), 256, 0, c->stream>>>(c->M, pts, n, c->d_slot_of);
+    k_ds_compact<<<nblk((long long)n * 32, 256), 256, 0, c->stream>>>(c->M);
+    c->launches += 6;
+    CU(cudaGetLastError());
+    return LIINIT_OK;
+}
+
+void fill_pose(PoseD& P, const double* R, const double* p, const double* RLI, const double* TLI) {
+    memcpy(P.R, R, 72);
+    memcpy(P.p, p, 24);
+    memcpy(P.RLI, RLI, 72);
+    memcpy(P.TLI, TLI, 24);
+}
+
+template <bool IMU>
+void launch_search(Ctx* c, const PoseD& P, int grid) {
+    switch (c->tile) {
+        case 32: k_icp_search<32, IMU><<<grid, 256, 0, c->stream>>>(c->M, c->S, P, c->d_partials, c->d_done, c->d_out); break;
+        case 16: k_icp_search<16, IMU><<<grid, 256, 0, c->stream>>>(c->M, c->S, P, c->d_partials, c->d_done, c->d_out); break;
+        default: k_icp_search<8, IMU><<<grid, 256, 0, c->stream>>>(c->M, c->S, P, c->d_partials, c->d_done, c->d_out); break;
+    }
+}
+
+int run_pass(Ctx* c, const double* R, const double* p, const double* RLI, const double* TLI, int imu_en, int search) {
+    if (c->scan_n <= 0) return fail(c, LIINIT_ERR_INVALID, "no scan uploaded");
+    if (!search && !c->have_neighbors) return fail(c, LIINIT_ERR_INVALID, "reuse pass before any search pass");
+    PoseD P;
+    fill_pose(P, R, p, RLI, TLI);
+    CU(cudaEventRecord(c->ev0, c->stream));
+    if (search) {
+        int ntiles = (c->scan_n + c->tile - 1) / c->tile;
+        int grid = nblk(ntiles, 8);
+        if (grid > c->max_blocks) grid = c->max_blocks;
+        if (imu_en) launch_search<true>(c, P, grid); else launch_search<false>(c, P, grid);
+        c->have_neighbors = true;
+    } else {
+        int grid = nblk(c->scan_n, 256);
+        if (grid > c->max_blocks) grid = c->max_blocks;
+        if (imu_en)
+            k_icp_reuse<true><<<grid, 256, 0, c->stream>>>(c->M, c->S, P, c->d_partials, c->d_done, c->d_out);
+        else
+            k_icp_reuse<false><<<grid, 256, 0, c->stream>>>(c->M, c->S, P, c->d_partials, c->d_done, c->d_out);
+    }
+    CU(cudaEventRecord(c->ev1, c->stream));
+    c->launches += 1;
+    c->last_launches = 1;
+    CU(cudaGetLastError());
+    return LIINIT_OK;
+}
+
+}  // namespace
+
+struct liinit_ctx {
+    Ctx c;
+};
+
+extern "C" {
+
+const char* liinit_last_error(const liinit_ctx* h) { return h ? h->c.err.c_str() : g_create_error.c_str(); }
+
+int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
+    if (!cfg || !out) {
+        g_create_error = "null argument";
+        return LIINIT_ERR_INVALID;
+    }
+    *out = nullptr;
+    if (!(cfg->filter_size_map > 0.f) || cfg->max_map_points <= 0 || cfg->max_scan_points <= 0) {
+        g_create_error = "filter_size_map, max_map_points and max_scan_points must be positive";
+        return LIINIT_ERR_INVALID;
+    }
+    liinit_ctx* h = new liinit_ctx();
+    Ctx* c = &h->c;
+    c->cfg = *cfg;
+    auto bail = [&](int code) {
+        g_create_error = c->err;
+        liinit_destroy(h);
+        return code;
+    };
+#define CUC(call)                                                                 \
+    do {                                                                          \
+        cudaError_t _e = (call);                                                  \
+        if (_e != cudaSuccess) {                                                  \
+            c->err = std::string(#call) + ": " + cudaGetErrorString(_e);          \
+            return bail(LIINIT_ERR_CUDA);                                         \
+        }                                                                         \
+    } while (0)
+    int ndev = 0;
+    CUC(cudaGetDeviceCount(&ndev));
+    if (cfg->device_id < 0 || cfg->device_id >= ndev) {
+        c->err = "device_id out of range (no usable CUDA device; there is no CPU fallback)";
+        return bail(LIINIT_ERR_CUDA);
+    }
+    c->device = cfg->device_id;
+    CUC(cudaSetDevice(c->device));
+    cudaDeviceProp prop;
+    CUC(cudaGetDeviceProperties(&prop, c->device));
+    c->num_sms = prop.multiProcessorCount;
+    CUC(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    CUC(cudaEventCreate(&c->ev0));
+    CUC(cudaEventCreate(&c->ev1));
+
+    int bs = cfg->brick_cells_log2 > 0 ? cfg->brick_cells_log2 : 2;
+    if (bs < 1 || bs > 4) {
+        c->err = "brick_cells_log2 must be in [1,4]";
+        return bail(LIINIT_ERR_INVALID);
+    }
+    int hl = cfg->hash_capacity_log2;
+    if (hl <= 0) {
+        // ~ one brick per 4 live points worst case for surface maps, load factor <= 0.5
+        long long want = (long long)cfg->max_map_points / 2;
+        hl = 16;
+        while ((1ll << hl) < want && hl < 28) hl++;
+    }
+    if (hl < 10 || hl > 30) {
+        c->err = "hash_capacity_log2 out of range";
+        return bail(LIINIT_ERR_INVALID);
+    }
+    c->hash_slots = 1u << hl;
+    c->tile = (cfg->knn_tile == 8 || cfg->knn_tile == 16 || cfg->knn_tile == 32) ? cfg->knn_tile : 8;
+
+    MapDev& M = c->M;
+    M.mask = c->hash_slots - 1;
+    M.ds = cfg->filter_size_map;
+    M.bshift = bs;
+    // slabs grow geometrically and old slabs are abandoned: 3x live capacity + per-brick minimum slack
+    unsigned long long pool = (unsigned long long)cfg->max_map_points * 3ull + (1ull << 20);
+    if (pool > 0x7fffff00ull) pool = 0x7fffff00ull;   // ids are int32 pool offsets
+    M.pool_cap = pool;
+    CUC(cudaMalloc(&M.ent, (size_t)c->hash_slots * sizeof(uint4)));
+    CUC(cudaMalloc(&M.aux, (size_t)c->hash_slots * sizeof(uint4)));
+    CUC(cudaMalloc(&M.pool, (size_t)pool * sizeof(float4)));
+    CUC(cudaMalloc(&M.pool_top, sizeof(unsigned long long)));
+    int batch = cfg->max_scan_points > (1 << 20) ? cfg->max_scan_points : (1 << 20);
+    c->stage_pts_cap = batch;
+    CUC(cudaMalloc(&M.touched_list, (size_t)batch * sizeof(int)));
+    CUC(cudaMalloc(&c->d_counters, sizeof(int) * CNT_COUNT));
+    M.counters = c->d_counters;
+    CUC(cudaMallocHost(&c->h_counters, sizeof(int) * CNT_COUNT));
+    c->stage_raw_floats = (size_t)batch * 12;
+    CUC(cudaMalloc(&c->d_stage_raw, c->stage_raw_floats * 4));
+    CUC(cudaMalloc(&c->d_stage_pts, (size_t)batch * sizeof(float4)));
+    CUC(cudaMalloc(&c->d_slot_of, (size_t)batch * sizeof(int)));
+    CUC(cudaMalloc(&c->d_vslot_of, (size_t)batch * sizeof(int)));
+    CUC(cudaMalloc(&c->d_flag, (size_t)batch * sizeof(int)));
+    CUC(cudaMalloc(&c->d_q_d2, (size_t)batch * 5 * sizeof(float)));
+    {
+        int vl = 10;
+        while ((1ll << vl) < 2ll * batch) vl++;
+        c->V.mask = (1u << vl) - 1;
+        CUC(cudaMalloc(&c->V.keys, ((size_t)c->V.mask + 1) * 8));
+        CUC(cudaMalloc(&c->V.best, ((size_t)c->V.mask + 1) * 8));
+    }
+    int ns = cfg->max_scan_points;
+    CUC(cudaMalloc(&c->d_body, (size_t)ns * sizeof(float4)));
+    CUC(cudaMalloc(&c->d_world, (size_t)ns * sizeof(float4)));
+    CUC(cudaMalloc(&c->d_near_ids, (size_t)batch * 5 * sizeof(int)));
+    CUC(cudaMalloc(&c->d_selected, (size_t)ns));
+    CUC(cudaMalloc(&c->d_normvec, (size_t)ns * sizeof(float4)));
+    c->max_blocks = c->num_sms * 16;
+    CUC(cudaMalloc(&c->d_partials, (size_t)c->max_blocks * 96 * sizeof(double)));
+    CUC(cudaMalloc(&c->d_done, sizeof(unsigned)));
+    CUC(cudaMalloc(&c->d_out, 160 * sizeof(double)));
+    CUC(cudaMallocHost(&c->h_out, 160 * sizeof(double)));
+    CUC(cudaMemsetAsync(c->d_done, 0, sizeof(unsigned), c->stream));
+    CUC(cudaMemsetAsync(c->d_counters, 0, sizeof(int) * CNT_COUNT, c->stream));
+    CUC(cudaMemsetAsync(M.pool_top, 0, sizeof(unsigned long long), c->stream));
+    k_map_clear<<<nblk(c->hash_slots, 256), 256, 0, c->stream>>>(M.ent, M.aux, c->hash_slots);
+    c->launches++;
+    CUC(cudaGetLastError());
+    CUC(cudaStreamSynchronize(c->stream));
+    c->S.body = c->d_body;
+    c->S.world = c->d_world;
+    c->S.near_ids = c->d_near_ids;
+    c->S.selected = c->d_selected;
+    c->S.normvec = c->d_normvec;
+    c->S.n = 0;
+#undef CUC
+    *out = h;
+    return LIINIT_OK;
+}
+
+int liinit_destroy(liinit_ctx* h) {
+    if (!h) return LIINIT_OK;
+    Ctx* c = &h->c;
+    cudaSetDevice(c->device);
+    if (c->own_stream) cudaStreamSynchronize(c->own_stream);
+    cudaFree(c->M.ent); cudaFree(c->M.aux); cudaFree(c->M.pool); cudaFree(c->M.pool_top); cudaFree(c->M.touched_list);
+    cudaFree(c->d_counters); cudaFreeHost(c->h_counters); cudaFree(c->d_stage_raw); cudaFree(c->d_stage_pts);
+    cudaFree(c->d_slot_of); cudaFree(c->d_vslot_of); cudaFree(c->d_flag); cudaFree(c->V.keys); cudaFree(c->V.best);
+    cudaFree(c->d_body); cudaFree(c->d_world); cudaFree(c->d_near_ids); cudaFree(c->d_selected); cudaFree(c->d_normvec);
+    cudaFree(c->d_partials); cudaFree(c->d_done); cudaFree(c->d_out); cudaFreeHost(c->h_out); cudaFree(c->d_q_d2);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete h;
+    return LIINIT_OK;
+}
+
+int liinit_set_stream(liinit_ctx* h, void* cuda_stream) {
+    if (!h) return LIINIT_ERR_INVALID;
+    Ctx* c = &h->c;
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return LIINIT_OK;
+}
+
+int liinit_map_build(liinit_ctx* h, const float* xyz, int stride, int n) {
+    if (!h || (!xyz && n > 0) || n < 0) return LIINIT_ERR_INVALID;
+    Ctx* c = &h->c;
+    CU(cudaSetDevice(c->device));
+    if (n > c->cfg.max_map_points) return fail(c, LIINIT_ERR_CAPACITY, "n exceeds max_map_points");
+    // KD_TREE::Build replaces the tree (ikd_Tree.cpp:337-339)
+    CU(cudaMemsetAsync(c->d_counters, 0, sizeof(int) * CNT_COUNT, c->stream));
+    CU(cudaMemsetAsync(c->M.pool_top, 0, sizeof(unsigned long long), c->stream));
+    k_map_clear<<<nblk(c->hash_slots, 256), 256, 0, c->stream>>>(c->M.ent, c->M.aux, c->hash_slots);
+    c->launches++;
+    c->have_neighbors = false;
+    for (long long off = 0; off < n; off += c->stage_pts_cap) {
+        int m = (int)((n - off < c->stage_pts_cap) ? (n - off) : c->stage_pts_cap);
+        int r = stage_points(c, xyz + (size_t)off * stride, stride, m);
+        if (r) return r;
+        r = plain_insert(c, c->d_stage_pts, m, nullptr, 0);
+        if (r) return r;
+        // the staging buffers are reused by the next chunk
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    int r = fetch_counters(c);
+    if (r) return r;
+    return check_map_err(c);
+}
+
+int liinit_map_add_points(liinit_ctx* h, const float* xyz, int stride, int n, int downsample_on, int* added) {
+    if (!h || (!xyz && n > 0) || n < 0) return LIINIT_ERR_INVALID;
+    Ctx* c = &h->c;
+    CU(cudaSetDevice(c->device));
+    c->have_neighbors = false;   // pool offsets may move
+    int total = 0;
+    for (long long off = 0; off < n; off += c->stage_pts_cap) {
+        int m = (int)((n - off < c->stage_pts_cap) ? (n - off) : c->stage_pts_cap);
+        int r = stage_points(c, xyz + (size_t)off * stride, stride, m);
+        if (r) return r;
+        r = downsample_on ? downsample_insert(c, c->d_stage_pts, m, nullptr, 0) : plain_insert(c, c->d_stage_pts, m, nullptr, 0);
+        if (r) return r;
+        r = fetch_counters(c);
+        if (r) return r;
+        r = check_map_err(c);
+        if (r) return r;
+        total += downsample_on ? c->h_counters[CNT_CHANGED] : m;
+    }
+    if (added) *added = total;
+    return LIINIT_OK;
+}
+
+int liinit_map_validnum(liinit_ctx* h, int* n) {
+    if (!h || !n) return LIINIT_ERR_INVALID;
+    Ctx* c = &h->c;
+    CU(cudaSetDevice(c->device));
+    int r = fetch_counters(c);
+    if (r) return r;
+    *n = c->h_counters[CNT_LIVE];
+    return LIINIT_OK;
+}
+
+int liinit_map_size(liinit_ctx* h, int* n) { return liinit_map_validnum(h, n); }
+
+int liinit_map_stats(liinit_ctx* h, int* bricks, int* hash_slots, long long* pool_used, long long* pool_cap) {
+    if (!h) return LIINIT_ERR_INVALID;
+    Ctx* c = &h->c;
+    CU(cudaSetDevice(c->device));
+    int r = fetch_counters(c);
+    if (r) return r;
+    unsigned long long top = 0;
+    CU(cudaMemcpyAsync(&top, c->M.pool_top, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (bricks) *bricks = c->h_counters[CNT_BRICKS];
+    if (hash_slots) *hash_slots = (int)c->hash_slots;
+    if (pool_used) *pool_used = (long long)top;
+    if (pool_cap) *pool_cap = (long long)c->M.pool_cap;
+    return LIINIT_OK;
+}
+
+int liinit_map_download(liinit_ctx* h, float* xyz, int cap, int* n) {
+    if (!h || !n || cap < 0) return LIINIT_ERR_INVALID;
+    Ctx* c = &h->c;
+    CU(cudaSetDevice(c->device));
+    float* d_out = nullptr;
+    int* d_n = nullptr;
+    CU(cudaMalloc(&d_out, (size_t)(cap > 0 ? cap : 1) * 12));
+    CU(cudaMalloc(&d_n, 4));
+    CU(cudaMemsetAsync(d_n, 0, 4, c->stream));
+    k_map_flatten<<<nblk((long long)c->hash_slots * 32, 256), 256, 0, c->stream>>>(c->M, c->hash_slots, d_out, cap, d_n);
+    c->launches++;
+    int cnt = 0;
+    CU(cudaMemcpyAsync(&cnt, d_n, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    int m = cnt < cap ? cnt : cap;
+    if (m > 0 && xyz) CU(cudaMemcpy(xyz, d_out, (size_t)m * 12, cudaMemcpyDeviceToHost));
+    cudaFree(d_out);
+    cudaFree(d_n);
+    *n = cnt;
+    return LIINIT_OK;
+}
+
+int liinit_map_nearest_search(liinit_ctx* h, const float* q, int stride, int n, double max_dist, float* out_xyz, float* out_d2,
+                              int* out_cnt) {
+    if (!h || !q || n < 0) return LIINIT_ERR_INVALID;
+    Ctx* c = &h->c;
+    if (max_dist != 5.0) return fail(c, LIINIT_ERR_INVALID, "only max_dist = 5 (laserMapping.cpp:980) is supported");
+    CU(cudaSetDevice(c->device));
+    std::vector<int> ids((size_t)5 * (n > 0 ? n : 1));
+    std::vector<float4> pool_pts;
+    for (long long off = 0; off < n; off += c->stage_pts_cap) {
+        int m = (int)((n - off < c->stage_pts_cap) ? (n - off) : c->stage_pts_cap);
+        int r = stage_points(c, q + (size_t)off * stride, stride, m);
+        if (r) return r;
+        // d_vslot_of.. reuse: ids go to a scratch the size of batch*5 -> use d_near_ids only if scan not resident; allocate
+        int* d_ids = nullptr;
+        CU(cudaMalloc(&d_ids, (size_t)m * 5 * sizeof(int)));
+        int grid = nblk((long long)m * 32, 256);
+        if (grid > c->max_blocks) grid = c->max_blocks;
+        k_knn_queries<<<grid, 256, 0, c->stream>>>(c->M, c->d_stage_pts, m, d_ids, c->d_q_d2);
+        c->launches++;
+        CU(cudaMemcpyAsync(ids.data() + (size_t)off * 5, d_ids, (size_t)m * 5 * 4, cudaMemcpyDeviceToHost, c->stream));
+        if (out_d2) CU(cudaMemcpyAsync(out_d2 + (size_t)off * 5, c->d_q_d2, (size_t)m * 5 * 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        cudaFree(d_ids);
+    }
+    // gather neighbour coordinates (marshalling, not compute): fetch the used part of the pool
+    unsigned long long top = 0;
+    CU(cudaMemcpy(&top, c->M.pool_top, 8, cudaMemcpyDeviceToHost));
+    pool_pts.resize(top > 0 ? top : 1);
+    if (top > 0) CU(cudaMemcpy(pool_pts.data(), c->M.pool, (size_t)top * 16, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; i++) {
+        int cnt = 0;
+        for (int k = 0; k < 5; k++) {
+            int id = ids[(size_t)i * 5 + k];
+            size_t o = (size_t)i * 5 + k;
+            if (id >= 0) {
+                cnt++;
+                if (out_xyz) {
+                    out_xyz[3 * o] = pool_pts[id].x; out_xyz[3 * o + 1] = pool_pts[id].y; out_xyz[3 * o + 2] = pool_pts[id].z;
+                }
+            } else if (out_xyz) {
+                out_xyz[3 * o] = out_xyz[3 * o + 1] = out_xyz[3 * o + 2] = 0.f;
+            }
+        }
+        if (out_cnt) out_cnt[i] = cnt;
+        // PointType_CMP tie order (ikd_Tree.h:57-60)
+        if (out_xyz && out_d2) {
+            for (int pass = 0; pass < 4; pass++)
+                for (int k = 0; k + 1 < cnt; k++) {
+                    size_t a = (size_t)i * 5 + k, b = a + 1;
+                    if (std::fabs(out_d2[a] - out_d2[b]) < 1e-10f && out_xyz[3 * b] < out_xyz[3 * a]) {
+                        for (int t = 0; t < 3; t++) std::swap(out_xyz[3 * a + t], out_xyz[3 * b + t]);
+                        std::swap(out_d2[a], out_d2[b]);
+                    }
+                }
+        }
+    }
+    return LIINIT_OK;
+}
+
+int liinit_scan_upload(liinit_ctx* h, const float* body, int stride, int n) {
+    if (!h || !body || n <= 0) return LIINIT_ERR_INVALID;
+    Ctx* c = &h->c;
+    CU(cudaSetDevice(c->device));
+    if (n > c->cfg.max_scan_points) return fail(c, LIINIT_ERR_CAPACITY, "n exceeds max_scan_points");
+    if (stride == 4) {
+        CU(cudaMemcpyAsync(c->d_body, body, (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
+    } else if (stride == 3 || stride == 12) {
+        size_t nf = (size_t)n * stride;
+        if (nf > c->stage_raw_floats) return fail(c, LIINIT_ERR_CAPACITY, "scan exceeds staging capacity");
+        CU(cudaMemcpyAsync(c->d_stage_raw, body, nf * 4, cudaMemcpyHostToDevice, c->stream));
+        k_repack<<<nblk(n, 256), 256, 0, c->stream>>>(c->d_stage_raw, stride, n, c->d_body);
+        c->launches++;
+    } else {
+        return fail(c, LIINIT_ERR_INVALID, "stride_floats must be 3, 4 or 12");
+    }
+    // new scan: no neighbours, nothing selected (Nearest_Points / point_selected_surf start over at iteration 0)
+    CU(cudaMemsetAsync(c->d_selected, 0, (size_t)n, c->stream));
+    CU(cudaMemsetAsync(c->d_near_ids, 0xff, (size_t)n * 5 * sizeof(int), c->stream));
+    c->scan_n = n;
+    c->S.n = n;
+    c->have_neighbors = false;
+    CU(cudaGetLastError());
+    return LIINIT_OK;
+}
+
+int liinit_icp_iterate_device(liinit_ctx* h, const double* R, const double* p, const double* RLI, const double* TLI, int imu_en,
+                              int search, double* d_out160) {
+    if (!h || !R || !p || !RLI || !TLI || !d_out160) return LIINIT_ERR_INVALID;
+    Ctx* c = &h->c;
+    CU(cudaSetDevice(c->device));
+    int r = run_pass(c, R, p, RLI, TLI, imu_en, search);
+    if (r) return r;
+    CU(cudaMemcpyAsync(d_out160, c->d_out, 160 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    return LIINIT_OK;
+}
+
+int liinit_icp_iterate(liinit_ctx* h, const double* R, const double* p, const double* RLI, const double* TLI, int imu_en,
+                       int search, double* HtH, double* Htr, int* m, double* res_sq) {
+    if (!h || !R || !p || !RLI || !TLI || !HtH || !Htr || !m) return LIINIT_ERR_INVALID;
+    Ctx* c = &h->c;
+    CU(cudaSetDevice(c->device));
+    int r = run_pass(c, R, p, RLI, TLI, imu_en, search);
+    if (r) return r;
+    CU(cudaMemcpyAsync(c->h_out, c->d_out, 160 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    memcpy(HtH, c->h_out, 144 * sizeof(double));
+    memcpy(Htr, c->h_out + 144, 12 * sizeof(double));
+    if (res_sq) *res_sq = c->h_out[156];
+    *m = (int)llround(c->h_out[157]);
+    return LIINIT_OK;
+}
+
+int liinit_scan_download_state(liinit_ctx* h, float* world_xyz, float* near_xyz, int* near_cnt, unsigned char* selected,
+                               float* normvec) {
+    if (!h) return LIINIT_ERR_INVALID;
+    Ctx* c = &h->c;
+    CU(cudaSetDevice(c->device));
+    int n = c->scan_n;
+    if (n <= 0) return fail(c, LIINIT_ERR_INVALID, "no scan uploaded");
+    CU(cudaStreamSynchronize(c->stream));
+    if (world_xyz) {
+        std::vector<float4> w(n);
+        CU(cudaMemcpy(w.data(), c->d_world, (size_t)n * 16, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < n; i++) {
+            world_xyz[3 * (size_t)i] = w[i].x; world_xyz[3 * (size_t)i + 1] = w[i].y; world_xyz[3 * (size_t)i + 2] = w[i].z;
+        }
+    }
+    if (near_xyz || near_cnt) {
+        std::vector<int> ids((size_t)n * 5);
+        CU(cudaMemcpy(ids.data(), c->d_near_ids, (size_t)n * 5 * 4, cudaMemcpyDeviceToHost));
+        unsigned long long top = 0;
+        CU(cudaMemcpy(&top, c->M.pool_top, 8, cudaMemcpyDeviceToHost));
+        std::vector<float4> pool_pts(top > 0 ? top : 1);
+        if (top > 0) CU(cudaMemcpy(pool_pts.data(), c->M.pool, (size_t)top * 16, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < n; i++) {
+            int cnt = 0;
+            for (int k = 0; k < 5; k++) {
+                int id = ids[(size_t)i * 5 + k];
+                size_t o = (size_t)i * 5 + k;
+                if (id >= 0 && (unsigned long long)id < top) {
+                    cnt++;
+                    if (near_xyz) {
+                        near_xyz[3 * o] = pool_pts[id].x; near_xyz[3 * o + 1] = pool_pts[id].y; near_xyz[3 * o + 2] = pool_pts[id].z;
+                    }
+                } else if (near_xyz) {
+                    near_xyz[3 * o] = near_xyz[3 * o + 1] = near_xyz[3 * o + 2] = 0.f;
+                }
+            }
+            if (near_cnt) near_cnt[i] = cnt;
+        }
+    }
+    if (selected) CU(cudaMemcpy(selected, c->d_selected, (size_t)n, cudaMemcpyDeviceToHost));
+    if (normvec) CU(cudaMemcpy(normvec, c->d_normvec, (size_t)n * 16, cudaMemcpyDeviceToHost));
+    return LIINIT_OK;
+}
+
+int liinit_scan_download_effect(liinit_ctx* h, float* ori_xyz, float* normvec, int cap, int* m) {
+    if (!h || !m) return LIINIT_ERR_INVALID;
+    Ctx* c = &h->c;
+    CU(cudaSetDevice(c->device));
+    int n = c->scan_n;
+    if (n <= 0) return fail(c, LIINIT_ERR_INVALID, "no scan uploaded");
+    CU(cudaStreamSynchronize(c->stream));
+    std::vector<unsigned char> sel(n);
+    std::vector<float4> nv(n), body(n);
+    CU(cudaMemcpy(sel.data(), c->d_selected, (size_t)n, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(nv.data(), c->d_normvec, (size_t)n * 16, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(body.data(), c->d_body, (size_t)n * 16, cudaMemcpyDeviceToHost));
+    int k = 0;
+    for (int i = 0; i < n; i++) {   // order-preserving compaction (laserMapping.cpp:1013-1020)
+        if (!sel[i]) continue;
+        if (k < cap) {
+            if (ori_xyz) {
+                ori_xyz[3 * (size_t)k] = body[i].x; ori_xyz[3 * (size_t)k + 1] = body[i].y; ori_xyz[3 * (size_t)k + 2] = body[i].z;
+            }
+            if (normvec) memcpy(normvec + 4 * (size_t)k, &nv[i], 16);
+        }
+        k++;
+    }
+    *m = k;
+    return LIINIT_OK;
+}
+
+int liinit_map_incremental(liinit_ctx* h, const double* R, const double* p, const double* RLI, const double* TLI, double ds,
+                           int flg_EKF_inited, int* n_add, int* n_nod) {
+    if (!h || !R || !p || !RLI || !TLI) return LIINIT_ERR_INVALID;
+    Ctx* c = &h->c;
+    CU(cudaSetDevice(c->device));
+    int n = c->scan_n;
+    if (n <= 0) return fail(c, LIINIT_ERR_INVALID, "no scan uploaded");
+    PoseD P;
+    fill_pose(P, R, p, RLI, TLI);
+    static const int zeros[2] = {0, 0};
+    CU(cudaMemcpyAsync(c->d_counters + CNT_NADD, zeros, 2 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    k_incr_classify<<<nblk(n, 256), 256, 0, c->stream>>>(c->M, P, c->d_body, n, c->d_near_ids, ds, flg_EKF_inited, c->d_world,
+                                                        c->d_flag);
+    c->launches++;
+    CU(cudaGetLastError());
+    // Add_Points(PointToAdd, true) then Add_Points(PointNoNeedDownsample, false) (laserMapping.cpp:556-557).
+    // d_world (float4) is the point source; it stays untouched by the inserts.
+    int r = downsample_insert(c, c->d_world, n, c->d_flag, 1);
+    if (r) return r;
+    r = plain_insert(c, c->d_world, n, c->d_flag, 2);
+    if (r) return r;
+    c->have_neighbors = false;   // pool offsets may have moved; iteration 0 of the next scan searches anyway
+    r = fetch_counters(c);
+    if (r) return r;
+    if (n_add) *n_add = c->h_counters[CNT_NADD];
+    if (n_nod) *n_nod = c->h_counters[CNT_NNOD];
+    return check_map_err(c);
+}
+
+int liinit_last_pass_timing(liinit_ctx* h, float* kernel_ms, int* launches) {
+    if (!h) return LIINIT_ERR_INVALID;
+    Ctx* c = &h->c;
+    CU(cudaSetDevice(c->device));
+    CU(cudaEventSynchronize(c->ev1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->last_ms = ms;
+    if (kernel_ms) *kernel_ms = ms;
+    if (launches) *launches = c->last_launches;
+    return LIINIT_OK;
+}
+
+int liinit_launch_count(liinit_ctx* h, long long* launches) {
+    if (!h || !launches) return LIINIT_ERR_INVALID;
+    *launches = h->c.launches;
+    return LIINIT_OK;
+}
+
+}  // extern "C"

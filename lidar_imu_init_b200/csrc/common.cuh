@@ -39,18 +39,27 @@ struct PoseD {
     double TLI[3];   // offset_T_L_I
 };
 
+// Per-scan device state: the globals of laserMapping.cpp:102-125 the path touches.
+struct ScanDev {
+    const float4* body;     // feats_down_body (xyz, w unused)
+    float4* world;          // feats_down_world
+    int* near_ids;          // [N*5] pool offsets, -1 = missing (Nearest_Points)
+    unsigned char* selected;  // point_selected_surf
+    float4* normvec;        // (nx,ny,nz,pd2) f32
+    int n;
+};
+
 __device__ __forceinline__ unsigned long long li_pack_key(int x, int y, int z) {
     return ((unsigned long long)(unsigned)(x + LI_CELL_LIMIT) << 42) | ((unsigned long long)(unsigned)(y + LI_CELL_LIMIT) << 21) |
            (unsigned long long)(unsigned)(z + LI_CELL_LIMIT);
 }
 
+// Spatial hash of a packed key: three 32-bit multiplies (Teschner et al. primes) + a final avalanche step.
 __device__ __forceinline__ unsigned li_hash(unsigned long long k) {
-    k ^= k >> 33;
-    k *= 0xff51afd7ed558ccdull;
-    k ^= k >> 33;
-    k *= 0xc4ceb9fe1a85ec53ull;
-    k ^= k >> 33;
-    return (unsigned)k;
+    unsigned x = (unsigned)(k >> 42), y = (unsigned)(k >> 21) & 0x1fffffu, z = (unsigned)k & 0x1fffffu;
+    unsigned h = (x * 73856093u) ^ (y * 19349663u) ^ (z * 83492791u);
+    h ^= h >> 15;
+    return h;
 }
 
 // Voxel index exactly as the reference computes it: floor(x / downsample_size) in float

@@ -1,187 +1,13 @@
-// icp_kernels.cuh -- the hot path: fused 5-NN + plane fit + residual + Jacobian row + HtH/Htr reduction.
+// icp_kernels.cuh -- plane fit + residual + Jacobian row + HtH/Htr reduction (one scan point per lane).
 //
-// Replaces laserMapping.cpp:959-1071 (+ the dense reduction of :1080), esti_plane (common_lib.h:236-269) and
-// KD_TREE::Nearest_Search (ikd_Tree.cpp:349-379,825-968). DESIGN.md section 5 has the derivations.
+// Replaces laserMapping.cpp:989-1071 (+ the dense reduction of :1080) and esti_plane (common_lib.h:236-269).
+// The 5-NN that feeds it lives in knn_kernels.cuh. DESIGN.md section 5 has the derivations.
 //
-// Phase 1 (warp-cooperative, one scan point at a time): exact bounded 5-NN on the brick hash by ring expansion,
-//   32 lanes scanning a brick's slab with coalesced float4 loads, top-5 kept warp-uniform in registers.
-// Phase 2 (lane-parallel, one scan point per lane): fp64 column-pivoted Householder LSQ of the 5x3 system,
-//   residual, gating, Jacobian row; warp reduce-scatter of the 92 (imu) / 29 (lidar-only) accumulators.
+//   fp64 column-pivoted Householder LSQ of the 5x3 system, residual, gating, Jacobian row;
+//   warp reduce-scatter of the 92 (imu) / 29 (lidar-only) accumulators; per-block partials and a
+//   fixed-order final reduction by the last block (bit-reproducible).
 #pragma once
 #include "common.cuh"
-
-// ----------------------------------------------------------------------------------------------
-// warp-uniform sorted top-5
-struct Top5 {
-    float d[5];
-    int id[5];
-    int n;
-};
-
-__device__ __forceinline__ void top5_init(Top5& t) {
-#pragma unroll
-    for (int i = 0; i < 5; i++) {
-        t.d[i] = INFINITY;
-        t.id[i] = -1;
-    }
-    t.n = 0;
-}
-
-// uniform insert of (dm, idm): after every entry <= dm (first come first kept on ties, as the
-// reference's strict '<' replacement test, ikd_Tree.cpp:842).
-__device__ __forceinline__ void top5_insert(Top5& t, float dm, int idm) {
-    int p = 0;
-#pragma unroll
-    for (int i = 0; i < 5; i++) p += (t.d[i] <= dm) ? 1 : 0;
-#pragma unroll
-    for (int i = 4; i >= 1; i--) {
-        if (i > p) {
-            t.d[i] = t.d[i - 1];
-            t.id[i] = t.id[i - 1];
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < 5; i++) {
-        if (i == p) {
-            t.d[i] = dm;
-            t.id[i] = idm;
-        }
-    }
-    t.n = min(t.n + 1, 5);
-}
-
-// All lanes call. valid: this lane carries candidate (dc, idc). max_d2 = 5 (laserMapping.cpp:980).
-__device__ __forceinline__ void top5_consider(Top5& t, float dc, int idc, bool valid, float max_d2, int lane) {
-    bool pass = valid && (dc <= max_d2) && (dc < t.d[4]);   // d[4] = +inf while fewer than 5
-    unsigned m = __ballot_sync(LI_FULL, pass);
-    while (m) {
-        unsigned bits = pass ? __float_as_uint(dc) : 0xffffffffu;
-        unsigned mn = __reduce_min_sync(LI_FULL, bits);
-        unsigned who = __ballot_sync(LI_FULL, pass && bits == mn);
-        int src = __ffs(who) - 1;
-        int idm = __shfl_sync(LI_FULL, idc, src);
-        top5_insert(t, __uint_as_float(mn), idm);
-        if (lane == src) pass = false;
-        pass = pass && (dc < t.d[4]);
-        m = __ballot_sync(LI_FULL, pass);
-    }
-}
-
-// Scan one brick slab.
-__device__ __forceinline__ void knn_scan_slab(const float4* __restrict__ pool, unsigned first, unsigned count, float qx, float qy,
-                                              float qz, Top5& t, int lane) {
-    for (unsigned base = 0; base < count; base += 32) {
-        unsigned j = base + lane;
-        bool valid = j < count;
-        float dc = INFINITY;
-        if (valid) {
-            float4 p = __ldg(&pool[(size_t)first + j]);
-            dc = li_dist2(qx, qy, qz, p.x, p.y, p.z);
-        }
-        top5_consider(t, dc, (int)(first + j), valid, 5.0f, lane);
-    }
-}
-
-// Exact 5-NN of (qx,qy,qz) within squared distance 5, warp-cooperative. Result warp-uniform in t.
-__device__ __forceinline__ void knn5_warp(const MapDev& M, float qx, float qy, float qz, Top5& t, int lane) {
-    top5_init(t);
-    const int bs = M.bshift;
-    const float ds = M.ds;
-    const int bc = 1 << bs;
-    if (!(isfinite(qx) && isfinite(qy) && isfinite(qz))) return;
-    const float lim = (float)(LI_CELL_LIMIT - 8 * bc) * ds;
-    if (fabsf(qx) >= lim || fabsf(qy) >= lim || fabsf(qz) >= lim) return;
-    const int cx = li_cell(qx, ds), cy = li_cell(qy, ds), cz = li_cell(qz, ds);
-    const int bx = cx >> bs, by = cy >> bs, bz = cz >> bs;
-    const int half = bc >> 1;
-    const int dirx = ((cx & (bc - 1)) < half) ? -1 : 1;
-    const int diry = ((cy & (bc - 1)) < half) ? -1 : 1;
-    const int dirz = ((cz & (bc - 1)) < half) ? -1 : 1;
-    const float B = (float)bc * ds;
-    // slack for float cell assignment / edge products: relative 2^-23 effects, bounded generously
-    const float margin = 1e-6f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + 16.0f * B);
-    const int Rmax = (int)ceilf(2.2360680f / B) + 1;
-
-    for (int R = 0; R <= Rmax; R++) {
-        // candidate bricks of this stage
-        int S, total;
-        if (R == 0) {
-            S = 2;
-            total = 8;
-        } else {
-            S = 2 * R + 1;
-            total = S * S * S;
-        }
-        for (int base = 0; base < total; base += 32) {
-            int idx = base + lane;
-            bool want = idx < total;
-            int ox = 0, oy = 0, oz = 0;
-            if (want) {
-                if (R == 0) {
-                    ox = (idx & 1) ? dirx : 0;
-                    oy = (idx & 2) ? diry : 0;
-                    oz = (idx & 4) ? dirz : 0;
-                } else {
-                    ox = idx % S - R;
-                    oy = (idx / S) % S - R;
-                    oz = idx / (S * S) - R;
-                    if (R == 1) {
-                        // skip the 2x2x2 half-block already visited in stage 0
-                        if ((ox == 0 || ox == dirx) && (oy == 0 || oy == diry) && (oz == 0 || oz == dirz)) want = false;
-                    } else {
-                        if (max(abs(ox), max(abs(oy), abs(oz))) < R) want = false;   // inner cube done
-                    }
-                }
-            }
-            unsigned first = 0, count = 0;
-            float dbox = INFINITY;
-            bool found = false;
-            if (want) {
-                const int kx = bx + ox, ky = by + oy, kz = bz + oz;
-                // box distance (lower bound, widened by margin)
-                float lox = (float)(kx << bs) * ds - margin, hix = (float)((kx + 1) << bs) * ds + margin;
-                float loy = (float)(ky << bs) * ds - margin, hiy = (float)((ky + 1) << bs) * ds + margin;
-                float loz = (float)(kz << bs) * ds - margin, hiz = (float)((kz + 1) << bs) * ds + margin;
-                float ex = fmaxf(0.f, fmaxf(lox - qx, qx - hix));
-                float ey = fmaxf(0.f, fmaxf(loy - qy, qy - hiy));
-                float ez = fmaxf(0.f, fmaxf(loz - qz, qz - hiz));
-                dbox = (ex * ex + ey * ey + ez * ez) * (1.0f - 1e-6f);
-                if (dbox <= 5.0f) found = li_brick_find(M.ent, M.mask, li_pack_key(kx, ky, kz), first, count);
-                found = found && count > 0u;
-            }
-            unsigned fm = __ballot_sync(LI_FULL, found);
-            while (fm) {
-                int src = __ffs(fm) - 1;
-                fm &= fm - 1;
-                float db = __shfl_sync(LI_FULL, dbox, src);
-                unsigned f = __shfl_sync(LI_FULL, first, src);
-                unsigned c = __shfl_sync(LI_FULL, count, src);
-                if (t.n == 5 && db >= t.d[4]) continue;   // cannot improve (strict '<' rule)
-                knn_scan_slab(M.pool, f, c, qx, qy, qz, t, lane);
-            }
-        }
-        // explored region after this stage: bricks [bx-alo, bx+ahi] per axis
-        int lo_x, hi_x, lo_y, hi_y, lo_z, hi_z;
-        if (R == 0) {
-            lo_x = min(bx, bx + dirx); hi_x = max(bx, bx + dirx);
-            lo_y = min(by, by + diry); hi_y = max(by, by + diry);
-            lo_z = min(bz, bz + dirz); hi_z = max(bz, bz + dirz);
-        } else {
-            lo_x = bx - R; hi_x = bx + R;
-            lo_y = by - R; hi_y = by + R;
-            lo_z = bz - R; hi_z = bz + R;
-        }
-        float rx = fminf(qx - (float)(lo_x << bs) * ds, (float)((hi_x + 1) << bs) * ds - qx);
-        float ry = fminf(qy - (float)(lo_y << bs) * ds, (float)((hi_y + 1) << bs) * ds - qy);
-        float rz = fminf(qz - (float)(lo_z << bs) * ds, (float)((hi_z + 1) << bs) * ds - qz);
-        float r = fminf(rx, fminf(ry, rz)) - margin;
-        if (r > 0.f) {
-            float r2 = r * r * (1.0f - 1e-6f);
-            if (r2 > 5.0f) break;                      // everything within the search radius was seen
-            if (t.n == 5 && t.d[4] <= r2) break;       // no unseen point can be strictly closer
-        }
-    }
-}
 
 // ----------------------------------------------------------------------------------------------
 // Phase 2 math (per scan point, fp64)
@@ -491,18 +317,11 @@ __device__ __forceinline__ void block_finish(const double (&acc)[AccLayout<IMU>:
     if (threadIdx.x == 0) *done_counter = 0u;
 }
 
-struct ScanDev {
-    const float4* body;     // feats_down_body (xyz, w unused)
-    float4* world;          // feats_down_world
-    int* near_ids;          // [N*5] pool offsets, -1 = missing (Nearest_Points)
-    unsigned char* selected;  // point_selected_surf
-    float4* normvec;        // (nx,ny,nz,pd2) f32
-    int n;
-};
 
 // Order the 5 neighbours as PointType_CMP does (ikd_Tree.h:57-60): ascending distance, distances closer than
 // 1e-10 are ties broken by smaller x. The search already delivers ascending distances, only ties can move.
-__device__ __forceinline__ void tie_order(float4 (&nb)[5], int (&id)[5], float (&d)[5]) {
+__device__ __forceinline__ bool tie_order(float4 (&nb)[5], int (&id)[5], float (&d)[5]) {
+    bool moved = false;
 #pragma unroll
     for (int pass = 0; pass < 4; pass++) {
 #pragma unroll
@@ -511,80 +330,19 @@ __device__ __forceinline__ void tie_order(float4 (&nb)[5], int (&id)[5], float (
                 float4 tq = nb[k]; nb[k] = nb[k + 1]; nb[k + 1] = tq;
                 int ti = id[k]; id[k] = id[k + 1]; id[k + 1] = ti;
                 float td = d[k]; d[k] = d[k + 1]; d[k + 1] = td;
+                moved = true;
             }
         }
     }
+    return moved;
 }
 
-// ---- fused search pass -------------------------------------------------------------------------
-// One warp owns a tile of TILE consecutive scan points: transform (lane-parallel), 5-NN (warp-cooperative,
-// point after point), then plane/residual/Jacobian (lane-parallel) and the reduction.
-template <int TILE, bool IMU>
-__global__ void __launch_bounds__(256) k_icp_search(MapDev M, ScanDev S, PoseD P, double* __restrict__ partials,
-                                                    unsigned* __restrict__ done_counter, double* __restrict__ out160) {
-    typedef AccLayout<IMU> L;
-    const int lane = threadIdx.x & 31;
-    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int nwarps_total = (gridDim.x * blockDim.x) >> 5;
-    const int ntiles = (S.n + TILE - 1) / TILE;
-    double acc[L::K];
-#pragma unroll
-    for (int k = 0; k < L::K; k++) acc[k] = 0.0;
-
-    for (int tile = warp_global; tile < ntiles; tile += nwarps_total) {
-        const int q = tile * TILE + lane;
-        const bool active = (lane < TILE) && (q < S.n);
-        float bx = 0, by = 0, bz = 0, wx = 0, wy = 0, wz = 0;
-        if (active) {
-            float4 b = __ldg(&S.body[q]);
-            bx = b.x; by = b.y; bz = b.z;
-            li_body_to_world(P, bx, by, bz, wx, wy, wz);
-            S.world[q] = make_float4(wx, wy, wz, 0.f);
-        }
-        int my_id[5] = {-1, -1, -1, -1, -1};
-        float my_d[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-        const int in_tile = min(TILE, S.n - tile * TILE);
-        for (int j = 0; j < in_tile; j++) {
-            float qx = __shfl_sync(LI_FULL, wx, j), qy = __shfl_sync(LI_FULL, wy, j), qz = __shfl_sync(LI_FULL, wz, j);
-            Top5 t;
-            knn5_warp(M, qx, qy, qz, t, lane);
-            if (lane == j) {
-#pragma unroll
-                for (int k = 0; k < 5; k++) {
-                    my_id[k] = t.id[k];
-                    my_d[k] = t.d[k];
-                }
-            }
-        }
-        double row[L::NC];
-        double r = 0.0;
-        bool sel = false;
-#pragma unroll
-        for (int i = 0; i < L::NC; i++) row[i] = 0.0;
-        if (active) {
-            // selection gate (laserMapping.cpp:981-984): 5 found; d2[4] <= 5 holds by construction
-            if (my_id[4] >= 0) {
-                float4 nb[5];
-#pragma unroll
-                for (int k = 0; k < 5; k++) nb[k] = __ldg(&M.pool[my_id[k]]);
-                tie_order(nb, my_id, my_d);
-                float4 nvec;
-                sel = plane_and_row<IMU>(P, bx, by, bz, wx, wy, wz, nb, nvec, row, r);
-                if (sel) S.normvec[q] = nvec;
-            }
-#pragma unroll
-            for (int k = 0; k < 5; k++) S.near_ids[(size_t)q * 5 + k] = my_id[k];
-            S.selected[q] = sel ? 1 : 0;
-        }
-        warp_accumulate<IMU>(row, r, sel, lane, acc);
-    }
-    block_finish<IMU>(acc, partials, done_counter, out160);
-}
-
-// ---- reuse pass (nearest_search_en == false, laserMapping.cpp:989-994) ------------------------------
-// One scan point per lane: reuses the stored neighbour ids and the previous selection flag.
-template <bool IMU>
-__global__ void __launch_bounds__(256) k_icp_reuse(MapDev M, ScanDev S, PoseD P, double* __restrict__ partials,
+// ---- plane / residual / Jacobian / reduction pass -----------------------------------------------------
+// SEARCH = true : runs right after k_knn_scan of the same pass; the selection gate is "5 neighbours found"
+//                 (laserMapping.cpp:981-984; d2[4] <= 5 holds by construction of the search).
+// SEARCH = false: reuse pass (nearest_search_en == false, :989-994): previous flag and stored neighbours.
+template <bool IMU, bool SEARCH>
+__global__ void __launch_bounds__(256) k_icp_plane(MapDev M, ScanDev S, PoseD P, double* __restrict__ partials,
                                                    unsigned* __restrict__ done_counter, double* __restrict__ out160) {
     typedef AccLayout<IMU> L;
     const int lane = threadIdx.x & 31;
@@ -604,13 +362,26 @@ __global__ void __launch_bounds__(256) k_icp_reuse(MapDev M, ScanDev S, PoseD P,
             float4 b = __ldg(&S.body[q]);
             float wx, wy, wz;
             li_body_to_world(P, b.x, b.y, b.z, wx, wy, wz);
-            S.world[q] = make_float4(wx, wy, wz, 0.f);
-            if (S.selected[q]) {
-                int id4 = S.near_ids[(size_t)q * 5 + 4];
-                if (id4 >= 0) {
+            if (!SEARCH) S.world[q] = make_float4(wx, wy, wz, 0.f);
+            bool gate = SEARCH ? true : (S.selected[q] != 0);
+            if (gate) {
+                int id[5];
+#pragma unroll
+                for (int k = 0; k < 5; k++) id[k] = S.near_ids[(size_t)q * 5 + k];
+                if (id[4] >= 0) {
                     float4 nb[5];
 #pragma unroll
-                    for (int k = 0; k < 5; k++) nb[k] = __ldg(&M.pool[S.near_ids[(size_t)q * 5 + k]]);
+                    for (int k = 0; k < 5; k++) nb[k] = __ldg(&M.pool[id[k]]);
+                    if (SEARCH) {
+                        float d[5];
+#pragma unroll
+                        for (int k = 0; k < 5; k++) d[k] = li_dist2(wx, wy, wz, nb[k].x, nb[k].y, nb[k].z);
+                        bool moved = tie_order(nb, id, d);
+                        if (moved) {
+#pragma unroll
+                            for (int k = 0; k < 5; k++) S.near_ids[(size_t)q * 5 + k] = id[k];
+                        }
+                    }
                     float4 nvec;
                     sel = plane_and_row<IMU>(P, b.x, b.y, b.z, wx, wy, wz, nb, nvec, row, r);
                     if (sel) S.normvec[q] = nvec;
@@ -621,23 +392,4 @@ __global__ void __launch_bounds__(256) k_icp_reuse(MapDev M, ScanDev S, PoseD P,
         warp_accumulate<IMU>(row, r, sel, lane, acc);
     }
     block_finish<IMU>(acc, partials, done_counter, out160);
-}
-
-// ---- stand-alone Nearest_Search for arbitrary queries (tests / KD_TREE::Nearest_Search drop-in) ------
-__global__ void __launch_bounds__(256) k_knn_queries(MapDev M, const float4* __restrict__ q, int n, int* __restrict__ ids,
-                                                     float* __restrict__ d2) {
-    const int lane = threadIdx.x & 31;
-    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int nw = (gridDim.x * blockDim.x) >> 5;
-    for (int i = warp_global; i < n; i += nw) {
-        float4 p = __ldg(&q[i]);
-        Top5 t;
-        knn5_warp(M, p.x, p.y, p.z, t, lane);
-        if (lane < 5) {
-            int id = (lane == 0) ? t.id[0] : (lane == 1) ? t.id[1] : (lane == 2) ? t.id[2] : (lane == 3) ? t.id[3] : t.id[4];
-            float d = (lane == 0) ? t.d[0] : (lane == 1) ? t.d[1] : (lane == 2) ? t.d[2] : (lane == 3) ? t.d[3] : t.d[4];
-            ids[(size_t)i * 5 + lane] = id;
-            d2[(size_t)i * 5 + lane] = (id >= 0) ? d : -1.f;
-        }
-    }
 }

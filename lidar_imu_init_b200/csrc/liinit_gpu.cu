@@ -14,6 +14,7 @@
 
 #include "common.cuh"
 #include "icp_kernels.cuh"
+#include "knn_kernels.cuh"
 #include "map_kernels.cuh"
 
 namespace {
@@ -64,7 +65,7 @@ struct Ctx {
     long long launches = 0;
     float last_ms = 0.f;
     int last_launches = 0;
-    int tile = 8;
+    int group = 8;
 };
 
 #define CU(call)                                                                                     \
@@ -161,13 +162,19 @@ void fill_pose(PoseD& P, const double* R, const double* p, const double* RLI, co
     memcpy(P.TLI, TLI, 24);
 }
 
-template <bool IMU>
-void launch_search(Ctx* c, const PoseD& P, int grid) {
-    switch (c->tile) {
-        case 32: k_icp_search<32, IMU><<<grid, 256, 0, c->stream>>>(c->M, c->S, P, c->d_partials, c->d_done, c->d_out); break;
-        case 16: k_icp_search<16, IMU><<<grid, 256, 0, c->stream>>>(c->M, c->S, P, c->d_partials, c->d_done, c->d_out); break;
-        default: k_icp_search<8, IMU><<<grid, 256, 0, c->stream>>>(c->M, c->S, P, c->d_partials, c->d_done, c->d_out); break;
-    }
+template <int G>
+void launch_knn_scan(Ctx* c, const PoseD& P) {
+    long long threads = (long long)c->scan_n * G;
+    int grid = nblk(threads, 256);
+    if (grid > c->max_blocks) grid = c->max_blocks;
+    k_knn_scan<G><<<grid, 256, 0, c->stream>>>(c->M, c->S, P);
+}
+
+template <bool IMU, bool SEARCH>
+void launch_plane(Ctx* c, const PoseD& P) {
+    int grid = nblk(c->scan_n, 256);
+    if (grid > c->max_blocks) grid = c->max_blocks;
+    k_icp_plane<IMU, SEARCH><<<grid, 256, 0, c->stream>>>(c->M, c->S, P, c->d_partials, c->d_done, c->d_out);
 }
 
 int run_pass(Ctx* c, const double* R, const double* p, const double* RLI, const double* TLI, int imu_en, int search) {
@@ -177,22 +184,22 @@ int run_pass(Ctx* c, const double* R, const double* p, const double* RLI, const 
     fill_pose(P, R, p, RLI, TLI);
     CU(cudaEventRecord(c->ev0, c->stream));
     if (search) {
-        int ntiles = (c->scan_n + c->tile - 1) / c->tile;
-        int grid = nblk(ntiles, 8);
-        if (grid > c->max_blocks) grid = c->max_blocks;
-        if (imu_en) launch_search<true>(c, P, grid); else launch_search<false>(c, P, grid);
+        switch (c->group) {
+            case 4: launch_knn_scan<4>(c, P); break;
+            case 16: launch_knn_scan<16>(c, P); break;
+            case 32: launch_knn_scan<32>(c, P); break;
+            default: launch_knn_scan<8>(c, P); break;
+        }
+        if (imu_en) launch_plane<true, true>(c, P); else launch_plane<false, true>(c, P);
         c->have_neighbors = true;
+        c->launches += 2;
+        c->last_launches = 2;
     } else {
-        int grid = nblk(c->scan_n, 256);
-        if (grid > c->max_blocks) grid = c->max_blocks;
-        if (imu_en)
-            k_icp_reuse<true><<<grid, 256, 0, c->stream>>>(c->M, c->S, P, c->d_partials, c->d_done, c->d_out);
-        else
-            k_icp_reuse<false><<<grid, 256, 0, c->stream>>>(c->M, c->S, P, c->d_partials, c->d_done, c->d_out);
+        if (imu_en) launch_plane<true, false>(c, P); else launch_plane<false, false>(c, P);
+        c->launches += 1;
+        c->last_launches = 1;
     }
     CU(cudaEventRecord(c->ev1, c->stream));
-    c->launches += 1;
-    c->last_launches = 1;
     CU(cudaGetLastError());
     return LIINIT_OK;
 }
@@ -266,7 +273,7 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
         return bail(LIINIT_ERR_INVALID);
     }
     c->hash_slots = 1u << hl;
-    c->tile = (cfg->knn_tile == 8 || cfg->knn_tile == 16 || cfg->knn_tile == 32) ? cfg->knn_tile : 8;
+    c->group = (cfg->knn_group_lanes == 4 || cfg->knn_group_lanes == 8 || cfg->knn_group_lanes == 16 || cfg->knn_group_lanes == 32) ? cfg->knn_group_lanes : 8;
 
     MapDev& M = c->M;
     M.mask = c->hash_slots - 1;
@@ -467,9 +474,9 @@ int liinit_map_nearest_search(liinit_ctx* h, const float* q, int stride, int n, 
         // d_vslot_of.. reuse: ids go to a scratch the size of batch*5 -> use d_near_ids only if scan not resident; allocate
         int* d_ids = nullptr;
         CU(cudaMalloc(&d_ids, (size_t)m * 5 * sizeof(int)));
-        int grid = nblk((long long)m * 32, 256);
+        int grid = nblk((long long)m * 8, 256);
         if (grid > c->max_blocks) grid = c->max_blocks;
-        k_knn_queries<<<grid, 256, 0, c->stream>>>(c->M, c->d_stage_pts, m, d_ids, c->d_q_d2);
+        k_knn_queries<8><<<grid, 256, 0, c->stream>>>(c->M, c->d_stage_pts, m, d_ids, c->d_q_d2);
         c->launches++;
         CU(cudaMemcpyAsync(ids.data() + (size_t)off * 5, d_ids, (size_t)m * 5 * 4, cudaMemcpyDeviceToHost, c->stream));
         if (out_d2) CU(cudaMemcpyAsync(out_d2 + (size_t)off * 5, c->d_q_d2, (size_t)m * 5 * 4, cudaMemcpyDeviceToHost, c->stream));

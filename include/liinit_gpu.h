@@ -38,7 +38,7 @@ typedef struct liinit_config {
     int max_map_points;      /* capacity of the device map (live points); e.g. 50M for BASELINE config 4 */
     int max_scan_points;     /* capacity per scan (replaces the fixed 100000 caps, laserMapping.cpp:108-109,117-119) */
     int device_id;           /* CUDA device ordinal */
-    int brick_cells_log2;    /* voxels per brick edge = 1<<this; 0 -> default (2, i.e. brick edge = 4*ds) */
+    int brick_cells_log2;    /* voxels per brick edge = 1<<this; 0 -> default (3, i.e. brick edge = 8*ds) */
     int hash_capacity_log2;  /* brick hash slots = 1<<this; 0 -> derived from max_map_points */
     int knn_group_lanes;     /* lanes cooperating on one scan point in the 5-NN kernel: 4, 8, 16 or 32; 0 -> default (8) */
     int reserved[8];
@@ -101,6 +101,8 @@ int liinit_map_incremental(liinit_ctx* h, const double rot_end[9], const double 
 /* Device time in milliseconds of the kernels of the last liinit_icp_iterate* call (CUDA events on the context's
  * stream) and the number of kernel launches it made. */
 int liinit_last_pass_timing(liinit_ctx* h, float* kernel_ms, int* launches);
+/* Per-kernel device times of the last pass: the 5-NN kernel (0 for a reuse pass) and the plane/Jacobian/reduction kernel. */
+int liinit_last_pass_kernel_times(liinit_ctx* h, float* knn_ms, float* plane_ms);
 /* Cumulative number of kernels launched by this context. */
 int liinit_launch_count(liinit_ctx* h, long long* launches);
 /* Map statistics: bricks in use, hash slots, pool points in use / capacity. */

@@ -35,7 +35,7 @@ SYMBOLS = [
     "liinit_create", "liinit_destroy", "liinit_last_error", "liinit_set_stream", "liinit_map_build", "liinit_map_add_points",
     "liinit_map_validnum", "liinit_map_size", "liinit_map_download", "liinit_map_nearest_search", "liinit_scan_upload",
     "liinit_icp_iterate", "liinit_icp_iterate_device", "liinit_scan_download_effect", "liinit_scan_download_state",
-    "liinit_map_incremental", "liinit_last_pass_timing", "liinit_launch_count", "liinit_map_stats",
+    "liinit_map_incremental", "liinit_last_pass_timing", "liinit_last_pass_kernel_times", "liinit_launch_count", "liinit_map_stats",
 ]
 
 
@@ -72,6 +72,7 @@ def load():
     L.liinit_scan_download_state.argtypes = [vp, vp, vp, vp, vp, vp]
     L.liinit_map_incremental.argtypes = [vp, _f64, _f64, _f64, _f64, C.c_double, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.liinit_last_pass_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+    L.liinit_last_pass_kernel_times.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.liinit_launch_count.argtypes = [vp, C.POINTER(C.c_longlong)]
     L.liinit_map_stats.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     for s in SYMBOLS:
@@ -216,6 +217,11 @@ class LiInitGpu:
         ms, nl = C.c_float(0), C.c_int(0)
         self._ck(self.L.liinit_last_pass_timing(self.h, C.byref(ms), C.byref(nl)))
         return ms.value, nl.value
+
+    def last_pass_kernel_times(self):
+        a, b = C.c_float(0), C.c_float(0)
+        self._ck(self.L.liinit_last_pass_kernel_times(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def launch_count(self) -> int:
         n = C.c_longlong(0)

@@ -13,7 +13,7 @@
 // Phase 2 math (per scan point, fp64)
 
 // min ||A x - b||, A 5x3 (rows = neighbours), b = -1: column-pivoted Householder QR (the method behind
-// Eigen's colPivHouseholderQr().solve, common_lib.h:252). Operation order mirrors oracle/liinit_oracle.cpp.
+// Eigen's colPivHouseholderQr().solve, common_lib.h:252).
 __device__ __forceinline__ void lsq5x3(double (&A)[5][3], double (&x)[3]) {
     double b[5] = {-1.0, -1.0, -1.0, -1.0, -1.0};
     int p0 = 0, p1 = 1, p2 = 2;
@@ -292,7 +292,18 @@ __device__ __forceinline__ void block_finish(const double (&acc)[AccLayout<IMU>:
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    // last block: fixed-order sum over blocks -> bit-reproducible result for a given grid size
+    // last block: every value index is summed over the blocks by one warp -- lane l takes blocks l, l+32, ...
+    // (independent loads, pipelined), then a fixed shuffle tree. The order depends only on the grid size, so
+    // the result is bit-reproducible run to run.
+    __shared__ double s_tot[L::V];
+    for (int v = warp; v < L::NV; v += nwarps) {
+        double s = 0;
+        for (unsigned b = lane; b < gridDim.x; b += 32) s += __ldcg(&partials[(size_t)b * L::V + v]);
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(LI_FULL, s, o);
+        if (lane == 0) s_tot[v] = s;
+    }
+    __syncthreads();
     for (int o = threadIdx.x; o < 160; o += blockDim.x) {
         int src = -1;
         if (o < 144) {
@@ -307,12 +318,7 @@ __device__ __forceinline__ void block_finish(const double (&acc)[AccLayout<IMU>:
         } else if (o == 157) {
             src = L::NT + L::NC + 1;
         }
-        double s = 0;
-        if (src >= 0) {
-            const volatile double* pp = partials;
-            for (unsigned b = 0; b < gridDim.x; b++) s += pp[(size_t)b * L::V + src];
-        }
-        out160[o] = s;
+        out160[o] = (src >= 0) ? s_tot[src] : 0.0;
     }
     if (threadIdx.x == 0) *done_counter = 0u;
 }

@@ -27,7 +27,8 @@ struct Ctx {
     int num_sms = 148;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm = nullptr;
+    bool last_was_search = false;
     std::string err;
 
     // map
@@ -172,8 +173,9 @@ void launch_knn_scan(Ctx* c, const PoseD& P) {
 
 template <bool IMU, bool SEARCH>
 void launch_plane(Ctx* c, const PoseD& P) {
+    // one wave of 256-thread blocks (2 resident per SM at ~100-130 registers), grid-stride over the scan
     int grid = nblk(c->scan_n, 256);
-    if (grid > c->max_blocks) grid = c->max_blocks;
+    if (grid > c->num_sms * 2) grid = c->num_sms * 2;
     k_icp_plane<IMU, SEARCH><<<grid, 256, 0, c->stream>>>(c->M, c->S, P, c->d_partials, c->d_done, c->d_out);
 }
 
@@ -190,14 +192,17 @@ int run_pass(Ctx* c, const double* R, const double* p, const double* RLI, const 
             case 32: launch_knn_scan<32>(c, P); break;
             default: launch_knn_scan<8>(c, P); break;
         }
+        CU(cudaEventRecord(c->evm, c->stream));
         if (imu_en) launch_plane<true, true>(c, P); else launch_plane<false, true>(c, P);
         c->have_neighbors = true;
         c->launches += 2;
         c->last_launches = 2;
+        c->last_was_search = true;
     } else {
         if (imu_en) launch_plane<true, false>(c, P); else launch_plane<false, false>(c, P);
         c->launches += 1;
         c->last_launches = 1;
+        c->last_was_search = false;
     }
     CU(cudaEventRecord(c->ev1, c->stream));
     CU(cudaGetLastError());
@@ -255,8 +260,9 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
     c->stream = c->own_stream;
     CUC(cudaEventCreate(&c->ev0));
     CUC(cudaEventCreate(&c->ev1));
+    CUC(cudaEventCreate(&c->evm));
 
-    int bs = cfg->brick_cells_log2 > 0 ? cfg->brick_cells_log2 : 2;
+    int bs = cfg->brick_cells_log2 > 0 ? cfg->brick_cells_log2 : 3;
     if (bs < 1 || bs > 4) {
         c->err = "brick_cells_log2 must be in [1,4]";
         return bail(LIINIT_ERR_INVALID);
@@ -348,6 +354,7 @@ int liinit_destroy(liinit_ctx* h) {
     cudaFree(c->d_partials); cudaFree(c->d_done); cudaFree(c->d_out); cudaFreeHost(c->h_out); cudaFree(c->d_q_d2);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->evm) cudaEventDestroy(c->evm);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete h;
     return LIINIT_OK;
@@ -681,6 +688,23 @@ int liinit_last_pass_timing(liinit_ctx* h, float* kernel_ms, int* launches) {
     c->last_ms = ms;
     if (kernel_ms) *kernel_ms = ms;
     if (launches) *launches = c->last_launches;
+    return LIINIT_OK;
+}
+
+int liinit_last_pass_kernel_times(liinit_ctx* h, float* knn_ms, float* plane_ms) {
+    if (!h) return LIINIT_ERR_INVALID;
+    Ctx* c = &h->c;
+    CU(cudaSetDevice(c->device));
+    CU(cudaEventSynchronize(c->ev1));
+    float a = 0.f, b = 0.f;
+    if (c->last_was_search) {
+        CU(cudaEventElapsedTime(&a, c->ev0, c->evm));
+        CU(cudaEventElapsedTime(&b, c->evm, c->ev1));
+    } else {
+        CU(cudaEventElapsedTime(&b, c->ev0, c->ev1));
+    }
+    if (knn_ms) *knn_ms = a;
+    if (plane_ms) *plane_ms = b;
     return LIINIT_OK;
 }
 

@@ -14,7 +14,9 @@ CSRC = os.path.join(HERE, "csrc")
 GPU_LIB = os.path.join(HERE, "libliinit_gpu.so")
 HOST_LIB = os.path.join(HERE, "libliinit_host.so")
 
-NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+# --fmad=false: the fp32 distances and the fp64 plane / Jacobian arithmetic follow the reference's x86-64
+# build (-O3, no -march => no FMA contraction, CMakeLists.txt:8), so f32 outputs are bit-comparable with the oracle.
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "--fmad=false",
               "-Xcompiler", "-fPIC", "-shared"]
 
 

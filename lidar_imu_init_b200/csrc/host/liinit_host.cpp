@@ -1,0 +1,210 @@
+// liinit_host.cpp -- host side of the drop-in (see liinit_host.h). Everything here is O(24^3) per iteration.
+#include "liinit_host.h"
+
+#include <cmath>
+#include <cstring>
+
+namespace {
+
+constexpr int D = LIINIT_DIM_STATE;
+
+inline void mul33(const double* A, const double* B, double* C) {
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+}
+inline void mulT33(const double* A, const double* B, double* C) {   // A^T * B
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) C[3 * i + j] = A[i] * B[j] + A[3 + i] * B[3 + j] + A[6 + i] * B[6 + j];
+}
+
+// Dense inverse by LU with partial pivoting (what Eigen's .inverse() does for a 24x24, laserMapping.cpp:1081).
+bool invert(const double* A, double* X, int n) {
+    double lu[D * D];
+    int perm[D];
+    std::memcpy(lu, A, sizeof(double) * n * n);
+    for (int i = 0; i < n; i++) perm[i] = i;
+    for (int k = 0; k < n; k++) {
+        int piv = k;
+        double best = std::fabs(lu[k * n + k]);
+        for (int i = k + 1; i < n; i++)
+            if (std::fabs(lu[i * n + k]) > best) {
+                best = std::fabs(lu[i * n + k]);
+                piv = i;
+            }
+        if (best == 0.0) return false;
+        if (piv != k) {
+            for (int j = 0; j < n; j++) {
+                double t = lu[k * n + j];
+                lu[k * n + j] = lu[piv * n + j];
+                lu[piv * n + j] = t;
+            }
+            int t = perm[k];
+            perm[k] = perm[piv];
+            perm[piv] = t;
+        }
+        const double inv = 1.0 / lu[k * n + k];
+        for (int i = k + 1; i < n; i++) {
+            const double f = lu[i * n + k] * inv;
+            lu[i * n + k] = f;
+            for (int j = k + 1; j < n; j++) lu[i * n + j] -= f * lu[k * n + j];
+        }
+    }
+    for (int c = 0; c < n; c++) {
+        double y[D];
+        for (int i = 0; i < n; i++) {
+            double s = (perm[i] == c) ? 1.0 : 0.0;
+            for (int j = 0; j < i; j++) s -= lu[i * n + j] * y[j];
+            y[i] = s;
+        }
+        for (int i = n - 1; i >= 0; i--) {
+            double s = y[i];
+            for (int j = i + 1; j < n; j++) s -= lu[i * n + j] * X[j * n + c];
+            X[i * n + c] = s / lu[i * n + i];
+        }
+    }
+    return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+void liinit_so3_exp(const double v[3], double R[9]) {
+    const double n = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    static const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    if (n > 0.00001) {   // so3_math.h:66
+        const double r[3] = {v[0] / n, v[1] / n, v[2] / n};
+        const double K[9] = {0, -r[2], r[1], r[2], 0, -r[0], -r[1], r[0], 0};
+        double KK[9];
+        mul33(K, K, KK);
+        const double s = std::sin(n), c = 1.0 - std::cos(n);
+        for (int i = 0; i < 9; i++) R[i] = I[i] + s * K[i] + c * KK[i];
+    } else {
+        std::memcpy(R, I, sizeof(I));
+    }
+}
+
+void liinit_so3_log(const double R[9], double v[3]) {
+    const double tr = R[0] + R[4] + R[8];
+    const double theta = (tr > 3.0 - 1e-6) ? 0.0 : std::acos(0.5 * (tr - 1));
+    const double f = (std::fabs(theta) < 0.001) ? 0.5 : (0.5 * theta / std::sin(theta));
+    v[0] = f * (R[7] - R[5]);
+    v[1] = f * (R[2] - R[6]);
+    v[2] = f * (R[3] - R[1]);
+}
+
+void liinit_state_init(liinit_state* s) {
+    std::memset(s, 0, sizeof(*s));
+    s->rot_end[0] = s->rot_end[4] = s->rot_end[8] = 1.0;
+    s->offset_R_L_I[0] = s->offset_R_L_I[4] = s->offset_R_L_I[8] = 1.0;
+    for (int i = 0; i < D; i++) s->cov[i * D + i] = (i >= 15) ? 0.00001 : 1.0;   // INIT_COV, common_lib.h:79-80
+}
+
+void liinit_state_boxplus(liinit_state* s, const double* d) {
+    double E[9], R[9];
+    liinit_so3_exp(d, E);
+    mul33(s->rot_end, E, R);
+    std::memcpy(s->rot_end, R, sizeof(R));
+    liinit_so3_exp(d + 6, E);
+    mul33(s->offset_R_L_I, E, R);
+    std::memcpy(s->offset_R_L_I, R, sizeof(R));
+    for (int i = 0; i < 3; i++) {
+        s->pos_end[i] += d[3 + i];
+        s->offset_T_L_I[i] += d[9 + i];
+        s->vel_end[i] += d[12 + i];
+        s->bias_g[i] += d[15 + i];
+        s->bias_a[i] += d[18 + i];
+        s->gravity[i] += d[21 + i];
+    }
+}
+
+void liinit_state_boxminus(const liinit_state* a, const liinit_state* b, double* o) {
+    double rd[9];
+    mulT33(b->rot_end, a->rot_end, rd);
+    liinit_so3_log(rd, o);
+    mulT33(b->offset_R_L_I, a->offset_R_L_I, rd);
+    liinit_so3_log(rd, o + 6);
+    for (int i = 0; i < 3; i++) {
+        o[3 + i] = a->pos_end[i] - b->pos_end[i];
+        o[9 + i] = a->offset_T_L_I[i] - b->offset_T_L_I[i];
+        o[12 + i] = a->vel_end[i] - b->vel_end[i];
+        o[15 + i] = a->bias_g[i] - b->bias_g[i];
+        o[18 + i] = a->bias_a[i] - b->bias_a[i];
+        o[21 + i] = a->gravity[i] - b->gravity[i];
+    }
+}
+
+int liinit_ieskf_update(liinit_state* st, const liinit_state* prop, const double* HtH, const double* Htr, double* sol, double* KH) {
+    double S[D * D], K1[D * D];
+    if (!invert(st->cov, S, D)) return LIINIT_ERR_INVALID;      // cov^-1
+    for (int a = 0; a < 12; a++)
+        for (int b = 0; b < 12; b++) S[a * D + b] += 1000.0 * HtH[a * 12 + b];   // R_inv = 1000 (laserMapping.cpp:1050)
+    if (!invert(S, K1, D)) return LIINIT_ERR_INVALID;
+    double vec[D];
+    liinit_state_boxminus(prop, st, vec);
+    double G[D * 12];   // K*Hsub
+    for (int r = 0; r < D; r++)
+        for (int c = 0; c < 12; c++) {
+            double s = 0;
+            for (int a = 0; a < 12; a++) s += K1[r * D + a] * (1000.0 * HtH[a * 12 + c]);
+            G[r * 12 + c] = s;
+        }
+    for (int r = 0; r < D; r++) {
+        double s = 0, t = 0;
+        for (int a = 0; a < 12; a++) {
+            s += K1[r * D + a] * (1000.0 * Htr[a]);
+            t += G[r * 12 + a] * vec[a];
+        }
+        sol[r] = s + vec[r] - t;
+    }
+    liinit_state_boxplus(st, sol);
+    if (KH) std::memcpy(KH, G, sizeof(G));
+    return LIINIT_OK;
+}
+
+int liinit_scan_update(liinit_ctx* h, liinit_state* state, int max_iter, int imu_en, liinit_scan_stats* stats) {
+    if (!h || !state || max_iter < 1) return LIINIT_ERR_INVALID;
+    liinit_state prop = *state;            // state_propagat = state (laserMapping.cpp:910)
+    int rematch_num = 0, nearest_search_en = 1;
+    liinit_scan_stats st{};
+    double HtH[144], Htr[12], sol[D], KH[D * 12];
+    for (int it = 0; it < max_iter; it++) {
+        int m = 0;
+        double rs = 0;
+        st.search_passes += nearest_search_en;
+        int rc = liinit_icp_iterate(h, state->rot_end, state->pos_end, state->offset_R_L_I, state->offset_T_L_I, imu_en,
+                                    nearest_search_en, HtH, Htr, &m, &rs);
+        if (rc != LIINIT_OK) return rc;
+        rc = liinit_ieskf_update(state, &prop, HtH, Htr, sol, KH);
+        if (rc != LIINIT_OK) return rc;
+        st.iterations++;
+        st.effect_feat_num = m;
+        st.res_sq = rs;
+        const double rn = std::sqrt(sol[0] * sol[0] + sol[1] * sol[1] + sol[2] * sol[2]);
+        const double tn = std::sqrt(sol[3] * sol[3] + sol[4] * sol[4] + sol[5] * sol[5]);
+        st.last_rot_deg = rn * 57.3;
+        st.last_trans_cm = tn * 100;
+        const bool converged = (rn * 57.3 < 0.01) && (tn * 100 < 0.015);       // :1093-1094
+        st.converged = converged;
+        nearest_search_en = 0;                                                 // :1102-1106
+        if (converged || (rematch_num == 0 && it == max_iter - 2)) {
+            nearest_search_en = 1;
+            rematch_num++;
+        }
+        if (rematch_num >= 2 || it == max_iter - 1) {                          // :1109-1133
+            double nc[D * D];
+            for (int r = 0; r < D; r++)
+                for (int c = 0; c < D; c++) {
+                    double s = state->cov[r * D + c];
+                    for (int a = 0; a < 12; a++) s -= KH[r * 12 + a] * state->cov[a * D + c];
+                    nc[r * D + c] = s;
+                }
+            std::memcpy(state->cov, nc, sizeof(nc));
+            break;
+        }
+    }
+    if (stats) *stats = st;
+    return LIINIT_OK;
+}
+
+}  // extern "C"

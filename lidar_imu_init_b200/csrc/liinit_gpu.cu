@@ -128,10 +128,7 @@ int plain_insert(Ctx* c, const float4* pts, int n, const int* sel, int want) {
     if (n <= 0) return LIINIT_OK;
     int r = reset_batch_counters(c);
     if (r) return r;
-    if (sel)
-        k_ins_count_sel<<<nblk(n, 256), 256, 0, c->stream>>>(c->M, pts, n, sel, want, c->d_slot_of);
-    else
-        k_ins_count<<<nblk(n, 256), 256, 0, c->stream>>>(c->M, pts, n, c->d_slot_of);
+    k_ins_count<<<nblk(n, 256), 256, 0, c->stream>>>(c->M, pts, n, sel, want, c->d_slot_of);
     // number of touched bricks is unknown on the host: launch for the worst case (n warps), early exit inside
     k_ins_reserve<<<nblk((long long)n * 32, 256), 256, 0, c->stream>>>(c->M);
     k_ins_append<<<nblk(n, 256), 256, 0, c->stream>>>(c->M, pts, n, c->d_slot_of);
@@ -149,7 +146,7 @@ int downsample_insert(Ctx* c, const float4* pts, int n, const int* sel, int want
     k_ds_vote<<<nblk(n, 256), 256, 0, c->stream>>>(c->M, c->V, pts, n, sel, want, c->d_vslot_of);
     k_ds_reserve_votes<<<nblk(n, 256), 256, 0, c->stream>>>(c->M, c->V, pts, n, c->d_vslot_of, c->d_slot_of);
     k_ins_reserve<<<nblk((long long)n * 32, 256), 256, 0, c->stream>>>(c->M);
-    k_ds_apply<<<nblk((long long)n * 32, 256), 256, 0, c->stream>>>(c->M, pts, n, c->d_slot_of);
+    k_ds_apply<<<nblk((long long)n * 32, 256), 256, 0, c->stream>>>(c->M, pts, n, c->d_slot_of, c->d_vslot_of);
     k_ds_compact<<<nblk((long long)n * 32, 256), 256, 0, c->stream>>>(c->M);
     c->launches += 6;
     CU(cudaGetLastError());

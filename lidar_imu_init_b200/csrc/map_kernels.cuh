@@ -39,27 +39,75 @@ __device__ __forceinline__ unsigned li_voxel_in_brick(const MapDev& M, int cx, i
     return (unsigned)(((cx & m) << (2 * M.bshift)) | ((cy & m) << M.bshift) | (cz & m));
 }
 
+
+// Index of the downsample box that CONTAINS x as the reference tests membership (Search_by_range / Delete_by_range,
+// ikd_Tree.cpp:633,980): box k = [fl(k*ds), fl(fl(k*ds)+ds)). It equals the division index c = floor(fl(x/ds)) except
+// within one ulp of a box edge, where x can sit in box c-1 / c+1 or in NO box (the float boxes leave one-ulp gaps).
+// Grid-aligned synthetic scenes (walls at k*ds) hit this systematically, so it is reproduced exactly.
+#define LI_NO_BOX 0xfffffffeu
+__device__ __forceinline__ bool li_box_index(float x, float ds, int c, int& b) {
+    float cf = (float)c;
+    float mn = __fmul_rn(cf, ds), mx = __fadd_rn(mn, ds);
+    if (x >= mn && x < mx) { b = c; return true; }
+    if (x < mn) {
+        float m1 = __fmul_rn(cf - 1.0f, ds), x1 = __fadd_rn(m1, ds);
+        if (x >= m1 && x < x1) { b = c - 1; return true; }
+    } else {
+        float m1 = __fmul_rn(cf + 1.0f, ds), x1 = __fadd_rn(m1, ds);
+        if (x >= m1 && x < x1) { b = c + 1; return true; }
+    }
+    b = c;
+    return false;
+}
+
+// Where a map point is STORED: the brick of its box index (so that the box test of a later Add_Points finds it in
+// the brick of that box) and its voxel-in-brick id, or LI_NO_BOX when it lies in no downsample box.
+__device__ __forceinline__ void li_storage(const MapDev& M, float4 p, int cx, int cy, int cz, unsigned long long& brick_key, unsigned& vib) {
+    int bx, by, bz;
+    bool ok = li_box_index(p.x, M.ds, cx, bx);
+    ok = li_box_index(p.y, M.ds, cy, by) && ok;
+    ok = li_box_index(p.z, M.ds, cz, bz) && ok;
+    if (ok) {
+        brick_key = li_pack_key(bx >> M.bshift, by >> M.bshift, bz >> M.bshift);
+        vib = li_voxel_in_brick(M, bx, by, bz);
+    } else {
+        brick_key = li_pack_key(cx >> M.bshift, cy >> M.bshift, cz >> M.bshift);
+        vib = LI_NO_BOX;
+    }
+}
+
+// add a hash slot to the batch's touched list exactly once (aux.w is the membership flag)
+__device__ __forceinline__ void li_touch(const MapDev& M, int s) {
+    if (atomicExch(&M.aux[s].w, 1u) == 0u) M.touched_list[atomicAdd(&M.counters[CNT_TOUCHED], 1)] = s;
+}
+
 // ---- plain insert (Build, Add_Points(.., false)) -------------------------------------------------
 // pass 1: find-or-create the brick of every point, count pending points per brick.
-__global__ void k_ins_count(MapDev M, const float4* __restrict__ pts, int n, int* __restrict__ slot_of) {
+__global__ void k_ins_count(MapDev M, const float4* __restrict__ pts, int n, const int* __restrict__ sel, int want,
+                            int* __restrict__ slot_of) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    slot_of[i] = -1;
+    if (sel && sel[i] != want) return;
     int cx, cy, cz;
-    if (!li_point_cells(M, pts[i], cx, cy, cz)) {
-        slot_of[i] = -1;
+    float4 p = pts[i];
+    if (!li_point_cells(M, p, cx, cy, cz)) {
         atomicAdd(&M.counters[CNT_DROPPED], 1);
         return;
     }
+    unsigned long long key;
+    unsigned vib;
+    li_storage(M, p, cx, cy, cz, key, vib);
     bool created = false;
-    int s = li_brick_find_or_insert(M.ent, M.mask, li_pack_key(cx >> M.bshift, cy >> M.bshift, cz >> M.bshift), &created);
-    slot_of[i] = s;
+    int s = li_brick_find_or_insert(M.ent, M.mask, key, &created);
     if (s < 0) {
         atomicOr(&M.counters[CNT_ERR], ERR_HASH_FULL);
         return;
     }
+    slot_of[i] = s;
     if (created) atomicAdd(&M.counters[CNT_BRICKS], 1);
-    unsigned old = atomicAdd(&M.aux[s].y, 1u);
-    if (old == 0u) M.touched_list[atomicAdd(&M.counters[CNT_TOUCHED], 1)] = s;
+    atomicAdd(&M.aux[s].y, 1u);
+    li_touch(M, s);
 }
 
 // pass 2: one warp per touched brick -- grow its slab when count + pending exceeds the capacity.
@@ -105,7 +153,10 @@ __global__ void k_ins_append(MapDev M, const float4* __restrict__ pts, int n, co
     unsigned j = atomicAdd(&M.aux[s].z, 1u);
     float4 p = pts[i];
     int cx = li_cell(p.x, M.ds), cy = li_cell(p.y, M.ds), cz = li_cell(p.z, M.ds);
-    p.w = __uint_as_float(li_voxel_in_brick(M, cx, cy, cz));
+    unsigned long long key;
+    unsigned vib;
+    li_storage(M, p, cx, cy, cz, key, vib);
+    p.w = __uint_as_float(vib);
     M.pool[(size_t)e.z + e.w + j] = p;
 }
 
@@ -118,6 +169,7 @@ __global__ void k_ins_commit(MapDev M) {
     M.ent[s].w += f;
     M.aux[s].y = 0u;
     M.aux[s].z = 0u;
+    M.aux[s].w = 0u;
     atomicAdd(&M.counters[CNT_LIVE], (int)f);
 }
 
@@ -192,49 +244,69 @@ __global__ void k_ds_vote(MapDev M, VoxTmp V, const float4* __restrict__ pts, in
     atomicMin(&V.best[slot], v);
 }
 
-// pass D2: voxel winners reserve room in their brick.
-__global__ void k_ds_reserve_votes(MapDev M, VoxTmp V, const float4* __restrict__ pts, int n, const int* __restrict__ vslot_of,
-                                   int* __restrict__ slot_of) {
+// pass D2: voxel winners reserve room in the brick they would be STORED in and mark the brick of their BOX
+// (where the existing points they compete with live) as touched. The two differ only for ulp-edge points.
+__global__ void k_ds_reserve_votes(MapDev M, VoxTmp V, const float4* __restrict__ pts, int n, int* __restrict__ vslot_of /*in: voxel slot, out: box-brick slot*/,
+                                   int* __restrict__ slot_of /*out: storage-brick slot*/) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     slot_of[i] = -1;
     int vs = vslot_of[i];
+    vslot_of[i] = -1;
     if (vs < 0) return;
     unsigned long long b = V.best[vs];
     if ((unsigned)(b & 0xffffffffull) != 0xffffffffu - (unsigned)i) return;   // not this voxel's best new point
     float4 p = pts[i];
     int cx = li_cell(p.x, M.ds), cy = li_cell(p.y, M.ds), cz = li_cell(p.z, M.ds);
+    unsigned long long skey, bkey = li_pack_key(cx >> M.bshift, cy >> M.bshift, cz >> M.bshift);
+    unsigned vib;
+    li_storage(M, p, cx, cy, cz, skey, vib);
     bool created = false;
-    int s = li_brick_find_or_insert(M.ent, M.mask, li_pack_key(cx >> M.bshift, cy >> M.bshift, cz >> M.bshift), &created);
+    int s = li_brick_find_or_insert(M.ent, M.mask, skey, &created);
     if (s < 0) {
         atomicOr(&M.counters[CNT_ERR], ERR_HASH_FULL);
         return;
     }
     if (created) atomicAdd(&M.counters[CNT_BRICKS], 1);
     slot_of[i] = s;
-    unsigned old = atomicAdd(&M.aux[s].y, 1u);
-    if (old == 0u) M.touched_list[atomicAdd(&M.counters[CNT_TOUCHED], 1)] = s;
+    atomicAdd(&M.aux[s].y, 1u);
+    li_touch(M, s);
+    int sb = s;
+    if (bkey != skey) {
+        sb = -1;
+        unsigned h = li_hash(bkey) & M.mask;
+        for (unsigned t = 0; t <= M.mask; t++) {
+            unsigned long long k = *reinterpret_cast<volatile unsigned long long*>(&M.ent[h]);
+            if (k == bkey) { sb = (int)h; break; }
+            if (k == LI_EMPTY_KEY) break;
+            h = (h + 1) & M.mask;
+        }
+        if (sb >= 0) li_touch(M, sb);
+    }
+    vslot_of[i] = sb;
 }
 
 // pass D3: one warp per voxel winner. Compare with the voxel's live points, tombstone the losers
 // (w = 0xffffffff), append the new point if it wins. Different voxels of one brick touch disjoint
 // slab entries, appends go through aux.fill, so warps of the same brick do not race.
-__global__ void k_ds_apply(MapDev M, const float4* __restrict__ pts, int n, const int* __restrict__ slot_of) {
+__global__ void k_ds_apply(MapDev M, const float4* __restrict__ pts, int n, const int* __restrict__ slot_of,
+                           const int* __restrict__ box_slot_of) {
     int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (i >= n) return;
     int s = slot_of[i];
     if (s < 0) return;
-    uint4 e = M.ent[s];
-    uint4 a = M.aux[s];
-    if (a.y == 0u) return;   // reservation failed (pool full)
+    if (M.aux[s].y == 0u) return;   // reservation failed (pool full)
+    const int sb = box_slot_of[i];
     float4 p = pts[i];
     int cx = li_cell(p.x, M.ds), cy = li_cell(p.y, M.ds), cz = li_cell(p.z, M.ds);
-    unsigned vib = li_voxel_in_brick(M, cx, cy, cz);
+    const unsigned vib = li_voxel_in_brick(M, cx, cy, cz);   // id of p's BOX inside the box brick
     float dp = li_center_dist(p, M.ds);
-    // scan the live slab for this voxel's points
+    // scan the live slab of the box brick for the points of this box
     float best_d = INFINITY;
     unsigned best_j = 0xffffffffu;
     unsigned n_exist = 0;
+    uint4 e = make_uint4(0u, 0u, 0u, 0u);
+    if (sb >= 0) e = M.ent[sb];
     for (unsigned base = 0; base < e.w; base += 32) {
         unsigned j = base + lane;
         bool mine = false;
@@ -258,7 +330,7 @@ __global__ void k_ds_apply(MapDev M, const float4* __restrict__ pts, int n, cons
         }
     }
     bool existing_wins = (n_exist > 0) && (best_d < dp);   // strict: new point wins ties (ikd_Tree.cpp:405)
-    // tombstone every existing point of the voxel except a winning existing one
+    // tombstone every existing point of the box except a winning existing one
     if (n_exist > 0) {
         for (unsigned base = 0; base < e.w; base += 32) {
             unsigned j = base + lane;
@@ -270,9 +342,13 @@ __global__ void k_ds_apply(MapDev M, const float4* __restrict__ pts, int n, cons
     }
     if (lane == 0) {
         if (!existing_wins) {
+            uint4 es = M.ent[s];
             unsigned j = atomicAdd(&M.aux[s].z, 1u);
-            p.w = __uint_as_float(vib);
-            M.pool[(size_t)e.z + e.w + j] = p;
+            unsigned long long skey;
+            unsigned svib;
+            li_storage(M, p, cx, cy, cz, skey, svib);
+            p.w = __uint_as_float(svib);
+            M.pool[(size_t)es.z + es.w + j] = p;
         }
         if (!existing_wins || n_exist > 1) atomicAdd(&M.counters[CNT_CHANGED], 1);
     }
@@ -304,6 +380,7 @@ __global__ void k_ds_compact(MapDev M) {
         M.ent[s].w = wr;
         M.aux[s].y = 0u;
         M.aux[s].z = 0u;
+        M.aux[s].w = 0u;
         atomicAdd(&M.counters[CNT_LIVE], (int)wr - (int)e.w);
     }
 }
@@ -377,26 +454,3 @@ __global__ void k_incr_classify(MapDev M, PoseD P, const float4* __restrict__ bo
     if (f == 2) atomicAdd(&M.counters[CNT_NNOD], 1);
 }
 
-// plain insert restricted to flag[i]==want: reuse k_ins_* with a selection mask.
-__global__ void k_ins_count_sel(MapDev M, const float4* __restrict__ pts, int n, const int* __restrict__ sel, int want,
-                                int* __restrict__ slot_of) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    slot_of[i] = -1;
-    if (sel[i] != want) return;
-    int cx, cy, cz;
-    if (!li_point_cells(M, pts[i], cx, cy, cz)) {
-        atomicAdd(&M.counters[CNT_DROPPED], 1);
-        return;
-    }
-    bool created = false;
-    int s = li_brick_find_or_insert(M.ent, M.mask, li_pack_key(cx >> M.bshift, cy >> M.bshift, cz >> M.bshift), &created);
-    if (s < 0) {
-        atomicOr(&M.counters[CNT_ERR], ERR_HASH_FULL);
-        return;
-    }
-    slot_of[i] = s;
-    if (created) atomicAdd(&M.counters[CNT_BRICKS], 1);
-    unsigned old = atomicAdd(&M.aux[s].y, 1u);
-    if (old == 0u) M.touched_list[atomicAdd(&M.counters[CNT_TOUCHED], 1)] = s;
-}

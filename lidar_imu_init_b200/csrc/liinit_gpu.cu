@@ -44,6 +44,7 @@ struct Ctx {
     int* d_slot_of = nullptr;
     int* d_vslot_of = nullptr;
     int* d_flag = nullptr;
+    int* d_ins = nullptr;
     VoxTmp V{};
     // scan
     ScanDev S{};
@@ -143,11 +144,12 @@ int downsample_insert(Ctx* c, const float4* pts, int n, const int* sel, int want
     int r = reset_batch_counters(c);
     if (r) return r;
     k_vox_clear<<<nblk((long long)c->V.mask + 1, 256), 256, 0, c->stream>>>(c->V);
-    k_ds_vote<<<nblk(n, 256), 256, 0, c->stream>>>(c->M, c->V, pts, n, sel, want, c->d_vslot_of);
-    k_ds_reserve_votes<<<nblk(n, 256), 256, 0, c->stream>>>(c->M, c->V, pts, n, c->d_vslot_of, c->d_slot_of);
+    k_ds_link<<<nblk(n, 256), 256, 0, c->stream>>>(c->M, c->V, pts, n, sel, want, c->d_vslot_of, c->d_slot_of, c->d_ins);
     k_ins_reserve<<<nblk((long long)n * 32, 256), 256, 0, c->stream>>>(c->M);
-    k_ds_apply<<<nblk((long long)n * 32, 256), 256, 0, c->stream>>>(c->M, pts, n, c->d_slot_of, c->d_vslot_of);
-    k_ds_compact<<<nblk((long long)n * 32, 256), 256, 0, c->stream>>>(c->M);
+    k_ds_replay<<<nblk((long long)c->V.mask + 1, 128), 128, 0, c->stream>>>(c->M, c->V, pts, c->d_vslot_of, c->d_ins);
+    k_ds_append<<<nblk(n, 256), 256, 0, c->stream>>>(c->M, pts, n, c->d_slot_of, c->d_ins);
+    // tombstoned bricks were added to the touched list by the replay: worst case n + n bricks
+    k_ds_compact<<<nblk((long long)n * 64, 256), 256, 0, c->stream>>>(c->M);
     c->launches += 6;
     CU(cudaGetLastError());
     return LIINIT_OK;
@@ -292,7 +294,7 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
     CUC(cudaMalloc(&M.pool_top, sizeof(unsigned long long)));
     int batch = cfg->max_scan_points > (1 << 20) ? cfg->max_scan_points : (1 << 20);
     c->stage_pts_cap = batch;
-    CUC(cudaMalloc(&M.touched_list, (size_t)batch * sizeof(int)));
+    CUC(cudaMalloc(&M.touched_list, (size_t)batch * 2 * sizeof(int)));
     CUC(cudaMalloc(&c->d_counters, sizeof(int) * CNT_COUNT));
     M.counters = c->d_counters;
     CUC(cudaMallocHost(&c->h_counters, sizeof(int) * CNT_COUNT));
@@ -302,13 +304,14 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
     CUC(cudaMalloc(&c->d_slot_of, (size_t)batch * sizeof(int)));
     CUC(cudaMalloc(&c->d_vslot_of, (size_t)batch * sizeof(int)));
     CUC(cudaMalloc(&c->d_flag, (size_t)batch * sizeof(int)));
+    CUC(cudaMalloc(&c->d_ins, (size_t)batch * sizeof(int)));
     CUC(cudaMalloc(&c->d_q_d2, (size_t)batch * 5 * sizeof(float)));
     {
         int vl = 10;
         while ((1ll << vl) < 2ll * batch) vl++;
         c->V.mask = (1u << vl) - 1;
         CUC(cudaMalloc(&c->V.keys, ((size_t)c->V.mask + 1) * 8));
-        CUC(cudaMalloc(&c->V.best, ((size_t)c->V.mask + 1) * 8));
+        CUC(cudaMalloc(&c->V.head, ((size_t)c->V.mask + 1) * 4));
     }
     int ns = cfg->max_scan_points;
     CUC(cudaMalloc(&c->d_body, (size_t)ns * sizeof(float4)));
@@ -346,7 +349,7 @@ int liinit_destroy(liinit_ctx* h) {
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     cudaFree(c->M.ent); cudaFree(c->M.aux); cudaFree(c->M.pool); cudaFree(c->M.pool_top); cudaFree(c->M.touched_list);
     cudaFree(c->d_counters); cudaFreeHost(c->h_counters); cudaFree(c->d_stage_raw); cudaFree(c->d_stage_pts);
-    cudaFree(c->d_slot_of); cudaFree(c->d_vslot_of); cudaFree(c->d_flag); cudaFree(c->V.keys); cudaFree(c->V.best);
+    cudaFree(c->d_slot_of); cudaFree(c->d_vslot_of); cudaFree(c->d_flag); cudaFree(c->d_ins); cudaFree(c->V.keys); cudaFree(c->V.head);
     cudaFree(c->d_body); cudaFree(c->d_world); cudaFree(c->d_near_ids); cudaFree(c->d_selected); cudaFree(c->d_normvec);
     cudaFree(c->d_partials); cudaFree(c->d_done); cudaFree(c->d_out); cudaFreeHost(c->h_out); cudaFree(c->d_q_d2);
     if (c->ev0) cudaEventDestroy(c->ev0);

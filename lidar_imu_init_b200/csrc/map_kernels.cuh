@@ -174,10 +174,17 @@ __global__ void k_ins_commit(MapDev M) {
 }
 
 // ---- downsample insert (Add_Points(.., true)) --------------------------------------------------
-// Temporary voxel hash for the batch: vkeys (u64) + vbest (u64 = d_centre bits << 32 | ~index).
+// The reference walks the batch sequentially (ikd_Tree.cpp:388-426). For one downsample box the walk reduces to a
+// tiny state machine over the box's current content E (count, best distance to the box centre, best point):
+//   new point p (distance d_p):  p wins  <=>  !(E non-empty && d_best < d_p)      (strict '<': new wins ties)
+//   if |E| > 1 or p wins or same_point(p, best):   box is deleted, the winner is (re)inserted, E := {winner}
+// with two float-box subtleties that matter on grid-aligned data: a new point can lie OUTSIDE its own box (ulp edge:
+// then it is inserted but never seen by later box queries, E := {} after it wins), and an existing point belongs to
+// the box that CONTAINS it (li_box_index), not to the cell of its division index.
+// Boxes are independent of each other, so: one thread per box replays ITS new points in batch order.
 struct VoxTmp {
-    unsigned long long* keys;
-    unsigned long long* best;
+    unsigned long long* keys;   // box key (division cell of the new points)
+    int* head;                  // newest batch index linked into this box (-1 = none)
     unsigned mask;
 };
 
@@ -185,20 +192,10 @@ __global__ void k_vox_clear(VoxTmp V) {
     unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i > V.mask) return;
     V.keys[i] = LI_EMPTY_KEY;
-    V.best[i] = 0xffffffffffffffffull;
+    V.head[i] = -1;
 }
 
 // Distance of p to the centre of its downsample box, float arithmetic of ikd_Tree.cpp:389-401.
-__device__ __forceinline__ float li_center_dist(float4 p, float ds) {
-    float mnx = __fmul_rn(floorf(__fdiv_rn(p.x, ds)), ds), mxx = __fadd_rn(mnx, ds);
-    float mny = __fmul_rn(floorf(__fdiv_rn(p.y, ds)), ds), mxy = __fadd_rn(mny, ds);
-    float mnz = __fmul_rn(floorf(__fdiv_rn(p.z, ds)), ds), mxz = __fadd_rn(mnz, ds);
-    float mx = (float)__dadd_rn((double)mnx, __ddiv_rn((double)__fsub_rn(mxx, mnx), 2.0));
-    float my = (float)__dadd_rn((double)mny, __ddiv_rn((double)__fsub_rn(mxy, mny), 2.0));
-    float mz = (float)__dadd_rn((double)mnz, __ddiv_rn((double)__fsub_rn(mxz, mnz), 2.0));
-    return li_dist2(p.x, p.y, p.z, mx, my, mz);
-}
-// Same for an EXISTING point q tested against the box of voxel (cx,cy,cz) (its own voxel).
 __device__ __forceinline__ float li_center_dist_cell(float qx, float qy, float qz, int cx, int cy, int cz, float ds) {
     float mnx = __fmul_rn((float)cx, ds), mxx = __fadd_rn(mnx, ds);
     float mny = __fmul_rn((float)cy, ds), mxy = __fadd_rn(mny, ds);
@@ -209,12 +206,14 @@ __device__ __forceinline__ float li_center_dist_cell(float qx, float qy, float q
     return li_dist2(qx, qy, qz, mx, my, mz);
 }
 
-// pass D1: per new point, vote for the voxel's best new point (min centre distance, later index wins ties).
-__global__ void k_ds_vote(MapDev M, VoxTmp V, const float4* __restrict__ pts, int n, const int* __restrict__ sel /*optional: only sel[i]==want*/,
-                          int want, int* __restrict__ vslot_of) {
+// pass D1: link every selected new point into the list of its box; reserve one slot in the brick it would be stored in.
+__global__ void k_ds_link(MapDev M, VoxTmp V, const float4* __restrict__ pts, int n, const int* __restrict__ sel, int want,
+                          int* __restrict__ next_of, int* __restrict__ slot_of, int* __restrict__ ins) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    vslot_of[i] = -1;
+    next_of[i] = -2;   // not part of the batch
+    slot_of[i] = -1;
+    ins[i] = 0;
     if (sel && sel[i] != want) return;
     int cx, cy, cz;
     float4 p = pts[i];
@@ -222,6 +221,21 @@ __global__ void k_ds_vote(MapDev M, VoxTmp V, const float4* __restrict__ pts, in
         atomicAdd(&M.counters[CNT_DROPPED], 1);
         return;
     }
+    // storage brick: worst case every new point is inserted
+    unsigned long long skey;
+    unsigned svib;
+    li_storage(M, p, cx, cy, cz, skey, svib);
+    bool created = false;
+    int s = li_brick_find_or_insert(M.ent, M.mask, skey, &created);
+    if (s < 0) {
+        atomicOr(&M.counters[CNT_ERR], ERR_HASH_FULL);
+        return;
+    }
+    if (created) atomicAdd(&M.counters[CNT_BRICKS], 1);
+    slot_of[i] = s;
+    atomicAdd(&M.aux[s].y, 1u);
+    li_touch(M, s);
+    // box list
     unsigned long long key = li_pack_key(cx, cy, cz);
     unsigned h = li_hash(key) & V.mask;
     int slot = -1;
@@ -238,120 +252,110 @@ __global__ void k_ds_vote(MapDev M, VoxTmp V, const float4* __restrict__ pts, in
         atomicOr(&M.counters[CNT_ERR], ERR_HASH_FULL);
         return;
     }
-    vslot_of[i] = slot;
-    float d = li_center_dist(p, M.ds);
-    unsigned long long v = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)(0xffffffffu - (unsigned)i);
-    atomicMin(&V.best[slot], v);
+    next_of[i] = atomicExch(&V.head[slot], i);
 }
 
-// pass D2: voxel winners reserve room in the brick they would be STORED in and mark the brick of their BOX
-// (where the existing points they compete with live) as touched. The two differ only for ulp-edge points.
-__global__ void k_ds_reserve_votes(MapDev M, VoxTmp V, const float4* __restrict__ pts, int n, int* __restrict__ vslot_of /*in: voxel slot, out: box-brick slot*/,
-                                   int* __restrict__ slot_of /*out: storage-brick slot*/) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    slot_of[i] = -1;
-    int vs = vslot_of[i];
-    vslot_of[i] = -1;
-    if (vs < 0) return;
-    unsigned long long b = V.best[vs];
-    if ((unsigned)(b & 0xffffffffull) != 0xffffffffu - (unsigned)i) return;   // not this voxel's best new point
-    float4 p = pts[i];
-    int cx = li_cell(p.x, M.ds), cy = li_cell(p.y, M.ds), cz = li_cell(p.z, M.ds);
-    unsigned long long skey, bkey = li_pack_key(cx >> M.bshift, cy >> M.bshift, cz >> M.bshift);
-    unsigned vib;
-    li_storage(M, p, cx, cy, cz, skey, vib);
-    bool created = false;
-    int s = li_brick_find_or_insert(M.ent, M.mask, skey, &created);
-    if (s < 0) {
-        atomicOr(&M.counters[CNT_ERR], ERR_HASH_FULL);
-        return;
+// pass D3: one thread per box -- replay the box's new points in batch order (see the state machine above).
+// Existing losers are tombstoned (w = 0xffffffff), ins[i] = 1 marks the new points that end up in the map.
+__global__ void k_ds_replay(MapDev M, VoxTmp V, const float4* __restrict__ pts, const int* __restrict__ next_of,
+                            int* __restrict__ ins) {
+    unsigned v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v > V.mask) return;
+    int head = V.head[v];
+    if (head < 0) return;
+    // the box
+    float4 ph = pts[head];
+    const int cx = li_cell(ph.x, M.ds), cy = li_cell(ph.y, M.ds), cz = li_cell(ph.z, M.ds);
+    const unsigned vib = li_voxel_in_brick(M, cx, cy, cz);
+    // the brick that holds the box's existing points
+    unsigned first = 0, count = 0;
+    bool have = li_brick_find(M.ent, M.mask, li_pack_key(cx >> M.bshift, cy >> M.bshift, cz >> M.bshift), first, count);
+    // (li_brick_find uses the read-only path; ent is not modified between D2's reserve and this kernel)
+    int nE = 0;
+    float bd = INFINITY;
+    int bref = -1;          // >= 0: slot j of an existing point; <= -2: new point index -(bref+2)
+    float bxx = 0, byy = 0, bzz = 0;
+    if (have) {
+        for (unsigned j = 0; j < count; j++) {
+            float4 q = M.pool[(size_t)first + j];
+            if (__float_as_uint(q.w) != vib) continue;
+            nE++;
+            float d = li_center_dist_cell(q.x, q.y, q.z, cx, cy, cz, M.ds);
+            if (d < bd) { bd = d; bref = (int)j; bxx = q.x; byy = q.y; bzz = q.z; }
+        }
     }
-    if (created) atomicAdd(&M.counters[CNT_BRICKS], 1);
-    slot_of[i] = s;
-    atomicAdd(&M.aux[s].y, 1u);
-    li_touch(M, s);
-    int sb = s;
-    if (bkey != skey) {
-        sb = -1;
-        unsigned h = li_hash(bkey) & M.mask;
+    bool modified = false;
+    int changed = 0;
+    // batch order = ascending index: repeatedly take the smallest index greater than the last one processed
+    int last = -1;
+    for (;;) {
+        int cur = 0x7fffffff;
+        for (int t = head; t >= 0; t = next_of[t])
+            if (t > last && t < cur) cur = t;
+        if (cur == 0x7fffffff) break;
+        last = cur;
+        float4 p = pts[cur];
+        float dp = li_center_dist_cell(p.x, p.y, p.z, cx, cy, cz, M.ds);
+        bool newwins = !(nE > 0 && bd < dp);
+        bool same = newwins || (nE > 0 && fabsf(__fsub_rn(p.x, bxx)) < 1e-6f && fabsf(__fsub_rn(p.y, byy)) < 1e-6f &&
+                                fabsf(__fsub_rn(p.z, bzz)) < 1e-6f);   // same_point, EPSS (ikd_Tree.cpp:1269-1271)
+        if (nE > 1 || same) {
+            modified = true;
+            changed++;
+            if (newwins) {
+                if (bref <= -2) ins[-(bref + 2)] = 0;   // an earlier in-box new point is deleted with the box
+                ins[cur] = 1;
+                int ibx, iby, ibz;
+                bool inbox = li_box_index(p.x, M.ds, cx, ibx) && ibx == cx;
+                inbox = li_box_index(p.y, M.ds, cy, iby) && iby == cy && inbox;
+                inbox = li_box_index(p.z, M.ds, cz, ibz) && ibz == cz && inbox;
+                if (inbox) {
+                    nE = 1; bd = dp; bref = -(cur + 2); bxx = p.x; byy = p.y; bzz = p.z;
+                } else {
+                    nE = 0; bd = INFINITY; bref = -1;
+                }
+            } else {
+                nE = 1;   // the best point survives alone
+            }
+        }
+    }
+    if (modified && have) {
+        for (unsigned j = 0; j < count; j++) {
+            float4* qp = &M.pool[(size_t)first + j];
+            if (__float_as_uint(qp->w) == vib && !(nE == 1 && bref == (int)j)) qp->w = __uint_as_float(0xffffffffu);
+        }
+    }
+    if (changed) atomicAdd(&M.counters[CNT_CHANGED], changed);
+    // make sure the brick holding tombstones gets compacted
+    if (modified && have) {
+        unsigned h = li_hash(li_pack_key(cx >> M.bshift, cy >> M.bshift, cz >> M.bshift)) & M.mask;
         for (unsigned t = 0; t <= M.mask; t++) {
             unsigned long long k = *reinterpret_cast<volatile unsigned long long*>(&M.ent[h]);
-            if (k == bkey) { sb = (int)h; break; }
+            if (k == li_pack_key(cx >> M.bshift, cy >> M.bshift, cz >> M.bshift)) { li_touch(M, (int)h); break; }
             if (k == LI_EMPTY_KEY) break;
             h = (h + 1) & M.mask;
         }
-        if (sb >= 0) li_touch(M, sb);
     }
-    vslot_of[i] = sb;
 }
 
-// pass D3: one warp per voxel winner. Compare with the voxel's live points, tombstone the losers
-// (w = 0xffffffff), append the new point if it wins. Different voxels of one brick touch disjoint
-// slab entries, appends go through aux.fill, so warps of the same brick do not race.
-__global__ void k_ds_apply(MapDev M, const float4* __restrict__ pts, int n, const int* __restrict__ slot_of,
-                           const int* __restrict__ box_slot_of) {
-    int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+// pass D3b: append the new points that survived the replay.
+__global__ void k_ds_append(MapDev M, const float4* __restrict__ pts, int n, const int* __restrict__ slot_of,
+                            const int* __restrict__ ins) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (!ins[i]) return;
     int s = slot_of[i];
     if (s < 0) return;
+    uint4 e = M.ent[s];
     if (M.aux[s].y == 0u) return;   // reservation failed (pool full)
-    const int sb = box_slot_of[i];
+    unsigned j = atomicAdd(&M.aux[s].z, 1u);
     float4 p = pts[i];
     int cx = li_cell(p.x, M.ds), cy = li_cell(p.y, M.ds), cz = li_cell(p.z, M.ds);
-    const unsigned vib = li_voxel_in_brick(M, cx, cy, cz);   // id of p's BOX inside the box brick
-    float dp = li_center_dist(p, M.ds);
-    // scan the live slab of the box brick for the points of this box
-    float best_d = INFINITY;
-    unsigned best_j = 0xffffffffu;
-    unsigned n_exist = 0;
-    uint4 e = make_uint4(0u, 0u, 0u, 0u);
-    if (sb >= 0) e = M.ent[sb];
-    for (unsigned base = 0; base < e.w; base += 32) {
-        unsigned j = base + lane;
-        bool mine = false;
-        float d = INFINITY;
-        if (j < e.w) {
-            float4 q = M.pool[(size_t)e.z + j];
-            if (__float_as_uint(q.w) == vib) {
-                mine = true;
-                d = li_center_dist_cell(q.x, q.y, q.z, cx, cy, cz, M.ds);
-            }
-        }
-        unsigned mm = __ballot_sync(LI_FULL, mine);
-        n_exist += __popc(mm);
-        // lowest slot wins ties among existing points
-        unsigned bits = mine ? __float_as_uint(d) : 0xffffffffu;
-        unsigned mn = __reduce_min_sync(LI_FULL, bits);
-        if (mm && mn < __float_as_uint(best_d)) {
-            unsigned who = __ballot_sync(LI_FULL, mine && bits == mn);
-            best_d = __uint_as_float(mn);
-            best_j = base + (__ffs(who) - 1);
-        }
-    }
-    bool existing_wins = (n_exist > 0) && (best_d < dp);   // strict: new point wins ties (ikd_Tree.cpp:405)
-    // tombstone every existing point of the box except a winning existing one
-    if (n_exist > 0) {
-        for (unsigned base = 0; base < e.w; base += 32) {
-            unsigned j = base + lane;
-            if (j < e.w) {
-                float4* qp = &M.pool[(size_t)e.z + j];
-                if (__float_as_uint(qp->w) == vib && !(existing_wins && j == best_j)) qp->w = __uint_as_float(0xffffffffu);
-            }
-        }
-    }
-    if (lane == 0) {
-        if (!existing_wins) {
-            uint4 es = M.ent[s];
-            unsigned j = atomicAdd(&M.aux[s].z, 1u);
-            unsigned long long skey;
-            unsigned svib;
-            li_storage(M, p, cx, cy, cz, skey, svib);
-            p.w = __uint_as_float(svib);
-            M.pool[(size_t)es.z + es.w + j] = p;
-        }
-        if (!existing_wins || n_exist > 1) atomicAdd(&M.counters[CNT_CHANGED], 1);
-    }
+    unsigned long long key;
+    unsigned vib;
+    li_storage(M, p, cx, cy, cz, key, vib);
+    p.w = __uint_as_float(vib);
+    M.pool[(size_t)e.z + e.w + j] = p;
 }
 
 // pass D4: one warp per touched brick -- squeeze out tombstones over [0, count+fill), fix counts.

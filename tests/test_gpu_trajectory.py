@@ -41,10 +41,24 @@ def test_scan_sequence_matches_oracle(gpu_lib, oracle_mod, imu_en):
     g.map_build(w0)
     om.build(w0)
     st_g = host.state_from_pose(poses[0].rot_end, poses[0].pos_end, R_LI, T_LI)
+    cov = np.eye(24) * 1e-5
+    cov[0:3, 0:3] = np.eye(3) * 1e-3      # attitude prior
+    cov[3:6, 3:6] = np.eye(3) * 1e-2      # position prior
+    cov[6:9, 6:9] = np.eye(3) * 5e-5      # Rot_LI_cov (config/avia.yaml:18)
+    cov[9:12, 9:12] = np.eye(3) * 1e-5    # Trans_LI_cov (config/avia.yaml:19)
+    st_g[36:] = cov.reshape(-1)
     st_o = st_g.copy()
     max_dp = max_dr = 0.0
     for k in range(1, len(poses)):
-        # constant-position prior: start from the previous posterior (a poor prior on purpose: ~0.25 m / 1.5 deg off)
+        # motion prior (stands in for IMU / constant-velocity propagation, IMU_Processing.hpp): the true pose
+        # disturbed by 0.2 deg / 3 cm; extrinsic and covariance carried over, pose covariance re-inflated
+        prior = scenes.perturb_pose(poses[k], 500 + k, dtheta_deg=0.2, dpos=0.03)
+        for st in (st_g, st_o):
+            st[0:9] = prior.rot_end.reshape(9)
+            st[9:12] = prior.pos_end
+            c = st[36:].reshape(24, 24)
+            c[0:3, 0:3] += np.eye(3) * 1e-4
+            c[3:6, 3:6] += np.eye(3) * 1e-3
         g.scan_upload(scans[k])
         st_g, stats = host.scan_update(g, st_g, 5, imu_en)
         sc = oracle_mod.OracleScan(scans[k])
@@ -58,9 +72,9 @@ def test_scan_sequence_matches_oracle(gpu_lib, oracle_mod, imu_en):
         _, oa, on, _ = sc.map_incremental(om, Ro, po, RLo, TLo, ds)
         assert (na, nn) == (oa, on)
         assert g.map_validnum() == om.validnum()
-        # the estimate tracks the ground truth (LiDAR-only mode; with imu_en the 12-dim problem is weakly observable)
-        if not imu_en:
-            assert np.abs(pg - poses[k].pos_end).max() < 0.03 and _angle(Rg, poses[k].rot_end) < 0.004
+        # the estimate tracks the ground truth: LiDAR pose in the world = (R_end R_LI, R_end T_LI + pos)
+        gt_R, gt_p = poses[k].rot_end @ R_LI, poses[k].rot_end @ T_LI + poses[k].pos_end
+        assert np.abs(Rg @ TLg + pg - gt_p).max() < 0.02 and _angle(Rg @ RLg, gt_R) < 0.002
     assert max_dp < 1e-6 and max_dr < 1e-6, (max_dp, max_dr)
     assert np.allclose(st_g[36:], st_o[36:], rtol=1e-3, atol=1e-7)   # covariance
     g.close()

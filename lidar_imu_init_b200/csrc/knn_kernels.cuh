@@ -95,7 +95,7 @@ struct KnnGeom {
 
 // probe one brick (offset ox,oy,oz from the query's brick) if it can matter
 __device__ __forceinline__ bool probe_brick(const MapDev& M, const KnnGeom& g, int ox, int oy, int oz, float qx, float qy, float qz,
-                                            float bound2, bool full, unsigned& first, unsigned& count) {
+                                            float bound2, bool full, unsigned& first, unsigned& count, float& dbox) {
     const int kx = g.bx + ox, ky = g.by + oy, kz = g.bz + oz;
     const int bs = g.bs;
     float lox = (float)(kx << bs) * g.ds - g.margin, hix = (float)((kx + 1) << bs) * g.ds + g.margin;
@@ -104,7 +104,7 @@ __device__ __forceinline__ bool probe_brick(const MapDev& M, const KnnGeom& g, i
     float ex = fmaxf(0.f, fmaxf(lox - qx, qx - hix));
     float ey = fmaxf(0.f, fmaxf(loy - qy, qy - hiy));
     float ez = fmaxf(0.f, fmaxf(loz - qz, qz - hiz));
-    float dbox = (ex * ex + ey * ey + ez * ez) * (1.0f - 1e-6f);
+    dbox = (ex * ex + ey * ey + ez * ez) * (1.0f - 1e-6f);
     // while fewer than 5 are known every point with d2 <= 5 counts; afterwards only d2 < current 5th
     bool useful = full ? (dbox < bound2) : (dbox <= 5.0f);
     if (!useful) return false;
@@ -127,8 +127,9 @@ __device__ __forceinline__ void knn_ring(const MapDev& M, const KnnGeom& g, floa
             if (max(abs(ox), max(abs(oy), abs(oz))) < R) want = false;   // inner cube already visited
         }
         unsigned first = 0, count = 0;
+        float dbox;
         bool found = false;
-        if (want) found = probe_brick(M, g, ox, oy, oz, qx, qy, qz, g5, full, first, count);
+        if (want) found = probe_brick(M, g, ox, oy, oz, qx, qy, qz, g5, full, first, count, dbox);
         group_scan_found<G>(M.pool, found, first, count, qx, qy, qz, g5, ld, li, gmask, lane, gl);
     }
 }
@@ -154,10 +155,43 @@ __device__ __forceinline__ float explored_r2(const KnnGeom& g, int R, float qx, 
     return r * r * (1.0f - 1e-6f);
 }
 
-// Exact 5-NN of one query by a group of G lanes. gd/gi: ascending distances / pool offsets (-1 = missing).
+// Cheap upper bound on the group's 5th-smallest candidate distance: the 5th smallest of the lanes' BEST values
+// (each lane's ld[0]); +inf when fewer than 5 lanes hold a candidate. ~25 instructions instead of a full merge.
+__device__ __forceinline__ float group_bound5(float best, unsigned gmask, int lane) {
+    unsigned v = __float_as_uint(best);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        unsigned mn = __reduce_min_sync(gmask, v);
+        unsigned who = __ballot_sync(gmask, v == mn) & gmask;
+        if (lane == __ffs(who) - 1) v = 0x7f800000u;   // +inf
+    }
+    return __uint_as_float(__reduce_min_sync(gmask, v));
+}
+
+// scan one slab with all lanes of the group (thr: only candidates with d < thr and d <= 5 matter)
+template <int G>
+__device__ __forceinline__ void group_scan_slab(const float4* __restrict__ pool, unsigned f, unsigned c, float qx, float qy, float qz,
+                                                float thr, float (&ld)[5], int (&li)[5], int gl) {
+    for (unsigned j = gl; j < c; j += G) {
+        float4 p = __ldg(&pool[(size_t)f + j]);
+        float d = li_dist2(qx, qy, qz, p.x, p.y, p.z);
+        if (d <= 5.0f && d < thr && d < ld[4]) local_insert(ld, li, d, (int)(f + j));
+    }
+}
+
+// Exact 5-NN of one query by a group of G >= 8 lanes. gd/gi: ascending distances / pool offsets (-1 = missing).
+//
+//   phase A  seed: probe the 2x2x2 bricks nearest to the query (one round), scan the query's own brick first,
+//            derive a cheap bound, scan the other seven only if their box can beat it; merge -> (n, g5).
+//            Done if g5 lies within the explored block.
+//   phase A' (n < 5, sparse neighbourhood): ring expansion R = 1, 2, .. with the radius^2 = 5 bound until 5 are known.
+//   phase B  closure: every unexplored brick whose box intersects the open ball of radius sqrt(g5) is probed and
+//            scanned (bounding-box enumeration, no further rings). After it the merged top-5 is exact: a point
+//            closer than g5 can only live in a brick that intersects that ball.
 template <int G>
 __device__ __forceinline__ void knn5_group(const MapDev& M, float qx, float qy, float qz, float (&gd)[5], int (&gi)[5], unsigned gmask,
                                            int lane, int gl) {
+    static_assert(G >= 8, "stage 0 needs 8 lanes");
     float ld[5];
     int li[5];
 #pragma unroll
@@ -184,55 +218,112 @@ __device__ __forceinline__ void knn5_group(const MapDev& M, float qx, float qy, 
     // slack for float cell assignment / edge products: relative 2^-23 effects, bounded generously
     g.margin = 1e-6f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + 16.0f * B);
 
-    // stage 0: the 2x2x2 block of bricks nearest to the query
-    for (int base = 0; base < 8; base += G) {
-        int idx = base + gl;
+    // ---- phase A: seed -------------------------------------------------------------------------------
+    {
         unsigned first = 0, count = 0;
+        float dbox = INFINITY;
         bool found = false;
-        if (idx < 8) {
-            int ox = (idx & 1) ? g.dirx : 0, oy = (idx & 2) ? g.diry : 0, oz = (idx & 4) ? g.dirz : 0;
-            found = probe_brick(M, g, ox, oy, oz, qx, qy, qz, INFINITY, false, first, count);
+        if (gl < 8) {
+            int ox = (gl & 1) ? g.dirx : 0, oy = (gl & 2) ? g.diry : 0, oz = (gl & 4) ? g.dirz : 0;
+            found = probe_brick(M, g, ox, oy, oz, qx, qy, qz, INFINITY, false, first, count, dbox);
         }
-        group_scan_found<G>(M.pool, found, first, count, qx, qy, qz, INFINITY, ld, li, gmask, lane, gl);
+        unsigned fm = __ballot_sync(gmask, found) & gmask;
+        const int base_lane = lane - gl;
+        float bound = INFINITY;
+        if (fm & (1u << base_lane)) {   // the query's own brick
+            unsigned f = __shfl_sync(gmask, first, base_lane), c = __shfl_sync(gmask, count, base_lane);
+            group_scan_slab<G>(M.pool, f, c, qx, qy, qz, INFINITY, ld, li, gl);
+            bound = group_bound5(ld[0], gmask, lane);
+            fm &= ~(1u << base_lane);
+        }
+        while (fm) {
+            int src = __ffs(fm) - 1;
+            fm &= fm - 1;
+            float db = __shfl_sync(gmask, dbox, src);
+            if (!(db < bound)) continue;   // this brick cannot hold one of the 5 nearest
+            unsigned f = __shfl_sync(gmask, first, src), c = __shfl_sync(gmask, count, src);
+            group_scan_slab<G>(M.pool, f, c, qx, qy, qz, bound, ld, li, gl);
+            bound = fminf(bound, group_bound5(ld[0], gmask, lane));
+        }
     }
     group_merge<G>(ld, li, gd, gi, gmask, lane);
-    {
-        float r2 = explored_r2(g, 0, qx, qy, qz);
-        if (r2 > 5.0f || (gi[4] >= 0 && gd[4] <= r2)) return;
-    }
+    float r2 = explored_r2(g, 0, qx, qy, qz);
+    if (r2 > 5.0f || (gi[4] >= 0 && gd[4] <= r2)) return;
+    int Rdone = 0;
+    // ---- phase A': fewer than 5 known -> rings with the radius bound ----------------------------------
+    if (gi[4] < 0) {
 #define LI_RING(RR)                                                                                   \
-    {                                                                                                 \
-        bool full = gi[4] >= 0;                                                                       \
-        knn_ring<G, RR>(M, g, qx, qy, qz, full ? gd[4] : INFINITY, full, ld, li, gmask, lane, gl);   \
+    if (gi[4] < 0) {                                                                                  \
+        knn_ring<G, RR>(M, g, qx, qy, qz, INFINITY, false, ld, li, gmask, lane, gl);                  \
         group_merge<G>(ld, li, gd, gi, gmask, lane);                                                  \
-        float r2 = explored_r2(g, RR, qx, qy, qz);                                                    \
+        Rdone = RR;                                                                                   \
+        r2 = explored_r2(g, RR, qx, qy, qz);                                                          \
         if (r2 > 5.0f || (gi[4] >= 0 && gd[4] <= r2)) return;                                         \
     }
-    LI_RING(1)
-    LI_RING(2)
-    LI_RING(3)
-    LI_RING(4)
-    // bricks smaller than sqrt(5)/4: generic tail (rare configuration: ds < 0.14 with 4-voxel bricks)
-    const int Rmax = (int)ceilf(2.2360680f / B) + 1;
-    for (int R = 5; R <= Rmax; R++) {
-        bool full = gi[4] >= 0;
-        float g5 = full ? gd[4] : INFINITY;
-        const int S = 2 * R + 1, total = S * S * S;
+        LI_RING(1)
+        LI_RING(2)
+        LI_RING(3)
+        LI_RING(4)
+#undef LI_RING
+        const int Rmax = (int)ceilf(2.2360680f / B) + 1;
+        for (int R = 5; R <= Rmax && gi[4] < 0; R++) {
+            const int S = 2 * R + 1, total = S * S * S;
+            for (int base = 0; base < total; base += G) {
+                int idx = base + gl;
+                bool want = idx < total;
+                int ox = idx % S - R, oy = (idx / S) % S - R, oz = idx / (S * S) - R;
+                if (max(abs(ox), max(abs(oy), abs(oz))) < R) want = false;
+                unsigned first = 0, count = 0;
+                float dbox;
+                bool found = false;
+                if (want) found = probe_brick(M, g, ox, oy, oz, qx, qy, qz, INFINITY, false, first, count, dbox);
+                group_scan_found<G>(M.pool, found, first, count, qx, qy, qz, INFINITY, ld, li, gmask, lane, gl);
+            }
+            group_merge<G>(ld, li, gd, gi, gmask, lane);
+            Rdone = R;
+            r2 = explored_r2(g, R, qx, qy, qz);
+            if (r2 > 5.0f || (gi[4] >= 0 && gd[4] <= r2)) return;
+        }
+        if (gi[4] < 0) return;   // fewer than 5 points within the radius: everything within sqrt(5) was explored
+    }
+    // ---- phase B: closure over the ball of radius sqrt(g5) --------------------------------------------
+    {
+        const float g5 = gd[4];
+        const float r = sqrtf(g5) * (1.0f + 1e-6f) + g.margin;
+        // explored block (brick coordinates)
+        int ex0, ex1, ey0, ey1, ez0, ez1;
+        if (Rdone == 0) {
+            ex0 = min(g.bx, g.bx + g.dirx); ex1 = max(g.bx, g.bx + g.dirx);
+            ey0 = min(g.by, g.by + g.diry); ey1 = max(g.by, g.by + g.diry);
+            ez0 = min(g.bz, g.bz + g.dirz); ez1 = max(g.bz, g.bz + g.dirz);
+        } else {
+            ex0 = g.bx - Rdone; ex1 = g.bx + Rdone;
+            ey0 = g.by - Rdone; ey1 = g.by + Rdone;
+            ez0 = g.bz - Rdone; ez1 = g.bz + Rdone;
+        }
+        const int lx = li_cell(qx - r, g.ds) >> g.bs, hx = li_cell(qx + r, g.ds) >> g.bs;
+        const int ly = li_cell(qy - r, g.ds) >> g.bs, hy = li_cell(qy + r, g.ds) >> g.bs;
+        const int lz = li_cell(qz - r, g.ds) >> g.bs, hz = li_cell(qz + r, g.ds) >> g.bs;
+        const int nx = hx - lx + 1, ny = hy - ly + 1, nz = hz - lz + 1;
+        const int nxy = nx * ny, total = nxy * nz;
+        const float inv_nxy = 1.0f / (float)nxy, inv_nx = 1.0f / (float)nx;
         for (int base = 0; base < total; base += G) {
             int idx = base + gl;
             bool want = idx < total;
-            int ox = idx % S - R, oy = (idx / S) % S - R, oz = idx / (S * S) - R;
-            if (max(abs(ox), max(abs(oy), abs(oz))) < R) want = false;
+            int iz = (int)(((float)idx + 0.5f) * inv_nxy);
+            int rem = idx - iz * nxy;
+            int iy = (int)(((float)rem + 0.5f) * inv_nx);
+            int ix = rem - iy * nx;
+            int kx = lx + ix, ky = ly + iy, kz = lz + iz;
+            if (kx >= ex0 && kx <= ex1 && ky >= ey0 && ky <= ey1 && kz >= ez0 && kz <= ez1) want = false;   // explored
             unsigned first = 0, count = 0;
+            float dbox;
             bool found = false;
-            if (want) found = probe_brick(M, g, ox, oy, oz, qx, qy, qz, g5, full, first, count);
+            if (want) found = probe_brick(M, g, kx - g.bx, ky - g.by, kz - g.bz, qx, qy, qz, g5, true, first, count, dbox);
             group_scan_found<G>(M.pool, found, first, count, qx, qy, qz, g5, ld, li, gmask, lane, gl);
         }
         group_merge<G>(ld, li, gd, gi, gmask, lane);
-        float r2 = explored_r2(g, R, qx, qy, qz);
-        if (r2 > 5.0f || (gi[4] >= 0 && gd[4] <= r2)) return;
     }
-#undef LI_RING
 }
 
 // ---- search kernel of an ICP pass: world transform + 5-NN for every scan point -----------------------

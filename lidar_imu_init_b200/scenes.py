@@ -211,6 +211,19 @@ def scan_points(scene: Scene, pose: Pose, N: int, seed: int = 2, det_range: floa
         dims = ijk.max(0) + 1
         lin = ijk[:, 0] + dims[0] * (ijk[:, 1] + dims[1] * ijk[:, 2])
         Pb = Pb[np.argsort(lin, kind="stable")]
+    elif order == "morton":
+        # Z-order of 0.6 m body-frame cells: what a spatial sort at upload would produce
+        ijk = np.floor(Pb / 0.6).astype(np.int64)
+        ijk -= ijk.min(0, keepdims=True)
+        def spread(v):
+            v = v & 0x3ff
+            v = (v | (v << 16)) & 0x030000ff
+            v = (v | (v << 8)) & 0x0300f00f
+            v = (v | (v << 4)) & 0x030c30c3
+            v = (v | (v << 2)) & 0x09249249
+            return v
+        key = spread(ijk[:, 0]) | (spread(ijk[:, 1]) << 1) | (spread(ijk[:, 2]) << 2)
+        Pb = Pb[np.argsort(key, kind="stable")]
     elif order == "shuffle":
         Pb = Pb[rng.permutation(len(Pb))]
     elif order != "asis":

@@ -1,16 +1,22 @@
 // knn_kernels.cuh -- exact bounded 5-NN on the brick hash (replaces KD_TREE::Nearest_Search,
 // ikd_Tree.cpp:349-379, Search :825-968).
 //
-// G lanes (G = 4, 8, 16 or 32) cooperate on one query: a warp works on 32/G queries at once.
-//   * stage 0 probes the 2x2x2 block of bricks nearest to the query, stage R >= 1 the shell of the
-//     (2R+1)^3 block; a brick is probed only if its box can still hold a point closer than the current
-//     5th neighbour (or than the radius^2 = 5 bound while fewer than 5 are known);
-//   * a brick's slab is read with G consecutive lanes -> contiguous 16*G-byte segments;
-//   * every lane keeps a private sorted top-5 of the candidates IT saw; the group's top-5 is merged with
-//     redux.sync / shuffles at the end of each stage (the merge gives the pruning bound and the
-//     termination test: stop when the 5th distance is within the explored radius);
-//   * search is exact: ring expansion continues until no unexplored brick can intersect the ball.
-// Semantics matched (DESIGN.md section 5.1): candidates with d2 <= 5 only (ikd_Tree.cpp:842, sic), fp32
+// G lanes (G = 8, 16 or 32) cooperate on one query, so a warp works on Q = 32/G queries AT ONCE and IN LOCKSTEP:
+// every loop is warp-uniform (its trip count is the maximum over the warp's groups, idle groups are predicated
+// off) and every shuffle / ballot uses the full mask. Sub-mask *_sync intrinsics make the hardware run the groups
+// one after the other (measured in round 1: 11 of 32 lanes active); lockstep keeps all 32 lanes issuing together.
+//
+//   phase A  seed: one round probes the 2x2x2 bricks nearest to the query; the query's own brick is scanned first,
+//            a cheap bound (5th smallest of the lanes' best candidates) prunes the other seven; merge -> (n, g5).
+//            Done if g5 lies within the explored block.
+//   phase A' (n < 5, sparse neighbourhood): ring expansion R = 1, 2, .. with the radius^2 = 5 bound until 5 are known.
+//   phase B  closure: every unexplored brick whose box intersects the open ball of radius sqrt(g5) is probed and
+//            scanned (bounding-box enumeration). After it the merged top-5 is exact: a point closer than g5 can
+//            only live in a brick that intersects that ball.
+//
+// A brick's slab is read by G consecutive lanes -> contiguous 16*G-byte segments; every lane keeps a private sorted
+// top-5 of the candidates IT saw; the group's top-5 is merged at phase boundaries.
+// Semantics matched (DESIGN.md section 3): candidates with d2 <= 5 only (ikd_Tree.cpp:842, sic), fp32
 // (dx*dx+dy*dy)+dz*dz without FMA, ascending output; exact-tie handling is traversal dependent in the
 // reference and therefore excluded from the parity claim.
 #pragma once
@@ -18,9 +24,29 @@
 
 template <int G>
 struct Grp {
-    static constexpr int QPW = 32 / G;
-    __device__ static __forceinline__ unsigned mask(int lane) { return (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((lane / G) * G)); }
+    static constexpr int Q = 32 / G;
+    static constexpr unsigned GM = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
 };
+
+// ---- full-mask group primitives (all 32 lanes must call) -------------------------------------------------
+template <int G>
+__device__ __forceinline__ unsigned grp_ballot(bool p, int gbase) {
+    return (__ballot_sync(LI_FULL, p) >> gbase) & Grp<G>::GM;
+}
+template <int G, class T>
+__device__ __forceinline__ T grp_shfl(T v, int src_rel, int gbase) {
+    return __shfl_sync(LI_FULL, v, gbase + src_rel);
+}
+template <int G>
+__device__ __forceinline__ unsigned grp_min(unsigned v) {
+    if constexpr (G == 32) {
+        return __reduce_min_sync(LI_FULL, v);
+    } else {
+#pragma unroll
+        for (int o = G / 2; o >= 1; o >>= 1) v = min(v, __shfl_xor_sync(LI_FULL, v, o));
+        return v;
+    }
+}
 
 // sorted insert into a lane-private top-5 (precondition: d < ld[4]); stable w.r.t. equal distances
 __device__ __forceinline__ void local_insert(float (&ld)[5], int (&li)[5], float d, int id) {
@@ -40,8 +66,7 @@ __device__ __forceinline__ void local_insert(float (&ld)[5], int (&li)[5], float
 
 // Group-wide top-5 of the G private lists -> gd/gi (uniform in the group).
 template <int G>
-__device__ __forceinline__ void group_merge(const float (&ld)[5], const int (&li)[5], float (&gd)[5], int (&gi)[5], unsigned gmask,
-                                            int lane) {
+__device__ __forceinline__ void group_merge(const float (&ld)[5], const int (&li)[5], float (&gd)[5], int (&gi)[5], int gl, int gbase) {
     float cd[5];
     int ci[5];
 #pragma unroll
@@ -52,12 +77,12 @@ __device__ __forceinline__ void group_merge(const float (&ld)[5], const int (&li
 #pragma unroll
     for (int k = 0; k < 5; k++) {
         unsigned hb = __float_as_uint(cd[0]);
-        unsigned mn = __reduce_min_sync(gmask, hb);
-        unsigned who = __ballot_sync(gmask, hb == mn) & gmask;
+        unsigned mn = grp_min<G>(hb);
+        unsigned who = grp_ballot<G>(hb == mn, gbase);
         int src = __ffs(who) - 1;
         gd[k] = __uint_as_float(mn);
-        gi[k] = __shfl_sync(gmask, ci[0], src);
-        if (lane == src) {
+        gi[k] = grp_shfl<G>(ci[0], src, gbase);
+        if (gl == src) {
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 cd[i] = cd[i + 1];
@@ -69,23 +94,18 @@ __device__ __forceinline__ void group_merge(const float (&ld)[5], const int (&li
     }
 }
 
-// scan the slabs of the bricks found by the lanes of this group in the current round
+// Cheap upper bound on the group's 5th-smallest candidate distance: the 5th smallest of the lanes' BEST values
+// (each lane's ld[0]); +inf when fewer than 5 lanes hold a candidate.
 template <int G>
-__device__ __forceinline__ void group_scan_found(const float4* __restrict__ pool, bool found, unsigned first, unsigned count,
-                                                 float qx, float qy, float qz, float g5, float (&ld)[5], int (&li)[5],
-                                                 unsigned gmask, int lane, int gl) {
-    unsigned fm = __ballot_sync(gmask, found) & gmask;
-    while (fm) {
-        int src = __ffs(fm) - 1;
-        fm &= fm - 1;
-        unsigned f = __shfl_sync(gmask, first, src);
-        unsigned c = __shfl_sync(gmask, count, src);
-        for (unsigned j = gl; j < c; j += G) {
-            float4 p = __ldg(&pool[(size_t)f + j]);
-            float d = li_dist2(qx, qy, qz, p.x, p.y, p.z);
-            if (d <= 5.0f && d < g5 && d < ld[4]) local_insert(ld, li, d, (int)(f + j));
-        }
+__device__ __forceinline__ float group_bound5(float best, int gl, int gbase) {
+    unsigned v = __float_as_uint(best);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        unsigned mn = grp_min<G>(v);
+        unsigned who = grp_ballot<G>(v == mn, gbase);
+        if (gl == __ffs(who) - 1) v = 0x7f800000u;   // +inf
     }
+    return __uint_as_float(grp_min<G>(v));
 }
 
 struct KnnGeom {
@@ -112,25 +132,27 @@ __device__ __forceinline__ bool probe_brick(const MapDev& M, const KnnGeom& g, i
     return found && count > 0u;
 }
 
-template <int G, int R>
-__device__ __forceinline__ void knn_ring(const MapDev& M, const KnnGeom& g, float qx, float qy, float qz, float g5, bool full,
-                                         float (&ld)[5], int (&li)[5], unsigned gmask, int lane, int gl) {
-    constexpr int S = 2 * R + 1;
-    constexpr int total = S * S * S;
-    for (int base = 0; base < total; base += G) {
-        int idx = base + gl;
-        bool want = idx < total;
-        int ox = idx % S - R, oy = (idx / S) % S - R, oz = idx / (S * S) - R;
-        if (R == 1) {
-            if ((ox == 0 || ox == g.dirx) && (oy == 0 || oy == g.diry) && (oz == 0 || oz == g.dirz)) want = false;   // stage 0 block
-        } else {
-            if (max(abs(ox), max(abs(oy), abs(oz))) < R) want = false;   // inner cube already visited
+// Lockstep scan of the bricks found by the lanes of each group in the current probe round. thr: only candidates with
+// d < thr (and d <= 5) matter. prune: skip bricks whose box distance is not below thr.
+template <int G>
+__device__ __forceinline__ void lockstep_scan_found(const float4* __restrict__ pool, bool found, unsigned first, unsigned count, float dbox,
+                                                    float qx, float qy, float qz, float thr, float (&ld)[5], int (&li)[5], int gl, int gbase) {
+    unsigned fm = grp_ballot<G>(found, gbase);
+    while (__any_sync(LI_FULL, fm != 0u)) {
+        const bool has = fm != 0u;
+        const int src = has ? (__ffs(fm) - 1) : 0;
+        fm &= fm - 1u;
+        const float db = grp_shfl<G>(dbox, src, gbase);
+        const unsigned f = grp_shfl<G>(first, src, gbase);
+        const unsigned c = grp_shfl<G>(count, src, gbase);
+        const unsigned cnt = (has && db < thr) ? c : 0u;
+        for (unsigned j = gl; __any_sync(LI_FULL, j < cnt); j += G) {
+            if (j < cnt) {
+                float4 p = __ldg(&pool[(size_t)f + j]);
+                float d = li_dist2(qx, qy, qz, p.x, p.y, p.z);
+                if (d <= 5.0f && d < thr && d < ld[4]) local_insert(ld, li, d, (int)(f + j));
+            }
         }
-        unsigned first = 0, count = 0;
-        float dbox;
-        bool found = false;
-        if (want) found = probe_brick(M, g, ox, oy, oz, qx, qy, qz, g5, full, first, count, dbox);
-        group_scan_found<G>(M.pool, found, first, count, qx, qy, qz, g5, ld, li, gmask, lane, gl);
     }
 }
 
@@ -155,42 +177,11 @@ __device__ __forceinline__ float explored_r2(const KnnGeom& g, int R, float qx, 
     return r * r * (1.0f - 1e-6f);
 }
 
-// Cheap upper bound on the group's 5th-smallest candidate distance: the 5th smallest of the lanes' BEST values
-// (each lane's ld[0]); +inf when fewer than 5 lanes hold a candidate. ~25 instructions instead of a full merge.
-__device__ __forceinline__ float group_bound5(float best, unsigned gmask, int lane) {
-    unsigned v = __float_as_uint(best);
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        unsigned mn = __reduce_min_sync(gmask, v);
-        unsigned who = __ballot_sync(gmask, v == mn) & gmask;
-        if (lane == __ffs(who) - 1) v = 0x7f800000u;   // +inf
-    }
-    return __uint_as_float(__reduce_min_sync(gmask, v));
-}
-
-// scan one slab with all lanes of the group (thr: only candidates with d < thr and d <= 5 matter)
+// Exact 5-NN of Q = 32/G queries by one warp in lockstep. ALL 32 lanes must call; `valid` is group-uniform.
+// gd/gi: ascending distances / pool offsets (-1 = missing), uniform within each group.
 template <int G>
-__device__ __forceinline__ void group_scan_slab(const float4* __restrict__ pool, unsigned f, unsigned c, float qx, float qy, float qz,
-                                                float thr, float (&ld)[5], int (&li)[5], int gl) {
-    for (unsigned j = gl; j < c; j += G) {
-        float4 p = __ldg(&pool[(size_t)f + j]);
-        float d = li_dist2(qx, qy, qz, p.x, p.y, p.z);
-        if (d <= 5.0f && d < thr && d < ld[4]) local_insert(ld, li, d, (int)(f + j));
-    }
-}
-
-// Exact 5-NN of one query by a group of G >= 8 lanes. gd/gi: ascending distances / pool offsets (-1 = missing).
-//
-//   phase A  seed: probe the 2x2x2 bricks nearest to the query (one round), scan the query's own brick first,
-//            derive a cheap bound, scan the other seven only if their box can beat it; merge -> (n, g5).
-//            Done if g5 lies within the explored block.
-//   phase A' (n < 5, sparse neighbourhood): ring expansion R = 1, 2, .. with the radius^2 = 5 bound until 5 are known.
-//   phase B  closure: every unexplored brick whose box intersects the open ball of radius sqrt(g5) is probed and
-//            scanned (bounding-box enumeration, no further rings). After it the merged top-5 is exact: a point
-//            closer than g5 can only live in a brick that intersects that ball.
-template <int G>
-__device__ __forceinline__ void knn5_group(const MapDev& M, float qx, float qy, float qz, float (&gd)[5], int (&gi)[5], unsigned gmask,
-                                           int lane, int gl) {
+__device__ __forceinline__ void knn5_lockstep(const MapDev& M, bool valid, float qx, float qy, float qz, float (&gd)[5], int (&gi)[5],
+                                              int gl, int gbase) {
     static_assert(G >= 8, "stage 0 needs 8 lanes");
     float ld[5];
     int li[5];
@@ -205,90 +196,93 @@ __device__ __forceinline__ void knn5_group(const MapDev& M, float qx, float qy, 
     g.bs = M.bshift;
     g.ds = M.ds;
     const int bc = 1 << g.bs;
-    if (!(isfinite(qx) && isfinite(qy) && isfinite(qz))) return;
+    const float B = (float)bc * g.ds;
     const float lim = (float)(LI_CELL_LIMIT - 16 * bc) * g.ds;
-    if (fabsf(qx) >= lim || fabsf(qy) >= lim || fabsf(qz) >= lim) return;
+    bool act = valid && isfinite(qx) && isfinite(qy) && isfinite(qz) && fabsf(qx) < lim && fabsf(qy) < lim && fabsf(qz) < lim;
+    if (!act) {
+        qx = 0.f; qy = 0.f; qz = 0.f;
+    }
     const int cx = li_cell(qx, g.ds), cy = li_cell(qy, g.ds), cz = li_cell(qz, g.ds);
     g.bx = cx >> g.bs; g.by = cy >> g.bs; g.bz = cz >> g.bs;
     const int half = bc >> 1;
     g.dirx = ((cx & (bc - 1)) < half) ? -1 : 1;
     g.diry = ((cy & (bc - 1)) < half) ? -1 : 1;
     g.dirz = ((cz & (bc - 1)) < half) ? -1 : 1;
-    const float B = (float)bc * g.ds;
     // slack for float cell assignment / edge products: relative 2^-23 effects, bounded generously
     g.margin = 1e-6f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + 16.0f * B);
 
-    // ---- phase A: seed -------------------------------------------------------------------------------
+    // ---- phase A: seed ---------------------------------------------------------------------------------
     {
         unsigned first = 0, count = 0;
         float dbox = INFINITY;
         bool found = false;
-        if (gl < 8) {
+        if (act && gl < 8) {
             int ox = (gl & 1) ? g.dirx : 0, oy = (gl & 2) ? g.diry : 0, oz = (gl & 4) ? g.dirz : 0;
             found = probe_brick(M, g, ox, oy, oz, qx, qy, qz, INFINITY, false, first, count, dbox);
         }
-        unsigned fm = __ballot_sync(gmask, found) & gmask;
-        const int base_lane = lane - gl;
+        unsigned fm = grp_ballot<G>(found, gbase);   // bit 0 = the query's own brick: taken first
         float bound = INFINITY;
-        if (fm & (1u << base_lane)) {   // the query's own brick
-            unsigned f = __shfl_sync(gmask, first, base_lane), c = __shfl_sync(gmask, count, base_lane);
-            group_scan_slab<G>(M.pool, f, c, qx, qy, qz, INFINITY, ld, li, gl);
-            bound = group_bound5(ld[0], gmask, lane);
-            fm &= ~(1u << base_lane);
-        }
-        while (fm) {
-            int src = __ffs(fm) - 1;
-            fm &= fm - 1;
-            float db = __shfl_sync(gmask, dbox, src);
-            if (!(db < bound)) continue;   // this brick cannot hold one of the 5 nearest
-            unsigned f = __shfl_sync(gmask, first, src), c = __shfl_sync(gmask, count, src);
-            group_scan_slab<G>(M.pool, f, c, qx, qy, qz, bound, ld, li, gl);
-            bound = fminf(bound, group_bound5(ld[0], gmask, lane));
-        }
-    }
-    group_merge<G>(ld, li, gd, gi, gmask, lane);
-    float r2 = explored_r2(g, 0, qx, qy, qz);
-    if (r2 > 5.0f || (gi[4] >= 0 && gd[4] <= r2)) return;
-    int Rdone = 0;
-    // ---- phase A': fewer than 5 known -> rings with the radius bound ----------------------------------
-    if (gi[4] < 0) {
-#define LI_RING(RR)                                                                                   \
-    if (gi[4] < 0) {                                                                                  \
-        knn_ring<G, RR>(M, g, qx, qy, qz, INFINITY, false, ld, li, gmask, lane, gl);                  \
-        group_merge<G>(ld, li, gd, gi, gmask, lane);                                                  \
-        Rdone = RR;                                                                                   \
-        r2 = explored_r2(g, RR, qx, qy, qz);                                                          \
-        if (r2 > 5.0f || (gi[4] >= 0 && gd[4] <= r2)) return;                                         \
-    }
-        LI_RING(1)
-        LI_RING(2)
-        LI_RING(3)
-        LI_RING(4)
-#undef LI_RING
-        const int Rmax = (int)ceilf(2.2360680f / B) + 1;
-        for (int R = 5; R <= Rmax && gi[4] < 0; R++) {
-            const int S = 2 * R + 1, total = S * S * S;
-            for (int base = 0; base < total; base += G) {
-                int idx = base + gl;
-                bool want = idx < total;
-                int ox = idx % S - R, oy = (idx / S) % S - R, oz = idx / (S * S) - R;
-                if (max(abs(ox), max(abs(oy), abs(oz))) < R) want = false;
-                unsigned first = 0, count = 0;
-                float dbox;
-                bool found = false;
-                if (want) found = probe_brick(M, g, ox, oy, oz, qx, qy, qz, INFINITY, false, first, count, dbox);
-                group_scan_found<G>(M.pool, found, first, count, qx, qy, qz, INFINITY, ld, li, gmask, lane, gl);
+        while (__any_sync(LI_FULL, fm != 0u)) {
+            const bool has = fm != 0u;
+            const int src = has ? (__ffs(fm) - 1) : 0;
+            fm &= fm - 1u;
+            const float db = grp_shfl<G>(dbox, src, gbase);
+            const unsigned f = grp_shfl<G>(first, src, gbase);
+            const unsigned c = grp_shfl<G>(count, src, gbase);
+            const unsigned cnt = (has && db < bound) ? c : 0u;   // a brick whose box is beyond the bound holds none of the 5
+            for (unsigned j = gl; __any_sync(LI_FULL, j < cnt); j += G) {
+                if (j < cnt) {
+                    float4 p = __ldg(&M.pool[(size_t)f + j]);
+                    float d = li_dist2(qx, qy, qz, p.x, p.y, p.z);
+                    if (d <= 5.0f && d < bound && d < ld[4]) local_insert(ld, li, d, (int)(f + j));
+                }
             }
-            group_merge<G>(ld, li, gd, gi, gmask, lane);
+            bound = fminf(bound, group_bound5<G>(ld[0], gl, gbase));
+        }
+    }
+    group_merge<G>(ld, li, gd, gi, gl, gbase);
+    float r2 = explored_r2(g, 0, qx, qy, qz);
+    bool done = !act || r2 > 5.0f || (gi[4] >= 0 && gd[4] <= r2);
+    int Rdone = 0;
+
+    // ---- phase A': fewer than 5 known -> rings with the radius bound (sparse neighbourhoods, open air) ------
+    const int Rmax = (int)ceilf(2.2360680f / B) + 1;
+    for (int R = 1; R <= Rmax; R++) {
+        const bool need = !done && gi[4] < 0;
+        if (!__any_sync(LI_FULL, need)) break;
+        const int S = 2 * R + 1, total = S * S * S;
+        const float inv_s = 1.0f / (float)S, inv_ss = 1.0f / (float)(S * S);
+        for (int base = 0; base < total; base += G) {
+            const int idx = base + gl;
+            bool want = need && idx < total;
+            const int oz_ = (int)(((float)idx + 0.5f) * inv_ss);
+            const int rem = idx - oz_ * S * S;
+            const int oy_ = (int)(((float)rem + 0.5f) * inv_s);
+            const int ox = rem - oy_ * S - R, oy = oy_ - R, oz = oz_ - R;
+            if (R == 1) {
+                if ((ox == 0 || ox == g.dirx) && (oy == 0 || oy == g.diry) && (oz == 0 || oz == g.dirz)) want = false;   // stage 0 block
+            } else {
+                if (max(abs(ox), max(abs(oy), abs(oz))) < R) want = false;   // inner cube already visited
+            }
+            unsigned first = 0, count = 0;
+            float dbox = INFINITY;
+            bool found = false;
+            if (want) found = probe_brick(M, g, ox, oy, oz, qx, qy, qz, INFINITY, false, first, count, dbox);
+            lockstep_scan_found<G>(M.pool, found, first, count, dbox, qx, qy, qz, INFINITY, ld, li, gl, gbase);
+        }
+        group_merge<G>(ld, li, gd, gi, gl, gbase);
+        if (need) {
             Rdone = R;
             r2 = explored_r2(g, R, qx, qy, qz);
-            if (r2 > 5.0f || (gi[4] >= 0 && gd[4] <= r2)) return;
+            done = r2 > 5.0f || (gi[4] >= 0 && gd[4] <= r2);
         }
-        if (gi[4] < 0) return;   // fewer than 5 points within the radius: everything within sqrt(5) was explored
     }
-    // ---- phase B: closure over the ball of radius sqrt(g5) --------------------------------------------
-    {
-        const float g5 = gd[4];
+    if (gi[4] < 0) done = true;   // fewer than 5 points within the radius: everything within sqrt(5) was explored
+
+    // ---- phase B: closure over the ball of radius sqrt(g5) -----------------------------------------------
+    if (__any_sync(LI_FULL, !done)) {
+        const bool need = !done;
+        const float g5 = need ? gd[4] : 0.f;
         const float r = sqrtf(g5) * (1.0f + 1e-6f) + g.margin;
         // explored block (brick coordinates)
         int ex0, ex1, ey0, ey1, ez0, ez1;
@@ -305,43 +299,48 @@ __device__ __forceinline__ void knn5_group(const MapDev& M, float qx, float qy, 
         const int ly = li_cell(qy - r, g.ds) >> g.bs, hy = li_cell(qy + r, g.ds) >> g.bs;
         const int lz = li_cell(qz - r, g.ds) >> g.bs, hz = li_cell(qz + r, g.ds) >> g.bs;
         const int nx = hx - lx + 1, ny = hy - ly + 1, nz = hz - lz + 1;
-        const int nxy = nx * ny, total = nxy * nz;
+        const int nxy = nx * ny;
+        const int total = need ? nxy * nz : 0;
         const float inv_nxy = 1.0f / (float)nxy, inv_nx = 1.0f / (float)nx;
-        for (int base = 0; base < total; base += G) {
-            int idx = base + gl;
+        for (int base = 0; __any_sync(LI_FULL, base < total); base += G) {
+            const int idx = base + gl;
             bool want = idx < total;
-            int iz = (int)(((float)idx + 0.5f) * inv_nxy);
-            int rem = idx - iz * nxy;
-            int iy = (int)(((float)rem + 0.5f) * inv_nx);
-            int ix = rem - iy * nx;
-            int kx = lx + ix, ky = ly + iy, kz = lz + iz;
+            const int iz = (int)(((float)idx + 0.5f) * inv_nxy);
+            const int rem = idx - iz * nxy;
+            const int iy = (int)(((float)rem + 0.5f) * inv_nx);
+            const int ix = rem - iy * nx;
+            const int kx = lx + ix, ky = ly + iy, kz = lz + iz;
             if (kx >= ex0 && kx <= ex1 && ky >= ey0 && ky <= ey1 && kz >= ez0 && kz <= ez1) want = false;   // explored
             unsigned first = 0, count = 0;
-            float dbox;
+            float dbox = INFINITY;
             bool found = false;
             if (want) found = probe_brick(M, g, kx - g.bx, ky - g.by, kz - g.bz, qx, qy, qz, g5, true, first, count, dbox);
-            group_scan_found<G>(M.pool, found, first, count, qx, qy, qz, g5, ld, li, gmask, lane, gl);
+            lockstep_scan_found<G>(M.pool, found, first, count, dbox, qx, qy, qz, g5, ld, li, gl, gbase);
         }
-        group_merge<G>(ld, li, gd, gi, gmask, lane);
+        group_merge<G>(ld, li, gd, gi, gl, gbase);
     }
 }
 
 // ---- search kernel of an ICP pass: world transform + 5-NN for every scan point -----------------------
 template <int G>
 __global__ void __launch_bounds__(256) k_knn_scan(MapDev M, ScanDev S, PoseD P) {
+    constexpr int Q = Grp<G>::Q;
     const int lane = threadIdx.x & 31;
-    const int gl = lane % G;
-    const unsigned gmask = Grp<G>::mask(lane);
-    const int group_global = (blockIdx.x * blockDim.x + threadIdx.x) / G;
-    const int ngroups = (gridDim.x * blockDim.x) / G;
-    for (int q = group_global; q < S.n; q += ngroups) {
-        float4 b = __ldg(&S.body[q]);
-        float wx, wy, wz;
-        li_body_to_world(P, b.x, b.y, b.z, wx, wy, wz);
+    const int gl = lane % G, gid = lane / G, gbase = gid * G;
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int qb = warp_global * Q; qb < S.n; qb += nwarps * Q) {   // warp-uniform
+        const int q = qb + gid;
+        const bool valid = q < S.n;
+        float wx = 0.f, wy = 0.f, wz = 0.f;
+        if (valid) {
+            float4 b = __ldg(&S.body[q]);
+            li_body_to_world(P, b.x, b.y, b.z, wx, wy, wz);
+        }
         float gd[5];
         int gi[5];
-        knn5_group<G>(M, wx, wy, wz, gd, gi, gmask, lane, gl);
-        if (gl == 0) {
+        knn5_lockstep<G>(M, valid, wx, wy, wz, gd, gi, gl, gbase);
+        if (valid && gl == 0) {
             S.world[q] = make_float4(wx, wy, wz, 0.f);
 #pragma unroll
             for (int k = 0; k < 5; k++) S.near_ids[(size_t)q * 5 + k] = gi[k];
@@ -353,17 +352,20 @@ __global__ void __launch_bounds__(256) k_knn_scan(MapDev M, ScanDev S, PoseD P) 
 template <int G>
 __global__ void __launch_bounds__(256) k_knn_queries(MapDev M, const float4* __restrict__ qpts, int n, int* __restrict__ ids,
                                                      float* __restrict__ d2) {
+    constexpr int Q = Grp<G>::Q;
     const int lane = threadIdx.x & 31;
-    const int gl = lane % G;
-    const unsigned gmask = Grp<G>::mask(lane);
-    const int group_global = (blockIdx.x * blockDim.x + threadIdx.x) / G;
-    const int ngroups = (gridDim.x * blockDim.x) / G;
-    for (int q = group_global; q < n; q += ngroups) {
-        float4 p = __ldg(&qpts[q]);
+    const int gl = lane % G, gid = lane / G, gbase = gid * G;
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int qb = warp_global * Q; qb < n; qb += nwarps * Q) {
+        const int q = qb + gid;
+        const bool valid = q < n;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) p = __ldg(&qpts[q]);
         float gd[5];
         int gi[5];
-        knn5_group<G>(M, p.x, p.y, p.z, gd, gi, gmask, lane, gl);
-        if (gl == 0) {
+        knn5_lockstep<G>(M, valid, p.x, p.y, p.z, gd, gi, gl, gbase);
+        if (valid && gl == 0) {
 #pragma unroll
             for (int k = 0; k < 5; k++) {
                 ids[(size_t)q * 5 + k] = gi[k];

@@ -94,18 +94,21 @@ __device__ __forceinline__ void group_merge(const float (&ld)[5], const int (&li
     }
 }
 
-// Cheap upper bound on the group's 5th-smallest candidate distance: the 5th smallest of the lanes' BEST values
-// (each lane's ld[0]); +inf when fewer than 5 lanes hold a candidate.
+// Cheap upper bound on the group's 5th-smallest candidate distance: the 5th smallest among the lanes' two best
+// values (ld[0], ld[1]); +inf when fewer than 5 such candidates exist. Any 5 distinct candidates bound the true 5th.
 template <int G>
-__device__ __forceinline__ float group_bound5(float best, int gl, int gbase) {
-    unsigned v = __float_as_uint(best);
+__device__ __forceinline__ float group_bound5(const float (&ld)[5], int gl, int gbase) {
+    unsigned a = __float_as_uint(ld[0]), b = __float_as_uint(ld[1]);   // a <= b (sorted list)
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        unsigned mn = grp_min<G>(v);
-        unsigned who = grp_ballot<G>(v == mn, gbase);
-        if (gl == __ffs(who) - 1) v = 0x7f800000u;   // +inf
+        unsigned mn = grp_min<G>(a);
+        unsigned who = grp_ballot<G>(a == mn, gbase);
+        if (gl == __ffs(who) - 1) {   // pop this lane's head
+            a = b;
+            b = 0x7f800000u;
+        }
     }
-    return __uint_as_float(grp_min<G>(v));
+    return __uint_as_float(grp_min<G>(a));
 }
 
 struct KnnGeom {
@@ -125,8 +128,9 @@ __device__ __forceinline__ bool probe_brick(const MapDev& M, const KnnGeom& g, i
     float ey = fmaxf(0.f, fmaxf(loy - qy, qy - hiy));
     float ez = fmaxf(0.f, fmaxf(loz - qz, qz - hiz));
     dbox = (ex * ex + ey * ey + ez * ez) * (1.0f - 1e-6f);
-    // while fewer than 5 are known every point with d2 <= 5 counts; afterwards only d2 < current 5th
-    bool useful = full ? (dbox < bound2) : (dbox <= 5.0f);
+    // only points with d2 <= 5 count, and only bricks whose box can beat the current bound on the 5th distance
+    bool useful = (dbox <= 5.0f) && (dbox < bound2);
+    (void)full;
     if (!useful) return false;
     bool found = li_brick_find(M.ent, M.mask, li_pack_key(kx, ky, kz), first, count);
     return found && count > 0u;
@@ -182,7 +186,6 @@ __device__ __forceinline__ float explored_r2(const KnnGeom& g, int R, float qx, 
 template <int G>
 __device__ __forceinline__ void knn5_lockstep(const MapDev& M, bool valid, float qx, float qy, float qz, float (&gd)[5], int (&gi)[5],
                                               int gl, int gbase) {
-    static_assert(G >= 8, "stage 0 needs 8 lanes");
     float ld[5];
     int li[5];
 #pragma unroll
@@ -213,31 +216,35 @@ __device__ __forceinline__ void knn5_lockstep(const MapDev& M, bool valid, float
 
     // ---- phase A: seed ---------------------------------------------------------------------------------
     {
-        unsigned first = 0, count = 0;
-        float dbox = INFINITY;
-        bool found = false;
-        if (act && gl < 8) {
-            int ox = (gl & 1) ? g.dirx : 0, oy = (gl & 2) ? g.diry : 0, oz = (gl & 4) ? g.dirz : 0;
-            found = probe_brick(M, g, ox, oy, oz, qx, qy, qz, INFINITY, false, first, count, dbox);
-        }
-        unsigned fm = grp_ballot<G>(found, gbase);   // bit 0 = the query's own brick: taken first
         float bound = INFINITY;
-        while (__any_sync(LI_FULL, fm != 0u)) {
-            const bool has = fm != 0u;
-            const int src = has ? (__ffs(fm) - 1) : 0;
-            fm &= fm - 1u;
-            const float db = grp_shfl<G>(dbox, src, gbase);
-            const unsigned f = grp_shfl<G>(first, src, gbase);
-            const unsigned c = grp_shfl<G>(count, src, gbase);
-            const unsigned cnt = (has && db < bound) ? c : 0u;   // a brick whose box is beyond the bound holds none of the 5
-            for (unsigned j = gl; __any_sync(LI_FULL, j < cnt); j += G) {
-                if (j < cnt) {
-                    float4 p = __ldg(&M.pool[(size_t)f + j]);
-                    float d = li_dist2(qx, qy, qz, p.x, p.y, p.z);
-                    if (d <= 5.0f && d < bound && d < ld[4]) local_insert(ld, li, d, (int)(f + j));
-                }
+#pragma unroll
+        for (int base = 0; base < 8; base += G) {
+            unsigned first = 0, count = 0;
+            float dbox = INFINITY;
+            bool found = false;
+            const int idx = base + gl;
+            if (act && idx < 8) {
+                int ox = (idx & 1) ? g.dirx : 0, oy = (idx & 2) ? g.diry : 0, oz = (idx & 4) ? g.dirz : 0;
+                found = probe_brick(M, g, ox, oy, oz, qx, qy, qz, bound, false, first, count, dbox);
             }
-            bound = fminf(bound, group_bound5<G>(ld[0], gl, gbase));
+            unsigned fm = grp_ballot<G>(found, gbase);   // bit 0 of round 0 = the query's own brick: taken first
+            while (__any_sync(LI_FULL, fm != 0u)) {
+                const bool has = fm != 0u;
+                const int src = has ? (__ffs(fm) - 1) : 0;
+                fm &= fm - 1u;
+                const float db = grp_shfl<G>(dbox, src, gbase);
+                const unsigned f = grp_shfl<G>(first, src, gbase);
+                const unsigned c = grp_shfl<G>(count, src, gbase);
+                const unsigned cnt = (has && db < bound) ? c : 0u;   // a brick whose box is beyond the bound holds none of the 5
+                for (unsigned j = gl; __any_sync(LI_FULL, j < cnt); j += G) {
+                    if (j < cnt) {
+                        float4 p = __ldg(&M.pool[(size_t)f + j]);
+                        float d = li_dist2(qx, qy, qz, p.x, p.y, p.z);
+                        if (d <= 5.0f && d < bound && d < ld[4]) local_insert(ld, li, d, (int)(f + j));
+                    }
+                }
+                bound = fminf(bound, group_bound5<G>(ld, gl, gbase));
+            }
         }
     }
     group_merge<G>(ld, li, gd, gi, gl, gbase);

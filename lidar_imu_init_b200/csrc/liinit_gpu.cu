@@ -186,6 +186,7 @@ int run_pass(Ctx* c, const double* R, const double* p, const double* RLI, const 
     CU(cudaEventRecord(c->ev0, c->stream));
     if (search) {
         switch (c->group) {
+            case 4: launch_knn_scan<4>(c, P); break;
             case 16: launch_knn_scan<16>(c, P); break;
             case 32: launch_knn_scan<32>(c, P); break;
             default: launch_knn_scan<8>(c, P); break;
@@ -277,7 +278,7 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
         return bail(LIINIT_ERR_INVALID);
     }
     c->hash_slots = 1u << hl;
-    c->group = (cfg->knn_group_lanes == 8 || cfg->knn_group_lanes == 16 || cfg->knn_group_lanes == 32) ? cfg->knn_group_lanes : 8;
+    c->group = (cfg->knn_group_lanes == 4 || cfg->knn_group_lanes == 8 || cfg->knn_group_lanes == 16 || cfg->knn_group_lanes == 32) ? cfg->knn_group_lanes : 8;
 
     MapDev& M = c->M;
     M.mask = c->hash_slots - 1;

@@ -48,7 +48,7 @@ def test_knn_matches_oracle(gpu_lib, oracle_mod, small_case):
 
 
 @pytest.mark.parametrize("imu_en", [False, True])
-@pytest.mark.parametrize("tile", [8, 16, 32])
+@pytest.mark.parametrize("tile", [4, 8, 32])
 def test_search_and_reuse_pass(gpu_lib, oracle_mod, imu_en, tile):
     c = scenes.make_config("C2", N=20000, M=200000, open_air_frac=0.02, imu_en=imu_en)
     p = c["pose_init"]

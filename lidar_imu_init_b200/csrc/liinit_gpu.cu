@@ -68,6 +68,7 @@ struct Ctx {
     float last_ms = 0.f;
     int last_launches = 0;
     int group = 8;
+    float rho2 = 0.2f;   // squared seed radius of the 5-NN search
 };
 
 #define CU(call)                                                                                     \
@@ -167,7 +168,7 @@ void launch_knn_scan(Ctx* c, const PoseD& P) {
     long long threads = (long long)c->scan_n * G;
     int grid = nblk(threads, 256);
     if (grid > c->max_blocks) grid = c->max_blocks;
-    k_knn_scan<G><<<grid, 256, 0, c->stream>>>(c->M, c->S, P);
+    k_knn_scan<G><<<grid, 256, 0, c->stream>>>(c->M, c->S, P, c->rho2);
 }
 
 template <bool IMU, bool SEARCH>
@@ -280,6 +281,11 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
     c->hash_slots = 1u << hl;
     c->group = (cfg->knn_group_lanes == 4 || cfg->knn_group_lanes == 8 || cfg->knn_group_lanes == 16 || cfg->knn_group_lanes == 32) ? cfg->knn_group_lanes : 8;
 
+    {
+        float cells = cfg->knn_seed_radius_cells > 0.f ? cfg->knn_seed_radius_cells : 3.0f;
+        float rho = cells * cfg->filter_size_map;
+        c->rho2 = rho * rho;
+    }
     MapDev& M = c->M;
     M.mask = c->hash_slots - 1;
     M.ds = cfg->filter_size_map;
@@ -483,7 +489,7 @@ int liinit_map_nearest_search(liinit_ctx* h, const float* q, int stride, int n, 
         CU(cudaMalloc(&d_ids, (size_t)m * 5 * sizeof(int)));
         int grid = nblk((long long)m * 8, 256);
         if (grid > c->max_blocks) grid = c->max_blocks;
-        k_knn_queries<8><<<grid, 256, 0, c->stream>>>(c->M, c->d_stage_pts, m, d_ids, c->d_q_d2);
+        k_knn_queries<8><<<grid, 256, 0, c->stream>>>(c->M, c->d_stage_pts, m, d_ids, c->d_q_d2, c->rho2);
         c->launches++;
         CU(cudaMemcpyAsync(ids.data() + (size_t)off * 5, d_ids, (size_t)m * 5 * 4, cudaMemcpyDeviceToHost, c->stream));
         if (out_d2) CU(cudaMemcpyAsync(out_d2 + (size_t)off * 5, c->d_q_d2, (size_t)m * 5 * 4, cudaMemcpyDeviceToHost, c->stream));

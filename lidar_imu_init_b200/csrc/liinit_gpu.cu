@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "icp_kernels.cuh"
 #include "knn_kernels.cuh"
+#include "knn_tpq.cuh"
 #include "map_kernels.cuh"
 
 namespace {
@@ -171,6 +172,16 @@ void launch_knn_scan(Ctx* c, const PoseD& P) {
     k_knn_scan<G><<<grid, 256, 0, c->stream>>>(c->M, c->S, P, c->rho2);
 }
 
+constexpr int TPQ_CH = 32, TPQ_NB = 8;
+constexpr size_t TPQ_SMEM = 4 * TpqCfg<TPQ_CH, TPQ_NB>::WARP_TILE_F4 * sizeof(float4);
+
+void launch_knn_scan_tpq(Ctx* c, const PoseD& P) {
+    int grid = nblk(c->scan_n, 128);
+    int cap = c->num_sms * 12;
+    if (grid > cap) grid = cap;
+    k_knn_scan_tpq<TPQ_CH, TPQ_NB><<<grid, 128, TPQ_SMEM, c->stream>>>(c->M, c->S, P, c->rho2);
+}
+
 template <bool IMU, bool SEARCH>
 void launch_plane(Ctx* c, const PoseD& P) {
     // one wave of 256-thread blocks (2 resident per SM at ~100-130 registers), grid-stride over the scan
@@ -187,6 +198,7 @@ int run_pass(Ctx* c, const double* R, const double* p, const double* RLI, const 
     CU(cudaEventRecord(c->ev0, c->stream));
     if (search) {
         switch (c->group) {
+            case 1: launch_knn_scan_tpq(c, P); break;
             case 4: launch_knn_scan<4>(c, P); break;
             case 16: launch_knn_scan<16>(c, P); break;
             case 32: launch_knn_scan<32>(c, P); break;
@@ -256,6 +268,8 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
     cudaDeviceProp prop;
     CUC(cudaGetDeviceProperties(&prop, c->device));
     c->num_sms = prop.multiProcessorCount;
+    CUC(cudaFuncSetAttribute(k_knn_scan_tpq<TPQ_CH, TPQ_NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TPQ_SMEM));
+    CUC(cudaFuncSetAttribute(k_knn_queries_tpq<TPQ_CH, TPQ_NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TPQ_SMEM));
     CUC(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     CUC(cudaEventCreate(&c->ev0));
@@ -279,7 +293,7 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
         return bail(LIINIT_ERR_INVALID);
     }
     c->hash_slots = 1u << hl;
-    c->group = (cfg->knn_group_lanes == 4 || cfg->knn_group_lanes == 8 || cfg->knn_group_lanes == 16 || cfg->knn_group_lanes == 32) ? cfg->knn_group_lanes : 8;
+    c->group = (cfg->knn_group_lanes == 1 || cfg->knn_group_lanes == 4 || cfg->knn_group_lanes == 8 || cfg->knn_group_lanes == 16 || cfg->knn_group_lanes == 32) ? cfg->knn_group_lanes : 8;
 
     {
         float cells = cfg->knn_seed_radius_cells > 0.f ? cfg->knn_seed_radius_cells : 3.0f;
@@ -487,9 +501,15 @@ int liinit_map_nearest_search(liinit_ctx* h, const float* q, int stride, int n, 
         // d_vslot_of.. reuse: ids go to a scratch the size of batch*5 -> use d_near_ids only if scan not resident; allocate
         int* d_ids = nullptr;
         CU(cudaMalloc(&d_ids, (size_t)m * 5 * sizeof(int)));
-        int grid = nblk((long long)m * 8, 256);
-        if (grid > c->max_blocks) grid = c->max_blocks;
-        k_knn_queries<8><<<grid, 256, 0, c->stream>>>(c->M, c->d_stage_pts, m, d_ids, c->d_q_d2, c->rho2);
+        if (c->group == 1) {
+            int grid = nblk(m, 128);
+            if (grid > c->num_sms * 12) grid = c->num_sms * 12;
+            k_knn_queries_tpq<TPQ_CH, TPQ_NB><<<grid, 128, TPQ_SMEM, c->stream>>>(c->M, c->d_stage_pts, m, d_ids, c->d_q_d2, c->rho2);
+        } else {
+            int grid = nblk((long long)m * 8, 256);
+            if (grid > c->max_blocks) grid = c->max_blocks;
+            k_knn_queries<8><<<grid, 256, 0, c->stream>>>(c->M, c->d_stage_pts, m, d_ids, c->d_q_d2, c->rho2);
+        }
         c->launches++;
         CU(cudaMemcpyAsync(ids.data() + (size_t)off * 5, d_ids, (size_t)m * 5 * 4, cudaMemcpyDeviceToHost, c->stream));
         if (out_d2) CU(cudaMemcpyAsync(out_d2 + (size_t)off * 5, c->d_q_d2, (size_t)m * 5 * 4, cudaMemcpyDeviceToHost, c->stream));

@@ -30,9 +30,10 @@ def small_case():
     return scenes.make_config("C2", N=20000, M=200000, open_air_frac=0.02)
 
 
-def test_knn_matches_oracle(gpu_lib, oracle_mod, small_case):
+@pytest.mark.parametrize("group", [1, 8])
+def test_knn_matches_oracle(gpu_lib, oracle_mod, small_case, group):
     c = small_case
-    g = gpu_lib.LiInitGpu(c["ds"], max_map_points=400000, max_scan_points=50000)
+    g = gpu_lib.LiInitGpu(c["ds"], max_map_points=400000, max_scan_points=50000, knn_group_lanes=group)
     g.map_build(c["map_xyz"])
     assert g.map_validnum() == len(c["map_xyz"])
     om = oracle_mod.OracleMap(c["ds"], _best_backend(oracle_mod))
@@ -48,7 +49,7 @@ def test_knn_matches_oracle(gpu_lib, oracle_mod, small_case):
 
 
 @pytest.mark.parametrize("imu_en", [False, True])
-@pytest.mark.parametrize("tile", [4, 8, 32])
+@pytest.mark.parametrize("tile", [1, 4, 8, 32])
 def test_search_and_reuse_pass(gpu_lib, oracle_mod, imu_en, tile):
     c = scenes.make_config("C2", N=20000, M=200000, open_air_frac=0.02, imu_en=imu_en)
     p = c["pose_init"]

@@ -7,7 +7,7 @@ import argparse
 ap = argparse.ArgumentParser()
 ap.add_argument("--N", type=int, default=240000)
 ap.add_argument("--M", type=int, default=5000000)
-ap.add_argument("--groups", default="4,8,16")
+ap.add_argument("--groups", default="1,4")
 ap.add_argument("--bricks", default="2")
 ap.add_argument("--air", type=float, default=0.01)
 ap.add_argument("--order", default="voxel")

@@ -144,17 +144,20 @@ __device__ __forceinline__ void lockstep_scan_found(const float4* __restrict__ p
 //                merge -> (n, g5);  stop if n == 5 and g5 <= hi2 (no unscanned brick can hold a closer point) or hi2 >= 5;
 //                otherwise lo2 = hi2 and hi2 = g5 if 5 are known (one closing step) else 4*hi2 (sparse neighbourhood).
 // The first shell is a guess (rho = seed radius): with a dense map most queries finish in it, the rest need one closing step.
+//
+// budget: number of shells this call may run (<= 0: until done). On entry gd/gi may carry the result of earlier shells
+// (resume: lo2_io/hi2_io as left by the previous call); on exit lo2_io/hi2_io describe the NEXT shell and the return
+// value says whether the query is finished. Splitting the shells over kernel launches keeps a warp's groups in step:
+// the easy majority (one shell) is not held up by the groups that need a closing shell or a sparse-area search.
 template <int G>
-__device__ __forceinline__ void knn5_lockstep(const MapDev& M, float rho2, bool valid, float qx, float qy, float qz, float (&gd)[5],
-                                              int (&gi)[5], int gl, int gbase) {
+__device__ __forceinline__ bool knn5_lockstep(const MapDev& M, float& lo2_io, float& hi2_io, int budget, bool valid, float qx, float qy,
+                                              float qz, float (&gd)[5], int (&gi)[5], int gl, int gbase) {
     float ld[5];
     int li[5];
 #pragma unroll
-    for (int i = 0; i < 5; i++) {
-        ld[i] = INFINITY;
-        li[i] = -1;
-        gd[i] = INFINITY;
-        gi[i] = -1;
+    for (int i = 0; i < 5; i++) {   // lane 0 of the group resumes with what earlier shells found
+        ld[i] = (gl == 0) ? gd[i] : INFINITY;
+        li[i] = (gl == 0) ? gi[i] : -1;
     }
     KnnGeom g;
     g.bs = M.bshift;
@@ -173,8 +176,10 @@ __device__ __forceinline__ void knn5_lockstep(const MapDev& M, float rho2, bool 
     g.margin = 1e-6f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + 16.0f * B);
 
     bool done = !act;
-    float lo2 = 0.f, hi2 = rho2;
-    while (__any_sync(LI_FULL, !done)) {
+    float lo2 = lo2_io, hi2 = hi2_io;
+    int shells = 0;
+    while (__any_sync(LI_FULL, !done) && (budget <= 0 || shells < budget)) {
+        shells++;
         const bool need = !done;
         const bool last = hi2 >= 5.0f;   // the radius bound d2 <= 5 is inclusive (ikd_Tree.cpp:842)
         const float r = sqrtf(fminf(hi2, 5.0f)) * (1.0f + 1e-6f) + g.margin;
@@ -227,31 +232,72 @@ __device__ __forceinline__ void knn5_lockstep(const MapDev& M, float rho2, bool 
             }
         }
     }
+    lo2_io = lo2;
+    hi2_io = hi2;
+    return done;
 }
 
-// ---- search kernel of an ICP pass: world transform + 5-NN for every scan point -----------------------
+// ---- search kernels of an ICP pass: world transform + 5-NN for every scan point -----------------------
+// Per-scan search state on the device (beside ScanDev): distances of the current neighbours, the next shell of
+// unfinished queries and two work queues.
+struct KnnWork {
+    float* near_d2;     // [N*5]
+    float2* shell;      // [N] (lo2, hi2) of the next shell
+    int* queue[2];      // unfinished query indices after pass 0 / pass 1
+    int* qcount;        // [2]
+};
+
+// mode 0: all scan points, first shell only; unfinished -> queue[0]
+// mode 1: queue[0], one more shell (the closing shell for most); unfinished -> queue[1]
+// mode 2: queue[1], until done (sparse neighbourhoods, open air)
 template <int G>
-__global__ void __launch_bounds__(256) k_knn_scan(MapDev M, ScanDev S, PoseD P, float rho2) {
+__global__ void __launch_bounds__(256) k_knn_scan(MapDev M, ScanDev S, PoseD P, float rho2, KnnWork W, int mode) {
     constexpr int Q = Grp<G>::Q;
     const int lane = threadIdx.x & 31;
     const int gl = lane % G, gid = lane / G, gbase = gid * G;
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (int qb = warp_global * Q; qb < S.n; qb += nwarps * Q) {   // warp-uniform
-        const int q = qb + gid;
-        const bool valid = q < S.n;
+    const int n_items = (mode == 0) ? S.n : W.qcount[mode - 1];
+    for (int ib = warp_global * Q; ib < n_items; ib += nwarps * Q) {   // warp-uniform
+        const int item = ib + gid;
+        const bool valid = item < n_items;
+        int q = 0;
+        if (valid) q = (mode == 0) ? item : W.queue[mode - 1][item];
         float wx = 0.f, wy = 0.f, wz = 0.f;
+        float gd[5];
+        int gi[5];
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            gd[k] = INFINITY;
+            gi[k] = -1;
+        }
+        float lo2 = 0.f, hi2 = rho2;
         if (valid) {
             float4 b = __ldg(&S.body[q]);
             li_body_to_world(P, b.x, b.y, b.z, wx, wy, wz);
+            if (mode != 0) {
+                float2 sh = W.shell[q];
+                lo2 = sh.x;
+                hi2 = sh.y;
+#pragma unroll
+                for (int k = 0; k < 5; k++) {
+                    gi[k] = S.near_ids[(size_t)q * 5 + k];
+                    float d = W.near_d2[(size_t)q * 5 + k];
+                    gd[k] = (gi[k] >= 0) ? d : INFINITY;
+                }
+            }
         }
-        float gd[5];
-        int gi[5];
-        knn5_lockstep<G>(M, rho2, valid, wx, wy, wz, gd, gi, gl, gbase);
+        const bool done = knn5_lockstep<G>(M, lo2, hi2, (mode == 2) ? 0 : 1, valid, wx, wy, wz, gd, gi, gl, gbase);
         if (valid && gl == 0) {
-            S.world[q] = make_float4(wx, wy, wz, 0.f);
+            if (mode == 0) S.world[q] = make_float4(wx, wy, wz, 0.f);
 #pragma unroll
             for (int k = 0; k < 5; k++) S.near_ids[(size_t)q * 5 + k] = gi[k];
+            if (!done) {
+#pragma unroll
+                for (int k = 0; k < 5; k++) W.near_d2[(size_t)q * 5 + k] = gd[k];
+                W.shell[q] = make_float2(lo2, hi2);
+                W.queue[mode][atomicAdd(&W.qcount[mode], 1)] = q;
+            }
         }
     }
 }
@@ -272,7 +318,13 @@ __global__ void __launch_bounds__(256) k_knn_queries(MapDev M, const float4* __r
         if (valid) p = __ldg(&qpts[q]);
         float gd[5];
         int gi[5];
-        knn5_lockstep<G>(M, rho2, valid, p.x, p.y, p.z, gd, gi, gl, gbase);
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            gd[k] = INFINITY;
+            gi[k] = -1;
+        }
+        float lo2 = 0.f, hi2 = rho2;
+        knn5_lockstep<G>(M, lo2, hi2, 0, valid, p.x, p.y, p.z, gd, gi, gl, gbase);
         if (valid && gl == 0) {
 #pragma unroll
             for (int k = 0; k < 5; k++) {

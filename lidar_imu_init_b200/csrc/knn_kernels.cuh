@@ -238,18 +238,18 @@ __device__ __forceinline__ bool knn5_lockstep(const MapDev& M, float& lo2_io, fl
 }
 
 // ---- search kernels of an ICP pass: world transform + 5-NN for every scan point -----------------------
-// Per-scan search state on the device (beside ScanDev): distances of the current neighbours, the next shell of
-// unfinished queries and two work queues.
+// Per-scan search state on the device (beside ScanDev): distances of the current neighbours and the next shell of
+// every query (hi2 < 0: finished).
 struct KnnWork {
     float* near_d2;     // [N*5]
-    float2* shell;      // [N] (lo2, hi2) of the next shell
-    int* queue[2];      // unfinished query indices after pass 0 / pass 1
-    int* qcount;        // [2]
+    float2* shell;      // [N] (lo2, hi2) of the next shell; hi2 < 0 when the query is done
 };
 
-// mode 0: all scan points, first shell only; unfinished -> queue[0]
-// mode 1: queue[0], one more shell (the closing shell for most); unfinished -> queue[1]
-// mode 2: queue[1], until done (sparse neighbourhoods, open air)
+// mode 0: all scan points, first shell only.
+// mode 1: the unfinished ones, one more shell (the closing shell for most).
+// mode 2: what is still unfinished, until done (sparse neighbourhoods, open air).
+// Modes 1/2 walk the scan in chunks of 32 consecutive points and ballot-compact the unfinished ones, so the spatial
+// order of the scan (cache locality, similar work inside a warp) survives without queues or atomics.
 template <int G>
 __global__ void __launch_bounds__(256) k_knn_scan(MapDev M, ScanDev S, PoseD P, float rho2, KnnWork W, int mode) {
     constexpr int Q = Grp<G>::Q;
@@ -257,46 +257,53 @@ __global__ void __launch_bounds__(256) k_knn_scan(MapDev M, ScanDev S, PoseD P, 
     const int gl = lane % G, gid = lane / G, gbase = gid * G;
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    const int n_items = (mode == 0) ? S.n : W.qcount[mode - 1];
-    for (int ib = warp_global * Q; ib < n_items; ib += nwarps * Q) {   // warp-uniform
-        const int item = ib + gid;
-        const bool valid = item < n_items;
-        int q = 0;
-        if (valid) q = (mode == 0) ? item : W.queue[mode - 1][item];
-        float wx = 0.f, wy = 0.f, wz = 0.f;
-        float gd[5];
-        int gi[5];
-#pragma unroll
-        for (int k = 0; k < 5; k++) {
-            gd[k] = INFINITY;
-            gi[k] = -1;
+    for (int cb = warp_global * 32; cb < S.n; cb += nwarps * 32) {   // warp-uniform
+        unsigned pend = 0xffffffffu;
+        if (mode != 0) {
+            const int ql = cb + lane;
+            pend = __ballot_sync(LI_FULL, ql < S.n && W.shell[ql].y >= 0.f);
+        } else if (cb + 32 > S.n) {
+            pend = (1u << (S.n - cb)) - 1u;
         }
-        float lo2 = 0.f, hi2 = rho2;
-        if (valid) {
-            float4 b = __ldg(&S.body[q]);
-            li_body_to_world(P, b.x, b.y, b.z, wx, wy, wz);
-            if (mode != 0) {
-                float2 sh = W.shell[q];
-                lo2 = sh.x;
-                hi2 = sh.y;
+        const int cnt = __popc(pend);
+        for (int k0 = 0; k0 < cnt; k0 += Q) {   // warp-uniform
+            const int k = k0 + gid;
+            const bool valid = k < cnt;
+            const int q = cb + (int)__fns(pend, 0, (valid ? k : 0) + 1);   // k-th pending point of the chunk
+            float wx = 0.f, wy = 0.f, wz = 0.f;
+            float gd[5];
+            int gi[5];
 #pragma unroll
-                for (int k = 0; k < 5; k++) {
-                    gi[k] = S.near_ids[(size_t)q * 5 + k];
-                    float d = W.near_d2[(size_t)q * 5 + k];
-                    gd[k] = (gi[k] >= 0) ? d : INFINITY;
+            for (int t = 0; t < 5; t++) {
+                gd[t] = INFINITY;
+                gi[t] = -1;
+            }
+            float lo2 = 0.f, hi2 = rho2;
+            if (valid) {
+                float4 b = __ldg(&S.body[q]);
+                li_body_to_world(P, b.x, b.y, b.z, wx, wy, wz);
+                if (mode != 0) {
+                    float2 sh = W.shell[q];
+                    lo2 = sh.x;
+                    hi2 = sh.y;
+#pragma unroll
+                    for (int t = 0; t < 5; t++) {
+                        gi[t] = S.near_ids[(size_t)q * 5 + t];
+                        float d = W.near_d2[(size_t)q * 5 + t];
+                        gd[t] = (gi[t] >= 0) ? d : INFINITY;
+                    }
                 }
             }
-        }
-        const bool done = knn5_lockstep<G>(M, lo2, hi2, (mode == 2) ? 0 : 1, valid, wx, wy, wz, gd, gi, gl, gbase);
-        if (valid && gl == 0) {
-            if (mode == 0) S.world[q] = make_float4(wx, wy, wz, 0.f);
+            const bool done = knn5_lockstep<G>(M, lo2, hi2, (mode == 2) ? 0 : 1, valid, wx, wy, wz, gd, gi, gl, gbase);
+            if (valid && gl == 0) {
+                if (mode == 0) S.world[q] = make_float4(wx, wy, wz, 0.f);
 #pragma unroll
-            for (int k = 0; k < 5; k++) S.near_ids[(size_t)q * 5 + k] = gi[k];
-            if (!done) {
+                for (int t = 0; t < 5; t++) S.near_ids[(size_t)q * 5 + t] = gi[t];
+                if (!done) {
 #pragma unroll
-                for (int k = 0; k < 5; k++) W.near_d2[(size_t)q * 5 + k] = gd[k];
-                W.shell[q] = make_float2(lo2, hi2);
-                W.queue[mode][atomicAdd(&W.qcount[mode], 1)] = q;
+                    for (int t = 0; t < 5; t++) W.near_d2[(size_t)q * 5 + t] = gd[t];
+                }
+                W.shell[q] = done ? make_float2(0.f, -1.f) : make_float2(lo2, hi2);
             }
         }
     }

@@ -169,15 +169,14 @@ void fill_pose(PoseD& P, const double* R, const double* p, const double* RLI, co
 // The later launches size their loops from the device-side queue counters (grid-stride), so no host round trip.
 template <int G>
 void launch_knn_scan(Ctx* c, const PoseD& P) {
-    long long threads = (long long)c->scan_n * G;
-    int grid = nblk(threads, 256);
+    int grid = nblk(nblk(c->scan_n, 32), 8);   // one 32-point chunk per warp
     if (grid > c->max_blocks) grid = c->max_blocks;
-    cudaMemsetAsync(c->W.qcount, 0, 2 * sizeof(int), c->stream);
     k_knn_scan<G><<<grid, 256, 0, c->stream>>>(c->M, c->S, P, c->rho2, c->W, 0);
-    int g1 = grid / 2 > 0 ? grid / 2 : 1;
-    k_knn_scan<G><<<g1, 256, 0, c->stream>>>(c->M, c->S, P, c->rho2, c->W, 1);
-    int g2 = grid / 8 > 0 ? grid / 8 : 1;
-    k_knn_scan<G><<<g2, 256, 0, c->stream>>>(c->M, c->S, P, c->rho2, c->W, 2);
+    // every warp of the later passes owns whole 32-point chunks
+    int gc = nblk(nblk(c->scan_n, 32), 8);
+    if (gc > c->max_blocks) gc = c->max_blocks;
+    k_knn_scan<G><<<gc, 256, 0, c->stream>>>(c->M, c->S, P, c->rho2, c->W, 1);
+    k_knn_scan<G><<<gc, 256, 0, c->stream>>>(c->M, c->S, P, c->rho2, c->W, 2);
 }
 
 constexpr int TPQ_CH = 32, TPQ_NB = 8;
@@ -349,9 +348,6 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
     CUC(cudaMalloc(&c->d_normvec, (size_t)ns * sizeof(float4)));
     CUC(cudaMalloc(&c->W.near_d2, (size_t)ns * 5 * sizeof(float)));
     CUC(cudaMalloc(&c->W.shell, (size_t)ns * sizeof(float2)));
-    CUC(cudaMalloc(&c->W.queue[0], (size_t)ns * sizeof(int)));
-    CUC(cudaMalloc(&c->W.queue[1], (size_t)ns * sizeof(int)));
-    CUC(cudaMalloc(&c->W.qcount, 2 * sizeof(int)));
     c->max_blocks = c->num_sms * 16;
     CUC(cudaMalloc(&c->d_partials, (size_t)c->max_blocks * 96 * sizeof(double)));
     CUC(cudaMalloc(&c->d_done, sizeof(unsigned)));
@@ -383,7 +379,7 @@ int liinit_destroy(liinit_ctx* h) {
     cudaFree(c->M.ent); cudaFree(c->M.aux); cudaFree(c->M.pool); cudaFree(c->M.pool_top); cudaFree(c->M.touched_list);
     cudaFree(c->d_counters); cudaFreeHost(c->h_counters); cudaFree(c->d_stage_raw); cudaFree(c->d_stage_pts);
     cudaFree(c->d_slot_of); cudaFree(c->d_vslot_of); cudaFree(c->d_flag); cudaFree(c->d_ins); cudaFree(c->V.keys); cudaFree(c->V.head);
-    cudaFree(c->d_body); cudaFree(c->d_world); cudaFree(c->d_near_ids); cudaFree(c->d_selected); cudaFree(c->d_normvec); cudaFree(c->W.near_d2); cudaFree(c->W.shell); cudaFree(c->W.queue[0]); cudaFree(c->W.queue[1]); cudaFree(c->W.qcount);
+    cudaFree(c->d_body); cudaFree(c->d_world); cudaFree(c->d_near_ids); cudaFree(c->d_selected); cudaFree(c->d_normvec); cudaFree(c->W.near_d2); cudaFree(c->W.shell);
     cudaFree(c->d_partials); cudaFree(c->d_done); cudaFree(c->d_out); cudaFreeHost(c->h_out); cudaFree(c->d_q_d2);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);

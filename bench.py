@@ -283,7 +283,7 @@ def run_gpu(args, rank, world, local_rank):
                                + ("1 GPU" if world == 1 else f"{world} GPUs, map replicated, one 240k-pt shard per rank, NCCL all-reduce of 160 f64"),
                    "scan_points_per_gpu": N, "map_points": args.map_points, "filter_size_map": c["ds"], "imu_en": False,
                    "initial_pose": "ground truth (+) 0.5 deg / 5 cm", "open_air_frac": 0.01, "scan_order": "voxel-grid order",
-                   "l2": "flushed between timed steps (256 MiB memset outside the events)", "knn_group_lanes": args.group or 8,
+                   "l2": "flushed between timed steps (256 MiB memset outside the events)", "knn_group_lanes": args.group or 4,
                    "brick_cells_log2": args.brick or 3, "selected_points": m_sel, "map_build_s": build_s},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(N * 16 + 192), "d2h_bytes_per_step": 160 * 8,
                 "ms_per_step": e2e_ms / args.steps},

@@ -40,8 +40,8 @@ typedef struct liinit_config {
     int device_id;           /* CUDA device ordinal */
     int brick_cells_log2;    /* voxels per brick edge = 1<<this; 0 -> default (3, i.e. brick edge = 8*ds) */
     int hash_capacity_log2;  /* brick hash slots = 1<<this; 0 -> derived from max_map_points */
-    int knn_group_lanes;     /* lanes cooperating on one scan point in the 5-NN kernel: 8, 16 or 32; 0 -> default (8) */
-    float knn_seed_radius_cells; /* first search shell of the 5-NN kernel, in map voxels (radius = this * filter_size_map); 0 -> default (3) */
+    int knn_group_lanes;     /* lanes cooperating on one scan point in the 5-NN kernel: 1 (thread per point, smem-staged), 4, 8, 16 or 32; 0 -> default (4) */
+    float knn_seed_radius_cells; /* first search shell of the 5-NN kernel, in map voxels (radius = this * filter_size_map); 0 -> default (2) */
     int reserved[7];
 } liinit_config;
 

@@ -40,7 +40,8 @@ SYMBOLS = [
 
 
 def lib_path() -> str:
-    return _build.GPU_LIB
+    # LIINIT_GPU_LIB: developer override to A/B alternative builds of the same C-ABI
+    return os.environ.get("LIINIT_GPU_LIB") or _build.GPU_LIB
 
 
 def load():

@@ -9,6 +9,10 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef LI_PLANE_MIN_BLOCKS
+#define LI_PLANE_MIN_BLOCKS 2
+#endif
+
 // ----------------------------------------------------------------------------------------------
 // Phase 2 math (per scan point, fp64)
 
@@ -348,7 +352,7 @@ __device__ __forceinline__ bool tie_order(float4 (&nb)[5], int (&id)[5], float (
 //                 (laserMapping.cpp:981-984; d2[4] <= 5 holds by construction of the search).
 // SEARCH = false: reuse pass (nearest_search_en == false, :989-994): previous flag and stored neighbours.
 template <bool IMU, bool SEARCH>
-__global__ void __launch_bounds__(256) k_icp_plane(MapDev M, ScanDev S, PoseD P, double* __restrict__ partials,
+__global__ void __launch_bounds__(256, LI_PLANE_MIN_BLOCKS) k_icp_plane(MapDev M, ScanDev S, PoseD P, double* __restrict__ partials,
                                                    unsigned* __restrict__ done_counter, double* __restrict__ out160) {
     typedef AccLayout<IMU> L;
     const int lane = threadIdx.x & 31;

@@ -18,6 +18,10 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef LI_KNN_MIN_BLOCKS
+#define LI_KNN_MIN_BLOCKS 4   // resident 256-thread blocks per SM the search kernel is compiled for (register budget)
+#endif
+
 template <int G>
 struct Grp {
     static constexpr int Q = 32 / G;
@@ -144,20 +148,17 @@ __device__ __forceinline__ void lockstep_scan_found(const float4* __restrict__ p
 //                merge -> (n, g5);  stop if n == 5 and g5 <= hi2 (no unscanned brick can hold a closer point) or hi2 >= 5;
 //                otherwise lo2 = hi2 and hi2 = g5 if 5 are known (one closing step) else 4*hi2 (sparse neighbourhood).
 // The first shell is a guess (rho = seed radius): with a dense map most queries finish in it, the rest need one closing step.
-//
-// budget: number of shells this call may run (<= 0: until done). On entry gd/gi may carry the result of earlier shells
-// (resume: lo2_io/hi2_io as left by the previous call); on exit lo2_io/hi2_io describe the NEXT shell and the return
-// value says whether the query is finished. Splitting the shells over kernel launches keeps a warp's groups in step:
-// the easy majority (one shell) is not held up by the groups that need a closing shell or a sparse-area search.
 template <int G>
-__device__ __forceinline__ bool knn5_lockstep(const MapDev& M, float& lo2_io, float& hi2_io, int budget, bool valid, float qx, float qy,
-                                              float qz, float (&gd)[5], int (&gi)[5], int gl, int gbase) {
+__device__ __forceinline__ void knn5_lockstep(const MapDev& M, float rho2, bool valid, float qx, float qy, float qz, float (&gd)[5],
+                                              int (&gi)[5], int gl, int gbase) {
     float ld[5];
     int li[5];
 #pragma unroll
-    for (int i = 0; i < 5; i++) {   // lane 0 of the group resumes with what earlier shells found
-        ld[i] = (gl == 0) ? gd[i] : INFINITY;
-        li[i] = (gl == 0) ? gi[i] : -1;
+    for (int i = 0; i < 5; i++) {
+        ld[i] = INFINITY;
+        li[i] = -1;
+        gd[i] = INFINITY;
+        gi[i] = -1;
     }
     KnnGeom g;
     g.bs = M.bshift;
@@ -176,10 +177,8 @@ __device__ __forceinline__ bool knn5_lockstep(const MapDev& M, float& lo2_io, fl
     g.margin = 1e-6f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + 16.0f * B);
 
     bool done = !act;
-    float lo2 = lo2_io, hi2 = hi2_io;
-    int shells = 0;
-    while (__any_sync(LI_FULL, !done) && (budget <= 0 || shells < budget)) {
-        shells++;
+    float lo2 = 0.f, hi2 = rho2;
+    while (__any_sync(LI_FULL, !done)) {
         const bool need = !done;
         const bool last = hi2 >= 5.0f;   // the radius bound d2 <= 5 is inclusive (ikd_Tree.cpp:842)
         const float r = sqrtf(fminf(hi2, 5.0f)) * (1.0f + 1e-6f) + g.margin;
@@ -232,79 +231,31 @@ __device__ __forceinline__ bool knn5_lockstep(const MapDev& M, float& lo2_io, fl
             }
         }
     }
-    lo2_io = lo2;
-    hi2_io = hi2;
-    return done;
 }
 
-// ---- search kernels of an ICP pass: world transform + 5-NN for every scan point -----------------------
-// Per-scan search state on the device (beside ScanDev): distances of the current neighbours and the next shell of
-// every query (hi2 < 0: finished).
-struct KnnWork {
-    float* near_d2;     // [N*5]
-    float2* shell;      // [N] (lo2, hi2) of the next shell; hi2 < 0 when the query is done
-};
-
-// mode 0: all scan points, first shell only.
-// mode 1: the unfinished ones, one more shell (the closing shell for most).
-// mode 2: what is still unfinished, until done (sparse neighbourhoods, open air).
-// Modes 1/2 walk the scan in chunks of 32 consecutive points and ballot-compact the unfinished ones, so the spatial
-// order of the scan (cache locality, similar work inside a warp) survives without queues or atomics.
+// ---- search kernel of an ICP pass: world transform + 5-NN for every scan point -----------------------
 template <int G>
-__global__ void __launch_bounds__(256) k_knn_scan(MapDev M, ScanDev S, PoseD P, float rho2, KnnWork W, int mode) {
+__global__ void __launch_bounds__(256, LI_KNN_MIN_BLOCKS) k_knn_scan(MapDev M, ScanDev S, PoseD P, float rho2) {
     constexpr int Q = Grp<G>::Q;
     const int lane = threadIdx.x & 31;
     const int gl = lane % G, gid = lane / G, gbase = gid * G;
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (int cb = warp_global * 32; cb < S.n; cb += nwarps * 32) {   // warp-uniform
-        unsigned pend = 0xffffffffu;
-        if (mode != 0) {
-            const int ql = cb + lane;
-            pend = __ballot_sync(LI_FULL, ql < S.n && W.shell[ql].y >= 0.f);
-        } else if (cb + 32 > S.n) {
-            pend = (1u << (S.n - cb)) - 1u;
+    for (int qb = warp_global * Q; qb < S.n; qb += nwarps * Q) {   // warp-uniform
+        const int q = qb + gid;
+        const bool valid = q < S.n;
+        float wx = 0.f, wy = 0.f, wz = 0.f;
+        if (valid) {
+            float4 b = __ldg(&S.body[q]);
+            li_body_to_world(P, b.x, b.y, b.z, wx, wy, wz);
         }
-        const int cnt = __popc(pend);
-        for (int k0 = 0; k0 < cnt; k0 += Q) {   // warp-uniform
-            const int k = k0 + gid;
-            const bool valid = k < cnt;
-            const int q = cb + (int)__fns(pend, 0, (valid ? k : 0) + 1);   // k-th pending point of the chunk
-            float wx = 0.f, wy = 0.f, wz = 0.f;
-            float gd[5];
-            int gi[5];
+        float gd[5];
+        int gi[5];
+        knn5_lockstep<G>(M, rho2, valid, wx, wy, wz, gd, gi, gl, gbase);
+        if (valid && gl == 0) {
+            S.world[q] = make_float4(wx, wy, wz, 0.f);
 #pragma unroll
-            for (int t = 0; t < 5; t++) {
-                gd[t] = INFINITY;
-                gi[t] = -1;
-            }
-            float lo2 = 0.f, hi2 = rho2;
-            if (valid) {
-                float4 b = __ldg(&S.body[q]);
-                li_body_to_world(P, b.x, b.y, b.z, wx, wy, wz);
-                if (mode != 0) {
-                    float2 sh = W.shell[q];
-                    lo2 = sh.x;
-                    hi2 = sh.y;
-#pragma unroll
-                    for (int t = 0; t < 5; t++) {
-                        gi[t] = S.near_ids[(size_t)q * 5 + t];
-                        float d = W.near_d2[(size_t)q * 5 + t];
-                        gd[t] = (gi[t] >= 0) ? d : INFINITY;
-                    }
-                }
-            }
-            const bool done = knn5_lockstep<G>(M, lo2, hi2, (mode == 2) ? 0 : 1, valid, wx, wy, wz, gd, gi, gl, gbase);
-            if (valid && gl == 0) {
-                if (mode == 0) S.world[q] = make_float4(wx, wy, wz, 0.f);
-#pragma unroll
-                for (int t = 0; t < 5; t++) S.near_ids[(size_t)q * 5 + t] = gi[t];
-                if (!done) {
-#pragma unroll
-                    for (int t = 0; t < 5; t++) W.near_d2[(size_t)q * 5 + t] = gd[t];
-                }
-                W.shell[q] = done ? make_float2(0.f, -1.f) : make_float2(lo2, hi2);
-            }
+            for (int k = 0; k < 5; k++) S.near_ids[(size_t)q * 5 + k] = gi[k];
         }
     }
 }
@@ -325,13 +276,7 @@ __global__ void __launch_bounds__(256) k_knn_queries(MapDev M, const float4* __r
         if (valid) p = __ldg(&qpts[q]);
         float gd[5];
         int gi[5];
-#pragma unroll
-        for (int k = 0; k < 5; k++) {
-            gd[k] = INFINITY;
-            gi[k] = -1;
-        }
-        float lo2 = 0.f, hi2 = rho2;
-        knn5_lockstep<G>(M, lo2, hi2, 0, valid, p.x, p.y, p.z, gd, gi, gl, gbase);
+        knn5_lockstep<G>(M, rho2, valid, p.x, p.y, p.z, gd, gi, gl, gbase);
         if (valid && gl == 0) {
 #pragma unroll
             for (int k = 0; k < 5; k++) {

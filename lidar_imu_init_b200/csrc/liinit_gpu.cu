@@ -49,7 +49,6 @@ struct Ctx {
     VoxTmp V{};
     // scan
     ScanDev S{};
-    KnnWork W{};
     float4* d_body = nullptr;
     float4* d_world = nullptr;
     int* d_near_ids = nullptr;
@@ -69,8 +68,8 @@ struct Ctx {
     long long launches = 0;
     float last_ms = 0.f;
     int last_launches = 0;
-    int group = 8;
-    float rho2 = 0.2f;   // squared seed radius of the 5-NN search
+    int group = 4;
+    float rho2 = 0.09f;   // squared seed radius of the 5-NN search
 };
 
 #define CU(call)                                                                                     \
@@ -165,18 +164,12 @@ void fill_pose(PoseD& P, const double* R, const double* p, const double* RLI, co
     memcpy(P.TLI, TLI, 24);
 }
 
-// three launches: first shell for everybody, closing shell for the unfinished, open-ended search for the sparse rest.
-// The later launches size their loops from the device-side queue counters (grid-stride), so no host round trip.
 template <int G>
 void launch_knn_scan(Ctx* c, const PoseD& P) {
-    int grid = nblk(nblk(c->scan_n, 32), 8);   // one 32-point chunk per warp
+    long long threads = (long long)c->scan_n * G;
+    int grid = nblk(threads, 256);
     if (grid > c->max_blocks) grid = c->max_blocks;
-    k_knn_scan<G><<<grid, 256, 0, c->stream>>>(c->M, c->S, P, c->rho2, c->W, 0);
-    // every warp of the later passes owns whole 32-point chunks
-    int gc = nblk(nblk(c->scan_n, 32), 8);
-    if (gc > c->max_blocks) gc = c->max_blocks;
-    k_knn_scan<G><<<gc, 256, 0, c->stream>>>(c->M, c->S, P, c->rho2, c->W, 1);
-    k_knn_scan<G><<<gc, 256, 0, c->stream>>>(c->M, c->S, P, c->rho2, c->W, 2);
+    k_knn_scan<G><<<grid, 256, 0, c->stream>>>(c->M, c->S, P, c->rho2);
 }
 
 constexpr int TPQ_CH = 32, TPQ_NB = 8;
@@ -206,16 +199,16 @@ int run_pass(Ctx* c, const double* R, const double* p, const double* RLI, const 
     if (search) {
         switch (c->group) {
             case 1: launch_knn_scan_tpq(c, P); break;
-            case 4: launch_knn_scan<4>(c, P); break;
             case 16: launch_knn_scan<16>(c, P); break;
             case 32: launch_knn_scan<32>(c, P); break;
-            default: launch_knn_scan<8>(c, P); break;
+            case 8: launch_knn_scan<8>(c, P); break;
+            default: launch_knn_scan<4>(c, P); break;
         }
         CU(cudaEventRecord(c->evm, c->stream));
         if (imu_en) launch_plane<true, true>(c, P); else launch_plane<false, true>(c, P);
         c->have_neighbors = true;
-        c->launches += (c->group == 1) ? 2 : 4;
-        c->last_launches = (c->group == 1) ? 2 : 4;
+        c->launches += 2;
+        c->last_launches = 2;
         c->last_was_search = true;
     } else {
         if (imu_en) launch_plane<true, false>(c, P); else launch_plane<false, false>(c, P);
@@ -300,10 +293,10 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
         return bail(LIINIT_ERR_INVALID);
     }
     c->hash_slots = 1u << hl;
-    c->group = (cfg->knn_group_lanes == 1 || cfg->knn_group_lanes == 4 || cfg->knn_group_lanes == 8 || cfg->knn_group_lanes == 16 || cfg->knn_group_lanes == 32) ? cfg->knn_group_lanes : 8;
+    c->group = (cfg->knn_group_lanes == 1 || cfg->knn_group_lanes == 4 || cfg->knn_group_lanes == 8 || cfg->knn_group_lanes == 16 || cfg->knn_group_lanes == 32) ? cfg->knn_group_lanes : 4;
 
     {
-        float cells = cfg->knn_seed_radius_cells > 0.f ? cfg->knn_seed_radius_cells : 3.0f;
+        float cells = cfg->knn_seed_radius_cells > 0.f ? cfg->knn_seed_radius_cells : 2.0f;
         float rho = cells * cfg->filter_size_map;
         c->rho2 = rho * rho;
     }
@@ -346,8 +339,6 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
     CUC(cudaMalloc(&c->d_near_ids, (size_t)batch * 5 * sizeof(int)));
     CUC(cudaMalloc(&c->d_selected, (size_t)ns));
     CUC(cudaMalloc(&c->d_normvec, (size_t)ns * sizeof(float4)));
-    CUC(cudaMalloc(&c->W.near_d2, (size_t)ns * 5 * sizeof(float)));
-    CUC(cudaMalloc(&c->W.shell, (size_t)ns * sizeof(float2)));
     c->max_blocks = c->num_sms * 16;
     CUC(cudaMalloc(&c->d_partials, (size_t)c->max_blocks * 96 * sizeof(double)));
     CUC(cudaMalloc(&c->d_done, sizeof(unsigned)));
@@ -379,7 +370,7 @@ int liinit_destroy(liinit_ctx* h) {
     cudaFree(c->M.ent); cudaFree(c->M.aux); cudaFree(c->M.pool); cudaFree(c->M.pool_top); cudaFree(c->M.touched_list);
     cudaFree(c->d_counters); cudaFreeHost(c->h_counters); cudaFree(c->d_stage_raw); cudaFree(c->d_stage_pts);
     cudaFree(c->d_slot_of); cudaFree(c->d_vslot_of); cudaFree(c->d_flag); cudaFree(c->d_ins); cudaFree(c->V.keys); cudaFree(c->V.head);
-    cudaFree(c->d_body); cudaFree(c->d_world); cudaFree(c->d_near_ids); cudaFree(c->d_selected); cudaFree(c->d_normvec); cudaFree(c->W.near_d2); cudaFree(c->W.shell);
+    cudaFree(c->d_body); cudaFree(c->d_world); cudaFree(c->d_near_ids); cudaFree(c->d_selected); cudaFree(c->d_normvec);
     cudaFree(c->d_partials); cudaFree(c->d_done); cudaFree(c->d_out); cudaFreeHost(c->h_out); cudaFree(c->d_q_d2);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);

@@ -18,8 +18,14 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef LI_KNN_U
+#define LI_KNN_U 4           // slab loads issued back to back per lane before the distances are evaluated
+#endif
+#ifndef LI_KNN_THREADS
+#define LI_KNN_THREADS 128
+#endif
 #ifndef LI_KNN_MIN_BLOCKS
-#define LI_KNN_MIN_BLOCKS 4   // resident 256-thread blocks per SM the search kernel is compiled for (register budget)
+#define LI_KNN_MIN_BLOCKS 8   // resident blocks per SM the search kernel is compiled for (register budget)
 #endif
 
 template <int G>
@@ -96,7 +102,7 @@ __device__ __forceinline__ void group_merge(const float (&ld)[5], const int (&li
 
 // Lockstep scan of one slab per group (cnt = 0 for idle groups): U loads are issued back to back before any distance
 // is evaluated, so U independent L2 round trips overlap (the rolled loop exposed one full latency per 16*G bytes).
-template <int G, int U = 3>
+template <int G, int U = LI_KNN_U>
 __device__ __forceinline__ void group_scan_pipelined(const float4* __restrict__ pool, unsigned f, unsigned cnt, float qx, float qy, float qz,
                                                      float thr, float (&ld)[5], int (&li)[5], int gl) {
     for (unsigned j0 = gl; __any_sync(LI_FULL, j0 < cnt); j0 += U * G) {
@@ -170,21 +176,22 @@ __device__ __forceinline__ void knn5_lockstep(const MapDev& M, float rho2, bool 
     if (!act) {
         qx = 0.f; qy = 0.f; qz = 0.f;
     }
-    const int cx = li_cell(qx, g.ds), cy = li_cell(qy, g.ds), cz = li_cell(qz, g.ds);
-    g.bx = cx >> g.bs; g.by = cy >> g.bs; g.bz = cz >> g.bs;
-    g.dirx = g.diry = g.dirz = 0;
     // slack for float cell assignment / edge products: relative 2^-23 effects, bounded generously
     g.margin = 1e-6f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + 16.0f * B);
 
+    const float inv_ds = 1.0f / g.ds;
+    const float slk = 0.02f + 4e-7f * (fabsf(qx) + fabsf(qy) + fabsf(qz)) * inv_ds;   // cells; covers the reciprocal-multiply rounding
     bool done = !act;
     float lo2 = 0.f, hi2 = rho2;
     while (__any_sync(LI_FULL, !done)) {
         const bool need = !done;
         const bool last = hi2 >= 5.0f;   // the radius bound d2 <= 5 is inclusive (ikd_Tree.cpp:842)
         const float r = sqrtf(fminf(hi2, 5.0f)) * (1.0f + 1e-6f) + g.margin;
-        const int lx = li_cell(qx - r, g.ds) >> g.bs, hx = li_cell(qx + r, g.ds) >> g.bs;
-        const int ly = li_cell(qy - r, g.ds) >> g.bs, hy = li_cell(qy + r, g.ds) >> g.bs;
-        const int lz = li_cell(qz - r, g.ds) >> g.bs, hz = li_cell(qz + r, g.ds) >> g.bs;
+        // conservative cell range of the ball's bounding box: reciprocal multiply + a small slack (slk) instead of the IEEE
+        // division of li_cell (only the enumeration range, never a point's cell, is computed this way)
+        const int lx = (int)floorf((qx - r) * inv_ds - slk) >> g.bs, hx = (int)floorf((qx + r) * inv_ds + slk) >> g.bs;
+        const int ly = (int)floorf((qy - r) * inv_ds - slk) >> g.bs, hy = (int)floorf((qy + r) * inv_ds + slk) >> g.bs;
+        const int lz = (int)floorf((qz - r) * inv_ds - slk) >> g.bs, hz = (int)floorf((qz + r) * inv_ds + slk) >> g.bs;
         const int nx = hx - lx + 1, ny = hy - ly + 1, nz = hz - lz + 1;
         const int nxy = nx * ny;
         const int total = need ? nxy * nz : 0;
@@ -235,7 +242,7 @@ __device__ __forceinline__ void knn5_lockstep(const MapDev& M, float rho2, bool 
 
 // ---- search kernel of an ICP pass: world transform + 5-NN for every scan point -----------------------
 template <int G>
-__global__ void __launch_bounds__(256, LI_KNN_MIN_BLOCKS) k_knn_scan(MapDev M, ScanDev S, PoseD P, float rho2) {
+__global__ void __launch_bounds__(LI_KNN_THREADS, LI_KNN_MIN_BLOCKS) k_knn_scan(MapDev M, ScanDev S, PoseD P, float rho2) {
     constexpr int Q = Grp<G>::Q;
     const int lane = threadIdx.x & 31;
     const int gl = lane % G, gid = lane / G, gbase = gid * G;

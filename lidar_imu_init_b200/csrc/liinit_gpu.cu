@@ -167,9 +167,10 @@ void fill_pose(PoseD& P, const double* R, const double* p, const double* RLI, co
 template <int G>
 void launch_knn_scan(Ctx* c, const PoseD& P) {
     long long threads = (long long)c->scan_n * G;
-    int grid = nblk(threads, 256);
-    if (grid > c->max_blocks) grid = c->max_blocks;
-    k_knn_scan<G><<<grid, 256, 0, c->stream>>>(c->M, c->S, P, c->rho2);
+    int grid = nblk(threads, LI_KNN_THREADS);
+    int cap = c->max_blocks * (256 / LI_KNN_THREADS);
+    if (grid > cap) grid = cap;
+    k_knn_scan<G><<<grid, LI_KNN_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2);
 }
 
 constexpr int TPQ_CH = 32, TPQ_NB = 8;

@@ -6,8 +6,8 @@ from lidar_imu_init_b200 import scenes, capi
 ap = argparse.ArgumentParser()
 ap.add_argument("--N", type=int, default=240000)
 ap.add_argument("--M", type=int, default=5000000)
-ap.add_argument("--group", type=int, default=8)
-ap.add_argument("--brick", type=int, default=3)
+ap.add_argument("--group", type=int, default=0)
+ap.add_argument("--brick", type=int, default=0)
 ap.add_argument("--imu", type=int, default=0)
 ap.add_argument("--passes", type=int, default=4)
 ap.add_argument("--rho", type=float, default=0.0)

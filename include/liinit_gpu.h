@@ -71,6 +71,12 @@ int liinit_map_nearest_search(liinit_ctx* h, const float* q_xyz, int stride_floa
 /* per-scan hot path (replaces laserMapping.cpp:936-1080) ---------------------------- */
 /* feats_down_body (laserMapping.cpp:917-919): once per scan; resets selection flags / neighbour lists. */
 int liinit_scan_upload(liinit_ctx* h, const float* body_xyz, int stride_floats, int n);
+/* Raw (undistorted, not yet downsampled) scan: voxel-grid filter on the device, then the result becomes the resident scan.
+ * Replaces downSizeFilterSurf.setInputCloud/filter (laserMapping.cpp:122,823,917-918 = PCL VoxelGrid, leaf = mapping/filter_size_surf)
+ * followed by liinit_scan_upload. n_down = feats_down_size. Output order: first input point of every leaf (see voxelgrid_kernels.cuh). */
+int liinit_scan_upload_raw(liinit_ctx* h, const float* xyz, int stride_floats, int n, float leaf_size, int* n_down);
+/* The resident scan (feats_down_body) as packed xyz. */
+int liinit_scan_download_body(liinit_ctx* h, float* xyz, int cap_points, int* n);
 /* One ICP pass, laserMapping.cpp:959-1071 + the reduction of :1080.
  *   rot_end, pos_end, R_LI (offset_R_L_I), T_LI (offset_T_L_I): the pose part of StatesGroup (common_lib.h:160-163).
  *   imu_en: 12-column Jacobian (:1054-1062) else 6 columns (:1063-1066).

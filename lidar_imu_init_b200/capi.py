@@ -33,7 +33,7 @@ _i32 = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 
 SYMBOLS = [
     "liinit_create", "liinit_destroy", "liinit_last_error", "liinit_set_stream", "liinit_map_build", "liinit_map_add_points",
-    "liinit_map_validnum", "liinit_map_size", "liinit_map_download", "liinit_map_nearest_search", "liinit_scan_upload",
+    "liinit_map_validnum", "liinit_map_size", "liinit_map_download", "liinit_map_nearest_search", "liinit_scan_upload", "liinit_scan_upload_raw", "liinit_scan_download_body",
     "liinit_icp_iterate", "liinit_icp_iterate_device", "liinit_scan_download_effect", "liinit_scan_download_state",
     "liinit_map_incremental", "liinit_last_pass_timing", "liinit_last_pass_kernel_times", "liinit_launch_count", "liinit_map_stats",
 ]
@@ -67,6 +67,8 @@ def load():
     L.liinit_map_download.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int)]
     L.liinit_map_nearest_search.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, vp, vp, vp]
     L.liinit_scan_upload.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.liinit_scan_upload_raw.argtypes = [vp, vp, C.c_int, C.c_int, C.c_float, C.POINTER(C.c_int)]
+    L.liinit_scan_download_body.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int)]
     L.liinit_icp_iterate.argtypes = [vp, _f64, _f64, _f64, _f64, C.c_int, C.c_int, _f64, _f64, C.POINTER(C.c_int), C.POINTER(C.c_double)]
     L.liinit_icp_iterate_device.argtypes = [vp, _f64, _f64, _f64, _f64, C.c_int, C.c_int, vp]
     L.liinit_scan_download_effect.argtypes = [vp, vp, vp, C.c_int, C.POINTER(C.c_int)]
@@ -170,6 +172,20 @@ class LiInitGpu:
         a = _pts(body)
         self._ck(self.L.liinit_scan_upload(self.h, _ptr(a), a.shape[1], a.shape[0]))
         self.scan_n = a.shape[0]
+
+    def scan_upload_raw(self, pts, leaf_size: float) -> int:
+        """Voxel-grid downsample on the device (PCL VoxelGrid semantics), result becomes the resident scan."""
+        a = _pts(pts)
+        nd = C.c_int(0)
+        self._ck(self.L.liinit_scan_upload_raw(self.h, _ptr(a), a.shape[1], a.shape[0], float(leaf_size), C.byref(nd)))
+        self.scan_n = nd.value
+        return nd.value
+
+    def scan_body(self):
+        n = C.c_int(0)
+        out = np.zeros((max(self.scan_n, 1), 3), np.float32)
+        self._ck(self.L.liinit_scan_download_body(self.h, _ptr(out), self.scan_n, C.byref(n)))
+        return out[:n.value]
 
     def scan_upload_ptr(self, host_ptr: int, stride: int, n: int):
         """Upload from a raw host pointer (e.g. pinned torch tensor)."""

@@ -17,6 +17,7 @@
 #include "knn_kernels.cuh"
 #include "knn_tpq.cuh"
 #include "map_kernels.cuh"
+#include "voxelgrid_kernels.cuh"
 
 namespace {
 
@@ -46,6 +47,10 @@ struct Ctx {
     int* d_vslot_of = nullptr;
     int* d_flag = nullptr;
     int* d_ins = nullptr;
+    int* d_vg_imin = nullptr;      // voxel-grid: first point index per leaf
+    int* d_vg_block = nullptr;     // voxel-grid: per-block flag sums
+    int* d_vg_misc = nullptr;      // [0..5] min/max (ordered ints), [6] out count, [7] error bits
+    VgParams* d_vg_params = nullptr;
     VoxTmp V{};
     // scan
     ScanDev S{};
@@ -333,6 +338,10 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
         c->V.mask = (1u << vl) - 1;
         CUC(cudaMalloc(&c->V.keys, ((size_t)c->V.mask + 1) * 8));
         CUC(cudaMalloc(&c->V.head, ((size_t)c->V.mask + 1) * 4));
+        CUC(cudaMalloc(&c->d_vg_imin, ((size_t)c->V.mask + 1) * 4));
+        CUC(cudaMalloc(&c->d_vg_block, ((size_t)batch / 1024 + 2) * 4));
+        CUC(cudaMalloc(&c->d_vg_misc, 8 * 4));
+        CUC(cudaMalloc(&c->d_vg_params, sizeof(VgParams)));
     }
     int ns = cfg->max_scan_points;
     CUC(cudaMalloc(&c->d_body, (size_t)ns * sizeof(float4)));
@@ -370,7 +379,7 @@ int liinit_destroy(liinit_ctx* h) {
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     cudaFree(c->M.ent); cudaFree(c->M.aux); cudaFree(c->M.pool); cudaFree(c->M.pool_top); cudaFree(c->M.touched_list);
     cudaFree(c->d_counters); cudaFreeHost(c->h_counters); cudaFree(c->d_stage_raw); cudaFree(c->d_stage_pts);
-    cudaFree(c->d_slot_of); cudaFree(c->d_vslot_of); cudaFree(c->d_flag); cudaFree(c->d_ins); cudaFree(c->V.keys); cudaFree(c->V.head);
+    cudaFree(c->d_slot_of); cudaFree(c->d_vslot_of); cudaFree(c->d_flag); cudaFree(c->d_ins); cudaFree(c->V.keys); cudaFree(c->V.head); cudaFree(c->d_vg_imin); cudaFree(c->d_vg_block); cudaFree(c->d_vg_misc); cudaFree(c->d_vg_params);
     cudaFree(c->d_body); cudaFree(c->d_world); cudaFree(c->d_near_ids); cudaFree(c->d_selected); cudaFree(c->d_normvec);
     cudaFree(c->d_partials); cudaFree(c->d_done); cudaFree(c->d_out); cudaFreeHost(c->h_out); cudaFree(c->d_q_d2);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -575,6 +584,63 @@ int liinit_scan_upload(liinit_ctx* h, const float* body, int stride, int n) {
     c->S.n = n;
     c->have_neighbors = false;
     CU(cudaGetLastError());
+    return LIINIT_OK;
+}
+
+int liinit_scan_upload_raw(liinit_ctx* h, const float* xyz, int stride, int n, float leaf_size, int* n_down) {
+    if (!h || !xyz || n <= 0 || !(leaf_size > 0.f)) return LIINIT_ERR_INVALID;
+    Ctx* c = &h->c;
+    CU(cudaSetDevice(c->device));
+    int r = stage_points(c, xyz, stride, n);   // -> d_stage_pts[0..n)
+    if (r) return r;
+    const int inf_pos = 0x7f800000, inf_neg = (int)0xff800000 ^ 0x7fffffff;   // ordered-int images of +inf / -inf
+    const int init[8] = {inf_pos, inf_pos, inf_pos, inf_neg, inf_neg, inf_neg, 0, 0};
+    CU(cudaMemcpyAsync(c->d_vg_misc, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+    const int nb = nblk(n, 1024);
+    k_vg_clear<<<nblk((long long)c->V.mask + 1, 256), 256, 0, c->stream>>>(c->V, c->d_vg_imin);
+    k_vg_minmax<<<nblk(n, 256), 256, 0, c->stream>>>(c->d_stage_pts, n, c->d_vg_misc);
+    k_vg_params<<<1, 32, 0, c->stream>>>(c->d_vg_misc, leaf_size, c->d_vg_params);
+    k_vg_link<<<nblk(n, 256), 256, 0, c->stream>>>(c->d_stage_pts, n, c->d_vg_params, c->V, c->d_vg_imin, c->d_vslot_of, c->d_slot_of,
+                                                     c->d_vg_misc + 7);
+    k_vg_flag<<<nb, 1024, 0, c->stream>>>(n, c->d_slot_of, c->d_vg_imin, c->d_flag, c->d_vg_block);
+    k_vg_scan_blocks<<<1, 1024, 0, c->stream>>>(nb, c->d_vg_block, c->d_vg_misc + 6);
+    k_vg_centroid<<<nb, 1024, 0, c->stream>>>(c->d_stage_pts, n, c->d_flag, c->d_vg_block, c->d_slot_of, c->V, c->d_vslot_of, c->d_body,
+                                              c->cfg.max_scan_points, c->d_vg_misc + 7);
+    c->launches += 7;
+    CU(cudaGetLastError());
+    int res[8];
+    VgParams P;
+    CU(cudaMemcpyAsync(res, c->d_vg_misc, sizeof(res), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(&P, c->d_vg_params, sizeof(P), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (P.overflow) return fail(c, LIINIT_ERR_INVALID, "voxel grid: leaf size too small for the cloud extent (index overflow) or no finite point");
+    if (res[7] & 1) return fail(c, LIINIT_ERR_CAPACITY, "voxel grid: leaf hash full");
+    if (res[7] & 2) return fail(c, LIINIT_ERR_CAPACITY, "voxel grid: more leaves than max_scan_points");
+    const int m = res[6];
+    if (m <= 0) return fail(c, LIINIT_ERR_INVALID, "voxel grid: no output points");
+    CU(cudaMemsetAsync(c->d_selected, 0, (size_t)m, c->stream));
+    CU(cudaMemsetAsync(c->d_near_ids, 0xff, (size_t)m * 5 * sizeof(int), c->stream));
+    c->scan_n = m;
+    c->S.n = m;
+    c->have_neighbors = false;
+    if (n_down) *n_down = m;
+    return LIINIT_OK;
+}
+
+int liinit_scan_download_body(liinit_ctx* h, float* xyz, int cap, int* n) {
+    if (!h || !n) return LIINIT_ERR_INVALID;
+    Ctx* c = &h->c;
+    CU(cudaSetDevice(c->device));
+    *n = c->scan_n;
+    int m = c->scan_n < cap ? c->scan_n : cap;
+    if (m > 0 && xyz) {
+        std::vector<float4> b(m);
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaMemcpy(b.data(), c->d_body, (size_t)m * 16, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < m; i++) {
+            xyz[3 * (size_t)i] = b[i].x; xyz[3 * (size_t)i + 1] = b[i].y; xyz[3 * (size_t)i + 2] = b[i].z;
+        }
+    }
     return LIINIT_OK;
 }
 

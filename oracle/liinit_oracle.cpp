@@ -1041,6 +1041,59 @@ int oracle_map_incremental(void* scan, void* map, const double* rot_end, const d
                            add_flag);
 }
 
+// PCL VoxelGrid<PointT>::applyFilter restated for xyz (PCL >= 1.8, pcl/filters/impl/voxel_grid.hpp; third-party, pinned
+// only as ">= 1.8" by the reference README:57; call site laserMapping.cpp:122,823,917-918). Output in PCL's order (ascending
+// leaf index); the summation order inside a leaf is the input order (PCL's std::sort leaves it unspecified).
+// Returns the number of output points, or -1 on the "leaf size too small" overflow.
+int oracle_voxel_grid(const float* xyz, int n, float leaf, float* out) {
+    const float inv = 1.0f / leaf;
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int i = 0; i < n; i++) {
+        const float* p = xyz + 3 * (size_t)i;
+        if (!std::isfinite(p[0]) || !std::isfinite(p[1]) || !std::isfinite(p[2])) continue;
+        for (int a = 0; a < 3; a++) {
+            mn[a] = std::min(mn[a], p[a]);
+            mx[a] = std::max(mx[a], p[a]);
+        }
+    }
+    if (!(mn[0] <= mx[0])) return -1;
+    int min_b[3], div_b[3];
+    for (int a = 0; a < 3; a++) {
+        min_b[a] = (int)std::floor(mn[a] * inv);
+        int max_b = (int)std::floor(mx[a] * inv);
+        div_b[a] = max_b - min_b[a] + 1;
+    }
+    if ((int64_t)div_b[0] * (int64_t)div_b[1] * (int64_t)div_b[2] > (int64_t)2147483647) return -1;
+    const int m1 = div_b[0], m2 = div_b[0] * div_b[1];
+    std::vector<std::pair<unsigned, int>> iv;
+    iv.reserve(n);
+    for (int i = 0; i < n; i++) {
+        const float* p = xyz + 3 * (size_t)i;
+        if (!std::isfinite(p[0]) || !std::isfinite(p[1]) || !std::isfinite(p[2])) continue;
+        int i0 = (int)(std::floor(p[0] * inv) - (float)min_b[0]);
+        int i1 = (int)(std::floor(p[1] * inv) - (float)min_b[1]);
+        int i2 = (int)(std::floor(p[2] * inv) - (float)min_b[2]);
+        iv.emplace_back((unsigned)(i0 + i1 * m1 + i2 * m2), i);
+    }
+    std::stable_sort(iv.begin(), iv.end(), [](const std::pair<unsigned, int>& a, const std::pair<unsigned, int>& b) { return a.first < b.first; });
+    int k = 0;
+    size_t s = 0;
+    while (s < iv.size()) {
+        size_t e = s;
+        float cx = 0.f, cy = 0.f, cz = 0.f;
+        while (e < iv.size() && iv[e].first == iv[s].first) {
+            const float* p = xyz + 3 * (size_t)iv[e].second;
+            cx += p[0]; cy += p[1]; cz += p[2];
+            e++;
+        }
+        float c = (float)(e - s);
+        out[3 * (size_t)k] = cx / c; out[3 * (size_t)k + 1] = cy / c; out[3 * (size_t)k + 2] = cz / c;
+        k++;
+        s = e;
+    }
+    return k;
+}
+
 // esti_plane alone (for the numpy lstsq cross-check). nb: 15 floats. Returns valid flag.
 int oracle_esti_plane(const float* nb, double* pabcd) {
     P3 p[5];

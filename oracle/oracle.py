@@ -82,6 +82,8 @@ def load(prefer_ref: bool = True):
     L.oracle_scan_update.argtypes = [C.c_void_p, C.c_void_p, _f64p, C.c_int, C.c_int, C.c_int, _i32p]
     L.oracle_map_incremental.restype = C.c_int
     L.oracle_map_incremental.argtypes = [C.c_void_p, C.c_void_p, _f64p, _f64p, _f64p, _f64p, C.c_double, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]
+    L.oracle_voxel_grid.restype = C.c_int
+    L.oracle_voxel_grid.argtypes = [_f32p, C.c_int, C.c_float, _f32p]
     L.oracle_esti_plane.restype = C.c_int
     L.oracle_esti_plane.argtypes = [_f32p, _f64p]
     L.oracle_so3_exp.argtypes = [_f64p, _f64p]
@@ -223,6 +225,16 @@ class OracleScan:
         c = self.L.oracle_map_incremental(self.h, omap.h, _c64(rot_end).reshape(9), _c64(pos_end), _c64(R_LI).reshape(9), _c64(T_LI),
                                           float(ds), int(flg_EKF_inited), C.byref(n_add), C.byref(n_nod), _opt(flags))
         return c, n_add.value, n_nod.value, flags
+
+
+def voxel_grid(xyz, leaf):
+    """PCL VoxelGrid restatement (xyz centroids, ascending leaf index). Returns [m,3] float32."""
+    xyz = _c32(xyz).reshape(-1, 3)
+    out = np.zeros((max(len(xyz), 1), 3), np.float32)
+    m = load().oracle_voxel_grid(xyz, len(xyz), float(leaf), out)
+    if m < 0:
+        raise ValueError("leaf size too small (index overflow) or no finite point")
+    return out[:m]
 
 
 def esti_plane(nb):

@@ -56,18 +56,21 @@ __global__ void k_vg_params(const int* __restrict__ mm, float leaf, VgParams* __
     q.inv_leaf = 1.0f / leaf;   // Eigen::Array4f::Ones() / leaf_size (float)
     q.overflow = 0;
     long long d[3];
+    double ext = 1.0;
     for (int a = 0; a < 3; a++) {
         float lo = li_ord2f(mm[a]), hi = li_ord2f(mm[3 + a]);
         if (!(lo <= hi)) {
             q.overflow = 1;
             lo = hi = 0.f;
         }
+        ext *= floor((double)__fmul_rn(__fsub_rn(hi, lo), q.inv_leaf)) + 1.0;   // PCL's pre-check: dx*dy*dz must fit int32
         q.min_b[a] = (int)floorf(__fmul_rn(lo, q.inv_leaf));
         int mb = (int)floorf(__fmul_rn(hi, q.inv_leaf));
         d[a] = (long long)mb - (long long)q.min_b[a] + 1;
         q.div_b[a] = (int)d[a];
     }
-    if (d[0] * d[1] * d[2] > 2147483647ll) q.overflow = 1;
+    if (ext > 2147483647.0) q.overflow = 1;
+    if (!q.overflow && d[0] * d[1] * d[2] > 2147483647ll) q.overflow = 1;
     q.mul1 = q.div_b[0];
     q.mul2 = q.div_b[0] * q.div_b[1];
     *P = q;

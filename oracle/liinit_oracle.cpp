@@ -1057,6 +1057,12 @@ int oracle_voxel_grid(const float* xyz, int n, float leaf, float* out) {
         }
     }
     if (!(mn[0] <= mx[0])) return -1;
+    // "Leaf size is too small for the input dataset. Integer indices would overflow." (PCL checks this first)
+    {
+        double dx = std::floor((double)((mx[0] - mn[0]) * inv)) + 1, dy = std::floor((double)((mx[1] - mn[1]) * inv)) + 1,
+               dz = std::floor((double)((mx[2] - mn[2]) * inv)) + 1;
+        if (dx * dy * dz > 2147483647.0) return -1;
+    }
     int min_b[3], div_b[3];
     for (int a = 0; a < 3; a++) {
         min_b[a] = (int)std::floor(mn[a] * inv);

@@ -105,21 +105,18 @@ __device__ __forceinline__ void group_merge(const float (&ld)[5], const int (&li
 template <int G, int U = LI_KNN_U>
 __device__ __forceinline__ void group_scan_pipelined(const float4* __restrict__ pool, unsigned f, unsigned cnt, float qx, float qy, float qz,
                                                      float thr, float (&ld)[5], int (&li)[5], int gl) {
-    const float4* __restrict__ sp = pool + f;
-    float4 p[U];
-#pragma unroll
-    for (int u = 0; u < U; u++) p[u] = make_float4(0.f, 0.f, 0.f, 0.f);   // defined once; lanes past the slab end keep stale values
     for (unsigned j0 = gl; __any_sync(LI_FULL, j0 < cnt); j0 += U * G) {
+        float4 p[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
             unsigned j = j0 + u * G;
-            if (j < cnt) p[u] = __ldg(sp + j);
+            p[u] = (j < cnt) ? __ldg(&pool[(size_t)f + j]) : make_float4(1e18f, 1e18f, 1e18f, 0.f);
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
             unsigned j = j0 + u * G;
-            float d = li_dist2(qx, qy, qz, p[u].x, p[u].y, p[u].z);
-            if (j < cnt && d <= 5.0f && d < thr && d < ld[4]) local_insert(ld, li, d, (int)(f + j));   // gated by j < cnt
+            float d = li_dist2(qx, qy, qz, p[u].x, p[u].y, p[u].z);   // padding lanes give d = +inf
+            if (j < cnt && d <= 5.0f && d < thr && d < ld[4]) local_insert(ld, li, d, (int)(f + j));
         }
     }
 }

@@ -207,6 +207,7 @@ int run_pass(Ctx* c, const double* R, const double* p, const double* RLI, const 
             case 1: launch_knn_scan_tpq(c, P); break;
             case 16: launch_knn_scan<16>(c, P); break;
             case 32: launch_knn_scan<32>(c, P); break;
+            case 2: launch_knn_scan<2>(c, P); break;
             case 8: launch_knn_scan<8>(c, P); break;
             default: launch_knn_scan<4>(c, P); break;
         }
@@ -299,7 +300,7 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
         return bail(LIINIT_ERR_INVALID);
     }
     c->hash_slots = 1u << hl;
-    c->group = (cfg->knn_group_lanes == 1 || cfg->knn_group_lanes == 4 || cfg->knn_group_lanes == 8 || cfg->knn_group_lanes == 16 || cfg->knn_group_lanes == 32) ? cfg->knn_group_lanes : 4;
+    c->group = (cfg->knn_group_lanes == 1 || cfg->knn_group_lanes == 2 || cfg->knn_group_lanes == 4 || cfg->knn_group_lanes == 8 || cfg->knn_group_lanes == 16 || cfg->knn_group_lanes == 32) ? cfg->knn_group_lanes : 4;
 
     {
         float cells = cfg->knn_seed_radius_cells > 0.f ? cfg->knn_seed_radius_cells : 2.0f;

@@ -78,12 +78,19 @@ def box_scene(L: float, W: float, H: float, n_slabs_x: int = 0, n_slabs_y: int =
 
 
 def scene_for_points(M: int, ds: float = 0.15, aspect=(300.0, 160.0, 20.0)) -> Scene:
-    """Box with the given aspect ratio scaled so its surfaces hold >= M ds-cells."""
+    """Box with the given aspect ratio scaled so its surfaces hold >= M ds-cells (about 2 % more)."""
     L, W, H = aspect
     area0 = 2 * (L * W + L * H + W * H)
-    need = M * ds * ds * 1.02
-    s = np.sqrt(need / area0)
-    return box_scene(L * s, W * s, H * s)
+    s = np.sqrt(M * ds * ds * 1.02 / area0)
+
+    def cells(sc):
+        return sum(max(int(np.floor(r.a / ds)), 1) * max(int(np.floor(r.b / ds)), 1) for r in sc.rects)
+
+    scene = box_scene(L * s, W * s, H * s)
+    while cells(scene) < M:   # small scenes lose whole rows to the floor(); grow until enough
+        s *= 1.01
+        scene = box_scene(L * s, W * s, H * s)
+    return scene
 
 
 def map_points(scene: Scene, ds: float, M: int | None = None, seed: int = 1, sigma: float = 0.01,

@@ -44,6 +44,7 @@ def emit(obj):
         sys.stdout.flush()
 
 
+NCU_DRAM_BYTES_KNN = 116_571_136  # 109.96 MB read + 6.61 MB written, profiles/r01_ncu_full_final_metrics.txt
 ALG_BYTES_PER_POINT = 132  # 16 body + 80 neighbours + 16 normal/residual + 20 ids
 METRIC = "ICP points*iters/s (search pass), 240k-pt scan vs 5M-pt map"
 UNIT = "points*iters/s"
@@ -290,10 +291,11 @@ def run_gpu(args, rank, world, local_rank):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "k_knn_scan (5-NN search, dominant kernel of the pass)", "achieved": ach, "peak": peak,
-                     "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src, "traffic": None,
+                     "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src, "traffic": NCU_DRAM_BYTES_KNN,
                      "algorithmic_bytes_per_launch": ALG_BYTES_PER_POINT * N, "kernel_ms": knn_ms, "plane_kernel_ms": plane_ms,
                      "kernel_ms_l2_warm": knn_warm, "plane_kernel_ms_l2_warm": plane_warm,
-                     "note": "traffic (dram bytes) comes from the ncu capture under profiles/; see DESIGN.md section 7"},
+                     "note": "traffic = dram__bytes_read.sum + dram__bytes_write.sum of one k_knn_scan launch from the ncu --set full capture in "
+                             "profiles/r01_ncu_full_final_metrics.txt (cold cache: ncu flushes between replays), bytes per launch"},
     }
     # ---- extras (not part of the contract value): the other pass kinds of a real scan -----------------------
     if world == 1:

@@ -58,6 +58,10 @@ int liinit_map_build(liinit_ctx* h, const float* xyz, int stride_floats, int n);
 /* KD_TREE::Add_Points(points, downsample_on) (ikd_Tree.cpp:381-456; call sites laserMapping.cpp:556-557).
  * added: number of voxels whose content changed (downsample_on) / points appended. */
 int liinit_map_add_points(liinit_ctx* h, const float* xyz, int stride_floats, int n, int downsample_on, int* added);
+/* KD_TREE::Delete_Point_Boxes (ikd_Tree.cpp:500-520; SURVEY.md row N1 -- the node computes cub_needrm at
+ * laserMapping.cpp:260-305 but never passes it on). boxes: nbox x {min x,y,z, max x,y,z} (BoxPointType, ikd_Tree.h:63-66);
+ * a point is deleted iff min <= p < max on every axis (:633). deleted: number of points removed. */
+int liinit_map_delete_boxes(liinit_ctx* h, const float* boxes, int nbox, int* deleted);
 /* KD_TREE::validnum / size (ikd_Tree.cpp:71-88,120-137; laserMapping.cpp:932-933,1142): live points. */
 int liinit_map_validnum(liinit_ctx* h, int* n);
 int liinit_map_size(liinit_ctx* h, int* n);

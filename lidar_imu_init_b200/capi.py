@@ -32,7 +32,7 @@ _f64 = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
 _i32 = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 
 SYMBOLS = [
-    "liinit_create", "liinit_destroy", "liinit_last_error", "liinit_set_stream", "liinit_map_build", "liinit_map_add_points",
+    "liinit_create", "liinit_destroy", "liinit_last_error", "liinit_set_stream", "liinit_map_build", "liinit_map_add_points", "liinit_map_delete_boxes",
     "liinit_map_validnum", "liinit_map_size", "liinit_map_download", "liinit_map_nearest_search", "liinit_scan_upload", "liinit_scan_upload_raw", "liinit_scan_download_body",
     "liinit_icp_iterate", "liinit_icp_iterate_device", "liinit_scan_download_effect", "liinit_scan_download_state",
     "liinit_map_incremental", "liinit_last_pass_timing", "liinit_last_pass_kernel_times", "liinit_launch_count", "liinit_map_stats",
@@ -62,6 +62,7 @@ def load():
     L.liinit_set_stream.argtypes = [vp, vp]
     L.liinit_map_build.argtypes = [vp, vp, C.c_int, C.c_int]
     L.liinit_map_add_points.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    L.liinit_map_delete_boxes.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int)]
     L.liinit_map_validnum.argtypes = [vp, C.POINTER(C.c_int)]
     L.liinit_map_size.argtypes = [vp, C.POINTER(C.c_int)]
     L.liinit_map_download.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int)]
@@ -140,6 +141,13 @@ class LiInitGpu:
             return 0
         self._ck(self.L.liinit_map_add_points(self.h, _ptr(a), a.shape[1], a.shape[0], int(downsample_on), C.byref(added)))
         return added.value
+
+    def map_delete_boxes(self, boxes) -> int:
+        """boxes: [n, 6] float32 rows {min x,y,z, max x,y,z}; returns the number of deleted points."""
+        b = np.ascontiguousarray(boxes, dtype=np.float32).reshape(-1, 6)
+        d = C.c_int(0)
+        self._ck(self.L.liinit_map_delete_boxes(self.h, _ptr(b), len(b), C.byref(d)))
+        return d.value
 
     def map_validnum(self) -> int:
         n = C.c_int(0)

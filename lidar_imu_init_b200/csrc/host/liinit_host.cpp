@@ -207,4 +207,46 @@ int liinit_scan_update(liinit_ctx* h, liinit_state* state, int max_iter, int imu
     return LIINIT_OK;
 }
 
+int liinit_fov_segment(const double* pos, double cube_len, double det_range, float* box, int* initialized, float* out) {
+    const double MOV_THRESHOLD = 1.5;   // laserMapping.cpp:58
+    if (!*initialized) {                 // :266-272
+        for (int i = 0; i < 3; i++) {
+            box[i] = (float)(pos[i] - cube_len / 2.0);
+            box[3 + i] = (float)(pos[i] + cube_len / 2.0);
+        }
+        *initialized = 1;
+        return 0;
+    }
+    float dist[3][2];
+    bool need_move = false;
+    for (int i = 0; i < 3; i++) {        // :274-281
+        dist[i][0] = (float)std::fabs(pos[i] - (double)box[i]);
+        dist[i][1] = (float)std::fabs(pos[i] - (double)box[3 + i]);
+        if (dist[i][0] <= MOV_THRESHOLD * det_range || dist[i][1] <= MOV_THRESHOLD * det_range) need_move = true;
+    }
+    if (!need_move) return 0;
+    float nb[6];
+    std::memcpy(nb, box, sizeof(nb));
+    const double a = (cube_len - 2.0 * MOV_THRESHOLD * det_range) * 0.5 * 0.9, b = det_range * (MOV_THRESHOLD - 1);
+    const float mov_dist = (float)(a > b ? a : b);   // :285-286
+    int n = 0;
+    for (int i = 0; i < 3; i++) {        // :287-301
+        float tmp[6];
+        std::memcpy(tmp, box, sizeof(tmp));
+        if (dist[i][0] <= MOV_THRESHOLD * det_range) {
+            nb[3 + i] -= mov_dist;
+            nb[i] -= mov_dist;
+            tmp[i] = box[3 + i] - mov_dist;
+            std::memcpy(out + 6 * n++, tmp, sizeof(tmp));
+        } else if (dist[i][1] <= MOV_THRESHOLD * det_range) {
+            nb[3 + i] += mov_dist;
+            nb[i] += mov_dist;
+            tmp[3 + i] = box[i] + mov_dist;
+            std::memcpy(out + 6 * n++, tmp, sizeof(tmp));
+        }
+    }
+    std::memcpy(box, nb, sizeof(nb));
+    return n;
+}
+
 }  // extern "C"

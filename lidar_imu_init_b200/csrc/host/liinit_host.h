@@ -59,6 +59,13 @@ int liinit_ieskf_update(liinit_state* state, const liinit_state* state_propagat,
  * state: in = propagated prior (state_propagat = state, :910), out = posterior. */
 int liinit_scan_update(liinit_ctx* h, liinit_state* state, int max_iteration, int imu_en, liinit_scan_stats* stats);
 
+/* lasermap_fov_segment (laserMapping.cpp:260-305): keeps a cube_len-sized local map box around the LiDAR and, when the
+ * LiDAR comes within MOV_THRESHOLD*det_range of a face, shifts the box and returns the slabs that fell out of it
+ * (cub_needrm) -- the boxes to hand to liinit_map_delete_boxes. local_box: {min xyz, max xyz}, state kept by the caller;
+ * *initialized: Localmap_Initialized. boxes_out: room for 3 boxes (18 floats). Returns the number of boxes (0..3). */
+int liinit_fov_segment(const double pos_LiD[3], double cube_len, double det_range, float local_box[6], int* initialized,
+                       float boxes_out[18]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -447,6 +447,27 @@ int liinit_map_add_points(liinit_ctx* h, const float* xyz, int stride, int n, in
     return LIINIT_OK;
 }
 
+int liinit_map_delete_boxes(liinit_ctx* h, const float* boxes, int nbox, int* deleted) {
+    if (!h || (!boxes && nbox > 0) || nbox < 0) return LIINIT_ERR_INVALID;
+    Ctx* c = &h->c;
+    CU(cudaSetDevice(c->device));
+    if (deleted) *deleted = 0;
+    if (nbox == 0) return LIINIT_OK;
+    if ((size_t)nbox * 6 > c->stage_raw_floats) return fail(c, LIINIT_ERR_CAPACITY, "too many boxes");
+    CU(cudaMemcpyAsync(c->d_stage_raw, boxes, (size_t)nbox * 6 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync(c->d_vg_misc + 6, 0, sizeof(int), c->stream));
+    k_map_delete_boxes<<<nblk((long long)c->hash_slots * 32, 256), 256, 0, c->stream>>>(c->M, c->hash_slots, c->d_stage_raw, nbox,
+                                                                                          c->d_vg_misc + 6);
+    c->launches++;
+    c->have_neighbors = false;   // pool offsets inside the touched slabs moved
+    CU(cudaGetLastError());
+    int cnt = 0;
+    CU(cudaMemcpyAsync(&cnt, c->d_vg_misc + 6, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (deleted) *deleted = cnt;
+    return LIINIT_OK;
+}
+
 int liinit_map_validnum(liinit_ctx* h, int* n) {
     if (!h || !n) return LIINIT_ERR_INVALID;
     Ctx* c = &h->c;

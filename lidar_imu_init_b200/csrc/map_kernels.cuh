@@ -389,6 +389,41 @@ __global__ void k_ds_compact(MapDev M) {
     }
 }
 
+// ---- box delete (KD_TREE::Delete_Point_Boxes, ikd_Tree.cpp:500-520 -> Delete_by_range :608-670) -----------------
+// A live point is deleted iff some box contains it under the reference's half-open float test
+// vertex_min <= c && vertex_max > c on every axis (:633). One warp per hash slot: tombstone-free in-place squeeze.
+__global__ void k_map_delete_boxes(MapDev M, unsigned slots, const float* __restrict__ boxes /* n x {min xyz, max xyz} */, int nbox,
+                                   int* __restrict__ deleted) {
+    int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if ((unsigned)w >= slots) return;
+    uint4 e = M.ent[w];
+    unsigned long long k = (unsigned long long)e.x | ((unsigned long long)e.y << 32);
+    if (k == LI_EMPTY_KEY || e.w == 0u) return;
+    unsigned wr = 0;
+    for (unsigned base = 0; base < e.w; base += 32) {
+        unsigned j = base + lane;
+        float4 q = make_float4(0, 0, 0, 0);
+        bool keep = false;
+        if (j < e.w) {
+            q = M.pool[(size_t)e.z + j];
+            keep = true;
+            for (int b = 0; b < nbox; b++) {
+                const float* bx = boxes + 6 * b;
+                if (bx[0] <= q.x && bx[3] > q.x && bx[1] <= q.y && bx[4] > q.y && bx[2] <= q.z && bx[5] > q.z) keep = false;
+            }
+        }
+        unsigned mm = __ballot_sync(LI_FULL, keep);
+        if (keep) M.pool[(size_t)e.z + wr + __popc(mm & ((1u << lane) - 1u))] = q;
+        wr += __popc(mm);
+        __syncwarp();
+    }
+    if (lane == 0 && wr != e.w) {
+        M.ent[w].w = wr;
+        atomicAdd(&M.counters[CNT_LIVE], (int)wr - (int)e.w);
+        atomicAdd(deleted, (int)(e.w - wr));
+    }
+}
+
 // ---- flatten -------------------------------------------------------------------------------------
 __global__ void k_map_flatten(MapDev M, unsigned slots, float* __restrict__ out, int cap, int* __restrict__ out_n) {
     int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;

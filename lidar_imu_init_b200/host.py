@@ -36,6 +36,9 @@ def load():
     L.liinit_ieskf_update.argtypes = [_f64, _f64, _f64, _f64, _f64, C.c_void_p]
     L.liinit_scan_update.restype = C.c_int
     L.liinit_scan_update.argtypes = [C.c_void_p, _f64, C.c_int, C.c_int, C.POINTER(ScanStats)]
+    L.liinit_fov_segment.restype = C.c_int
+    L.liinit_fov_segment.argtypes = [_f64, C.c_double, C.c_double, np.ctypeslib.ndpointer(dtype=np.float32, flags='C_CONTIGUOUS'), C.POINTER(C.c_int),
+                                     np.ctypeslib.ndpointer(dtype=np.float32, flags='C_CONTIGUOUS')]
     _LIB = L
     return L
 
@@ -90,3 +93,17 @@ def scan_update(gpu: capi.LiInitGpu, state, max_iteration=5, imu_en=False):
     if rc != 0:
         raise capi.LiInitError(rc, (gpu.L.liinit_last_error(gpu.h) or b"").decode())
     return s, {k: getattr(st, k) for k, _ in ScanStats._fields_}
+
+
+class FovSegmenter:
+    """lasermap_fov_segment (laserMapping.cpp:260-305) with its two globals (LocalMap_Points, Localmap_Initialized)."""
+
+    def __init__(self, cube_len: float, det_range: float):
+        self.cube_len, self.det_range = float(cube_len), float(det_range)
+        self.box = np.zeros(6, np.float32)
+        self.init = C.c_int(0)
+
+    def update(self, pos_lidar):
+        out = np.zeros(18, np.float32)
+        n = load().liinit_fov_segment(np.ascontiguousarray(pos_lidar, np.float64), self.cube_len, self.det_range, self.box, C.byref(self.init), out)
+        return out.reshape(3, 6)[:n].copy()

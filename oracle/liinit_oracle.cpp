@@ -196,6 +196,7 @@ struct MapBase {
     virtual ~MapBase() {}
     virtual void build(const float* xyz, int n) = 0;
     virtual int add_points(const float* xyz, int n, bool downsample_on) = 0;
+    virtual int delete_boxes(const float* boxes, int nbox) = 0;   // KD_TREE::Delete_Point_Boxes
     virtual int size() = 0;       // KD_TREE::size(): nodes incl. lazily deleted
     virtual int validnum() = 0;   // live points
     virtual int flatten(float* out, int cap) = 0;
@@ -303,6 +304,24 @@ struct MapRestated : MapBase {
         dirty = true;
         return counter;
     }
+    int delete_boxes(const float* boxes, int nbox) override {   // Delete_by_range point test (ikd_Tree.cpp:633)
+        int c = 0;
+        for (size_t i = 0; i < pts.size(); i++) {
+            if (!alive[i]) continue;
+            const P3& p = pts[i];
+            for (int b = 0; b < nbox; b++) {
+                const float* x = boxes + 6 * b;
+                if (x[0] <= p.x && x[3] > p.x && x[1] <= p.y && x[4] > p.y && x[2] <= p.z && x[5] > p.z) {
+                    alive[i] = 0;
+                    n_alive--;
+                    c++;
+                    break;
+                }
+            }
+        }
+        dirty = true;
+        return c;
+    }
     int size() override { return (int)pts.size(); }
     int validnum() override { return n_alive; }
     bool empty() override { return pts.empty(); }
@@ -366,6 +385,15 @@ struct MapIkd : MapBase {
         PointVector v(n);
         for (int i = 0; i < n; i++) v[i] = mk(xyz + 3 * (size_t)i);
         return t->Add_Points(v, downsample_on);
+    }
+    int delete_boxes(const float* boxes, int nbox) override {
+        std::vector<BoxPointType> v(nbox);
+        for (int b = 0; b < nbox; b++)
+            for (int a = 0; a < 3; a++) {
+                v[b].vertex_min[a] = boxes[6 * b + a];
+                v[b].vertex_max[a] = boxes[6 * b + 3 + a];
+            }
+        return t->Delete_Point_Boxes(v);
     }
     int size() override { return t->size(); }
     int validnum() override { return t->validnum(); }
@@ -851,6 +879,7 @@ void oracle_map_build(void* m, const float* xyz, int n) { static_cast<MapBase*>(
 int oracle_map_add_points(void* m, const float* xyz, int n, int downsample_on) {
     return static_cast<MapBase*>(m)->add_points(xyz, n, downsample_on != 0);
 }
+int oracle_map_delete_boxes(void* m, const float* boxes, int nbox) { return static_cast<MapBase*>(m)->delete_boxes(boxes, nbox); }
 int oracle_map_size(void* m) { return static_cast<MapBase*>(m)->size(); }
 int oracle_map_validnum(void* m) { return static_cast<MapBase*>(m)->validnum(); }
 int oracle_map_flatten(void* m, float* out, int cap) { return static_cast<MapBase*>(m)->flatten(out, cap); }

@@ -61,6 +61,8 @@ def load(prefer_ref: bool = True):
     L.oracle_map_build.argtypes = [C.c_void_p, _f32p, C.c_int]
     L.oracle_map_add_points.restype = C.c_int
     L.oracle_map_add_points.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_int]
+    L.oracle_map_delete_boxes.restype = C.c_int
+    L.oracle_map_delete_boxes.argtypes = [C.c_void_p, _f32p, C.c_int]
     L.oracle_map_size.restype = C.c_int
     L.oracle_map_size.argtypes = [C.c_void_p]
     L.oracle_map_validnum.restype = C.c_int
@@ -132,6 +134,10 @@ class OracleMap:
         if len(xyz) == 0:
             return 0
         return self.L.oracle_map_add_points(self.h, xyz, len(xyz), int(downsample_on))
+
+    def delete_boxes(self, boxes) -> int:
+        b = _c32(boxes).reshape(-1, 6)
+        return self.L.oracle_map_delete_boxes(self.h, b, len(b)) if len(b) else 0
 
     def size(self):
         return self.L.oracle_map_size(self.h)

@@ -49,3 +49,19 @@ def test_ieskf_information_form_matches_literal(host_lib, oracle_mod, imu_en):
     assert np.allclose(sol_inf, sol_lit, rtol=1e-5, atol=1e-9)
     assert np.allclose(s_inf[:36], s_lit[:36], rtol=0, atol=1e-8)      # pose part: far inside the 1e-3 bar
     assert np.allclose(KH_inf, KH_lit, rtol=1e-4, atol=1e-5)
+
+
+def test_fov_segment_follows_reference_logic(host_lib):
+    """lasermap_fov_segment (laserMapping.cpp:260-305): first call centres the cube, later calls shift it when the LiDAR
+    comes within 1.5*det_range of a face and report the slabs that fell out."""
+    cube, det = 1000.0, 100.0
+    seg = host_lib.FovSegmenter(cube, det)
+    assert len(seg.update([0.0, 0.0, 0.0])) == 0 and np.allclose(seg.box, [-500] * 3 + [500] * 3)
+    assert len(seg.update([100.0, 0.0, 0.0])) == 0                      # 400 m from the +x face > 150 m
+    boxes = seg.update([360.0, 0.0, 0.0])                                # 140 m from the +x face -> move
+    mov = max((cube - 2 * 1.5 * det) * 0.5 * 0.9, det * 0.5)             # = 315
+    assert len(boxes) == 1
+    assert np.allclose(boxes[0], [-500, -500, -500, -500 + mov, 500, 500])   # the slab left behind on the -x side
+    assert np.allclose(seg.box, [-500 + mov, -500, -500, 500 + mov, 500, 500])
+    b2 = seg.update([360.0, -370.0, 0.0])                                # now near the -y face
+    assert len(b2) == 1 and np.allclose(b2[0], [-185, 500 - mov, -500, 815, 500, 500])

@@ -122,8 +122,8 @@ __device__ __forceinline__ void group_scan_pipelined(const float4* __restrict__ 
 }
 
 struct KnnGeom {
-    int bx, by, bz, dirx, diry, dirz, bs;
-    float ds, margin;
+    int bs;             // log2(voxels per brick edge)
+    float ds, margin;   // voxel edge; rounding slack added to every pruning box
 };
 
 // Lockstep scan of the bricks found by the lanes of each group in the current probe round. thr: only candidates with

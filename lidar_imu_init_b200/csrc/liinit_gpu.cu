@@ -178,6 +178,10 @@ void launch_knn_scan(Ctx* c, const PoseD& P) {
     k_knn_scan<G><<<grid, LI_KNN_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2);
 }
 
+#ifndef LI_PLANE_WAVES
+#define LI_PLANE_WAVES 1   // the plane pass runs LI_PLANE_WAVES x (2 blocks per SM); each thread strides over the scan
+#endif
+
 constexpr int TPQ_CH = 32, TPQ_NB = 8;
 constexpr size_t TPQ_SMEM = 4 * TpqCfg<TPQ_CH, TPQ_NB>::WARP_TILE_F4 * sizeof(float4);
 
@@ -192,7 +196,7 @@ template <bool IMU, bool SEARCH>
 void launch_plane(Ctx* c, const PoseD& P) {
     // one wave of 256-thread blocks (2 resident per SM at ~100-130 registers), grid-stride over the scan
     int grid = nblk(c->scan_n, 256);
-    if (grid > c->num_sms * 2) grid = c->num_sms * 2;
+    if (grid > c->num_sms * 2 * LI_PLANE_WAVES) grid = c->num_sms * 2 * LI_PLANE_WAVES;
     k_icp_plane<IMU, SEARCH><<<grid, 256, 0, c->stream>>>(c->M, c->S, P, c->d_partials, c->d_done, c->d_out);
 }
 

@@ -100,24 +100,38 @@ __device__ __forceinline__ void group_merge(const float (&ld)[5], const int (&li
     }
 }
 
-// Lockstep scan of one slab per group (cnt = 0 for idle groups): U loads are issued back to back before any distance
-// is evaluated, so U independent L2 round trips overlap (the rolled loop exposed one full latency per 16*G bytes).
+// Lockstep scan of one slab per group (cnt = 0 for idle groups). U loads are issued back to back before any distance
+// is evaluated and the NEXT batch is already in flight while the current one is processed (double buffering), so the
+// L2 round trips overlap with the arithmetic. One compare per candidate: tau = min(thr, 5+, lane's 5th best).
 template <int G, int U = LI_KNN_U>
 __device__ __forceinline__ void group_scan_pipelined(const float4* __restrict__ pool, unsigned f, unsigned cnt, float qx, float qy, float qz,
                                                      float thr, float (&ld)[5], int (&li)[5], int gl) {
+    const float4* __restrict__ sp = pool + f;
+    const float cap5 = __uint_as_float(0x40a00001u);   // smallest float above 5: d <= 5 <=> d < cap5
+    const float thr5 = fminf(thr, cap5);
+    float tau = fminf(thr5, ld[4]);
+    float4 p[U], pn[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        unsigned j = gl + u * G;
+        p[u] = (j < cnt) ? __ldg(sp + j) : make_float4(1e18f, 1e18f, 1e18f, 0.f);
+    }
     for (unsigned j0 = gl; __any_sync(LI_FULL, j0 < cnt); j0 += U * G) {
-        float4 p[U];
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            unsigned j = j0 + u * G;
-            p[u] = (j < cnt) ? __ldg(&pool[(size_t)f + j]) : make_float4(1e18f, 1e18f, 1e18f, 0.f);
+        for (int u = 0; u < U; u++) {   // prefetch the next batch
+            unsigned j = j0 + (U + u) * G;
+            pn[u] = (j < cnt) ? __ldg(sp + j) : make_float4(1e18f, 1e18f, 1e18f, 0.f);
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            unsigned j = j0 + u * G;
-            float d = li_dist2(qx, qy, qz, p[u].x, p[u].y, p[u].z);   // padding lanes give d = +inf
-            if (j < cnt && d <= 5.0f && d < thr && d < ld[4]) local_insert(ld, li, d, (int)(f + j));
+            float d = li_dist2(qx, qy, qz, p[u].x, p[u].y, p[u].z);   // padding gives d = +inf
+            if (d < tau) {
+                local_insert(ld, li, d, (int)(f + j0 + u * G));
+                tau = fminf(thr5, ld[4]);
+            }
         }
+#pragma unroll
+        for (int u = 0; u < U; u++) p[u] = pn[u];
     }
 }
 

@@ -256,15 +256,16 @@ __device__ __forceinline__ void knn5_lockstep(const MapDev& M, float rho2, bool 
 
 // ---- search kernel of an ICP pass: world transform + 5-NN for every scan point -----------------------
 template <int G>
-__global__ void __launch_bounds__(LI_KNN_THREADS, LI_KNN_MIN_BLOCKS) k_knn_scan(MapDev M, ScanDev S, PoseD P, float rho2) {
+__global__ void __launch_bounds__(LI_KNN_THREADS, LI_KNN_MIN_BLOCKS) k_knn_scan(MapDev M, ScanDev S, PoseD P, float rho2, int q_begin,
+                                                                                int q_end) {
     constexpr int Q = Grp<G>::Q;
     const int lane = threadIdx.x & 31;
     const int gl = lane % G, gid = lane / G, gbase = gid * G;
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (int qb = warp_global * Q; qb < S.n; qb += nwarps * Q) {   // warp-uniform
+    for (int qb = q_begin + warp_global * Q; qb < q_end; qb += nwarps * Q) {   // warp-uniform; [q_begin, q_end) = this launch's slice
         const int q = qb + gid;
-        const bool valid = q < S.n;
+        const bool valid = q < q_end;
         float wx = 0.f, wy = 0.f, wz = 0.f;
         if (valid) {
             float4 b = __ldg(&S.body[q]);

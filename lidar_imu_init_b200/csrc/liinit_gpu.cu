@@ -19,6 +19,10 @@
 #include "map_kernels.cuh"
 #include "voxelgrid_kernels.cuh"
 
+#ifndef LI_UPLOAD_CHUNKS
+#define LI_UPLOAD_CHUNKS 4   // scan upload is split into this many copies; the first search pass starts per chunk
+#endif
+
 namespace {
 
 thread_local std::string g_create_error;
@@ -31,11 +35,11 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm = nullptr;
     // chunked scan upload on a copy stream: the first search pass starts on chunk k as soon as it has landed
-    static constexpr int NCH = 4;
+    static constexpr int NCH = LI_UPLOAD_CHUNKS;
     cudaStream_t cstream = nullptr;
-    cudaEvent_t ev_chunk[NCH] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_chunk[NCH] = {};
     cudaEvent_t ev_main = nullptr;
-    int chunk_lo[NCH + 1] = {0, 0, 0, 0, 0};
+    int chunk_lo[NCH + 1] = {};
     bool upload_pending = false;
     bool last_was_search = false;
     std::string err;
@@ -66,6 +70,8 @@ struct Ctx {
     int* d_near_ids = nullptr;
     unsigned char* d_selected = nullptr;
     float4* d_normvec = nullptr;
+    int* d_sparse_queue = nullptr;
+    int* d_sparse_count = nullptr;
     int scan_n = 0;
     bool have_neighbors = false;
     // reduction
@@ -192,11 +198,17 @@ void launch_knn_range(Ctx* c, const PoseD& P, int lo, int hi) {
 
 // One launch over the resident scan, or -- right after a chunked upload -- one launch per chunk, each waiting only
 // for its own chunk's copy, so the host-to-device transfer hides behind the search of the previous chunks.
+void launch_knn_sparse(Ctx* c) {
+    k_knn_sparse<<<c->num_sms * 4, 128, 0, c->stream>>>(c->M, c->S, c->rho2);
+    c->launches++;
+}
+
 template <int G>
 int launch_knn_scan(Ctx* c, const PoseD& P) {
     if (!c->upload_pending) {
         launch_knn_range<G>(c, P, 0, c->scan_n);
-        return 1;
+        launch_knn_sparse(c);
+        return 2;
     }
     int nl = 0;
     for (int k = 0; k < Ctx::NCH; k++) {
@@ -207,7 +219,8 @@ int launch_knn_scan(Ctx* c, const PoseD& P) {
         }
     }
     c->upload_pending = false;
-    return nl;
+    launch_knn_sparse(c);
+    return nl + 1;
 }
 
 // everything except the search pass needs the whole scan: make the compute stream wait for the copy stream
@@ -399,6 +412,9 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
     CUC(cudaMalloc(&c->d_near_ids, (size_t)batch * 5 * sizeof(int)));
     CUC(cudaMalloc(&c->d_selected, (size_t)ns));
     CUC(cudaMalloc(&c->d_normvec, (size_t)ns * sizeof(float4)));
+    CUC(cudaMalloc(&c->d_sparse_queue, (size_t)ns * sizeof(int)));
+    CUC(cudaMalloc(&c->d_sparse_count, sizeof(int)));
+    CUC(cudaMemsetAsync(c->d_sparse_count, 0, sizeof(int), c->stream));
     c->max_blocks = c->num_sms * 16;
     CUC(cudaMalloc(&c->d_partials, (size_t)c->max_blocks * 96 * sizeof(double)));
     CUC(cudaMalloc(&c->d_done, sizeof(unsigned)));
@@ -416,6 +432,8 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
     c->S.near_ids = c->d_near_ids;
     c->S.selected = c->d_selected;
     c->S.normvec = c->d_normvec;
+    c->S.sparse_queue = c->d_sparse_queue;
+    c->S.sparse_count = c->d_sparse_count;
     c->S.n = 0;
 #undef CUC
     *out = h;
@@ -430,7 +448,7 @@ int liinit_destroy(liinit_ctx* h) {
     cudaFree(c->M.ent); cudaFree(c->M.aux); cudaFree(c->M.pool); cudaFree(c->M.pool_top); cudaFree(c->M.touched_list);
     cudaFree(c->d_counters); cudaFreeHost(c->h_counters); cudaFree(c->d_stage_raw); cudaFree(c->d_stage_pts);
     cudaFree(c->d_slot_of); cudaFree(c->d_vslot_of); cudaFree(c->d_flag); cudaFree(c->d_ins); cudaFree(c->V.keys); cudaFree(c->V.head); cudaFree(c->d_vg_imin); cudaFree(c->d_vg_block); cudaFree(c->d_vg_misc); cudaFree(c->d_vg_params);
-    cudaFree(c->d_body); cudaFree(c->d_world); cudaFree(c->d_near_ids); cudaFree(c->d_selected); cudaFree(c->d_normvec);
+    cudaFree(c->d_body); cudaFree(c->d_world); cudaFree(c->d_near_ids); cudaFree(c->d_selected); cudaFree(c->d_normvec); cudaFree(c->d_sparse_queue); cudaFree(c->d_sparse_count);
     cudaFree(c->d_partials); cudaFree(c->d_done); cudaFree(c->d_out); cudaFreeHost(c->h_out); cudaFree(c->d_q_d2);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);

@@ -46,8 +46,6 @@ struct ScanDev {
     int* near_ids;          // [N*5] pool offsets, -1 = missing (Nearest_Points)
     unsigned char* selected;  // point_selected_surf
     float4* normvec;        // (nx,ny,nz,pd2) f32
-    int* sparse_queue;      // scan points whose first search shell found fewer than 5 neighbours
-    int* sparse_count;
     int n;
 };
 

@@ -356,7 +356,6 @@ __global__ void __launch_bounds__(256, LI_PLANE_MIN_BLOCKS) k_icp_plane(MapDev M
                                                    unsigned* __restrict__ done_counter, double* __restrict__ out160) {
     typedef AccLayout<IMU> L;
     const int lane = threadIdx.x & 31;
-    if (SEARCH && blockIdx.x == 0 && threadIdx.x == 0) *S.sparse_count = 0;   // the search kernels before this one are done with the queue
     double acc[L::K];
 #pragma unroll
     for (int k = 0; k < L::K; k++) acc[k] = 0.0;

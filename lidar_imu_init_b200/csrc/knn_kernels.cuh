@@ -168,12 +168,9 @@ __device__ __forceinline__ void lockstep_scan_found(const float4* __restrict__ p
 //                merge -> (n, g5);  stop if n == 5 and g5 <= hi2 (no unscanned brick can hold a closer point) or hi2 >= 5;
 //                otherwise lo2 = hi2 and hi2 = g5 if 5 are known (one closing step) else 4*hi2 (sparse neighbourhood).
 // The first shell is a guess (rho = seed radius): with a dense map most queries finish in it, the rest need one closing step.
-// defer_sparse: a query that still knows fewer than 5 neighbours after its first shell (sparse neighbourhood, open air) is
-// abandoned here (returns true) so that it does not hold its warp through the long growing-shell search; the caller queues it
-// for k_knn_sparse, which gives it a whole warp.
 template <int G>
-__device__ __forceinline__ bool knn5_lockstep(const MapDev& M, float rho2, bool valid, float qx, float qy, float qz, float (&gd)[5],
-                                              int (&gi)[5], int gl, int gbase, bool defer_sparse) {
+__device__ __forceinline__ void knn5_lockstep(const MapDev& M, float rho2, bool valid, float qx, float qy, float qz, float (&gd)[5],
+                                              int (&gi)[5], int gl, int gbase) {
     float ld[5];
     int li[5];
 #pragma unroll
@@ -196,7 +193,6 @@ __device__ __forceinline__ bool knn5_lockstep(const MapDev& M, float rho2, bool 
     // slack for float cell assignment / edge products: relative 2^-23 effects, bounded generously
     g.margin = 1e-6f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + 16.0f * B);
 
-    bool deferred = false;
     const float inv_ds = 1.0f / g.ds;
     const float slk = 0.02f + 4e-7f * (fabsf(qx) + fabsf(qy) + fabsf(qz)) * inv_ds;   // cells; covers the reciprocal-multiply rounding
     bool done = !act;
@@ -248,9 +244,6 @@ __device__ __forceinline__ bool knn5_lockstep(const MapDev& M, float rho2, bool 
             const bool full = gi[4] >= 0;
             if (last || (full && gd[4] <= hi2)) {
                 done = true;
-            } else if (!full && defer_sparse) {
-                done = true;
-                deferred = true;
             } else {
                 lo2 = hi2;
                 hi2 = full ? fminf(gd[4] * (1.0f + 1e-6f), 5.0f) : fminf(4.0f * hi2, 5.0f);
@@ -259,21 +252,19 @@ __device__ __forceinline__ bool knn5_lockstep(const MapDev& M, float rho2, bool 
             }
         }
     }
-    return deferred;
 }
 
 // ---- search kernel of an ICP pass: world transform + 5-NN for every scan point -----------------------
 template <int G>
-__global__ void __launch_bounds__(LI_KNN_THREADS, LI_KNN_MIN_BLOCKS) k_knn_scan(MapDev M, ScanDev S, PoseD P, float rho2, int q_begin,
-                                                                                int q_end) {
+__global__ void __launch_bounds__(LI_KNN_THREADS, LI_KNN_MIN_BLOCKS) k_knn_scan(MapDev M, ScanDev S, PoseD P, float rho2) {
     constexpr int Q = Grp<G>::Q;
     const int lane = threadIdx.x & 31;
     const int gl = lane % G, gid = lane / G, gbase = gid * G;
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (int qb = q_begin + warp_global * Q; qb < q_end; qb += nwarps * Q) {   // warp-uniform; [q_begin, q_end) = this launch's slice
+    for (int qb = warp_global * Q; qb < S.n; qb += nwarps * Q) {   // warp-uniform
         const int q = qb + gid;
-        const bool valid = q < q_end;
+        const bool valid = q < S.n;
         float wx = 0.f, wy = 0.f, wz = 0.f;
         if (valid) {
             float4 b = __ldg(&S.body[q]);
@@ -281,31 +272,9 @@ __global__ void __launch_bounds__(LI_KNN_THREADS, LI_KNN_MIN_BLOCKS) k_knn_scan(
         }
         float gd[5];
         int gi[5];
-        const bool deferred = knn5_lockstep<G>(M, rho2, valid, wx, wy, wz, gd, gi, gl, gbase, true);
+        knn5_lockstep<G>(M, rho2, valid, wx, wy, wz, gd, gi, gl, gbase);
         if (valid && gl == 0) {
-            if (deferred) S.sparse_queue[atomicAdd(S.sparse_count, 1)] = q;
             S.world[q] = make_float4(wx, wy, wz, 0.f);
-#pragma unroll
-            for (int k = 0; k < 5; k++) S.near_ids[(size_t)q * 5 + k] = gi[k];
-        }
-    }
-}
-
-// ---- second kernel of a search pass: the queued sparse queries, one whole warp each ---------------------------
-// 32 lanes probe 32 bricks of a growing shell at once, so an open-air query costs a handful of L2 round trips instead
-// of holding a lockstep warp of the main kernel for tens of microseconds (the main kernel's tail).
-__global__ void __launch_bounds__(128) k_knn_sparse(MapDev M, ScanDev S, float rho2) {
-    const int lane = threadIdx.x & 31;
-    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    const int n_items = *S.sparse_count;
-    for (int it = warp_global; it < n_items; it += nwarps) {
-        const int q = S.sparse_queue[it];
-        const float4 w = S.world[q];
-        float gd[5];
-        int gi[5];
-        knn5_lockstep<32>(M, rho2, true, w.x, w.y, w.z, gd, gi, lane, 0, false);
-        if (lane == 0) {
 #pragma unroll
             for (int k = 0; k < 5; k++) S.near_ids[(size_t)q * 5 + k] = gi[k];
         }
@@ -328,7 +297,7 @@ __global__ void __launch_bounds__(256) k_knn_queries(MapDev M, const float4* __r
         if (valid) p = __ldg(&qpts[q]);
         float gd[5];
         int gi[5];
-        knn5_lockstep<G>(M, rho2, valid, p.x, p.y, p.z, gd, gi, gl, gbase, false);
+        knn5_lockstep<G>(M, rho2, valid, p.x, p.y, p.z, gd, gi, gl, gbase);
         if (valid && gl == 0) {
 #pragma unroll
             for (int k = 0; k < 5; k++) {

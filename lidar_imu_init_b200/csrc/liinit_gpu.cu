@@ -19,10 +19,6 @@
 #include "map_kernels.cuh"
 #include "voxelgrid_kernels.cuh"
 
-#ifndef LI_UPLOAD_CHUNKS
-#define LI_UPLOAD_CHUNKS 4   // scan upload is split into this many copies; the first search pass starts per chunk
-#endif
-
 namespace {
 
 thread_local std::string g_create_error;
@@ -34,13 +30,6 @@ struct Ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm = nullptr;
-    // chunked scan upload on a copy stream: the first search pass starts on chunk k as soon as it has landed
-    static constexpr int NCH = LI_UPLOAD_CHUNKS;
-    cudaStream_t cstream = nullptr;
-    cudaEvent_t ev_chunk[NCH] = {};
-    cudaEvent_t ev_main = nullptr;
-    int chunk_lo[NCH + 1] = {};
-    bool upload_pending = false;
     bool last_was_search = false;
     std::string err;
 
@@ -70,8 +59,6 @@ struct Ctx {
     int* d_near_ids = nullptr;
     unsigned char* d_selected = nullptr;
     float4* d_normvec = nullptr;
-    int* d_sparse_queue = nullptr;
-    int* d_sparse_count = nullptr;
     int scan_n = 0;
     bool have_neighbors = false;
     // reduction
@@ -106,11 +93,8 @@ int fail(Ctx* c, int code, const std::string& msg) {
     return code;
 }
 
-void join_upload(Ctx* c);
-
 // copy n points with a float stride from host to d_stage_pts[0..n) as float4
 int stage_points(Ctx* c, const float* xyz, int stride, int n) {
-    join_upload(c);   // the staging buffers may still be in use by a chunked scan upload
     if (n > c->stage_pts_cap) return fail(c, LIINIT_ERR_CAPACITY, "batch exceeds staging capacity");
     if (stride == 4) {
         CU(cudaMemcpyAsync(c->d_stage_pts, xyz, (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
@@ -186,48 +170,12 @@ void fill_pose(PoseD& P, const double* R, const double* p, const double* RLI, co
 }
 
 template <int G>
-void launch_knn_range(Ctx* c, const PoseD& P, int lo, int hi) {
-    if (hi <= lo) return;
-    long long threads = (long long)(hi - lo) * G;
+void launch_knn_scan(Ctx* c, const PoseD& P) {
+    long long threads = (long long)c->scan_n * G;
     int grid = nblk(threads, LI_KNN_THREADS);
     int cap = c->max_blocks * (256 / LI_KNN_THREADS);
     if (grid > cap) grid = cap;
-    k_knn_scan<G><<<grid, LI_KNN_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, lo, hi);
-    c->launches++;
-}
-
-// One launch over the resident scan, or -- right after a chunked upload -- one launch per chunk, each waiting only
-// for its own chunk's copy, so the host-to-device transfer hides behind the search of the previous chunks.
-void launch_knn_sparse(Ctx* c) {
-    k_knn_sparse<<<c->num_sms * 4, 128, 0, c->stream>>>(c->M, c->S, c->rho2);
-    c->launches++;
-}
-
-template <int G>
-int launch_knn_scan(Ctx* c, const PoseD& P) {
-    if (!c->upload_pending) {
-        launch_knn_range<G>(c, P, 0, c->scan_n);
-        launch_knn_sparse(c);
-        return 2;
-    }
-    int nl = 0;
-    for (int k = 0; k < Ctx::NCH; k++) {
-        cudaStreamWaitEvent(c->stream, c->ev_chunk[k], 0);
-        if (c->chunk_lo[k + 1] > c->chunk_lo[k]) {
-            launch_knn_range<G>(c, P, c->chunk_lo[k], c->chunk_lo[k + 1]);
-            nl++;
-        }
-    }
-    c->upload_pending = false;
-    launch_knn_sparse(c);
-    return nl + 1;
-}
-
-// everything except the search pass needs the whole scan: make the compute stream wait for the copy stream
-void join_upload(Ctx* c) {
-    if (!c->upload_pending) return;
-    for (int k = 0; k < Ctx::NCH; k++) cudaStreamWaitEvent(c->stream, c->ev_chunk[k], 0);
-    c->upload_pending = false;
+    k_knn_scan<G><<<grid, LI_KNN_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2);
 }
 
 #ifndef LI_PLANE_WAVES
@@ -238,7 +186,6 @@ constexpr int TPQ_CH = 32, TPQ_NB = 8;
 constexpr size_t TPQ_SMEM = 4 * TpqCfg<TPQ_CH, TPQ_NB>::WARP_TILE_F4 * sizeof(float4);
 
 void launch_knn_scan_tpq(Ctx* c, const PoseD& P) {
-    join_upload(c);
     int grid = nblk(c->scan_n, 128);
     int cap = c->num_sms * 12;
     if (grid > cap) grid = cap;
@@ -260,23 +207,21 @@ int run_pass(Ctx* c, const double* R, const double* p, const double* RLI, const 
     fill_pose(P, R, p, RLI, TLI);
     CU(cudaEventRecord(c->ev0, c->stream));
     if (search) {
-        int nl = 1;
         switch (c->group) {
-            case 1: launch_knn_scan_tpq(c, P); c->launches++; break;
-            case 2: nl = launch_knn_scan<2>(c, P); break;
-            case 8: nl = launch_knn_scan<8>(c, P); break;
-            case 16: nl = launch_knn_scan<16>(c, P); break;
-            case 32: nl = launch_knn_scan<32>(c, P); break;
-            default: nl = launch_knn_scan<4>(c, P); break;
+            case 1: launch_knn_scan_tpq(c, P); break;
+            case 16: launch_knn_scan<16>(c, P); break;
+            case 32: launch_knn_scan<32>(c, P); break;
+            case 2: launch_knn_scan<2>(c, P); break;
+            case 8: launch_knn_scan<8>(c, P); break;
+            default: launch_knn_scan<4>(c, P); break;
         }
         CU(cudaEventRecord(c->evm, c->stream));
         if (imu_en) launch_plane<true, true>(c, P); else launch_plane<false, true>(c, P);
         c->have_neighbors = true;
-        c->launches += 1;
-        c->last_launches = nl + 1;
+        c->launches += 2;
+        c->last_launches = 2;
         c->last_was_search = true;
     } else {
-        join_upload(c);
         if (imu_en) launch_plane<true, false>(c, P); else launch_plane<false, false>(c, P);
         c->launches += 1;
         c->last_launches = 1;
@@ -341,9 +286,6 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
     CUC(cudaEventCreate(&c->ev0));
     CUC(cudaEventCreate(&c->ev1));
     CUC(cudaEventCreate(&c->evm));
-    CUC(cudaStreamCreateWithFlags(&c->cstream, cudaStreamNonBlocking));
-    for (int i = 0; i < Ctx::NCH; i++) CUC(cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming));
-    CUC(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
 
     int bs = cfg->brick_cells_log2 > 0 ? cfg->brick_cells_log2 : 3;
     if (bs < 1 || bs > 4) {
@@ -412,9 +354,6 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
     CUC(cudaMalloc(&c->d_near_ids, (size_t)batch * 5 * sizeof(int)));
     CUC(cudaMalloc(&c->d_selected, (size_t)ns));
     CUC(cudaMalloc(&c->d_normvec, (size_t)ns * sizeof(float4)));
-    CUC(cudaMalloc(&c->d_sparse_queue, (size_t)ns * sizeof(int)));
-    CUC(cudaMalloc(&c->d_sparse_count, sizeof(int)));
-    CUC(cudaMemsetAsync(c->d_sparse_count, 0, sizeof(int), c->stream));
     c->max_blocks = c->num_sms * 16;
     CUC(cudaMalloc(&c->d_partials, (size_t)c->max_blocks * 96 * sizeof(double)));
     CUC(cudaMalloc(&c->d_done, sizeof(unsigned)));
@@ -432,8 +371,6 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
     c->S.near_ids = c->d_near_ids;
     c->S.selected = c->d_selected;
     c->S.normvec = c->d_normvec;
-    c->S.sparse_queue = c->d_sparse_queue;
-    c->S.sparse_count = c->d_sparse_count;
     c->S.n = 0;
 #undef CUC
     *out = h;
@@ -448,14 +385,11 @@ int liinit_destroy(liinit_ctx* h) {
     cudaFree(c->M.ent); cudaFree(c->M.aux); cudaFree(c->M.pool); cudaFree(c->M.pool_top); cudaFree(c->M.touched_list);
     cudaFree(c->d_counters); cudaFreeHost(c->h_counters); cudaFree(c->d_stage_raw); cudaFree(c->d_stage_pts);
     cudaFree(c->d_slot_of); cudaFree(c->d_vslot_of); cudaFree(c->d_flag); cudaFree(c->d_ins); cudaFree(c->V.keys); cudaFree(c->V.head); cudaFree(c->d_vg_imin); cudaFree(c->d_vg_block); cudaFree(c->d_vg_misc); cudaFree(c->d_vg_params);
-    cudaFree(c->d_body); cudaFree(c->d_world); cudaFree(c->d_near_ids); cudaFree(c->d_selected); cudaFree(c->d_normvec); cudaFree(c->d_sparse_queue); cudaFree(c->d_sparse_count);
+    cudaFree(c->d_body); cudaFree(c->d_world); cudaFree(c->d_near_ids); cudaFree(c->d_selected); cudaFree(c->d_normvec);
     cudaFree(c->d_partials); cudaFree(c->d_done); cudaFree(c->d_out); cudaFreeHost(c->h_out); cudaFree(c->d_q_d2);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->evm) cudaEventDestroy(c->evm);
-    for (int i = 0; i < Ctx::NCH; i++) if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]);
-    if (c->ev_main) cudaEventDestroy(c->ev_main);
-    if (c->cstream) { cudaStreamSynchronize(c->cstream); cudaStreamDestroy(c->cstream); }
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete h;
     return LIINIT_OK;
@@ -465,7 +399,6 @@ int liinit_set_stream(liinit_ctx* h, void* cuda_stream) {
     if (!h) return LIINIT_ERR_INVALID;
     Ctx* c = &h->c;
     CU(cudaSetDevice(c->device));
-    join_upload(c);
     CU(cudaStreamSynchronize(c->stream));
     c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
     return LIINIT_OK;
@@ -525,7 +458,6 @@ int liinit_map_delete_boxes(liinit_ctx* h, const float* boxes, int nbox, int* de
     if (deleted) *deleted = 0;
     if (nbox == 0) return LIINIT_OK;
     if ((size_t)nbox * 6 > c->stage_raw_floats) return fail(c, LIINIT_ERR_CAPACITY, "too many boxes");
-    join_upload(c);
     CU(cudaMemcpyAsync(c->d_stage_raw, boxes, (size_t)nbox * 6 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemsetAsync(c->d_vg_misc + 6, 0, sizeof(int), c->stream));
     k_map_delete_boxes<<<nblk((long long)c->hash_slots * 32, 256), 256, 0, c->stream>>>(c->M, c->hash_slots, c->d_stage_raw, nbox,
@@ -660,32 +592,17 @@ int liinit_scan_upload(liinit_ctx* h, const float* body, int stride, int n) {
     Ctx* c = &h->c;
     CU(cudaSetDevice(c->device));
     if (n > c->cfg.max_scan_points) return fail(c, LIINIT_ERR_CAPACITY, "n exceeds max_scan_points");
-    if (stride != 3 && stride != 4 && stride != 12) return fail(c, LIINIT_ERR_INVALID, "stride_floats must be 3, 4 or 12");
-    if (stride != 4 && (size_t)n * stride > c->stage_raw_floats) return fail(c, LIINIT_ERR_CAPACITY, "scan exceeds staging capacity");
-    // the copy stream may overwrite d_body only after everything queued on the compute stream has read it
-    CU(cudaEventRecord(c->ev_main, c->stream));
-    CU(cudaStreamWaitEvent(c->cstream, c->ev_main, 0));
-    for (int k = 0; k <= Ctx::NCH; k++) {   // chunk boundaries on multiples of 32 points
-        long long b = ((long long)n * k / Ctx::NCH + 31) / 32 * 32;
-        c->chunk_lo[k] = (int)(b < n ? b : n);
+    if (stride == 4) {
+        CU(cudaMemcpyAsync(c->d_body, body, (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
+    } else if (stride == 3 || stride == 12) {
+        size_t nf = (size_t)n * stride;
+        if (nf > c->stage_raw_floats) return fail(c, LIINIT_ERR_CAPACITY, "scan exceeds staging capacity");
+        CU(cudaMemcpyAsync(c->d_stage_raw, body, nf * 4, cudaMemcpyHostToDevice, c->stream));
+        k_repack<<<nblk(n, 256), 256, 0, c->stream>>>(c->d_stage_raw, stride, n, c->d_body);
+        c->launches++;
+    } else {
+        return fail(c, LIINIT_ERR_INVALID, "stride_floats must be 3, 4 or 12");
     }
-    c->chunk_lo[0] = 0;
-    c->chunk_lo[Ctx::NCH] = n;
-    for (int k = 0; k < Ctx::NCH; k++) {
-        const int lo = c->chunk_lo[k], m = c->chunk_lo[k + 1] - lo;
-        if (m > 0) {
-            if (stride == 4) {
-                CU(cudaMemcpyAsync(c->d_body + lo, body + (size_t)lo * 4, (size_t)m * 16, cudaMemcpyHostToDevice, c->cstream));
-            } else {
-                CU(cudaMemcpyAsync(c->d_stage_raw + (size_t)lo * stride, body + (size_t)lo * stride, (size_t)m * stride * 4, cudaMemcpyHostToDevice,
-                                   c->cstream));
-                k_repack<<<nblk(m, 256), 256, 0, c->cstream>>>(c->d_stage_raw + (size_t)lo * stride, stride, m, c->d_body + lo);
-                c->launches++;
-            }
-        }
-        CU(cudaEventRecord(c->ev_chunk[k], c->cstream));
-    }
-    c->upload_pending = true;
     // new scan: no neighbours, nothing selected (Nearest_Points / point_selected_surf start over at iteration 0)
     CU(cudaMemsetAsync(c->d_selected, 0, (size_t)n, c->stream));
     CU(cudaMemsetAsync(c->d_near_ids, 0xff, (size_t)n * 5 * sizeof(int), c->stream));
@@ -744,7 +661,6 @@ int liinit_scan_download_body(liinit_ctx* h, float* xyz, int cap, int* n) {
     int m = c->scan_n < cap ? c->scan_n : cap;
     if (m > 0 && xyz) {
         std::vector<float4> b(m);
-        join_upload(c);
         CU(cudaStreamSynchronize(c->stream));
         CU(cudaMemcpy(b.data(), c->d_body, (size_t)m * 16, cudaMemcpyDeviceToHost));
         for (int i = 0; i < m; i++) {
@@ -788,7 +704,6 @@ int liinit_scan_download_state(liinit_ctx* h, float* world_xyz, float* near_xyz,
     CU(cudaSetDevice(c->device));
     int n = c->scan_n;
     if (n <= 0) return fail(c, LIINIT_ERR_INVALID, "no scan uploaded");
-    join_upload(c);
     CU(cudaStreamSynchronize(c->stream));
     if (world_xyz) {
         std::vector<float4> w(n);
@@ -832,7 +747,6 @@ int liinit_scan_download_effect(liinit_ctx* h, float* ori_xyz, float* normvec, i
     CU(cudaSetDevice(c->device));
     int n = c->scan_n;
     if (n <= 0) return fail(c, LIINIT_ERR_INVALID, "no scan uploaded");
-    join_upload(c);
     CU(cudaStreamSynchronize(c->stream));
     std::vector<unsigned char> sel(n);
     std::vector<float4> nv(n), body(n);
@@ -861,7 +775,6 @@ int liinit_map_incremental(liinit_ctx* h, const double* R, const double* p, cons
     CU(cudaSetDevice(c->device));
     int n = c->scan_n;
     if (n <= 0) return fail(c, LIINIT_ERR_INVALID, "no scan uploaded");
-    join_upload(c);
     PoseD P;
     fill_pose(P, R, p, RLI, TLI);
     static const int zeros[2] = {0, 0};

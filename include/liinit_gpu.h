@@ -75,6 +75,21 @@ int liinit_map_nearest_search(liinit_ctx* h, const float* q_xyz, int stride_floa
 /* per-scan hot path (replaces laserMapping.cpp:936-1080) ---------------------------- */
 /* feats_down_body (laserMapping.cpp:917-919): once per scan; resets selection flags / neighbour lists. */
 int liinit_scan_upload(liinit_ctx* h, const float* body_xyz, int stride_floats, int n);
+/* ---- raw-scan front end: raw points -> undistort -> voxel grid -> resident scan ---- */
+/* Stage a raw cloud on the device. time_index: float index of the per-point time offset in MILLISECONDS inside a point
+ * (9 = PointType.curvature, src/preprocess.cpp), or -1 when there is none. */
+int liinit_raw_upload(liinit_ctx* h, const float* pts, int stride_floats, int time_index, int n);
+/* Forward_propagation_without_imu's un-distortion loop (IMU_Processing.hpp:246-266; constant-velocity model, LO mode):
+ * omega = state.bias_g (angular velocity), rot_end / vel_end = the PROPAGATED state. In place on the staged cloud. */
+int liinit_raw_undistort_cv(liinit_ctx* h, const double omega[3], const double rot_end[9], const double vel_end[3]);
+/* propagation_and_undist's back-propagation loop (IMU_Processing.hpp:390-415). poses: the IMUpose table, npose x 22 doubles
+ * {offset_time, acc[3], gyr[3], vel[3], pos[3], rot[9]} (Pose6D, common_lib.h:184-199); the state is the propagated one. */
+int liinit_raw_undistort_imu(liinit_ctx* h, const double* poses, int npose, const double rot_end[9], const double pos_end[3],
+                             const double R_LI[9], const double T_LI[3]);
+/* The staged raw cloud as packed xyz (after whatever undistortion ran). */
+int liinit_raw_download(liinit_ctx* h, float* xyz, int cap_points, int* n);
+/* downSizeFilterSurf.filter (laserMapping.cpp:917-918): voxel grid over the staged cloud -> the resident scan. */
+int liinit_raw_downsample(liinit_ctx* h, float leaf_size, int* n_down);
 /* Raw (undistorted, not yet downsampled) scan: voxel-grid filter on the device, then the result becomes the resident scan.
  * Replaces downSizeFilterSurf.setInputCloud/filter (laserMapping.cpp:122,823,917-918 = PCL VoxelGrid, leaf = mapping/filter_size_surf)
  * followed by liinit_scan_upload. n_down = feats_down_size. Output order: first input point of every leaf (see voxelgrid_kernels.cuh). */

@@ -33,7 +33,8 @@ _i32 = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 
 SYMBOLS = [
     "liinit_create", "liinit_destroy", "liinit_last_error", "liinit_set_stream", "liinit_map_build", "liinit_map_add_points", "liinit_map_delete_boxes",
-    "liinit_map_validnum", "liinit_map_size", "liinit_map_download", "liinit_map_nearest_search", "liinit_scan_upload", "liinit_scan_upload_raw", "liinit_scan_download_body",
+    "liinit_map_validnum", "liinit_map_size", "liinit_map_download", "liinit_map_nearest_search", "liinit_scan_upload", "liinit_scan_upload_raw", "liinit_scan_download_body", "liinit_raw_upload", "liinit_raw_undistort_cv", "liinit_raw_undistort_imu",
+    "liinit_raw_download", "liinit_raw_downsample",
     "liinit_icp_iterate", "liinit_icp_iterate_device", "liinit_scan_download_effect", "liinit_scan_download_state",
     "liinit_map_incremental", "liinit_last_pass_timing", "liinit_last_pass_kernel_times", "liinit_launch_count", "liinit_map_stats",
 ]
@@ -69,6 +70,11 @@ def load():
     L.liinit_map_nearest_search.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, vp, vp, vp]
     L.liinit_scan_upload.argtypes = [vp, vp, C.c_int, C.c_int]
     L.liinit_scan_upload_raw.argtypes = [vp, vp, C.c_int, C.c_int, C.c_float, C.POINTER(C.c_int)]
+    L.liinit_raw_upload.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int]
+    L.liinit_raw_undistort_cv.argtypes = [vp, _f64, _f64, _f64]
+    L.liinit_raw_undistort_imu.argtypes = [vp, _f64, C.c_int, _f64, _f64, _f64, _f64]
+    L.liinit_raw_download.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int)]
+    L.liinit_raw_downsample.argtypes = [vp, C.c_float, C.POINTER(C.c_int)]
     L.liinit_scan_download_body.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int)]
     L.liinit_icp_iterate.argtypes = [vp, _f64, _f64, _f64, _f64, C.c_int, C.c_int, _f64, _f64, C.POINTER(C.c_int), C.POINTER(C.c_double)]
     L.liinit_icp_iterate_device.argtypes = [vp, _f64, _f64, _f64, _f64, C.c_int, C.c_int, vp]
@@ -186,6 +192,34 @@ class LiInitGpu:
         a = _pts(pts)
         nd = C.c_int(0)
         self._ck(self.L.liinit_scan_upload_raw(self.h, _ptr(a), a.shape[1], a.shape[0], float(leaf_size), C.byref(nd)))
+        self.scan_n = nd.value
+        return nd.value
+
+    # ---- raw-scan front end ----
+    def raw_upload(self, pts, time_index: int = -1):
+        a = np.ascontiguousarray(pts, dtype=np.float32)
+        self._ck(self.L.liinit_raw_upload(self.h, _ptr(a), a.shape[1], int(time_index), a.shape[0]))
+        self.raw_n = a.shape[0]
+
+    def raw_undistort_cv(self, omega, rot_end, vel_end):
+        self._ck(self.L.liinit_raw_undistort_cv(self.h, np.ascontiguousarray(omega, np.float64), np.ascontiguousarray(rot_end, np.float64).reshape(9),
+                                                np.ascontiguousarray(vel_end, np.float64)))
+
+    def raw_undistort_imu(self, poses, rot_end, pos_end, R_LI, T_LI):
+        P = np.ascontiguousarray(poses, np.float64).reshape(-1, 22)
+        self._ck(self.L.liinit_raw_undistort_imu(self.h, P.reshape(-1), len(P), np.ascontiguousarray(rot_end, np.float64).reshape(9),
+                                                 np.ascontiguousarray(pos_end, np.float64), np.ascontiguousarray(R_LI, np.float64).reshape(9),
+                                                 np.ascontiguousarray(T_LI, np.float64)))
+
+    def raw_points(self):
+        n = C.c_int(0)
+        out = np.zeros((max(getattr(self, "raw_n", 0), 1), 3), np.float32)
+        self._ck(self.L.liinit_raw_download(self.h, _ptr(out), len(out), C.byref(n)))
+        return out[:n.value]
+
+    def raw_downsample(self, leaf_size: float) -> int:
+        nd = C.c_int(0)
+        self._ck(self.L.liinit_raw_downsample(self.h, float(leaf_size), C.byref(nd)))
         self.scan_n = nd.value
         return nd.value
 

@@ -18,6 +18,7 @@
 #include "knn_tpq.cuh"
 #include "map_kernels.cuh"
 #include "voxelgrid_kernels.cuh"
+#include "undistort_kernels.cuh"
 
 namespace {
 
@@ -51,6 +52,9 @@ struct Ctx {
     int* d_vg_block = nullptr;     // voxel-grid: per-block flag sums
     int* d_vg_misc = nullptr;      // [0..5] min/max (ordered ints), [6] out count, [7] error bits
     VgParams* d_vg_params = nullptr;
+    int raw_n = 0;                          // raw (not yet downsampled) cloud staged in d_stage_pts, w = time [ms]
+    unsigned long long* d_tmin_idx = nullptr;
+    double* d_poses = nullptr;              // IMU pose table for the undistortion (<= 4096 x 22 doubles)
     VoxTmp V{};
     // scan
     ScanDev S{};
@@ -96,6 +100,7 @@ int fail(Ctx* c, int code, const std::string& msg) {
 // copy n points with a float stride from host to d_stage_pts[0..n) as float4
 int stage_points(Ctx* c, const float* xyz, int stride, int n) {
     if (n > c->stage_pts_cap) return fail(c, LIINIT_ERR_CAPACITY, "batch exceeds staging capacity");
+    c->raw_n = 0;   // the staging buffer is shared with the raw-scan front end
     if (stride == 4) {
         CU(cudaMemcpyAsync(c->d_stage_pts, xyz, (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
         return LIINIT_OK;
@@ -347,6 +352,8 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
         CUC(cudaMalloc(&c->d_vg_block, ((size_t)batch / 1024 + 2) * 4));
         CUC(cudaMalloc(&c->d_vg_misc, 8 * 4));
         CUC(cudaMalloc(&c->d_vg_params, sizeof(VgParams)));
+        CUC(cudaMalloc(&c->d_tmin_idx, 8));
+        CUC(cudaMalloc(&c->d_poses, 4096 * LI_POSE6D_DOUBLES * sizeof(double)));
     }
     int ns = cfg->max_scan_points;
     CUC(cudaMalloc(&c->d_body, (size_t)ns * sizeof(float4)));
@@ -384,7 +391,7 @@ int liinit_destroy(liinit_ctx* h) {
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     cudaFree(c->M.ent); cudaFree(c->M.aux); cudaFree(c->M.pool); cudaFree(c->M.pool_top); cudaFree(c->M.touched_list);
     cudaFree(c->d_counters); cudaFreeHost(c->h_counters); cudaFree(c->d_stage_raw); cudaFree(c->d_stage_pts);
-    cudaFree(c->d_slot_of); cudaFree(c->d_vslot_of); cudaFree(c->d_flag); cudaFree(c->d_ins); cudaFree(c->V.keys); cudaFree(c->V.head); cudaFree(c->d_vg_imin); cudaFree(c->d_vg_block); cudaFree(c->d_vg_misc); cudaFree(c->d_vg_params);
+    cudaFree(c->d_slot_of); cudaFree(c->d_vslot_of); cudaFree(c->d_flag); cudaFree(c->d_ins); cudaFree(c->V.keys); cudaFree(c->V.head); cudaFree(c->d_vg_imin); cudaFree(c->d_vg_block); cudaFree(c->d_vg_misc); cudaFree(c->d_vg_params); cudaFree(c->d_tmin_idx); cudaFree(c->d_poses);
     cudaFree(c->d_body); cudaFree(c->d_world); cudaFree(c->d_near_ids); cudaFree(c->d_selected); cudaFree(c->d_normvec);
     cudaFree(c->d_partials); cudaFree(c->d_done); cudaFree(c->d_out); cudaFreeHost(c->h_out); cudaFree(c->d_q_d2);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -613,12 +620,87 @@ int liinit_scan_upload(liinit_ctx* h, const float* body, int stride, int n) {
     return LIINIT_OK;
 }
 
-int liinit_scan_upload_raw(liinit_ctx* h, const float* xyz, int stride, int n, float leaf_size, int* n_down) {
-    if (!h || !xyz || n <= 0 || !(leaf_size > 0.f)) return LIINIT_ERR_INVALID;
+int liinit_raw_upload(liinit_ctx* h, const float* pts, int stride, int time_index, int n) {
+    if (!h || !pts || n <= 0) return LIINIT_ERR_INVALID;
     Ctx* c = &h->c;
     CU(cudaSetDevice(c->device));
-    int r = stage_points(c, xyz, stride, n);   // -> d_stage_pts[0..n)
+    if (stride < 3 || time_index >= stride || (time_index >= 0 && time_index < 3)) return fail(c, LIINIT_ERR_INVALID, "bad stride / time_index");
+    if (n > c->stage_pts_cap || (size_t)n * stride > c->stage_raw_floats) return fail(c, LIINIT_ERR_CAPACITY, "raw cloud exceeds staging capacity");
+    CU(cudaMemcpyAsync(c->d_stage_raw, pts, (size_t)n * stride * 4, cudaMemcpyHostToDevice, c->stream));
+    k_repack_t<<<nblk(n, 256), 256, 0, c->stream>>>(c->d_stage_raw, stride, time_index, n, c->d_stage_pts);
+    c->launches++;
+    c->raw_n = n;
+    CU(cudaGetLastError());
+    return LIINIT_OK;
+}
+
+static int raw_time_range(Ctx* c) {
+    const int neg = (int)0xff800000 ^ 0x7fffffff;   // ordered-int image of -inf
+    const unsigned long long big = ~0ull;
+    CU(cudaMemcpyAsync(c->d_vg_misc + 5, &neg, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_tmin_idx, &big, 8, cudaMemcpyHostToDevice, c->stream));
+    k_time_range<<<nblk(c->raw_n, 256), 256, 0, c->stream>>>(c->d_stage_pts, c->raw_n, c->d_tmin_idx, c->d_vg_misc + 5);
+    c->launches++;
+    return LIINIT_OK;
+}
+
+int liinit_raw_undistort_cv(liinit_ctx* h, const double omega[3], const double rot_end[9], const double vel_end[3]) {
+    if (!h || !omega || !rot_end || !vel_end) return LIINIT_ERR_INVALID;
+    Ctx* c = &h->c;
+    CU(cudaSetDevice(c->device));
+    if (c->raw_n <= 0) return fail(c, LIINIT_ERR_INVALID, "no raw cloud staged (liinit_raw_upload)");
+    int r = raw_time_range(c);
     if (r) return r;
+    CvParams P;
+    for (int a = 0; a < 3; a++) {
+        P.omega[a] = omega[a];
+        P.vb[a] = rot_end[a] * vel_end[0] + rot_end[3 + a] * vel_end[1] + rot_end[6 + a] * vel_end[2];   // rot_end^T vel_end
+    }
+    k_undistort_cv<<<nblk(c->raw_n, 256), 256, 0, c->stream>>>(c->d_stage_pts, c->raw_n, P, c->d_vg_misc + 5, c->d_tmin_idx);
+    c->launches++;
+    CU(cudaGetLastError());
+    return LIINIT_OK;
+}
+
+int liinit_raw_undistort_imu(liinit_ctx* h, const double* poses, int npose, const double rot_end[9], const double pos_end[3],
+                             const double R_LI[9], const double T_LI[3]) {
+    if (!h || !poses || npose < 2 || !rot_end || !pos_end || !R_LI || !T_LI) return LIINIT_ERR_INVALID;
+    Ctx* c = &h->c;
+    CU(cudaSetDevice(c->device));
+    if (c->raw_n <= 0) return fail(c, LIINIT_ERR_INVALID, "no raw cloud staged (liinit_raw_upload)");
+    if (npose > 4096) return fail(c, LIINIT_ERR_CAPACITY, "IMU pose table too long");
+    CU(cudaMemcpyAsync(c->d_poses, poses, (size_t)npose * LI_POSE6D_DOUBLES * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    PoseD S;
+    fill_pose(S, rot_end, pos_end, R_LI, T_LI);
+    k_undistort_imu<<<nblk(c->raw_n, 256), 256, 0, c->stream>>>(c->d_stage_pts, c->raw_n, c->d_poses, npose, S);
+    c->launches++;
+    CU(cudaGetLastError());
+    return LIINIT_OK;
+}
+
+int liinit_raw_download(liinit_ctx* h, float* xyz, int cap, int* n) {
+    if (!h || !n) return LIINIT_ERR_INVALID;
+    Ctx* c = &h->c;
+    CU(cudaSetDevice(c->device));
+    *n = c->raw_n;
+    int m = c->raw_n < cap ? c->raw_n : cap;
+    if (m > 0 && xyz) {
+        std::vector<float4> b(m);
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaMemcpy(b.data(), c->d_stage_pts, (size_t)m * 16, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < m; i++) {
+            xyz[3 * (size_t)i] = b[i].x; xyz[3 * (size_t)i + 1] = b[i].y; xyz[3 * (size_t)i + 2] = b[i].z;
+        }
+    }
+    return LIINIT_OK;
+}
+
+int liinit_raw_downsample(liinit_ctx* h, float leaf_size, int* n_down) {
+    if (!h || !(leaf_size > 0.f)) return LIINIT_ERR_INVALID;
+    Ctx* c = &h->c;
+    CU(cudaSetDevice(c->device));
+    const int n = c->raw_n;
+    if (n <= 0) return fail(c, LIINIT_ERR_INVALID, "no raw cloud staged (liinit_raw_upload)");
     const int inf_pos = 0x7f800000, inf_neg = (int)0xff800000 ^ 0x7fffffff;   // ordered-int images of +inf / -inf
     const int init[8] = {inf_pos, inf_pos, inf_pos, inf_neg, inf_neg, inf_neg, 0, 0};
     CU(cudaMemcpyAsync(c->d_vg_misc, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
@@ -651,6 +733,12 @@ int liinit_scan_upload_raw(liinit_ctx* h, const float* xyz, int stride, int n, f
     c->have_neighbors = false;
     if (n_down) *n_down = m;
     return LIINIT_OK;
+}
+
+int liinit_scan_upload_raw(liinit_ctx* h, const float* xyz, int stride, int n, float leaf_size, int* n_down) {
+    int r = liinit_raw_upload(h, xyz, stride, -1, n);
+    if (r) return r;
+    return liinit_raw_downsample(h, leaf_size, n_down);
 }
 
 int liinit_scan_download_body(liinit_ctx* h, float* xyz, int cap, int* n) {

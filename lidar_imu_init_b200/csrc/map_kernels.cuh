@@ -17,6 +17,14 @@ __global__ void k_repack(const float* __restrict__ src, int stride, int n, float
     dst[i] = make_float4(s[0], s[1], s[2], 0.f);
 }
 
+// same, keeping one more float (a per-point time stamp, e.g. PointType.curvature) in w
+__global__ void k_repack_t(const float* __restrict__ src, int stride, int tidx, int n, float4* __restrict__ dst) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* s = src + (size_t)i * stride;
+    dst[i] = make_float4(s[0], s[1], s[2], tidx >= 0 ? s[tidx] : 0.f);
+}
+
 __global__ void k_map_clear(uint4* ent, uint4* aux, unsigned slots) {
     unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= slots) return;

@@ -1070,6 +1070,78 @@ int oracle_map_incremental(void* scan, void* map, const double* rot_end, const d
                            add_flag);
 }
 
+// Exp(ang_vel, dt) (so3_math.h:39-59)
+static void so3_exp_dt(const double* w, double dt, double* R) {
+    const double n = std::sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+    const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    if (n > 0.0000001) {
+        double r[3] = {w[0] / n, w[1] / n, w[2] / n};
+        double K[9], KK[9];
+        skew(r, K);
+        mat3_mul(K, K, KK);
+        const double a = n * dt, s = std::sin(a), c = 1.0 - std::cos(a);
+        for (int i = 0; i < 9; i++) R[i] = I[i] + s * K[i] + c * KK[i];
+    } else {
+        for (int i = 0; i < 9; i++) R[i] = I[i];
+    }
+}
+
+// The un-distortion loop of Forward_propagation_without_imu (IMU_Processing.hpp:208-212,246-266): time-sorted cloud walked
+// backwards from the last point down to (not including) the first. xyz in/out, t_ms = PointType.curvature.
+void oracle_undistort_cv(float* xyz, const float* t_ms, int n, const double* omega, const double* rot_end, const double* vel_end) {
+    std::vector<int> ord(n);
+    for (int i = 0; i < n; i++) ord[i] = i;
+    std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return t_ms[a] < t_ms[b]; });   // time_list (:15)
+    const double t_end = t_ms[ord[n - 1]] / double(1000);
+    double RT[9], vb[3];
+    mat3_T(rot_end, RT);
+    mat3_mul_vec(RT, vel_end, vb);
+    for (int k = n - 1; k != 0; k--) {
+        float* p = xyz + 3 * (size_t)ord[k];
+        const double dt_j = t_end - t_ms[ord[k]] / double(1000);
+        double R[9];
+        so3_exp_dt(omega, -dt_j, R);
+        double P[3] = {p[0], p[1], p[2]}, o[3];
+        mat3_mul_vec(R, P, o);
+        for (int a = 0; a < 3; a++) p[a] = (float)(o[a] + (-vb[a] * dt_j));
+    }
+}
+
+// The back-propagation loop of propagation_and_undist (IMU_Processing.hpp:390-415). poses: npose x 22 doubles
+// {offset_time, acc[3], gyr[3], vel[3], pos[3], rot[9]}.
+void oracle_undistort_imu(float* xyz, const float* t_ms, int n, const double* poses, int npose, const double* rot_end,
+                          const double* pos_end, const double* R_LI, const double* T_LI) {
+    std::vector<int> ord(n);
+    for (int i = 0; i < n; i++) ord[i] = i;
+    std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return t_ms[a] < t_ms[b]; });
+    double RT[9], RLIT[9];
+    mat3_T(rot_end, RT);
+    mat3_T(R_LI, RLIT);
+    int it = n - 1;
+    bool stop = false;
+    for (int kp = npose - 1; kp != 0 && !stop; kp--) {
+        const double* h = poses + (size_t)(kp - 1) * 22;
+        for (; t_ms[ord[it]] / double(1000) > h[0]; it--) {
+            float* p = xyz + 3 * (size_t)ord[it];
+            const double dt = t_ms[ord[it]] / double(1000) - h[0];
+            double E[9], Ri[9], Pi[3], q[3], u[3], v[3], w[3];
+            so3_exp_dt(h + 4, dt, E);
+            mat3_mul(h + 13, E, Ri);
+            for (int a = 0; a < 3; a++) Pi[a] = h[10 + a] + h[7 + a] * dt + 0.5 * h[1 + a] * dt * dt;
+            double pin[3] = {p[0], p[1], p[2]};
+            mat3_mul_vec(R_LI, pin, q);
+            for (int a = 0; a < 3; a++) q[a] += T_LI[a];
+            mat3_mul_vec(Ri, q, u);
+            for (int a = 0; a < 3; a++) u[a] = u[a] + Pi[a] - pos_end[a];
+            mat3_mul_vec(RT, u, v);
+            for (int a = 0; a < 3; a++) v[a] -= T_LI[a];
+            mat3_mul_vec(RLIT, v, w);
+            for (int a = 0; a < 3; a++) p[a] = (float)w[a];
+            if (it == 0) { stop = true; break; }
+        }
+    }
+}
+
 // PCL VoxelGrid<PointT>::applyFilter restated for xyz (PCL >= 1.8, pcl/filters/impl/voxel_grid.hpp; third-party, pinned
 // only as ">= 1.8" by the reference README:57; call site laserMapping.cpp:122,823,917-918). Output in PCL's order (ascending
 // leaf index); the summation order inside a leaf is the input order (PCL's std::sort leaves it unspecified).

@@ -84,6 +84,8 @@ def load(prefer_ref: bool = True):
     L.oracle_scan_update.argtypes = [C.c_void_p, C.c_void_p, _f64p, C.c_int, C.c_int, C.c_int, _i32p]
     L.oracle_map_incremental.restype = C.c_int
     L.oracle_map_incremental.argtypes = [C.c_void_p, C.c_void_p, _f64p, _f64p, _f64p, _f64p, C.c_double, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]
+    L.oracle_undistort_cv.argtypes = [_f32p, _f32p, C.c_int, _f64p, _f64p, _f64p]
+    L.oracle_undistort_imu.argtypes = [_f32p, _f32p, C.c_int, _f64p, C.c_int, _f64p, _f64p, _f64p, _f64p]
     L.oracle_voxel_grid.restype = C.c_int
     L.oracle_voxel_grid.argtypes = [_f32p, C.c_int, C.c_float, _f32p]
     L.oracle_esti_plane.restype = C.c_int
@@ -231,6 +233,19 @@ class OracleScan:
         c = self.L.oracle_map_incremental(self.h, omap.h, _c64(rot_end).reshape(9), _c64(pos_end), _c64(R_LI).reshape(9), _c64(T_LI),
                                           float(ds), int(flg_EKF_inited), C.byref(n_add), C.byref(n_nod), _opt(flags))
         return c, n_add.value, n_nod.value, flags
+
+
+def undistort_cv(xyz, t_ms, omega, rot_end, vel_end):
+    out = _c32(xyz).reshape(-1, 3).copy()
+    load().oracle_undistort_cv(out, _c32(t_ms), len(out), _c64(omega), _c64(rot_end).reshape(9), _c64(vel_end))
+    return out
+
+
+def undistort_imu(xyz, t_ms, poses, rot_end, pos_end, R_LI, T_LI):
+    out = _c32(xyz).reshape(-1, 3).copy()
+    P = _c64(poses).reshape(-1, 22)
+    load().oracle_undistort_imu(out, _c32(t_ms), len(out), P.reshape(-1), len(P), _c64(rot_end).reshape(9), _c64(pos_end), _c64(R_LI).reshape(9), _c64(T_LI))
+    return out
 
 
 def voxel_grid(xyz, leaf):

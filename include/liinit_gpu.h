@@ -92,7 +92,7 @@ int liinit_raw_download(liinit_ctx* h, float* xyz, int cap_points, int* n);
 int liinit_raw_downsample(liinit_ctx* h, float leaf_size, int* n_down);
 /* Raw (undistorted, not yet downsampled) scan: voxel-grid filter on the device, then the result becomes the resident scan.
  * Replaces downSizeFilterSurf.setInputCloud/filter (laserMapping.cpp:122,823,917-918 = PCL VoxelGrid, leaf = mapping/filter_size_surf)
- * followed by liinit_scan_upload. n_down = feats_down_size. Output order: first input point of every leaf (see voxelgrid_kernels.cuh). */
+ * followed by liinit_scan_upload. n_down = feats_down_size. Output order: ascending leaf index, as PCL. */
 int liinit_scan_upload_raw(liinit_ctx* h, const float* xyz, int stride_floats, int n, float leaf_size, int* n_down);
 /* The resident scan (feats_down_body) as packed xyz. */
 int liinit_scan_download_body(liinit_ctx* h, float* xyz, int cap_points, int* n);

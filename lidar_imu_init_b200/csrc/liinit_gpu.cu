@@ -49,7 +49,10 @@ struct Ctx {
     int* d_flag = nullptr;
     int* d_ins = nullptr;
     int* d_vg_imin = nullptr;      // voxel-grid: first point index per leaf
-    int* d_vg_block = nullptr;     // voxel-grid: per-block flag sums
+    int* d_vg_block = nullptr;     // (unused scratch)
+    unsigned* d_rs_keys = nullptr;  // radix sort ping-pong buffers + histogram
+    unsigned* d_rs_vals = nullptr;
+    int* d_rs_hist = nullptr;
     int* d_vg_misc = nullptr;      // [0..5] min/max (ordered ints), [6] out count, [7] error bits
     VgParams* d_vg_params = nullptr;
     int raw_n = 0;                          // raw (not yet downsampled) cloud staged in d_stage_pts, w = time [ms]
@@ -351,6 +354,9 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
         CUC(cudaMalloc(&c->d_vg_imin, ((size_t)c->V.mask + 1) * 4));
         CUC(cudaMalloc(&c->d_vg_block, ((size_t)batch / 1024 + 2) * 4));
         CUC(cudaMalloc(&c->d_vg_misc, 8 * 4));
+        CUC(cudaMalloc(&c->d_rs_keys, (size_t)batch * 4));
+        CUC(cudaMalloc(&c->d_rs_vals, (size_t)batch * 4));
+        CUC(cudaMalloc(&c->d_rs_hist, ((size_t)batch / RS_TILE + 2) * 256 * 4));
         CUC(cudaMalloc(&c->d_vg_params, sizeof(VgParams)));
         CUC(cudaMalloc(&c->d_tmin_idx, 8));
         CUC(cudaMalloc(&c->d_poses, 4096 * LI_POSE6D_DOUBLES * sizeof(double)));
@@ -391,7 +397,7 @@ int liinit_destroy(liinit_ctx* h) {
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     cudaFree(c->M.ent); cudaFree(c->M.aux); cudaFree(c->M.pool); cudaFree(c->M.pool_top); cudaFree(c->M.touched_list);
     cudaFree(c->d_counters); cudaFreeHost(c->h_counters); cudaFree(c->d_stage_raw); cudaFree(c->d_stage_pts);
-    cudaFree(c->d_slot_of); cudaFree(c->d_vslot_of); cudaFree(c->d_flag); cudaFree(c->d_ins); cudaFree(c->V.keys); cudaFree(c->V.head); cudaFree(c->d_vg_imin); cudaFree(c->d_vg_block); cudaFree(c->d_vg_misc); cudaFree(c->d_vg_params); cudaFree(c->d_tmin_idx); cudaFree(c->d_poses);
+    cudaFree(c->d_slot_of); cudaFree(c->d_vslot_of); cudaFree(c->d_flag); cudaFree(c->d_ins); cudaFree(c->V.keys); cudaFree(c->V.head); cudaFree(c->d_vg_imin); cudaFree(c->d_vg_block); cudaFree(c->d_vg_misc); cudaFree(c->d_rs_keys); cudaFree(c->d_rs_vals); cudaFree(c->d_rs_hist); cudaFree(c->d_vg_params); cudaFree(c->d_tmin_idx); cudaFree(c->d_poses);
     cudaFree(c->d_body); cudaFree(c->d_world); cudaFree(c->d_near_ids); cudaFree(c->d_selected); cudaFree(c->d_normvec);
     cudaFree(c->d_partials); cudaFree(c->d_done); cudaFree(c->d_out); cudaFreeHost(c->h_out); cudaFree(c->d_q_d2);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -710,10 +716,27 @@ int liinit_raw_downsample(liinit_ctx* h, float leaf_size, int* n_down) {
     k_vg_params<<<1, 32, 0, c->stream>>>(c->d_vg_misc, leaf_size, c->d_vg_params);
     k_vg_link<<<nblk(n, 256), 256, 0, c->stream>>>(c->d_stage_pts, n, c->d_vg_params, c->V, c->d_vg_imin, c->d_vslot_of, c->d_slot_of,
                                                      c->d_vg_misc + 7);
-    k_vg_flag<<<nb, 1024, 0, c->stream>>>(n, c->d_slot_of, c->d_vg_imin, c->d_flag, c->d_vg_block);
-    k_vg_scan_blocks<<<1, 1024, 0, c->stream>>>(nb, c->d_vg_block, c->d_vg_misc + 6);
-    k_vg_centroid<<<nb, 1024, 0, c->stream>>>(c->d_stage_pts, n, c->d_flag, c->d_vg_block, c->d_slot_of, c->V, c->d_vslot_of, c->d_body,
-                                              c->cfg.max_scan_points, c->d_vg_misc + 7);
+    // one (leaf index, first point) pair per leaf, sorted by leaf index: PCL's output order
+    unsigned* k0 = reinterpret_cast<unsigned*>(c->d_flag);
+    unsigned* v0 = reinterpret_cast<unsigned*>(c->d_ins);
+    unsigned* k1 = c->d_rs_keys;
+    unsigned* v1 = c->d_rs_vals;
+    k_vg_collect<<<nblk((long long)c->V.mask + 1, 256), 256, 0, c->stream>>>(c->V, c->d_vg_imin, k0, v0, c->d_vg_misc + 6);
+    {
+        // the number of leaves is only known on the device: sort with the worst-case tile count, the kernels read the real n
+        const int ntiles = nblk(n, RS_TILE);
+        for (int pass = 0; pass < 4; pass++) {
+            k_rs_hist_dev<<<nblk(ntiles, 4), 128, 0, c->stream>>>(k0, c->d_vg_misc + 6, 8 * pass, ntiles, c->d_rs_hist);
+            k_rs_scan<<<1, 1024, 0, c->stream>>>(256 * ntiles, c->d_rs_hist);
+            k_rs_scatter_dev<<<nblk(ntiles, 4), 128, 0, c->stream>>>(k0, v0, c->d_vg_misc + 6, 8 * pass, ntiles, c->d_rs_hist, k1, v1);
+            unsigned* t = k0; k0 = k1; k1 = t;
+            t = v0; v0 = v1; v1 = t;
+        }
+    }
+    (void)nb;
+    k_vg_centroid_sorted<<<nblk(n, 256), 256, 0, c->stream>>>(c->d_stage_pts, v0, c->d_vg_misc + 6, c->d_slot_of, c->V, c->d_vslot_of, c->d_body,
+                                                               c->cfg.max_scan_points, c->d_vg_misc + 7);
+    c->launches += 12;
     c->launches += 7;
     CU(cudaGetLastError());
     int res[8];

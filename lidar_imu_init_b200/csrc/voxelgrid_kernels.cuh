@@ -6,11 +6,12 @@
 // idx = i + j*dx + k*dx*dy, one output point per occupied leaf = float centroid (sum / count) of its points.
 // PCL orders the output by idx and (std::sort, unstable) leaves the summation order inside a leaf unspecified; here
 // the summation order is the input order (deterministic, bit-equal to the oracle's stable restatement, within one
-// ulp per addend of any PCL build) and the output order is that of each leaf's first input point. Nothing on the
-// path depends on the order of feats_down_body (HtH / Htr are sums; Add_Points is order independent).
+// ulp per addend of any PCL build) and the output order is PCL's: ascending leaf index (radix sort of the unique leaf
+// keys, sort_kernels.cuh) -- which is also the spatially coherent order the 5-NN kernel likes.
 #pragma once
 #include "common.cuh"
 #include "map_kernels.cuh"
+#include "sort_kernels.cuh"
 
 struct VgParams {
     int min_b[3];
@@ -119,101 +120,28 @@ __global__ void k_vg_clear(VoxTmp V, int* __restrict__ imin) {
     imin[i] = 0x7fffffff;
 }
 
-// flag[i] = 1 for the first point of every leaf; block sums for the scan (1024 elements per block)
-__global__ void k_vg_flag(int n, const int* __restrict__ slot_of, const int* __restrict__ imin, int* __restrict__ flag,
-                          int* __restrict__ block_sums) {
-    __shared__ int s_w[32];
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int f = 0;
-    if (i < n) {
-        int s = slot_of[i];
-        f = (s >= 0 && imin[s] == i) ? 1 : 0;
-        flag[i] = f;
-    }
-    int w = f;
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) w += __shfl_xor_sync(LI_FULL, w, o);
-    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = w;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        int v = (threadIdx.x < (blockDim.x >> 5)) ? s_w[threadIdx.x] : 0;
-#pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(LI_FULL, v, o);
-        if (threadIdx.x == 0) block_sums[blockIdx.x] = v;
-    }
+// one (leaf index, first point index) pair per occupied leaf, in arbitrary order (sorted afterwards: keys are unique)
+__global__ void k_vg_collect(VoxTmp V, const int* __restrict__ imin, unsigned* __restrict__ keys, unsigned* __restrict__ vals,
+                             int* __restrict__ count) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > V.mask) return;
+    if (V.head[i] < 0) return;
+    int pos = atomicAdd(count, 1);
+    keys[pos] = (unsigned)V.keys[i];
+    vals[pos] = (unsigned)imin[i];
 }
 
-// exclusive scan of the block sums by one block (nb <= a few thousand); total -> *out_total
-__global__ void k_vg_scan_blocks(int nb, int* __restrict__ block_sums, int* __restrict__ out_total) {
-    __shared__ int s_carry;
-    __shared__ int s_w[32];
-    if (threadIdx.x == 0) s_carry = 0;
-    __syncthreads();
-    for (int base = 0; base < nb; base += blockDim.x) {
-        int i = base + threadIdx.x;
-        int v = (i < nb) ? block_sums[i] : 0;
-        int x = v;   // inclusive warp scan
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int y = __shfl_up_sync(LI_FULL, x, o);
-            if ((threadIdx.x & 31) >= o) x += y;
-        }
-        if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = x;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            int t = (threadIdx.x < (blockDim.x >> 5)) ? s_w[threadIdx.x] : 0;
-            int z = t;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int y = __shfl_up_sync(LI_FULL, z, o);
-                if (threadIdx.x >= o) z += y;
-            }
-            s_w[threadIdx.x] = z - t;   // exclusive warp offsets
-        }
-        __syncthreads();
-        int excl = s_carry + s_w[threadIdx.x >> 5] + x - v;
-        if (i < nb) block_sums[i] = excl;
-        __syncthreads();
-        if (threadIdx.x == blockDim.x - 1) s_carry = excl + v;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) *out_total = s_carry;
-}
-
-// one thread per leaf representative: sum the leaf's points in input order, write the centroid at its output slot
-__global__ void k_vg_centroid(const float4* __restrict__ pts, int n, const int* __restrict__ flag, const int* __restrict__ block_sums,
-                              const int* __restrict__ slot_of, VoxTmp V, const int* __restrict__ next_of, float4* __restrict__ out,
-                              int out_cap, int* __restrict__ err) {
-    __shared__ int s_w[32];
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int f = (i < n) ? flag[i] : 0;
-    // exclusive scan of the flags inside the block
-    int x = f;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int y = __shfl_up_sync(LI_FULL, x, o);
-        if ((threadIdx.x & 31) >= o) x += y;
-    }
-    if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = x;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        int t = (threadIdx.x < (blockDim.x >> 5)) ? s_w[threadIdx.x] : 0;
-        int z = t;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int y = __shfl_up_sync(LI_FULL, z, o);
-            if (threadIdx.x >= o) z += y;
-        }
-        s_w[threadIdx.x] = z - t;
-    }
-    __syncthreads();
-    if (!f) return;
-    int pos = block_sums[blockIdx.x] + s_w[threadIdx.x >> 5] + x - f;
+// one thread per leaf, leaves in ascending leaf index (PCL's output order): sum the leaf's points in input order
+__global__ void k_vg_centroid_sorted(const float4* __restrict__ pts, const unsigned* __restrict__ reps, const int* __restrict__ count,
+                                     const int* __restrict__ slot_of, VoxTmp V, const int* __restrict__ next_of, float4* __restrict__ out,
+                                     int out_cap, int* __restrict__ err) {
+    int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= *count) return;
     if (pos >= out_cap) {
         atomicOr(err, 2);
         return;
     }
-    int head = V.head[slot_of[i]];
+    int head = V.head[slot_of[reps[pos]]];
     float sx = 0.f, sy = 0.f, sz = 0.f;
     int cnt = 0, last = -1;
     for (;;) {   // ascending input index: repeatedly take the smallest index greater than the last one

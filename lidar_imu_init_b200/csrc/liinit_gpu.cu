@@ -145,26 +145,37 @@ int plain_insert(Ctx* c, const float4* pts, int n, const int* sel, int want) {
     int r = reset_batch_counters(c);
     if (r) return r;
     k_ins_count<<<nblk(n, 256), 256, 0, c->stream>>>(c->M, pts, n, sel, want, c->d_slot_of);
-    // number of touched bricks is unknown on the host: launch for the worst case (n warps), early exit inside
-    k_ins_reserve<<<nblk((long long)n * 32, 256), 256, 0, c->stream>>>(c->M);
+    // the number of touched bricks is only known on the device: fixed grids, grid-stride loops inside
+    const int gfix = c->num_sms * 8;
+    k_ins_reserve<<<gfix, 256, 0, c->stream>>>(c->M);
     k_ins_append<<<nblk(n, 256), 256, 0, c->stream>>>(c->M, pts, n, c->d_slot_of);
-    k_ins_commit<<<nblk(n, 256), 256, 0, c->stream>>>(c->M);
+    k_ins_commit<<<gfix, 256, 0, c->stream>>>(c->M);
     c->launches += 4;
     CU(cudaGetLastError());
     return LIINIT_OK;
+}
+
+// the temporary voxel hash, shrunk to the next power of two >= 2n slots (never beyond the allocation)
+VoxTmp sized_vox(Ctx* c, int n) {
+    VoxTmp V = c->V;
+    unsigned m = 1024;
+    while (m < 2u * (unsigned)n && m - 1 < c->V.mask) m <<= 1;
+    if (m - 1 < V.mask) V.mask = m - 1;
+    return V;
 }
 
 int downsample_insert(Ctx* c, const float4* pts, int n, const int* sel, int want) {
     if (n <= 0) return LIINIT_OK;
     int r = reset_batch_counters(c);
     if (r) return r;
-    k_vox_clear<<<nblk((long long)c->V.mask + 1, 256), 256, 0, c->stream>>>(c->V);
-    k_ds_link<<<nblk(n, 256), 256, 0, c->stream>>>(c->M, c->V, pts, n, sel, want, c->d_vslot_of, c->d_slot_of, c->d_ins);
-    k_ins_reserve<<<nblk((long long)n * 32, 256), 256, 0, c->stream>>>(c->M);
-    k_ds_replay<<<nblk((long long)c->V.mask + 1, 128), 128, 0, c->stream>>>(c->M, c->V, pts, c->d_vslot_of, c->d_ins);
+    VoxTmp V = sized_vox(c, n);   // batch-sized temporary hash: clearing / walking 2M slots for a 10k-point batch is waste
+    k_vox_clear<<<nblk((long long)V.mask + 1, 256), 256, 0, c->stream>>>(V);
+    k_ds_link<<<nblk(n, 256), 256, 0, c->stream>>>(c->M, V, pts, n, sel, want, c->d_vslot_of, c->d_slot_of, c->d_ins);
+    k_ins_reserve<<<c->num_sms * 8, 256, 0, c->stream>>>(c->M);
+    k_ds_replay<<<nblk((long long)V.mask + 1, 128), 128, 0, c->stream>>>(c->M, V, pts, c->d_vslot_of, c->d_ins);
     k_ds_append<<<nblk(n, 256), 256, 0, c->stream>>>(c->M, pts, n, c->d_slot_of, c->d_ins);
-    // tombstoned bricks were added to the touched list by the replay: worst case n + n bricks
-    k_ds_compact<<<nblk((long long)n * 64, 256), 256, 0, c->stream>>>(c->M);
+    // tombstoned bricks were added to the touched list by the replay (worst case n + n bricks): grid-stride inside
+    k_ds_compact<<<c->num_sms * 8, 256, 0, c->stream>>>(c->M);
     c->launches += 6;
     CU(cudaGetLastError());
     return LIINIT_OK;
@@ -711,17 +722,18 @@ int liinit_raw_downsample(liinit_ctx* h, float leaf_size, int* n_down) {
     const int init[8] = {inf_pos, inf_pos, inf_pos, inf_neg, inf_neg, inf_neg, 0, 0};
     CU(cudaMemcpyAsync(c->d_vg_misc, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
     const int nb = nblk(n, 1024);
-    k_vg_clear<<<nblk((long long)c->V.mask + 1, 256), 256, 0, c->stream>>>(c->V, c->d_vg_imin);
+    VoxTmp V = sized_vox(c, n);
+    k_vg_clear<<<nblk((long long)V.mask + 1, 256), 256, 0, c->stream>>>(V, c->d_vg_imin);
     k_vg_minmax<<<nblk(n, 256), 256, 0, c->stream>>>(c->d_stage_pts, n, c->d_vg_misc);
     k_vg_params<<<1, 32, 0, c->stream>>>(c->d_vg_misc, leaf_size, c->d_vg_params);
-    k_vg_link<<<nblk(n, 256), 256, 0, c->stream>>>(c->d_stage_pts, n, c->d_vg_params, c->V, c->d_vg_imin, c->d_vslot_of, c->d_slot_of,
+    k_vg_link<<<nblk(n, 256), 256, 0, c->stream>>>(c->d_stage_pts, n, c->d_vg_params, V, c->d_vg_imin, c->d_vslot_of, c->d_slot_of,
                                                      c->d_vg_misc + 7);
     // one (leaf index, first point) pair per leaf, sorted by leaf index: PCL's output order
     unsigned* k0 = reinterpret_cast<unsigned*>(c->d_flag);
     unsigned* v0 = reinterpret_cast<unsigned*>(c->d_ins);
     unsigned* k1 = c->d_rs_keys;
     unsigned* v1 = c->d_rs_vals;
-    k_vg_collect<<<nblk((long long)c->V.mask + 1, 256), 256, 0, c->stream>>>(c->V, c->d_vg_imin, k0, v0, c->d_vg_misc + 6);
+    k_vg_collect<<<nblk((long long)V.mask + 1, 256), 256, 0, c->stream>>>(V, c->d_vg_imin, k0, v0, c->d_vg_misc + 6);
     {
         // the number of leaves is only known on the device: sort with the worst-case tile count, the kernels read the real n
         const int ntiles = nblk(n, RS_TILE);
@@ -734,7 +746,7 @@ int liinit_raw_downsample(liinit_ctx* h, float leaf_size, int* n_down) {
         }
     }
     (void)nb;
-    k_vg_centroid_sorted<<<nblk(n, 256), 256, 0, c->stream>>>(c->d_stage_pts, v0, c->d_vg_misc + 6, c->d_slot_of, c->V, c->d_vslot_of, c->d_body,
+    k_vg_centroid_sorted<<<nblk(n, 256), 256, 0, c->stream>>>(c->d_stage_pts, v0, c->d_vg_misc + 6, c->d_slot_of, V, c->d_vslot_of, c->d_body,
                                                                c->cfg.max_scan_points, c->d_vg_misc + 7);
     c->launches += 12;
     c->launches += 7;

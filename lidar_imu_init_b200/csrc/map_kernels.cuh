@@ -120,8 +120,9 @@ __global__ void k_ins_count(MapDev M, const float4* __restrict__ pts, int n, con
 
 // pass 2: one warp per touched brick -- grow its slab when count + pending exceeds the capacity.
 __global__ void k_ins_reserve(MapDev M) {
-    int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (w >= M.counters[CNT_TOUCHED]) return;
+    const int lane = threadIdx.x & 31;
+    const int nw = (gridDim.x * blockDim.x) >> 5, ntouched = M.counters[CNT_TOUCHED];
+    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < ntouched; w += nw) {   // fixed grid, the count lives on the device
     int s = M.touched_list[w];
     uint4 e = M.ent[s];
     uint4 a = M.aux[s];
@@ -138,7 +139,7 @@ __global__ void k_ins_reserve(MapDev M) {
                 atomicOr(&M.counters[CNT_ERR], ERR_POOL_FULL);
                 M.aux[s].y = 0u;   // nothing will be appended to this brick
             }
-            return;
+            continue;
         }
         for (unsigned j = lane; j < e.w; j += 32) M.pool[off + j] = M.pool[e.z + j];
         if (lane == 0) {
@@ -147,6 +148,7 @@ __global__ void k_ins_reserve(MapDev M) {
         }
     }
     if (lane == 0) M.aux[s].z = 0u;
+    }
 }
 
 // pass 3: append. ent.count is not modified until the commit, so first+count is the append base.
@@ -170,15 +172,16 @@ __global__ void k_ins_append(MapDev M, const float4* __restrict__ pts, int n, co
 
 // pass 4: commit counts.
 __global__ void k_ins_commit(MapDev M) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= M.counters[CNT_TOUCHED]) return;
-    int s = M.touched_list[t];
-    unsigned f = M.aux[s].z;
-    M.ent[s].w += f;
-    M.aux[s].y = 0u;
-    M.aux[s].z = 0u;
-    M.aux[s].w = 0u;
-    atomicAdd(&M.counters[CNT_LIVE], (int)f);
+    const int nt = gridDim.x * blockDim.x, ntouched = M.counters[CNT_TOUCHED];
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ntouched; t += nt) {
+        int s = M.touched_list[t];
+        unsigned f = M.aux[s].z;
+        M.ent[s].w += f;
+        M.aux[s].y = 0u;
+        M.aux[s].z = 0u;
+        M.aux[s].w = 0u;
+        atomicAdd(&M.counters[CNT_LIVE], (int)f);
+    }
 }
 
 // ---- downsample insert (Add_Points(.., true)) --------------------------------------------------
@@ -368,8 +371,9 @@ __global__ void k_ds_append(MapDev M, const float4* __restrict__ pts, int n, con
 
 // pass D4: one warp per touched brick -- squeeze out tombstones over [0, count+fill), fix counts.
 __global__ void k_ds_compact(MapDev M) {
-    int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (w >= M.counters[CNT_TOUCHED]) return;
+    const int lane = threadIdx.x & 31;
+    const int nw = (gridDim.x * blockDim.x) >> 5, ntouched = M.counters[CNT_TOUCHED];
+    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < ntouched; w += nw) {
     int s = M.touched_list[w];
     uint4 e = M.ent[s];
     uint4 a = M.aux[s];
@@ -394,6 +398,7 @@ __global__ void k_ds_compact(MapDev M) {
         M.aux[s].z = 0u;
         M.aux[s].w = 0u;
         atomicAdd(&M.counters[CNT_LIVE], (int)wr - (int)e.w);
+    }
     }
 }
 

@@ -553,14 +553,14 @@ int liinit_map_nearest_search(liinit_ctx* h, const float* q, int stride, int n, 
     if (max_dist != 5.0) return fail(c, LIINIT_ERR_INVALID, "only max_dist = 5 (laserMapping.cpp:980) is supported");
     CU(cudaSetDevice(c->device));
     std::vector<int> ids((size_t)5 * (n > 0 ? n : 1));
-    std::vector<float4> pool_pts;
     for (long long off = 0; off < n; off += c->stage_pts_cap) {
         int m = (int)((n - off < c->stage_pts_cap) ? (n - off) : c->stage_pts_cap);
         int r = stage_points(c, q + (size_t)off * stride, stride, m);
         if (r) return r;
-        // d_vslot_of.. reuse: ids go to a scratch the size of batch*5 -> use d_near_ids only if scan not resident; allocate
         int* d_ids = nullptr;
+        float* d_xyz = nullptr;
         CU(cudaMalloc(&d_ids, (size_t)m * 5 * sizeof(int)));
+        CU(cudaMalloc(&d_xyz, (size_t)m * 15 * sizeof(float)));
         if (c->group == 1) {
             int grid = nblk(m, 128);
             if (grid > c->num_sms * 12) grid = c->num_sms * 12;
@@ -570,31 +570,19 @@ int liinit_map_nearest_search(liinit_ctx* h, const float* q, int stride, int n, 
             if (grid > c->max_blocks) grid = c->max_blocks;
             k_knn_queries<8><<<grid, 256, 0, c->stream>>>(c->M, c->d_stage_pts, m, d_ids, c->d_q_d2, c->rho2);
         }
-        c->launches++;
+        k_gather_xyz<<<nblk((long long)m * 5, 256), 256, 0, c->stream>>>(c->M.pool, d_ids, (long long)m * 5, d_xyz);
+        c->launches += 2;
         CU(cudaMemcpyAsync(ids.data() + (size_t)off * 5, d_ids, (size_t)m * 5 * 4, cudaMemcpyDeviceToHost, c->stream));
+        if (out_xyz) CU(cudaMemcpyAsync(out_xyz + (size_t)off * 15, d_xyz, (size_t)m * 15 * 4, cudaMemcpyDeviceToHost, c->stream));
         if (out_d2) CU(cudaMemcpyAsync(out_d2 + (size_t)off * 5, c->d_q_d2, (size_t)m * 5 * 4, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
         cudaFree(d_ids);
+        cudaFree(d_xyz);
     }
-    // gather neighbour coordinates (marshalling, not compute): fetch the used part of the pool
-    unsigned long long top = 0;
-    CU(cudaMemcpy(&top, c->M.pool_top, 8, cudaMemcpyDeviceToHost));
-    pool_pts.resize(top > 0 ? top : 1);
-    if (top > 0) CU(cudaMemcpy(pool_pts.data(), c->M.pool, (size_t)top * 16, cudaMemcpyDeviceToHost));
     for (int i = 0; i < n; i++) {
         int cnt = 0;
-        for (int k = 0; k < 5; k++) {
-            int id = ids[(size_t)i * 5 + k];
-            size_t o = (size_t)i * 5 + k;
-            if (id >= 0) {
-                cnt++;
-                if (out_xyz) {
-                    out_xyz[3 * o] = pool_pts[id].x; out_xyz[3 * o + 1] = pool_pts[id].y; out_xyz[3 * o + 2] = pool_pts[id].z;
-                }
-            } else if (out_xyz) {
-                out_xyz[3 * o] = out_xyz[3 * o + 1] = out_xyz[3 * o + 2] = 0.f;
-            }
-        }
+        for (int k = 0; k < 5; k++)
+            if (ids[(size_t)i * 5 + k] >= 0) cnt++;
         if (out_cnt) out_cnt[i] = cnt;
         // PointType_CMP tie order (ikd_Tree.h:57-60)
         if (out_xyz && out_d2) {
@@ -838,26 +826,22 @@ int liinit_scan_download_state(liinit_ctx* h, float* world_xyz, float* near_xyz,
     if (near_xyz || near_cnt) {
         std::vector<int> ids((size_t)n * 5);
         CU(cudaMemcpy(ids.data(), c->d_near_ids, (size_t)n * 5 * 4, cudaMemcpyDeviceToHost));
-        unsigned long long top = 0;
-        CU(cudaMemcpy(&top, c->M.pool_top, 8, cudaMemcpyDeviceToHost));
-        std::vector<float4> pool_pts(top > 0 ? top : 1);
-        if (top > 0) CU(cudaMemcpy(pool_pts.data(), c->M.pool, (size_t)top * 16, cudaMemcpyDeviceToHost));
-        for (int i = 0; i < n; i++) {
-            int cnt = 0;
-            for (int k = 0; k < 5; k++) {
-                int id = ids[(size_t)i * 5 + k];
-                size_t o = (size_t)i * 5 + k;
-                if (id >= 0 && (unsigned long long)id < top) {
-                    cnt++;
-                    if (near_xyz) {
-                        near_xyz[3 * o] = pool_pts[id].x; near_xyz[3 * o + 1] = pool_pts[id].y; near_xyz[3 * o + 2] = pool_pts[id].z;
-                    }
-                } else if (near_xyz) {
-                    near_xyz[3 * o] = near_xyz[3 * o + 1] = near_xyz[3 * o + 2] = 0.f;
-                }
-            }
-            if (near_cnt) near_cnt[i] = cnt;
+        if (near_xyz) {
+            float* d_xyz = nullptr;
+            CU(cudaMalloc(&d_xyz, (size_t)n * 15 * sizeof(float)));
+            k_gather_xyz<<<nblk((long long)n * 5, 256), 256, 0, c->stream>>>(c->M.pool, c->d_near_ids, (long long)n * 5, d_xyz);
+            c->launches++;
+            CU(cudaMemcpyAsync(near_xyz, d_xyz, (size_t)n * 15 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            cudaFree(d_xyz);
         }
+        if (near_cnt)
+            for (int i = 0; i < n; i++) {
+                int cnt = 0;
+                for (int k = 0; k < 5; k++)
+                    if (ids[(size_t)i * 5 + k] >= 0) cnt++;
+                near_cnt[i] = cnt;
+            }
     }
     if (selected) CU(cudaMemcpy(selected, c->d_selected, (size_t)n, cudaMemcpyDeviceToHost));
     if (normvec) CU(cudaMemcpy(normvec, c->d_normvec, (size_t)n * 16, cudaMemcpyDeviceToHost));

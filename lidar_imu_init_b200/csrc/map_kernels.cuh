@@ -437,6 +437,17 @@ __global__ void k_map_delete_boxes(MapDev M, unsigned slots, const float* __rest
     }
 }
 
+// neighbour ids (pool offsets, -1 = missing) -> packed xyz, so that downloads never ship the pool itself
+__global__ void k_gather_xyz(const float4* __restrict__ pool, const int* __restrict__ ids, long long n, float* __restrict__ out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int id = ids[i];
+    float4 q = (id >= 0) ? pool[id] : make_float4(0.f, 0.f, 0.f, 0.f);
+    out[3 * i] = q.x;
+    out[3 * i + 1] = q.y;
+    out[3 * i + 2] = q.z;
+}
+
 // ---- flatten -------------------------------------------------------------------------------------
 __global__ void k_map_flatten(MapDev M, unsigned slots, float* __restrict__ out, int cap, int* __restrict__ out_n) {
     int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;

@@ -75,6 +75,14 @@ int liinit_map_nearest_search(liinit_ctx* h, const float* q_xyz, int stride_floa
 /* per-scan hot path (replaces laserMapping.cpp:936-1080) ---------------------------- */
 /* feats_down_body (laserMapping.cpp:917-919): once per scan; resets selection flags / neighbour lists. */
 int liinit_scan_upload(liinit_ctx* h, const float* body_xyz, int stride_floats, int n);
+/* Same role, without the staging copy: body_xyz must be page-locked host memory the device can address (cudaHostAlloc,
+ * cudaHostRegister, a pinned torch tensor). Nothing is transferred by this call: the search kernel of the next
+ * liinit_icp_iterate pass reads the coordinates over PCIe itself and leaves the packed copy in HBM for the later
+ * passes of the scan (any other consumer triggers the copy first). The buffer must stay valid and unmodified until
+ * that first pass (or liinit_scan_update / liinit_map_incremental / liinit_scan_download_body) has returned; with
+ * liinit_icp_iterate_device, until the work queued on the stream has completed.
+ * LIINIT_ERR_INVALID when the pointer is not device-addressable page-locked memory. */
+int liinit_scan_attach_host(liinit_ctx* h, const float* pinned_body_xyz, int stride_floats, int n);
 /* ---- raw-scan front end: raw points -> undistort -> voxel grid -> resident scan ---- */
 /* Stage a raw cloud on the device. time_index: float index of the per-point time offset in MILLISECONDS inside a point
  * (9 = PointType.curvature, src/preprocess.cpp), or -1 when there is none. */

@@ -33,7 +33,7 @@ _i32 = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 
 SYMBOLS = [
     "liinit_create", "liinit_destroy", "liinit_last_error", "liinit_set_stream", "liinit_map_build", "liinit_map_add_points", "liinit_map_delete_boxes",
-    "liinit_map_validnum", "liinit_map_size", "liinit_map_download", "liinit_map_nearest_search", "liinit_scan_upload", "liinit_scan_upload_raw", "liinit_scan_download_body", "liinit_raw_upload", "liinit_raw_undistort_cv", "liinit_raw_undistort_imu",
+    "liinit_map_validnum", "liinit_map_size", "liinit_map_download", "liinit_map_nearest_search", "liinit_scan_upload", "liinit_scan_attach_host", "liinit_scan_upload_raw", "liinit_scan_download_body", "liinit_raw_upload", "liinit_raw_undistort_cv", "liinit_raw_undistort_imu",
     "liinit_raw_download", "liinit_raw_downsample",
     "liinit_icp_iterate", "liinit_icp_iterate_device", "liinit_scan_download_effect", "liinit_scan_download_state",
     "liinit_map_incremental", "liinit_last_pass_timing", "liinit_last_pass_kernel_times", "liinit_launch_count", "liinit_map_stats",
@@ -69,6 +69,7 @@ def load():
     L.liinit_map_download.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int)]
     L.liinit_map_nearest_search.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, vp, vp, vp]
     L.liinit_scan_upload.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.liinit_scan_attach_host.argtypes = [vp, vp, C.c_int, C.c_int]
     L.liinit_scan_upload_raw.argtypes = [vp, vp, C.c_int, C.c_int, C.c_float, C.POINTER(C.c_int)]
     L.liinit_raw_upload.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int]
     L.liinit_raw_undistort_cv.argtypes = [vp, _f64, _f64, _f64]
@@ -232,6 +233,11 @@ class LiInitGpu:
     def scan_upload_ptr(self, host_ptr: int, stride: int, n: int):
         """Upload from a raw host pointer (e.g. pinned torch tensor)."""
         self._ck(self.L.liinit_scan_upload(self.h, C.c_void_p(host_ptr), stride, n))
+        self.scan_n = n
+
+    def scan_attach_ptr(self, host_ptr: int, stride: int, n: int):
+        """Zero-copy variant: `host_ptr` is page-locked memory the first search pass reads over PCIe (see the header)."""
+        self._ck(self.L.liinit_scan_attach_host(self.h, C.c_void_p(host_ptr), stride, n))
         self.scan_n = n
 
     def icp_iterate(self, rot_end, pos_end, R_LI, T_LI, imu_en: bool, search: bool):

@@ -41,7 +41,7 @@ struct PoseD {
 
 // Per-scan device state: the globals of laserMapping.cpp:102-125 the path touches.
 struct ScanDev {
-    const float4* body;     // feats_down_body (xyz, w unused)
+    float4* body;           // feats_down_body (xyz, w unused)
     float4* world;          // feats_down_world
     int* near_ids;          // [N*5] pool offsets, -1 = missing (Nearest_Points)
     unsigned char* selected;  // point_selected_surf

@@ -49,6 +49,9 @@ public:
     }
     // feats_down_body upload (laserMapping.cpp:917-919)
     void UploadScan(const PointVector& body) { ck(liinit_scan_upload(h_, fptr(body), stride(), (int)body.size())); }
+    // body must live in page-locked memory (cudaHostRegister on the vector's storage) and stay untouched until the
+    // first search pass of the scan has returned: the search kernel reads it in place, no staging copy.
+    void AttachScan(const PointVector& body) { ck(liinit_scan_attach_host(h_, fptr(body), stride(), (int)body.size())); }
 
 private:
     static int stride() { return (int)(sizeof(PointT) / sizeof(float)); }

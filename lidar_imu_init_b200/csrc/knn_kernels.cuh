@@ -255,8 +255,13 @@ __device__ __forceinline__ void knn5_lockstep(const MapDev& M, float rho2, bool 
 }
 
 // ---- search kernel of an ICP pass: world transform + 5-NN for every scan point -----------------------
-template <int G>
-__global__ void __launch_bounds__(LI_KNN_THREADS, LI_KNN_MIN_BLOCKS) k_knn_scan(MapDev M, ScanDev S, PoseD P, float rho2) {
+// HOST = true: the scan has not been copied yet -- `raw` is a device-visible alias of the caller's page-locked host
+// buffer (liinit_scan_attach_host) and the kernel pulls the coordinates over PCIe itself (one contiguous
+// Q*stride*4-byte read per warp batch, hidden behind the other warps' searches), leaving the packed copy in
+// S.body for the plane kernel and the later passes. No staging copy, no repack launch in front of the search.
+template <int G, bool HOST>
+__global__ void __launch_bounds__(LI_KNN_THREADS, LI_KNN_MIN_BLOCKS)
+k_knn_scan(MapDev M, ScanDev S, PoseD P, float rho2, const float* __restrict__ raw, int stride) {
     constexpr int Q = Grp<G>::Q;
     const int lane = threadIdx.x & 31;
     const int gl = lane % G, gid = lane / G, gbase = gid * G;
@@ -266,7 +271,23 @@ __global__ void __launch_bounds__(LI_KNN_THREADS, LI_KNN_MIN_BLOCKS) k_knn_scan(
         const int q = qb + gid;
         const bool valid = q < S.n;
         float wx = 0.f, wy = 0.f, wz = 0.f;
-        if (valid) {
+        if (HOST) {
+            float bx = 0.f, by = 0.f, bz = 0.f;
+            if (G >= 4) {   // lanes 0..2 of the group fetch x, y, z: the warp's addresses are contiguous for stride 3
+                float v = 0.f;
+                if (valid && gl < 3) v = raw[(size_t)q * stride + gl];
+                bx = __shfl_sync(LI_FULL, v, gbase);
+                by = __shfl_sync(LI_FULL, v, gbase + 1);
+                bz = __shfl_sync(LI_FULL, v, gbase + 2);
+            } else if (valid) {
+                const float* s = raw + (size_t)q * stride;
+                bx = s[0]; by = s[1]; bz = s[2];
+            }
+            if (valid) {
+                if (gl == 0) S.body[q] = make_float4(bx, by, bz, 0.f);
+                li_body_to_world(P, bx, by, bz, wx, wy, wz);
+            }
+        } else if (valid) {
             float4 b = __ldg(&S.body[q]);
             li_body_to_world(P, b.x, b.y, b.z, wx, wy, wz);
         }

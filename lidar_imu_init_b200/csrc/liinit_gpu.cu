@@ -68,6 +68,8 @@ struct Ctx {
     float4* d_normvec = nullptr;
     int scan_n = 0;
     bool have_neighbors = false;
+    const float* attached = nullptr;   // device alias of a page-locked host scan not copied yet (liinit_scan_attach_host)
+    int attached_stride = 0;
     // reduction
     double* d_partials = nullptr;
     unsigned* d_done = nullptr;
@@ -188,13 +190,26 @@ void fill_pose(PoseD& P, const double* R, const double* p, const double* RLI, co
     memcpy(P.TLI, TLI, 24);
 }
 
+// An attached host scan that something other than the search kernel needs: pull it into d_body now.
+void materialize_scan(Ctx* c) {
+    if (!c->attached) return;
+    k_repack<<<nblk(c->scan_n, 256), 256, 0, c->stream>>>(c->attached, c->attached_stride, c->scan_n, c->d_body);
+    c->launches++;
+    c->attached = nullptr;
+}
+
 template <int G>
 void launch_knn_scan(Ctx* c, const PoseD& P) {
     long long threads = (long long)c->scan_n * G;
     int grid = nblk(threads, LI_KNN_THREADS);
     int cap = c->max_blocks * (256 / LI_KNN_THREADS);
     if (grid > cap) grid = cap;
-    k_knn_scan<G><<<grid, LI_KNN_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2);
+    if (c->attached) {
+        k_knn_scan<G, true><<<grid, LI_KNN_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, c->attached, c->attached_stride);
+        c->attached = nullptr;   // the kernel leaves the packed copy in d_body
+    } else {
+        k_knn_scan<G, false><<<grid, LI_KNN_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, nullptr, 0);
+    }
 }
 
 #ifndef LI_PLANE_WAVES
@@ -205,6 +220,7 @@ constexpr int TPQ_CH = 32, TPQ_NB = 8;
 constexpr size_t TPQ_SMEM = 4 * TpqCfg<TPQ_CH, TPQ_NB>::WARP_TILE_F4 * sizeof(float4);
 
 void launch_knn_scan_tpq(Ctx* c, const PoseD& P) {
+    materialize_scan(c);
     int grid = nblk(c->scan_n, 128);
     int cap = c->num_sms * 12;
     if (grid > cap) grid = cap;
@@ -604,6 +620,7 @@ int liinit_scan_upload(liinit_ctx* h, const float* body, int stride, int n) {
     Ctx* c = &h->c;
     CU(cudaSetDevice(c->device));
     if (n > c->cfg.max_scan_points) return fail(c, LIINIT_ERR_CAPACITY, "n exceeds max_scan_points");
+    c->attached = nullptr;
     if (stride == 4) {
         CU(cudaMemcpyAsync(c->d_body, body, (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
     } else if (stride == 3 || stride == 12) {
@@ -622,6 +639,27 @@ int liinit_scan_upload(liinit_ctx* h, const float* body, int stride, int n) {
     c->S.n = n;
     c->have_neighbors = false;
     CU(cudaGetLastError());
+    return LIINIT_OK;
+}
+
+int liinit_scan_attach_host(liinit_ctx* h, const float* pinned_body, int stride, int n) {
+    if (!h || !pinned_body || n <= 0) return LIINIT_ERR_INVALID;
+    Ctx* c = &h->c;
+    CU(cudaSetDevice(c->device));
+    if (n > c->cfg.max_scan_points) return fail(c, LIINIT_ERR_CAPACITY, "n exceeds max_scan_points");
+    if (stride != 3 && stride != 4 && stride != 12) return fail(c, LIINIT_ERR_INVALID, "stride_floats must be 3, 4 or 12");
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, pinned_body) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) {
+        cudaGetLastError();
+        return fail(c, LIINIT_ERR_INVALID, "scan_attach_host needs page-locked, device-mapped host memory (cudaHostAlloc / cudaHostRegister)");
+    }
+    c->attached = (const float*)at.devicePointer;
+    c->attached_stride = stride;
+    CU(cudaMemsetAsync(c->d_selected, 0, (size_t)n, c->stream));
+    CU(cudaMemsetAsync(c->d_near_ids, 0xff, (size_t)n * 5 * sizeof(int), c->stream));
+    c->scan_n = n;
+    c->S.n = n;
+    c->have_neighbors = false;
     return LIINIT_OK;
 }
 
@@ -754,6 +792,7 @@ int liinit_raw_downsample(liinit_ctx* h, float leaf_size, int* n_down) {
     c->scan_n = m;
     c->S.n = m;
     c->have_neighbors = false;
+    c->attached = nullptr;
     if (n_down) *n_down = m;
     return LIINIT_OK;
 }
@@ -771,6 +810,7 @@ int liinit_scan_download_body(liinit_ctx* h, float* xyz, int cap, int* n) {
     *n = c->scan_n;
     int m = c->scan_n < cap ? c->scan_n : cap;
     if (m > 0 && xyz) {
+        materialize_scan(c);
         std::vector<float4> b(m);
         CU(cudaStreamSynchronize(c->stream));
         CU(cudaMemcpy(b.data(), c->d_body, (size_t)m * 16, cudaMemcpyDeviceToHost));
@@ -882,6 +922,7 @@ int liinit_map_incremental(liinit_ctx* h, const double* R, const double* p, cons
     CU(cudaSetDevice(c->device));
     int n = c->scan_n;
     if (n <= 0) return fail(c, LIINIT_ERR_INVALID, "no scan uploaded");
+    materialize_scan(c);
     PoseD P;
     fill_pose(P, R, p, RLI, TLI);
     static const int zeros[2] = {0, 0};

@@ -141,11 +141,21 @@ class OracleMap:
         b = _c32(boxes).reshape(-1, 6)
         return self.L.oracle_map_delete_boxes(self.h, b, len(b)) if len(b) else 0
 
+    def _settled(self, fn):
+        # the verbatim ikd-Tree answers -1 while its rebuild thread holds the tree (ikd_Tree.cpp:71-88,120-137): ask again
+        import time
+        for _ in range(2000):
+            v = fn(self.h)
+            if v >= 0:
+                return v
+            time.sleep(0.002)
+        return v
+
     def size(self):
-        return self.L.oracle_map_size(self.h)
+        return self._settled(self.L.oracle_map_size)
 
     def validnum(self):
-        return self.L.oracle_map_validnum(self.h)
+        return self._settled(self.L.oracle_map_validnum)
 
     def flatten(self):
         n = self.L.oracle_map_flatten(self.h, np.zeros((1, 3), np.float32), 0)

@@ -29,3 +29,22 @@ ti2 = []
 for _ in range(30):
     t1 = time.perf_counter(); g.icp_iterate(p.rot_end, p.pos_end, p.R_LI, p.T_LI, False, True); ti2.append(time.perf_counter() - t1)
 print(f"resident iterate call {1e6*np.median(ti2):.1f} us (kernel {1e3*g.last_pass_timing()[0]:.1f} us)")
+
+# ---- zero-copy attach vs staged upload, end to end (host call -> accumulators back on the host) -----------------
+body3 = torch.from_numpy(np.ascontiguousarray(c["body_xyz"])).pin_memory()
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+def run(mode, stride, buf):
+    ts, ks = [], []
+    for i in range(25):
+        flush.zero_(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        (g.scan_attach_ptr if mode == "attach" else g.scan_upload_ptr)(buf.data_ptr(), stride, N)
+        g.icp_iterate(p.rot_end, p.pos_end, p.R_LI, p.T_LI, False, True)
+        t1 = time.perf_counter()
+        if i >= 5:
+            ts.append(t1 - t0); ks.append(g.last_pass_timing()[0])
+    return 1e3 * np.median(ts), np.median(ks)
+for mode in ("upload", "attach", "upload", "attach"):
+    for stride, buf in ((3, body3), (4, body4)):
+        t, k = run(mode, stride, buf)
+        print(f"e2e {mode:6s} stride {stride}: wall {t:.4f} ms | device pass {k:.4f} ms")

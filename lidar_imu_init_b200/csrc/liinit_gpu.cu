@@ -73,8 +73,8 @@ struct Ctx {
     // reduction
     double* d_partials = nullptr;
     unsigned* d_done = nullptr;
-    double* d_out = nullptr;    // 160
-    double* h_out = nullptr;    // pinned 160
+    double* h_out = nullptr;    // pinned + mapped 160
+    double* h_out_dev = nullptr;   // its device alias
     int max_blocks = 0;
     // knn query scratch
     float* d_q_d2 = nullptr;
@@ -228,14 +228,17 @@ void launch_knn_scan_tpq(Ctx* c, const PoseD& P) {
 }
 
 template <bool IMU, bool SEARCH>
-void launch_plane(Ctx* c, const PoseD& P) {
+void launch_plane(Ctx* c, const PoseD& P, double* out) {
     // one wave of 256-thread blocks (2 resident per SM at ~100-130 registers), grid-stride over the scan
     int grid = nblk(c->scan_n, 256);
     if (grid > c->num_sms * 2 * LI_PLANE_WAVES) grid = c->num_sms * 2 * LI_PLANE_WAVES;
-    k_icp_plane<IMU, SEARCH><<<grid, 256, 0, c->stream>>>(c->M, c->S, P, c->d_partials, c->d_done, c->d_out);
+    k_icp_plane<IMU, SEARCH><<<grid, 256, 0, c->stream>>>(c->M, c->S, P, c->d_partials, c->d_done, out);
 }
 
-int run_pass(Ctx* c, const double* R, const double* p, const double* RLI, const double* TLI, int imu_en, int search) {
+// out: where the last block of the plane kernel leaves the 160-double result block -- the caller's device buffer
+// (liinit_icp_iterate_device) or the device alias of the context's page-locked host block (liinit_icp_iterate: the
+// kernel writes the 1.28 kB over PCIe itself, no copy operation behind it).
+int run_pass(Ctx* c, const double* R, const double* p, const double* RLI, const double* TLI, int imu_en, int search, double* out) {
     if (c->scan_n <= 0) return fail(c, LIINIT_ERR_INVALID, "no scan uploaded");
     if (!search && !c->have_neighbors) return fail(c, LIINIT_ERR_INVALID, "reuse pass before any search pass");
     PoseD P;
@@ -251,13 +254,13 @@ int run_pass(Ctx* c, const double* R, const double* p, const double* RLI, const 
             default: launch_knn_scan<4>(c, P); break;
         }
         CU(cudaEventRecord(c->evm, c->stream));
-        if (imu_en) launch_plane<true, true>(c, P); else launch_plane<false, true>(c, P);
+        if (imu_en) launch_plane<true, true>(c, P, out); else launch_plane<false, true>(c, P, out);
         c->have_neighbors = true;
         c->launches += 2;
         c->last_launches = 2;
         c->last_was_search = true;
     } else {
-        if (imu_en) launch_plane<true, false>(c, P); else launch_plane<false, false>(c, P);
+        if (imu_en) launch_plane<true, false>(c, P, out); else launch_plane<false, false>(c, P, out);
         c->launches += 1;
         c->last_launches = 1;
         c->last_was_search = false;
@@ -397,8 +400,8 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
     c->max_blocks = c->num_sms * 16;
     CUC(cudaMalloc(&c->d_partials, (size_t)c->max_blocks * 96 * sizeof(double)));
     CUC(cudaMalloc(&c->d_done, sizeof(unsigned)));
-    CUC(cudaMalloc(&c->d_out, 160 * sizeof(double)));
-    CUC(cudaMallocHost(&c->h_out, 160 * sizeof(double)));
+    CUC(cudaHostAlloc(&c->h_out, 160 * sizeof(double), cudaHostAllocMapped));
+    CUC(cudaHostGetDevicePointer((void**)&c->h_out_dev, c->h_out, 0));
     CUC(cudaMemsetAsync(c->d_done, 0, sizeof(unsigned), c->stream));
     CUC(cudaMemsetAsync(c->d_counters, 0, sizeof(int) * CNT_COUNT, c->stream));
     CUC(cudaMemsetAsync(M.pool_top, 0, sizeof(unsigned long long), c->stream));
@@ -426,7 +429,7 @@ int liinit_destroy(liinit_ctx* h) {
     cudaFree(c->d_counters); cudaFreeHost(c->h_counters); cudaFree(c->d_stage_raw); cudaFree(c->d_stage_pts);
     cudaFree(c->d_slot_of); cudaFree(c->d_vslot_of); cudaFree(c->d_flag); cudaFree(c->d_ins); cudaFree(c->V.keys); cudaFree(c->V.head); cudaFree(c->d_vg_imin); cudaFree(c->d_vg_block); cudaFree(c->d_vg_misc); cudaFree(c->d_rs_keys); cudaFree(c->d_rs_vals); cudaFree(c->d_rs_hist); cudaFree(c->d_vg_params); cudaFree(c->d_tmin_idx); cudaFree(c->d_poses);
     cudaFree(c->d_body); cudaFree(c->d_world); cudaFree(c->d_near_ids); cudaFree(c->d_selected); cudaFree(c->d_normvec);
-    cudaFree(c->d_partials); cudaFree(c->d_done); cudaFree(c->d_out); cudaFreeHost(c->h_out); cudaFree(c->d_q_d2);
+    cudaFree(c->d_partials); cudaFree(c->d_done); cudaFreeHost(c->h_out); cudaFree(c->d_q_d2);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->evm) cudaEventDestroy(c->evm);
@@ -826,10 +829,7 @@ int liinit_icp_iterate_device(liinit_ctx* h, const double* R, const double* p, c
     if (!h || !R || !p || !RLI || !TLI || !d_out160) return LIINIT_ERR_INVALID;
     Ctx* c = &h->c;
     CU(cudaSetDevice(c->device));
-    int r = run_pass(c, R, p, RLI, TLI, imu_en, search);
-    if (r) return r;
-    CU(cudaMemcpyAsync(d_out160, c->d_out, 160 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-    return LIINIT_OK;
+    return run_pass(c, R, p, RLI, TLI, imu_en, search, d_out160);
 }
 
 int liinit_icp_iterate(liinit_ctx* h, const double* R, const double* p, const double* RLI, const double* TLI, int imu_en,
@@ -837,9 +837,8 @@ int liinit_icp_iterate(liinit_ctx* h, const double* R, const double* p, const do
     if (!h || !R || !p || !RLI || !TLI || !HtH || !Htr || !m) return LIINIT_ERR_INVALID;
     Ctx* c = &h->c;
     CU(cudaSetDevice(c->device));
-    int r = run_pass(c, R, p, RLI, TLI, imu_en, search);
+    int r = run_pass(c, R, p, RLI, TLI, imu_en, search, c->h_out_dev);
     if (r) return r;
-    CU(cudaMemcpyAsync(c->h_out, c->d_out, 160 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     memcpy(HtH, c->h_out, 144 * sizeof(double));
     memcpy(Htr, c->h_out + 144, 12 * sizeof(double));

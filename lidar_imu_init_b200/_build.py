@@ -2,6 +2,7 @@
 
   libliinit_gpu.so   CUDA kernels + C-ABI (include/liinit_gpu.h)       -- nvcc
   libliinit_host.so  host-side IESKF / per-scan driver over the C-ABI   -- g++ (see csrc/host)
+  libliinit_calib.so LI-Init batch initialisation, host only (include/liinit_calib.h) -- g++ (see csrc/calib)
 """
 from __future__ import annotations
 
@@ -13,6 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 GPU_LIB = os.path.join(HERE, "libliinit_gpu.so")
 HOST_LIB = os.path.join(HERE, "libliinit_host.so")
+CALIB_LIB = os.path.join(HERE, "libliinit_calib.so")
 
 # --fmad=false: the fp32 distances and the fp64 plane / Jacobian arithmetic follow the reference's x86-64
 # build (-O3, no -march => no FMA contraction, CMakeLists.txt:8), so f32 outputs are bit-comparable with the oracle.
@@ -67,9 +69,20 @@ def build_host(force: bool = False) -> str | None:
     return HOST_LIB
 
 
+def build_calib(force: bool = False) -> str:
+    src = os.path.join(CSRC, "calib", "li_calib.cpp")
+    inc = os.path.join(HERE, "..", "include")
+    if force or _newer(CALIB_LIB, [src, os.path.join(inc, "liinit_calib.h")]):
+        gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        # no FMA contraction: the filters follow the reference's x86-64 arithmetic operation by operation
+        subprocess.check_call([gxx, "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-I", inc, "-o", CALIB_LIB, src])
+    return CALIB_LIB
+
+
 def build_all(force: bool = False):
     build_gpu(force)
     build_host(force)
+    build_calib(force)
 
 
 if __name__ == "__main__":

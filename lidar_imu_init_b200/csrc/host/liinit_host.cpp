@@ -3,6 +3,7 @@
 
 #include <cmath>
 #include <cstring>
+#include <vector>
 
 namespace {
 
@@ -205,6 +206,36 @@ int liinit_scan_update(liinit_ctx* h, liinit_state* state, int max_iter, int imu
     }
     if (stats) *stats = st;
     return LIINIT_OK;
+}
+
+void liinit_propagate_cv(liinit_state* s, double dt, const double* cov_gyr_scale, const double* cov_acc_scale) {
+    // F is the identity except three 3x3 blocks, so F cov F^T touches rows / columns 0:6 only:
+    //   rows 0:3 <- E rows 0:3 + dt rows 15:18 ; rows 3:6 <- rows 3:6 + dt rows 12:15 ; then the same on the columns.
+    double w[3] = {-s->bias_g[0] * dt, -s->bias_g[1] * dt, -s->bias_g[2] * dt}, E[9];
+    liinit_so3_exp(w, E);
+    std::vector<double> T(D * D);
+    double* P = s->cov;
+    for (int c = 0; c < D; c++) {
+        for (int r = 0; r < D; r++) T[r * D + c] = P[r * D + c];
+        for (int r = 0; r < 3; r++)
+            T[r * D + c] = E[3 * r] * P[0 * D + c] + E[3 * r + 1] * P[1 * D + c] + E[3 * r + 2] * P[2 * D + c] + dt * P[(15 + r) * D + c];
+        for (int r = 0; r < 3; r++) T[(3 + r) * D + c] = P[(3 + r) * D + c] + dt * P[(12 + r) * D + c];
+    }
+    for (int r = 0; r < D; r++) {
+        for (int c = 0; c < D; c++) P[r * D + c] = T[r * D + c];
+        for (int c = 0; c < 3; c++)
+            P[r * D + c] = T[r * D + 0] * E[3 * c] + T[r * D + 1] * E[3 * c + 1] + T[r * D + 2] * E[3 * c + 2] + dt * T[r * D + 15 + c];
+        for (int c = 0; c < 3; c++) P[r * D + 3 + c] = T[r * D + 3 + c] + dt * T[r * D + 12 + c];
+    }
+    for (int i = 0; i < 3; i++) {
+        P[(15 + i) * D + 15 + i] += cov_gyr_scale[i] * dt * dt;
+        P[(12 + i) * D + 12 + i] += cov_acc_scale[i] * dt * dt;
+    }
+    double wf[3] = {s->bias_g[0] * dt, s->bias_g[1] * dt, s->bias_g[2] * dt}, Ef[9], R[9];
+    liinit_so3_exp(wf, Ef);
+    mul33(s->rot_end, Ef, R);
+    std::memcpy(s->rot_end, R, sizeof(R));
+    for (int i = 0; i < 3; i++) s->pos_end[i] += s->vel_end[i] * dt;
 }
 
 int liinit_fov_segment(const double* pos, double cube_len, double det_range, float* box, int* initialized, float* out) {

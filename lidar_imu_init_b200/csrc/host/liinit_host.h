@@ -59,6 +59,13 @@ int liinit_ieskf_update(liinit_state* state, const liinit_state* state_propagat,
  * state: in = propagated prior (state_propagat = state, :910), out = posterior. */
 int liinit_scan_update(liinit_ctx* h, liinit_state* state, int max_iteration, int imu_en, liinit_scan_stats* stats);
 
+/* State propagation of the LiDAR-only (constant-velocity) mode, ImuProcess::Forward_propagation_without_imu without its
+ * point loop (src/IMU_Processing.hpp:212-243; the loop :246-266 is liinit_raw_undistort_cv): bias_g stands for the
+ * angular velocity, vel_end for the linear velocity. cov <- F cov F^T + Q with F[0:3,0:3] = Exp(-bias_g dt),
+ * F[0:3,15:18] = F[3:6,12:15] = I dt, Q[15:18] = cov_gyr_scale dt^2, Q[12:15] = cov_acc_scale dt^2; then
+ * rot_end <- rot_end Exp(bias_g dt), pos_end += vel_end dt. dt: scan-to-scan time (0.1 for the first frame, :217-223). */
+void liinit_propagate_cv(liinit_state* s, double dt, const double cov_gyr_scale[3], const double cov_acc_scale[3]);
+
 /* lasermap_fov_segment (laserMapping.cpp:260-305): keeps a cube_len-sized local map box around the LiDAR and, when the
  * LiDAR comes within MOV_THRESHOLD*det_range of a face, shifts the box and returns the slabs that fell out of it
  * (cub_needrm) -- the boxes to hand to liinit_map_delete_boxes. local_box: {min xyz, max xyz}, state kept by the caller;

@@ -36,6 +36,8 @@ def load():
     L.liinit_ieskf_update.argtypes = [_f64, _f64, _f64, _f64, _f64, C.c_void_p]
     L.liinit_scan_update.restype = C.c_int
     L.liinit_scan_update.argtypes = [C.c_void_p, _f64, C.c_int, C.c_int, C.POINTER(ScanStats)]
+    L.liinit_propagate_cv.restype = None
+    L.liinit_propagate_cv.argtypes = [_f64, C.c_double, _f64, _f64]
     L.liinit_fov_segment.restype = C.c_int
     L.liinit_fov_segment.argtypes = [_f64, C.c_double, C.c_double, np.ctypeslib.ndpointer(dtype=np.float32, flags='C_CONTIGUOUS'), C.POINTER(C.c_int),
                                      np.ctypeslib.ndpointer(dtype=np.float32, flags='C_CONTIGUOUS')]
@@ -83,6 +85,15 @@ def ieskf_update(state, state_prop, HtH, Htr):
     if rc != 0:
         raise RuntimeError("liinit_ieskf_update failed (singular covariance?)")
     return s, sol, KH
+
+
+def propagate_cv(state, dt, cov_gyr_scale=0.1, cov_acc_scale=0.1):
+    """Constant-velocity propagation of the LiDAR-only mode (IMU_Processing.hpp:212-243); covariance scales as
+    mapping/gyr_cov, mapping/acc_cov (laserMapping.cpp:776-777,833-834)."""
+    s = np.ascontiguousarray(state, np.float64).copy()
+    load().liinit_propagate_cv(s, float(dt), np.full(3, cov_gyr_scale, np.float64) if np.isscalar(cov_gyr_scale) else np.ascontiguousarray(cov_gyr_scale, np.float64),
+                               np.full(3, cov_acc_scale, np.float64) if np.isscalar(cov_acc_scale) else np.ascontiguousarray(cov_acc_scale, np.float64))
+    return s
 
 
 def scan_update(gpu: capi.LiInitGpu, state, max_iteration=5, imu_en=False):

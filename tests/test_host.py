@@ -65,3 +65,31 @@ def test_fov_segment_follows_reference_logic(host_lib):
     assert np.allclose(seg.box, [-500 + mov, -500, -500, 500 + mov, 500, 500])
     b2 = seg.update([360.0, -370.0, 0.0])                                # now near the -y face
     assert len(b2) == 1 and np.allclose(b2[0], [-185, 500 - mov, -500, 815, 500, 500])
+
+
+def test_propagate_cv_matches_dense_formula():
+    """liinit_propagate_cv vs F cov F^T + Q written out densely (IMU_Processing.hpp:225-243)."""
+    from lidar_imu_init_b200 import host
+    from lidar_imu_init_b200.scenes import so3_exp
+    rng = np.random.default_rng(3)
+    s = host.state_init()
+    A = rng.standard_normal((24, 24))
+    cov = A @ A.T * 1e-2 + np.eye(24) * 1e-3
+    s[36:] = cov.reshape(-1)
+    s[0:9] = so3_exp(np.array([0.2, -0.1, 0.4])).reshape(9)
+    s[9:12] = [1.0, 2.0, 3.0]
+    s[24:27] = [0.3, -0.2, 0.1]       # vel_end
+    s[27:30] = [0.2, -0.4, 0.7]       # bias_g = angular velocity in the CV model
+    dt = 0.07
+    F = np.eye(24)
+    F[0:3, 0:3] = so3_exp(-s[27:30] * dt)
+    F[0:3, 15:18] = np.eye(3) * dt
+    F[3:6, 12:15] = np.eye(3) * dt
+    Q = np.zeros((24, 24))
+    Q[15:18, 15:18] = np.diag([0.1, 0.2, 0.3]) * dt * dt
+    Q[12:15, 12:15] = np.diag([0.4, 0.5, 0.6]) * dt * dt
+    o = host.propagate_cv(s, dt, np.array([0.1, 0.2, 0.3]), np.array([0.4, 0.5, 0.6]))
+    assert np.allclose(o[36:].reshape(24, 24), F @ cov @ F.T + Q, rtol=1e-13, atol=1e-15)
+    assert np.allclose(o[0:9].reshape(3, 3), s[0:9].reshape(3, 3) @ so3_exp(s[27:30] * dt), atol=1e-15)
+    assert np.allclose(o[9:12], s[9:12] + s[24:27] * dt)
+    assert np.array_equal(o[12:36], s[12:36])

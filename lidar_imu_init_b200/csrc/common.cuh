@@ -73,6 +73,24 @@ __device__ __forceinline__ float li_dist2(float ax, float ay, float az, float bx
     return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
+// Same value, two issue slots fewer: the x and y lanes go through Blackwell's packed fp32 pipe (sub.f32x2 / mul.f32x2 ->
+// FADD2 / FMUL2 on sm_100a; each half is an IEEE round-to-nearest operation, so the result is bit-identical to li_dist2).
+// qxy = {qx, qy} packed by li_pack_f32x2; p.x, p.y arrive adjacent from the 16-byte slab load, so the packing is free.
+__device__ __forceinline__ unsigned long long li_pack_f32x2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float li_dist2_packed(unsigned long long qxy, float qz, const float4& p) {
+    unsigned long long pxy = li_pack_f32x2(p.x, p.y), dxy, sq;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(dxy) : "l"(qxy), "l"(pxy));
+    asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(sq) : "l"(dxy));
+    float sx, sy;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(sx), "=f"(sy) : "l"(sq));
+    float dz = __fsub_rn(qz, p.z);
+    return __fadd_rn(__fadd_rn(sx, sy), __fmul_rn(dz, dz));
+}
+
 // Lookup only (searches). Returns true and (first,count) when the brick exists.
 __device__ __forceinline__ bool li_brick_find(const uint4* __restrict__ ent, unsigned mask, unsigned long long key,
                                               unsigned& first, unsigned& count) {

@@ -19,7 +19,7 @@
 #include "common.cuh"
 
 #ifndef LI_KNN_U
-#define LI_KNN_U 4           // slab loads issued back to back per lane before the distances are evaluated
+#define LI_KNN_U 3           // slab loads issued back to back per lane before the distances are evaluated
 #endif
 #ifndef LI_KNN_THREADS
 #define LI_KNN_THREADS 128
@@ -103,6 +103,87 @@ __device__ __forceinline__ void group_merge(const float (&ld)[5], const int (&li
 // Lockstep scan of one slab per group (cnt = 0 for idle groups). U loads are issued back to back before any distance
 // is evaluated and the NEXT batch is already in flight while the current one is processed (double buffering), so the
 // L2 round trips overlap with the arithmetic. One compare per candidate: tau = min(thr, 5+, lane's 5th best).
+//
+// Shape of the loop (from the SASS of the first version, profiles/r01_knn_scan_source_lines_final.txt: 64-bit address
+// arithmetic per load, three padding moves per candidate and twelve register moves per iteration to rotate the
+// buffers made up a third of the loop):
+//   * one running pointer per lane, the 2U loads of a round use constant offsets from it;
+//   * out-of-range slots are not padded: the load is predicated (the register keeps an old, finite point) and the
+//     range test is folded into the candidate's single compare;
+//   * the two buffers swap roles by unrolling the loop twice instead of being copied.
+#ifndef LI_SCAN_V2
+#define LI_SCAN_V2 1
+#endif
+#ifndef LI_GROUP_BOUND
+#define LI_GROUP_BOUND 0
+#endif
+#ifndef LI_DIST_PACKED
+#define LI_DIST_PACKED 1
+#endif
+#if LI_SCAN_V2
+// a float the compiler must treat as defined but that costs no instruction (contents: whatever the register held)
+__device__ __forceinline__ float li_stale_float() {
+    float v;
+    asm("" : "=f"(v));
+    return v;
+}
+template <int G, int U = LI_KNN_U>
+__device__ __forceinline__ void group_scan_pipelined(const float4* __restrict__ pool, unsigned f, unsigned cnt, float qx, float qy, float qz,
+                                                     float thr, float (&ld)[5], int (&li)[5], int gl) {
+    const float cap5 = __uint_as_float(0x40a00001u);   // smallest float above 5: d <= 5 <=> d < cap5
+    const float thr5 = fminf(thr, cap5);
+    float tau = fminf(thr5, ld[4]);
+    const unsigned long long qxy = li_pack_f32x2(qx, qy);
+    const float4* __restrict__ ptr = pool + f + gl;    // this lane's first candidate of the slab
+    int id = (int)f + gl;
+    int rem = (int)cnt - gl;                            // candidates left for this lane's column, in units of slab slots
+    float4 a[U], b[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {   // slots never loaded are never used: their compare is masked by the range test
+        a[u] = make_float4(li_stale_float(), li_stale_float(), li_stale_float(), 0.f);
+        b[u] = make_float4(li_stale_float(), li_stale_float(), li_stale_float(), 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++)
+        if (u * G < rem) a[u] = __ldg(ptr + u * G);
+    while (__any_sync(LI_FULL, rem > 0)) {
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            if ((U + u) * G < rem) b[u] = __ldg(ptr + (U + u) * G);
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+#if LI_DIST_PACKED
+            float d = li_dist2_packed(qxy, qz, a[u]);
+#else
+            float d = li_dist2(qx, qy, qz, a[u].x, a[u].y, a[u].z);
+#endif
+            if (d < tau && u * G < rem) {
+                local_insert(ld, li, d, id + u * G);
+                tau = fminf(thr5, ld[4]);
+            }
+        }
+        if (!__any_sync(LI_FULL, rem > U * G)) break;
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            if ((2 * U + u) * G < rem) a[u] = __ldg(ptr + (2 * U + u) * G);
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+#if LI_DIST_PACKED
+            float d = li_dist2_packed(qxy, qz, b[u]);
+#else
+            float d = li_dist2(qx, qy, qz, b[u].x, b[u].y, b[u].z);
+#endif
+            if (d < tau && (U + u) * G < rem) {
+                local_insert(ld, li, d, id + (U + u) * G);
+                tau = fminf(thr5, ld[4]);
+            }
+        }
+        ptr += 2 * U * G;
+        id += 2 * U * G;
+        rem -= 2 * U * G;
+    }
+}
+#else
 template <int G, int U = LI_KNN_U>
 __device__ __forceinline__ void group_scan_pipelined(const float4* __restrict__ pool, unsigned f, unsigned cnt, float qx, float qy, float qz,
                                                      float thr, float (&ld)[5], int (&li)[5], int gl) {
@@ -134,6 +215,7 @@ __device__ __forceinline__ void group_scan_pipelined(const float4* __restrict__ 
         for (int u = 0; u < U; u++) p[u] = pn[u];
     }
 }
+#endif
 
 struct KnnGeom {
     int bs;             // log2(voxels per brick edge)
@@ -153,8 +235,19 @@ __device__ __forceinline__ void lockstep_scan_found(const float4* __restrict__ p
         const float db = grp_shfl<G>(dbox, src, gbase);
         const unsigned f = grp_shfl<G>(first, src, gbase);
         const unsigned c = grp_shfl<G>(count, src, gbase);
+#if LI_GROUP_BOUND
+        // The group's 5th best so far is at most m = min over its lanes of their private 5th best (a lane holding five
+        // entries proves five candidates within its ld[4]). Candidates and whole bricks STRICTLY beyond m can never
+        // enter the final top-5 (ties at m are kept, so the result is the one the private bounds alone would give).
+        unsigned mb = grp_min<G>(__float_as_uint(ld[4]));
+        mb = min(mb + 1u, 0x7f800000u);                      // smallest float above m (inf stays inf)
+        const float thr_g = fminf(thr, __uint_as_float(mb));
+        const unsigned cnt = (has && db < thr_g) ? c : 0u;
+        group_scan_pipelined<G>(pool, f, cnt, qx, qy, qz, thr_g, ld, li, gl);
+#else
         const unsigned cnt = (has && db < thr) ? c : 0u;
         group_scan_pipelined<G>(pool, f, cnt, qx, qy, qz, thr, ld, li, gl);
+#endif
     }
 }
 

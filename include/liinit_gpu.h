@@ -31,6 +31,9 @@ extern "C" {
 
 #define LIINIT_NUM_MATCH_POINTS 5 /* include/common_lib.h:28 */
 
+#define LIINIT_KNN_BRICKS 1
+#define LIINIT_KNN_CELLS 2
+
 typedef struct liinit_ctx liinit_ctx;
 
 typedef struct liinit_config {
@@ -42,7 +45,9 @@ typedef struct liinit_config {
     int hash_capacity_log2;  /* brick hash slots = 1<<this; 0 -> derived from max_map_points */
     int knn_group_lanes;     /* lanes cooperating on one scan point in the 5-NN kernel: 1 (thread per point, smem-staged), 4, 8, 16 or 32; 0 -> default (4) */
     float knn_seed_radius_cells; /* first search shell of the 5-NN kernel, in map voxels (radius = this * filter_size_map); 0 -> default (2) */
-    int reserved[7];
+    int knn_index;           /* spatial index the 5-NN kernel searches: LIINIT_KNN_BRICKS (lockstep groups over whole bricks, knn_group_lanes applies),
+                                LIINIT_KNN_CELLS (thread per scan point over the per-brick cell directory; needs brick_cells_log2 = 3); 0 -> default */
+    int reserved[6];
 } liinit_config;
 
 /* lifecycle ------------------------------------------------------------------ */

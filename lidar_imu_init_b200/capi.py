@@ -24,7 +24,7 @@ class LiInitError(RuntimeError):
 
 class Config(C.Structure):
     _fields_ = [("filter_size_map", C.c_float), ("max_map_points", C.c_int), ("max_scan_points", C.c_int), ("device_id", C.c_int),
-                ("brick_cells_log2", C.c_int), ("hash_capacity_log2", C.c_int), ("knn_group_lanes", C.c_int), ("knn_seed_radius_cells", C.c_float), ("reserved", C.c_int * 7)]
+                ("brick_cells_log2", C.c_int), ("hash_capacity_log2", C.c_int), ("knn_group_lanes", C.c_int), ("knn_seed_radius_cells", C.c_float), ("knn_index", C.c_int), ("reserved", C.c_int * 6)]
 
 
 _f32 = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
@@ -108,9 +108,10 @@ class LiInitGpu:
     """One context = one GPU + one device-resident map + one resident scan."""
 
     def __init__(self, filter_size_map=0.15, max_map_points=6_000_000, max_scan_points=300_000, device_id=0, brick_cells_log2=0,
-                 hash_capacity_log2=0, knn_group_lanes=0, knn_seed_radius_cells=0.0):
+                 hash_capacity_log2=0, knn_group_lanes=0, knn_seed_radius_cells=0.0, knn_index=0):
         self.L = load()
-        cfg = Config(filter_size_map, max_map_points, max_scan_points, device_id, brick_cells_log2, hash_capacity_log2, knn_group_lanes, knn_seed_radius_cells)
+        cfg = Config(filter_size_map, max_map_points, max_scan_points, device_id, brick_cells_log2, hash_capacity_log2, knn_group_lanes, knn_seed_radius_cells,
+                     knn_index)
         h = C.c_void_p()
         rc = self.L.liinit_create(C.byref(cfg), C.byref(h))
         if rc != 0:

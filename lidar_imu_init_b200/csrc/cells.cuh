@@ -1,0 +1,339 @@
+// cells.cuh -- exact bounded 5-NN on a CELL DIRECTORY inside the brick hash, one scan point per thread
+// (second implementation of KD_TREE::Nearest_Search, ikd_Tree.cpp:349-379 / Search :825-968; selected with
+// liinit_config.knn_index = LIINIT_KNN_CELLS).
+//
+// Why: the lockstep brick search (knn_kernels.cuh) is instruction-issue bound because a brick (8x8x8 map voxels, 1.2 m at
+// ds = 0.15) is the smallest unit it can prune: a query whose five neighbours lie within 0.2 m still evaluates every
+// point of every brick its ball touches (~180 candidates per query at C2). Here every brick carries a directory of its
+// 4x4x4 CELLS (cell = 2x2x2 voxels, 0.3 m):
+//     cocc[slot]        64-bit occupancy mask, bit c = cell c holds at least one point, c = (cx << 4) | (cy << 2) | cz
+//     cdir[slot*64 + c] offset of cell c's first point inside the slab (u16); cell c ends where cell c+1 starts
+// and the slab is kept SORTED BY CELL (li_cells_refresh_brick, run on the touched bricks after every map update).
+// A query enumerates the bricks of its ball's bounding box as before, but inside a brick it visits only the occupied
+// cells of that box whose own box distance passes the shell / 5th-best tests, and scans just their points.
+//
+// The search is the same exact shell iteration as knn5_lockstep, stated on cells:
+//     invariant  every cell with dcell < lo2 has been scanned (or was pruned against a 5th-best that only shrinks)
+//     step       scan the cells with lo2 <= dcell < hi2 (<= 5 on the final radius) and dcell < current 5th best
+//     stop       5 known and d5 <= hi2, or hi2 >= 5 (the reference's radius: squared distance <= 5, ikd_Tree.cpp:842)
+//     next       lo2 = hi2;  hi2 = d5 if 5 are known (one closing step)  else 4 * hi2
+// One thread owns one query: a sorted top-5 in registers, no shuffles, no merges, no lockstep.
+//
+// Everything marked LI_HD is plain C++ (no intrinsics; the library is built with --fmad=false, IEEE division and square
+// root, so `a * b + c` is the same unfused arithmetic on both sides) and is ALSO compiled for the host by tests/emul,
+// where the identical source is checked against brute force without a GPU.
+#pragma once
+#include <math.h>
+
+#include "common.cuh"
+
+#define LI_CELLS_BSHIFT 3            // the directory is defined for 8x8x8-voxel bricks only
+#define LI_CDIR_UNINDEXED 0xffffu    // cdir[slot*64] of a brick too large for u16 offsets: scanned as one slab
+#define LI_NO_BOX_W 0xfffffffeu      // == LI_NO_BOX (map_kernels.cuh): the point lies in no downsample box
+
+#ifdef __CUDA_ARCH__
+#define LC_LDG(p) __ldg(p)
+#else
+#define LC_LDG(p) (*(p))
+#endif
+
+LI_HD unsigned lc_f2u(float f) {
+    union { float f; unsigned u; } c;
+    c.f = f;
+    return c.u;
+}
+LI_HD float lc_u2f(unsigned u) {
+    union { float f; unsigned u; } c;
+    c.u = u;
+    return c.f;
+}
+LI_HD int lc_imax(int a, int b) { return a > b ? a : b; }
+LI_HD int lc_imin(int a, int b) { return a < b ? a : b; }
+LI_HD int lc_ctz64(unsigned long long m) {
+#ifdef __CUDA_ARCH__
+    return __ffsll((long long)m) - 1;
+#else
+    return __builtin_ctzll(m);
+#endif
+}
+
+// Cell of a stored map point. Bricks and voxel-in-brick ids come from the point's BOX index (li_storage), so the cell
+// does too; a point in no box (ulp gap between two float boxes) was filed under its division index.
+LI_HD unsigned lc_cell_of(float4 p, float ds) {
+    const unsigned w = lc_f2u(p.w);
+    unsigned vx, vy, vz;
+    if (w == LI_NO_BOX_W) {
+        vx = (unsigned)((int)floorf(p.x / ds) & 7);
+        vy = (unsigned)((int)floorf(p.y / ds) & 7);
+        vz = (unsigned)((int)floorf(p.z / ds) & 7);
+    } else {
+        vx = (w >> 6) & 7u;
+        vy = (w >> 3) & 7u;
+        vz = w & 7u;
+    }
+    return ((vx >> 1) << 4) | ((vy >> 1) << 2) | (vz >> 1);
+}
+
+// (Re)build the directory of one brick: count per cell, prefix sums, in-place permutation of the slab (American-flag
+// pass: every swap puts one point into its final cell range, so at most `count` swaps). One thread per brick: the
+// slabs of a surface map hold tens of points, and the refresh runs once per map update, not per ICP pass.
+LI_HD void li_cells_refresh_brick(const MapDev& M, unsigned slot) {
+    const uint4 e = M.ent[slot];
+    const unsigned first = e.z, n = e.w;
+    unsigned short* dir = M.cdir + (size_t)slot * 64;
+    if (n > 0xfff0u) {
+        M.cocc[slot] = ~0ull;
+        dir[0] = LI_CDIR_UNINDEXED;
+        return;
+    }
+    unsigned short nxt[64], end[64];
+    for (int c = 0; c < 64; c++) nxt[c] = 0;
+    float4* slab = M.pool + first;
+    for (unsigned j = 0; j < n; j++) nxt[lc_cell_of(slab[j], M.ds)]++;
+    unsigned long long occ = 0ull;
+    unsigned acc = 0;
+    for (int c = 0; c < 64; c++) {
+        const unsigned k = nxt[c];
+        if (k) occ |= 1ull << c;
+        dir[c] = (unsigned short)acc;
+        nxt[c] = (unsigned short)acc;
+        acc += k;
+        end[c] = (unsigned short)acc;
+    }
+    M.cocc[slot] = occ;
+    for (int c = 0; c < 64; c++) {
+        while (nxt[c] < end[c]) {
+            const float4 p = slab[nxt[c]];
+            const unsigned k = lc_cell_of(p, M.ds);
+            if (k == (unsigned)c) {
+                nxt[c]++;
+            } else {
+                const unsigned dst = nxt[k]++;
+                const float4 q = slab[dst];
+                slab[dst] = p;
+                slab[nxt[c]] = q;
+            }
+        }
+    }
+}
+
+// sorted insert into the thread's top-5 (precondition d < ld[4]); equal distances keep their arrival order
+LI_HD void lc_insert(float (&ld)[5], int (&li)[5], float d, int id) {
+    ld[4] = d;
+    li[4] = id;
+#pragma unroll
+    for (int i = 4; i > 0; --i) {
+        const bool sw = ld[i] < ld[i - 1];
+        const float a = ld[i - 1], b = ld[i];
+        const int ia = li[i - 1], ib = li[i];
+        ld[i - 1] = sw ? b : a;
+        ld[i] = sw ? a : b;
+        li[i - 1] = sw ? ib : ia;
+        li[i] = sw ? ia : ib;
+    }
+}
+
+// lookup returning the hash slot (-1 = no such brick)
+LI_HD int lc_brick_find(const uint4* ent, unsigned mask, unsigned long long key, unsigned& first, unsigned& count) {
+    unsigned h = li_hash(key) & mask;
+    for (unsigned i = 0; i <= mask; i++) {
+        const uint4 e = LC_LDG(&ent[h]);
+        const unsigned long long k = (unsigned long long)e.x | ((unsigned long long)e.y << 32);
+        if (k == key) {
+            first = e.z;
+            count = e.w;
+            return (int)h;
+        }
+        if (k == LI_EMPTY_KEY) return -1;
+        h = (h + 1) & mask;
+    }
+    return -1;
+}
+
+// occupancy-mask bits of the cells with coordinate in [a, b] (0 <= a <= b <= 3) on one axis
+LI_HD unsigned long long lc_mask_x(int a, int b) { return (~0ull << (16 * a)) & (~0ull >> (48 - 16 * b)); }
+LI_HD unsigned long long lc_mask_y(int a, int b) {
+    const unsigned long long g = ((0xffffull << (4 * a)) & (0xffffull >> (12 - 4 * b))) & 0xffffull;
+    return g * 0x0001000100010001ull;
+}
+LI_HD unsigned long long lc_mask_z(int a, int b) {
+    const unsigned long long g = ((0xfull << a) & (0xfull >> (3 - b))) & 0xfull;
+    return g * 0x1111111111111111ull;
+}
+
+// Work counters of one query (host checker / cost model only; the device instantiation passes nullptr and COUNT = false).
+struct LcStats {
+    int rounds, bricks, probes, found, cells, cells_scanned, points, inserts;
+};
+
+LI_HD float lc_box_d2(float qx, float qy, float qz, float lox, float hix, float loy, float hiy, float loz, float hiz) {
+    const float ex = fmaxf(0.f, fmaxf(lox - qx, qx - hix));
+    const float ey = fmaxf(0.f, fmaxf(loy - qy, qy - hiy));
+    const float ez = fmaxf(0.f, fmaxf(loz - qz, qz - hiz));
+    return (ex * ex + ey * ey + ez * ez) * (1.0f - 1e-6f);
+}
+
+// Exact 5-NN of one query. ld / li: ascending squared distances / pool offsets (-1 = missing).
+template <bool COUNT>
+LI_HD void knn5_cells(const MapDev& M, float rho2, float qx, float qy, float qz, float (&ld)[5], int (&li)[5], LcStats* st) {
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        ld[i] = INFINITY;
+        li[i] = -1;
+    }
+    const float ds = M.ds;
+    const float cs = 2.0f * ds;   // cell edge (exact)
+    const float B = 8.0f * ds;
+    const float lim = (float)(LI_CELL_LIMIT - 16 * 8) * ds;
+    if (!(fabsf(qx) < lim && fabsf(qy) < lim && fabsf(qz) < lim)) return;   // also rejects NaN / inf
+    // Rounding slack, as in knn5_lockstep: box indices differ from real geometry by <~ |x| 2^-23; every pruning box is
+    // inflated by `margin`, squared bounds carry a (1 - 1e-6) factor, the enumeration range a slack in cells.
+    const float l1 = fabsf(qx) + fabsf(qy) + fabsf(qz);
+    const float margin = 1e-6f * (l1 + 16.0f * B);
+    const float inv_ds = 1.0f / ds;
+    const float slk = 0.02f + 4e-7f * l1 * inv_ds;
+    const float cap5 = lc_u2f(0x40a00001u);   // smallest float above 5: d <= 5 <=> d < cap5
+    const float4* __restrict__ pool = M.pool;
+    float lo2 = 0.f, hi2 = rho2;
+    for (;;) {
+        if (COUNT) st->rounds++;
+        const bool last = hi2 >= 5.0f;   // the radius bound d2 <= 5 is inclusive
+        const float r = sqrtf(fminf(hi2, 5.0f)) * (1.0f + 1e-6f) + margin;
+        // voxel range of the ball's bounding box (conservative), cells = voxels >> 1, bricks = voxels >> 3
+        const int lvx = (int)floorf((qx - r) * inv_ds - slk), hvx = (int)floorf((qx + r) * inv_ds + slk);
+        const int lvy = (int)floorf((qy - r) * inv_ds - slk), hvy = (int)floorf((qy + r) * inv_ds + slk);
+        const int lvz = (int)floorf((qz - r) * inv_ds - slk), hvz = (int)floorf((qz + r) * inv_ds + slk);
+        const int lcx = lvx >> 1, hcx = hvx >> 1, lcy = lvy >> 1, hcy = hvy >> 1, lcz = lvz >> 1, hcz = hvz >> 1;
+        float tau = fminf(ld[4], cap5);
+        for (int kz = lvz >> 3; kz <= (hvz >> 3); kz++) {
+            const float bloz = (float)(kz << 3) * ds - margin, bhiz = (float)((kz + 1) << 3) * ds + margin;
+            const int az = lc_imax(lcz - 4 * kz, 0), bz = lc_imin(hcz - 4 * kz, 3);
+            for (int ky = lvy >> 3; ky <= (hvy >> 3); ky++) {
+                const float bloy = (float)(ky << 3) * ds - margin, bhiy = (float)((ky + 1) << 3) * ds + margin;
+                const int ay = lc_imax(lcy - 4 * ky, 0), by = lc_imin(hcy - 4 * ky, 3);
+                for (int kx = lvx >> 3; kx <= (hvx >> 3); kx++) {
+                    if (COUNT) st->bricks++;
+                    const float blox = (float)(kx << 3) * ds - margin, bhix = (float)((kx + 1) << 3) * ds + margin;
+                    const float db = lc_box_d2(qx, qy, qz, blox, bhix, bloy, bhiy, bloz, bhiz);
+                    // a brick's box distance bounds its cells' from below: necessary conditions only (no lo2 test here)
+                    if (!((last ? db <= 5.0f : db < hi2) && db < ld[4])) continue;
+                    if (COUNT) st->probes++;
+                    unsigned first = 0, count = 0;
+                    const int slot = lc_brick_find(M.ent, M.mask, li_pack_key(kx, ky, kz), first, count);
+                    if (slot < 0 || count == 0u) continue;
+                    if (COUNT) st->found++;
+                    const unsigned short* __restrict__ dir = M.cdir + (size_t)slot * 64;
+                    if (LC_LDG(&dir[0]) == LI_CDIR_UNINDEXED) {
+                        // oversized brick: one unit under the brick-level shell rule
+                        if (db >= lo2) {
+                            for (unsigned j = 0; j < count; j++) {
+                                const float4 p = LC_LDG(&pool[first + j]);
+                                const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
+                                const float d = (dx * dx + dy * dy) + dz * dz;
+                                if (COUNT) st->points++;
+                                if (d < tau) {
+                                    lc_insert(ld, li, d, (int)(first + j));
+                                    tau = fminf(ld[4], cap5);
+                                    if (COUNT) st->inserts++;
+                                }
+                            }
+                        }
+                        continue;
+                    }
+                    const int ax = lc_imax(lcx - 4 * kx, 0), bx = lc_imin(hcx - 4 * kx, 3);
+                    unsigned long long m = LC_LDG(&M.cocc[slot]) & lc_mask_x(ax, bx) & lc_mask_y(ay, by) & lc_mask_z(az, bz);
+                    while (m) {
+                        const int c = lc_ctz64(m);
+                        m &= m - 1ull;
+                        if (COUNT) st->cells++;
+                        const int gx = 4 * kx + (c >> 4), gy = 4 * ky + ((c >> 2) & 3), gz = 4 * kz + (c & 3);
+                        const float dc = lc_box_d2(qx, qy, qz, (float)gx * cs - margin, (float)(gx + 1) * cs + margin, (float)gy * cs - margin,
+                                                   (float)(gy + 1) * cs + margin, (float)gz * cs - margin, (float)(gz + 1) * cs + margin);
+                        if (!(dc >= lo2 && (last ? dc <= 5.0f : dc < hi2) && dc < ld[4])) continue;
+                        if (COUNT) st->cells_scanned++;
+                        const unsigned s0 = LC_LDG(&dir[c]);
+                        const unsigned e0 = (c == 63) ? count : (unsigned)LC_LDG(&dir[c + 1]);
+                        for (unsigned j = s0; j < e0; j++) {
+                            const float4 p = LC_LDG(&pool[first + j]);
+                            // KD_TREE::calc_dist (ikd_Tree.cpp:1273-1277): (dx*dx + dy*dy) + dz*dz in f32, no FMA
+                            const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
+                            const float d = (dx * dx + dy * dy) + dz * dz;
+                            if (COUNT) st->points++;
+                            if (d < tau) {
+                                lc_insert(ld, li, d, (int)(first + j));
+                                tau = fminf(ld[4], cap5);
+                                if (COUNT) st->inserts++;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        const bool full = li[4] >= 0;
+        if (last || (full && ld[4] <= hi2)) break;
+        lo2 = hi2;
+        hi2 = full ? fminf(ld[4] * (1.0f + 1e-6f), 5.0f) : fminf(4.0f * hi2, 5.0f);
+    }
+}
+
+#ifdef __CUDACC__
+// ---- directory maintenance ---------------------------------------------------------------------------
+// after k_ins_commit / k_ds_compact: the bricks of the batch's touched list (count on the device: fixed grid)
+__global__ void k_cells_refresh_touched(MapDev M) {
+    const int nt = gridDim.x * blockDim.x, ntouched = M.counters[CNT_TOUCHED];
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ntouched; t += nt) li_cells_refresh_brick(M, (unsigned)M.touched_list[t]);
+}
+// after a box delete (any slab may have been squeezed)
+__global__ void k_cells_refresh_all(MapDev M, unsigned slots) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= slots) return;
+    const uint4 e = M.ent[i];
+    if (((unsigned long long)e.x | ((unsigned long long)e.y << 32)) == LI_EMPTY_KEY) return;
+    li_cells_refresh_brick(M, i);
+}
+
+// ---- search kernel of an ICP pass: world transform + 5-NN, one scan point per thread --------------------
+// HOST = true: the scan is still the caller's page-locked host buffer (liinit_scan_attach_host); consecutive lanes read
+// consecutive points, so for packed xyz a warp pulls one contiguous 384-byte run over PCIe.
+#ifndef LI_CELLS_THREADS
+#define LI_CELLS_THREADS 128
+#endif
+template <bool HOST>
+__global__ void __launch_bounds__(LI_CELLS_THREADS) k_knn_cells_scan(MapDev M, ScanDev S, PoseD P, float rho2, const float* __restrict__ raw, int stride) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= S.n) return;
+    float bx, by, bz;
+    if (HOST) {
+        const float* s = raw + (size_t)q * stride;
+        bx = s[0]; by = s[1]; bz = s[2];
+        S.body[q] = make_float4(bx, by, bz, 0.f);
+    } else {
+        const float4 b = __ldg(&S.body[q]);
+        bx = b.x; by = b.y; bz = b.z;
+    }
+    float wx, wy, wz;
+    li_body_to_world(P, bx, by, bz, wx, wy, wz);
+    float ld[5];
+    int li[5];
+    knn5_cells<false>(M, rho2, wx, wy, wz, ld, li, nullptr);
+    S.world[q] = make_float4(wx, wy, wz, 0.f);
+#pragma unroll
+    for (int k = 0; k < 5; k++) S.near_ids[(size_t)q * 5 + k] = li[k];
+}
+
+// ---- stand-alone Nearest_Search for arbitrary world-frame queries -----------------------------------------
+__global__ void __launch_bounds__(LI_CELLS_THREADS) k_knn_cells_queries(MapDev M, const float4* __restrict__ qpts, int n, int* __restrict__ ids,
+                                                                        float* __restrict__ d2, float rho2) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const float4 p = __ldg(&qpts[q]);
+    float ld[5];
+    int li[5];
+    knn5_cells<false>(M, rho2, p.x, p.y, p.z, ld, li, nullptr);
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        ids[(size_t)q * 5 + k] = li[k];
+        d2[(size_t)q * 5 + k] = (li[k] >= 0) ? ld[k] : -1.f;
+    }
+}
+#endif  // __CUDACC__

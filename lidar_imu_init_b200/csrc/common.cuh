@@ -8,7 +8,12 @@
 //   * pool: float4 points; every brick owns one contiguous, 128-byte aligned slab
 //     [first, first+cap) of which [first, first+count) are live. w carries the voxel-in-brick id.
 #pragma once
+#ifdef __CUDACC__
 #include <cuda_runtime.h>
+#else   // host-only parse (tests/emul: the cell-directory search is compiled for the CPU as its own checker)
+#include <vector_types.h>
+#include <vector_functions.h>
+#endif
 #include <stdint.h>
 
 #define LI_FULL 0xffffffffu
@@ -26,6 +31,10 @@ struct MapDev {
     int bshift;                    // log2(voxels per brick edge)
     int* touched_list;             // hash slots touched by the current update batch
     int* counters;                 // [0]=touched_n [1]=err flags [2]=n_live [3]=n_bricks [4]=changed voxels [5]=dropped pts
+    // cell directory (cells.cuh; only with knn_index = cells, else null): per hash slot the occupancy mask of the brick's
+    // 4x4x4 cells (cell = 2x2x2 voxels) and the start offset of every cell inside the slab, which is kept sorted by cell
+    unsigned long long* cocc;
+    unsigned short* cdir;          // [slots * 64]; cdir[slot*64] == 0xffff: brick not indexed (scan the whole slab)
 };
 
 enum { CNT_TOUCHED = 0, CNT_ERR = 1, CNT_LIVE = 2, CNT_BRICKS = 3, CNT_CHANGED = 4, CNT_DROPPED = 5, CNT_NADD = 6, CNT_NNOD = 7, CNT_COUNT = 16 };
@@ -49,18 +58,27 @@ struct ScanDev {
     int n;
 };
 
-__device__ __forceinline__ unsigned long long li_pack_key(int x, int y, int z) {
+// LI_HD: helpers that are also compiled for the host by the CPU checker of the cell-directory search (tests/emul)
+#ifdef __CUDACC__
+#define LI_HD __host__ __device__ __forceinline__
+#else
+#define LI_HD inline
+#endif
+
+LI_HD unsigned long long li_pack_key(int x, int y, int z) {
     return ((unsigned long long)(unsigned)(x + LI_CELL_LIMIT) << 42) | ((unsigned long long)(unsigned)(y + LI_CELL_LIMIT) << 21) |
            (unsigned long long)(unsigned)(z + LI_CELL_LIMIT);
 }
 
 // Spatial hash of a packed key: three 32-bit multiplies (Teschner et al. primes) + a final avalanche step.
-__device__ __forceinline__ unsigned li_hash(unsigned long long k) {
+LI_HD unsigned li_hash(unsigned long long k) {
     unsigned x = (unsigned)(k >> 42), y = (unsigned)(k >> 21) & 0x1fffffu, z = (unsigned)k & 0x1fffffu;
     unsigned h = (x * 73856093u) ^ (y * 19349663u) ^ (z * 83492791u);
     h ^= h >> 15;
     return h;
 }
+
+#ifdef __CUDACC__
 
 // Voxel index exactly as the reference computes it: floor(x / downsample_size) in float
 // (ikd_Tree.cpp:389). IEEE division, no reciprocal shortcut.
@@ -142,3 +160,4 @@ __device__ __forceinline__ void li_body_to_world(const PoseD& P, float bx, float
     wy = (float)g1;
     wz = (float)g2;
 }
+#endif  // __CUDACC__

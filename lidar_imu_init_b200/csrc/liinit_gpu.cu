@@ -8,6 +8,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -16,9 +17,14 @@
 #include "icp_kernels.cuh"
 #include "knn_kernels.cuh"
 #include "knn_tpq.cuh"
+#include "cells.cuh"
 #include "map_kernels.cuh"
 #include "voxelgrid_kernels.cuh"
 #include "undistort_kernels.cuh"
+
+#ifndef LIINIT_KNN_DEFAULT
+#define LIINIT_KNN_DEFAULT LIINIT_KNN_BRICKS   // what knn_index = 0 selects
+#endif
 
 namespace {
 
@@ -83,6 +89,7 @@ struct Ctx {
     float last_ms = 0.f;
     int last_launches = 0;
     int group = 4;
+    bool cells = false;   // knn_index = LIINIT_KNN_CELLS: per-brick cell directory + thread-per-point search (cells.cuh)
     float rho2 = 0.09f;   // squared seed radius of the 5-NN search
 };
 
@@ -141,6 +148,13 @@ int reset_batch_counters(Ctx* c) {
     return LIINIT_OK;
 }
 
+// cell directory of the bricks the batch touched (after the commit / compaction that fixed their counts)
+void refresh_cells_touched(Ctx* c) {
+    if (!c->cells) return;
+    k_cells_refresh_touched<<<c->num_sms * 8, 128, 0, c->stream>>>(c->M);
+    c->launches++;
+}
+
 // plain insert of pts[0..n) (optionally only flag==want)
 int plain_insert(Ctx* c, const float4* pts, int n, const int* sel, int want) {
     if (n <= 0) return LIINIT_OK;
@@ -153,6 +167,7 @@ int plain_insert(Ctx* c, const float4* pts, int n, const int* sel, int want) {
     k_ins_append<<<nblk(n, 256), 256, 0, c->stream>>>(c->M, pts, n, c->d_slot_of);
     k_ins_commit<<<gfix, 256, 0, c->stream>>>(c->M);
     c->launches += 4;
+    refresh_cells_touched(c);
     CU(cudaGetLastError());
     return LIINIT_OK;
 }
@@ -179,6 +194,7 @@ int downsample_insert(Ctx* c, const float4* pts, int n, const int* sel, int want
     // tombstoned bricks were added to the touched list by the replay (worst case n + n bricks): grid-stride inside
     k_ds_compact<<<c->num_sms * 8, 256, 0, c->stream>>>(c->M);
     c->launches += 6;
+    refresh_cells_touched(c);
     CU(cudaGetLastError());
     return LIINIT_OK;
 }
@@ -216,6 +232,16 @@ void launch_knn_scan(Ctx* c, const PoseD& P) {
 #define LI_PLANE_WAVES 1   // the plane pass runs LI_PLANE_WAVES x (2 blocks per SM); each thread strides over the scan
 #endif
 
+void launch_knn_cells_scan(Ctx* c, const PoseD& P) {
+    const int grid = nblk(c->scan_n, LI_CELLS_THREADS);
+    if (c->attached) {
+        k_knn_cells_scan<true><<<grid, LI_CELLS_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, c->attached, c->attached_stride);
+        c->attached = nullptr;   // the kernel leaves the packed copy in d_body
+    } else {
+        k_knn_cells_scan<false><<<grid, LI_CELLS_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, nullptr, 0);
+    }
+}
+
 constexpr int TPQ_CH = 32, TPQ_NB = 8;
 constexpr size_t TPQ_SMEM = 4 * TpqCfg<TPQ_CH, TPQ_NB>::WARP_TILE_F4 * sizeof(float4);
 
@@ -245,7 +271,8 @@ int run_pass(Ctx* c, const double* R, const double* p, const double* RLI, const 
     fill_pose(P, R, p, RLI, TLI);
     CU(cudaEventRecord(c->ev0, c->stream));
     if (search) {
-        switch (c->group) {
+        if (c->cells) launch_knn_cells_scan(c, P);
+        else switch (c->group) {
             case 1: launch_knn_scan_tpq(c, P); break;
             case 16: launch_knn_scan<16>(c, P); break;
             case 32: launch_knn_scan<32>(c, P); break;
@@ -345,6 +372,20 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
     c->group = (cfg->knn_group_lanes == 1 || cfg->knn_group_lanes == 2 || cfg->knn_group_lanes == 4 || cfg->knn_group_lanes == 8 || cfg->knn_group_lanes == 16 || cfg->knn_group_lanes == 32) ? cfg->knn_group_lanes : 4;
 
     {
+        int ki = cfg->knn_index;
+        if (ki == 0) {
+            // developer A/B switch: run an unmodified caller (tests, bench) against the other index
+            const char* e = getenv("LIINIT_KNN_INDEX");
+            ki = (e && *e) ? atoi(e) : LIINIT_KNN_DEFAULT;
+        }
+        if (ki != LIINIT_KNN_BRICKS && ki != LIINIT_KNN_CELLS) {
+            c->err = "knn_index must be 0, LIINIT_KNN_BRICKS or LIINIT_KNN_CELLS";
+            return bail(LIINIT_ERR_INVALID);
+        }
+        // the cell directory is defined for 8x8x8-voxel bricks; another brick size keeps the brick search
+        c->cells = (ki == LIINIT_KNN_CELLS) && bs == LI_CELLS_BSHIFT;
+    }
+    {
         float cells = cfg->knn_seed_radius_cells > 0.f ? cfg->knn_seed_radius_cells : 2.0f;
         float rho = cells * cfg->filter_size_map;
         c->rho2 = rho * rho;
@@ -361,6 +402,12 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
     CUC(cudaMalloc(&M.aux, (size_t)c->hash_slots * sizeof(uint4)));
     CUC(cudaMalloc(&M.pool, (size_t)pool * sizeof(float4)));
     CUC(cudaMalloc(&M.pool_top, sizeof(unsigned long long)));
+    M.cocc = nullptr;
+    M.cdir = nullptr;
+    if (c->cells) {
+        CUC(cudaMalloc(&M.cocc, (size_t)c->hash_slots * sizeof(unsigned long long)));
+        CUC(cudaMalloc(&M.cdir, (size_t)c->hash_slots * 64 * sizeof(unsigned short)));
+    }
     int batch = cfg->max_scan_points > (1 << 20) ? cfg->max_scan_points : (1 << 20);
     c->stage_pts_cap = batch;
     CUC(cudaMalloc(&M.touched_list, (size_t)batch * 2 * sizeof(int)));
@@ -425,7 +472,7 @@ int liinit_destroy(liinit_ctx* h) {
     Ctx* c = &h->c;
     cudaSetDevice(c->device);
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
-    cudaFree(c->M.ent); cudaFree(c->M.aux); cudaFree(c->M.pool); cudaFree(c->M.pool_top); cudaFree(c->M.touched_list);
+    cudaFree(c->M.ent); cudaFree(c->M.aux); cudaFree(c->M.pool); cudaFree(c->M.pool_top); cudaFree(c->M.touched_list); cudaFree(c->M.cocc); cudaFree(c->M.cdir);
     cudaFree(c->d_counters); cudaFreeHost(c->h_counters); cudaFree(c->d_stage_raw); cudaFree(c->d_stage_pts);
     cudaFree(c->d_slot_of); cudaFree(c->d_vslot_of); cudaFree(c->d_flag); cudaFree(c->d_ins); cudaFree(c->V.keys); cudaFree(c->V.head); cudaFree(c->d_vg_imin); cudaFree(c->d_vg_block); cudaFree(c->d_vg_misc); cudaFree(c->d_rs_keys); cudaFree(c->d_rs_vals); cudaFree(c->d_rs_hist); cudaFree(c->d_vg_params); cudaFree(c->d_tmin_idx); cudaFree(c->d_poses);
     cudaFree(c->d_body); cudaFree(c->d_world); cudaFree(c->d_near_ids); cudaFree(c->d_selected); cudaFree(c->d_normvec);
@@ -506,6 +553,10 @@ int liinit_map_delete_boxes(liinit_ctx* h, const float* boxes, int nbox, int* de
     k_map_delete_boxes<<<nblk((long long)c->hash_slots * 32, 256), 256, 0, c->stream>>>(c->M, c->hash_slots, c->d_stage_raw, nbox,
                                                                                           c->d_vg_misc + 6);
     c->launches++;
+    if (c->cells) {
+        k_cells_refresh_all<<<nblk(c->hash_slots, 128), 128, 0, c->stream>>>(c->M, c->hash_slots);
+        c->launches++;
+    }
     c->have_neighbors = false;   // pool offsets inside the touched slabs moved
     CU(cudaGetLastError());
     int cnt = 0;
@@ -580,7 +631,9 @@ int liinit_map_nearest_search(liinit_ctx* h, const float* q, int stride, int n, 
         float* d_xyz = nullptr;
         CU(cudaMalloc(&d_ids, (size_t)m * 5 * sizeof(int)));
         CU(cudaMalloc(&d_xyz, (size_t)m * 15 * sizeof(float)));
-        if (c->group == 1) {
+        if (c->cells) {
+            k_knn_cells_queries<<<nblk(m, LI_CELLS_THREADS), LI_CELLS_THREADS, 0, c->stream>>>(c->M, c->d_stage_pts, m, d_ids, c->d_q_d2, c->rho2);
+        } else if (c->group == 1) {
             int grid = nblk(m, 128);
             if (grid > c->num_sms * 12) grid = c->num_sms * 12;
             k_knn_queries_tpq<TPQ_CH, TPQ_NB><<<grid, 128, TPQ_SMEM, c->stream>>>(c->M, c->d_stage_pts, m, d_ids, c->d_q_d2, c->rho2);

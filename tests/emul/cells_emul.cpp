@@ -1,0 +1,186 @@
+// cells_emul.cpp -- CPU checker of the cell-directory 5-NN (lidar_imu_init_b200/csrc/cells.cuh).
+//
+// TEST INFRASTRUCTURE, not product: it compiles the SAME LI_HD source the sm_100a kernels are built from
+// (li_cells_refresh_brick, knn5_cells) for the host, over a brick hash laid out in host memory by the storage rule of
+// map_kernels.cuh (li_storage: brick and voxel id from the float BOX index, ikd_Tree.cpp:633,980), so that the search
+// logic (shell iteration on cells, range masks, directory offsets, rounding margins) can be checked against brute force
+// without a GPU. Nothing under lidar_imu_init_b200/ loads this file; the product has no CPU path.
+//
+// Build: g++ -O2 -std=c++17 -ffp-contract=off -fPIC -shared -I/usr/local/cuda/include cells_emul.cpp -o libcells_emul.so
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <unordered_map>
+#include <vector>
+
+#include "../../lidar_imu_init_b200/csrc/cells.cuh"
+
+namespace {
+
+struct Emul {
+    float ds = 0.15f;
+    std::unordered_map<unsigned long long, std::vector<float4>> bricks;   // slab content, in slab order
+    std::vector<uint4> ent;
+    std::vector<float4> pool;
+    std::vector<unsigned long long> cocc;
+    std::vector<unsigned short> cdir;
+    std::vector<int> counters;
+    MapDev M{};
+    int hash_log2 = 16;
+};
+
+// li_box_index (map_kernels.cuh), plain arithmetic (compiled with -ffp-contract=off)
+bool box_index(float x, float ds, int c, int& b) {
+    float cf = (float)c;
+    float mn = cf * ds, mx = mn + ds;
+    if (x >= mn && x < mx) { b = c; return true; }
+    if (x < mn) {
+        float m1 = (cf - 1.0f) * ds, x1 = m1 + ds;
+        if (x >= m1 && x < x1) { b = c - 1; return true; }
+    } else {
+        float m1 = (cf + 1.0f) * ds, x1 = m1 + ds;
+        if (x >= m1 && x < x1) { b = c + 1; return true; }
+    }
+    b = c;
+    return false;
+}
+
+void storage(float ds, float4& p, unsigned long long& key) {
+    int cx = (int)floorf(p.x / ds), cy = (int)floorf(p.y / ds), cz = (int)floorf(p.z / ds);
+    int bx, by, bz;
+    bool ok = box_index(p.x, ds, cx, bx);
+    ok = box_index(p.y, ds, cy, by) && ok;
+    ok = box_index(p.z, ds, cz, bz) && ok;
+    unsigned vib;
+    if (ok) {
+        key = li_pack_key(bx >> 3, by >> 3, bz >> 3);
+        vib = (unsigned)(((bx & 7) << 6) | ((by & 7) << 3) | (bz & 7));
+    } else {
+        key = li_pack_key(cx >> 3, cy >> 3, cz >> 3);
+        vib = LI_NO_BOX_W;
+    }
+    p.w = lc_u2f(vib);
+}
+
+void layout(Emul* E, bool refresh) {
+    const size_t slots = (size_t)1 << E->hash_log2;
+    E->ent.assign(slots, make_uint4(0xffffffffu, 0xffffffffu, 0u, 0u));
+    E->cocc.assign(slots, 0xdeadbeefdeadbeefull);   // garbage where nothing was refreshed, as on the device
+    E->cdir.assign(slots * 64, (unsigned short)0xabcd);
+    size_t total = 0;
+    for (auto& kv : E->bricks) total += ((kv.second.size() + 7) & ~size_t(7)) + 8;
+    E->pool.assign(total + 8, make_float4(NAN, NAN, NAN, 0.f));
+    E->M.ent = E->ent.data();
+    E->M.aux = nullptr;
+    E->M.mask = (unsigned)slots - 1;
+    E->M.pool = E->pool.data();
+    E->M.pool_cap = E->pool.size();
+    E->M.ds = E->ds;
+    E->M.bshift = 3;
+    E->M.cocc = E->cocc.data();
+    E->M.cdir = E->cdir.data();
+    size_t off = 0;
+    for (auto& kv : E->bricks) {
+        unsigned h = li_hash(kv.first) & E->M.mask;
+        while (!(E->ent[h].x == 0xffffffffu && E->ent[h].y == 0xffffffffu)) h = (h + 1) & E->M.mask;
+        E->ent[h] = make_uint4((unsigned)kv.first, (unsigned)(kv.first >> 32), (unsigned)off, (unsigned)kv.second.size());
+        std::memcpy(&E->pool[off], kv.second.data(), kv.second.size() * sizeof(float4));
+        if (refresh) {
+            li_cells_refresh_brick(E->M, h);
+            std::memcpy(kv.second.data(), &E->pool[off], kv.second.size() * sizeof(float4));   // the slab order is now the sorted one
+        }
+        off += ((kv.second.size() + 7) & ~size_t(7)) + 8;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+void* emul_create(const float* xyz, int n, float ds, int hash_log2) {
+    Emul* E = new Emul();
+    E->ds = ds;
+    E->hash_log2 = hash_log2;
+    for (int i = 0; i < n; i++) {
+        float4 p = make_float4(xyz[3 * (size_t)i], xyz[3 * (size_t)i + 1], xyz[3 * (size_t)i + 2], 0.f);
+        unsigned long long key;
+        storage(ds, p, key);
+        E->bricks[key].push_back(p);
+    }
+    layout(E, true);
+    return E;
+}
+
+// plain append (slab order: sorted old content, then the new points in batch order, as k_ins_append leaves it) + refresh
+void emul_add(void* h, const float* xyz, int n) {
+    Emul* E = (Emul*)h;
+    for (int i = 0; i < n; i++) {
+        float4 p = make_float4(xyz[3 * (size_t)i], xyz[3 * (size_t)i + 1], xyz[3 * (size_t)i + 2], 0.f);
+        unsigned long long key;
+        storage(E->ds, p, key);
+        E->bricks[key].push_back(p);
+    }
+    layout(E, true);
+}
+
+void emul_destroy(void* h) { delete (Emul*)h; }
+
+int emul_num_bricks(void* h) { return (int)((Emul*)h)->bricks.size(); }
+
+// directory invariants of every brick: offsets monotone, cell c = [dir[c], dir[c+1]), every point in the cell the
+// directory says, occupancy mask == non-empty cells. Returns the number of violations.
+int emul_check_directory(void* h) {
+    Emul* E = (Emul*)h;
+    int bad = 0;
+    for (size_t s = 0; s <= E->M.mask; s++) {
+        uint4 e = E->ent[s];
+        if (e.x == 0xffffffffu && e.y == 0xffffffffu) continue;
+        const unsigned short* dir = &E->cdir[s * 64];
+        if (dir[0] == LI_CDIR_UNINDEXED) {
+            if (e.w <= 0xfff0u) bad++;
+            continue;
+        }
+        if (dir[0] != 0) bad++;
+        unsigned long long occ = 0;
+        for (int c = 0; c < 64; c++) {
+            unsigned s0 = dir[c], e0 = (c == 63) ? e.w : dir[c + 1];
+            if (e0 < s0 || e0 > e.w) { bad++; continue; }
+            if (e0 > s0) occ |= 1ull << c;
+            for (unsigned j = s0; j < e0; j++)
+                if (lc_cell_of(E->pool[e.z + j], E->ds) != (unsigned)c) bad++;
+        }
+        if (occ != E->cocc[s]) bad++;
+    }
+    return bad;
+}
+
+// 5-NN of n queries (packed xyz). out_xyz [n*15], out_d2 [n*5] (-1 = missing), out_cnt [n], stats [n*8] or NULL.
+void emul_knn(void* h, const float* q, int n, float rho2, float* out_xyz, float* out_d2, int* out_cnt, int* stats) {
+    Emul* E = (Emul*)h;
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int i = 0; i < n; i++) {
+        float ld[5];
+        int li[5];
+        LcStats st;
+        std::memset(&st, 0, sizeof(st));
+        knn5_cells<true>(E->M, rho2, q[3 * (size_t)i], q[3 * (size_t)i + 1], q[3 * (size_t)i + 2], ld, li, &st);
+        int cnt = 0;
+        for (int k = 0; k < 5; k++) {
+            if (li[k] >= 0) {
+                cnt++;
+                const float4 p = E->pool[li[k]];
+                out_xyz[15 * (size_t)i + 3 * k] = p.x;
+                out_xyz[15 * (size_t)i + 3 * k + 1] = p.y;
+                out_xyz[15 * (size_t)i + 3 * k + 2] = p.z;
+                out_d2[5 * (size_t)i + k] = ld[k];
+            } else {
+                out_xyz[15 * (size_t)i + 3 * k] = out_xyz[15 * (size_t)i + 3 * k + 1] = out_xyz[15 * (size_t)i + 3 * k + 2] = 0.f;
+                out_d2[5 * (size_t)i + k] = -1.f;
+            }
+        }
+        out_cnt[i] = cnt;
+        if (stats) std::memcpy(stats + 8 * (size_t)i, &st, sizeof(st));
+    }
+}
+
+}  // extern "C"

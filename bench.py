@@ -45,7 +45,13 @@ def emit(obj):
         sys.stdout.flush()
 
 
-NCU_DRAM_BYTES_KNN = 116_571_136  # 109.96 MB read + 6.61 MB written, profiles/r01_ncu_full_final_metrics.txt
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the search kernel (ncu --set full, cold cache), per index:
+#   1 (bricks, k_knn_scan): 109.96 MB read + 6.61 MB written, profiles/r01_ncu_full_final_metrics.txt
+#   2 (cells, k_knn_cells_scan): filled in from profiles/ once captured (None = not captured yet)
+NCU_DRAM_BYTES_KNN = {1: 116_571_136, 2: None}
+NCU_DRAM_SOURCE = {1: "profiles/r01_ncu_full_final_metrics.txt", 2: "profiles/r01_ncu_cells_metrics.txt"}
+KNN_KERNEL = {1: "k_knn_scan (5-NN search on whole bricks, lockstep lane groups; dominant kernel of the pass)",
+              2: "k_knn_cells_scan (5-NN search on the per-brick cell directory, one scan point per thread; dominant kernel of the pass)"}
 ALG_BYTES_PER_POINT = 132  # 16 body + 80 neighbours + 16 normal/residual + 20 ids
 METRIC = "ICP points*iters/s (search pass), 240k-pt scan vs 5M-pt map"
 UNIT = "points*iters/s"
@@ -196,7 +202,8 @@ def run_gpu(args, rank, world, local_rank):
     N = len(c["body_xyz"])
     p = c["pose_init"]
     g = capi.LiInitGpu(c["ds"], max_map_points=int(args.map_points * 1.2) + 1000, max_scan_points=N + 16, device_id=local_rank,
-                       knn_group_lanes=args.group, brick_cells_log2=args.brick)
+                       knn_group_lanes=args.group, brick_cells_log2=args.brick, knn_index=args.knn_index)
+    kidx = g.knn_index()
     stream = torch.cuda.Stream(device=dev)
     g.set_stream(stream.cuda_stream)
     t0 = time.time()
@@ -294,20 +301,20 @@ def run_gpu(args, rank, world, local_rank):
                                + ("1 GPU" if world == 1 else f"{world} GPUs, map replicated, one 240k-pt shard per rank, NCCL all-reduce of 160 f64"),
                    "scan_points_per_gpu": N, "map_points": args.map_points, "filter_size_map": c["ds"], "imu_en": False,
                    "initial_pose": "ground truth (+) 0.5 deg / 5 cm", "open_air_frac": 0.01, "scan_order": "voxel-grid order",
-                   "l2": "flushed between timed steps (256 MiB memset outside the events)", "knn_group_lanes": args.group or 4,
-                   "brick_cells_log2": args.brick or 3, "selected_points": m_sel, "map_build_s": build_s},
+                   "l2": "flushed between timed steps (256 MiB memset outside the events)", "knn_index": {1: "bricks", 2: "cells"}[kidx],
+                   "knn_group_lanes": (args.group or 4) if kidx == 1 else None, "brick_cells_log2": args.brick or 3, "selected_points": m_sel, "map_build_s": build_s},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(N * 12 + 192), "d2h_bytes_per_step": 160 * 8,
                 "ms_per_step": e2e_ms / args.steps,
                 "host_input": "pinned packed xyz, read by the search kernel over PCIe (liinit_scan_attach_host, no staging copy)",
                 "ms_per_step_staged_copy": e2e_staged_ms / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "k_knn_scan (5-NN search, dominant kernel of the pass)", "achieved": ach, "peak": peak,
-                     "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src, "traffic": NCU_DRAM_BYTES_KNN,
+        "roofline": {"bound": "hbm", "kernel": KNN_KERNEL[kidx], "achieved": ach, "peak": peak,
+                     "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src, "traffic": NCU_DRAM_BYTES_KNN[kidx],
                      "algorithmic_bytes_per_launch": ALG_BYTES_PER_POINT * N, "kernel_ms": knn_ms, "plane_kernel_ms": plane_ms,
                      "kernel_ms_l2_warm": knn_warm, "plane_kernel_ms_l2_warm": plane_warm,
-                     "note": "traffic = dram__bytes_read.sum + dram__bytes_write.sum of one k_knn_scan launch from the ncu --set full capture in "
-                             "profiles/r01_ncu_full_final_metrics.txt (cold cache: ncu flushes between replays), bytes per launch"},
+                     "note": "traffic = dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel from the ncu --set full capture in "
+                             + NCU_DRAM_SOURCE[kidx] + " (cold cache: ncu flushes between replays), bytes per launch; null = not captured yet"},
     }
     # ---- extras (not part of the contract value): the other pass kinds of a real scan -----------------------
     if world == 1:
@@ -373,6 +380,7 @@ def main():
     ap.add_argument("--map-points", type=int, default=5_000_000)
     ap.add_argument("--group", type=int, default=0)
     ap.add_argument("--brick", type=int, default=0)
+    ap.add_argument("--knn-index", type=int, default=0, help="0 = library default, 1 = bricks (lockstep groups), 2 = cells (cell directory)")
     ap.add_argument("--cpu-sample", type=int, default=240_000)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -142,6 +142,8 @@ int liinit_map_incremental(liinit_ctx* h, const double rot_end[9], const double 
 int liinit_last_pass_timing(liinit_ctx* h, float* kernel_ms, int* launches);
 /* Per-kernel device times of the last pass: the 5-NN kernel (0 for a reuse pass) and the plane/Jacobian/reduction kernel. */
 int liinit_last_pass_kernel_times(liinit_ctx* h, float* knn_ms, float* plane_ms);
+/* The spatial index this context searches (LIINIT_KNN_BRICKS / LIINIT_KNN_CELLS) after defaults were resolved. */
+int liinit_knn_index(liinit_ctx* h, int* knn_index);
 /* Cumulative number of kernels launched by this context. */
 int liinit_launch_count(liinit_ctx* h, long long* launches);
 /* Map statistics: bricks in use, hash slots, pool points in use / capacity. */

@@ -36,7 +36,7 @@ SYMBOLS = [
     "liinit_map_validnum", "liinit_map_size", "liinit_map_download", "liinit_map_nearest_search", "liinit_scan_upload", "liinit_scan_attach_host", "liinit_scan_upload_raw", "liinit_scan_download_body", "liinit_raw_upload", "liinit_raw_undistort_cv", "liinit_raw_undistort_imu",
     "liinit_raw_download", "liinit_raw_downsample",
     "liinit_icp_iterate", "liinit_icp_iterate_device", "liinit_scan_download_effect", "liinit_scan_download_state",
-    "liinit_map_incremental", "liinit_last_pass_timing", "liinit_last_pass_kernel_times", "liinit_launch_count", "liinit_map_stats",
+    "liinit_map_incremental", "liinit_last_pass_timing", "liinit_last_pass_kernel_times", "liinit_launch_count", "liinit_map_stats", "liinit_knn_index",
 ]
 
 
@@ -85,6 +85,7 @@ def load():
     L.liinit_last_pass_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
     L.liinit_last_pass_kernel_times.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.liinit_launch_count.argtypes = [vp, C.POINTER(C.c_longlong)]
+    L.liinit_knn_index.argtypes = [vp, C.POINTER(C.c_int)]
     L.liinit_map_stats.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     for s in SYMBOLS:
         getattr(L, s).restype = getattr(L, s).restype if s == "liinit_last_error" else C.c_int
@@ -288,6 +289,12 @@ class LiInitGpu:
         a, b = C.c_float(0), C.c_float(0)
         self._ck(self.L.liinit_last_pass_kernel_times(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def knn_index(self) -> int:
+        """1 = LIINIT_KNN_BRICKS (lockstep groups over whole bricks), 2 = LIINIT_KNN_CELLS (cell directory, thread per point)."""
+        v = C.c_int()
+        self._ck(self.L.liinit_knn_index(self.h, C.byref(v)))
+        return v.value
 
     def launch_count(self) -> int:
         n = C.c_longlong(0)

@@ -161,9 +161,21 @@ LI_HD unsigned long long lc_mask_z(int a, int b) {
     return g * 0x1111111111111111ull;
 }
 
+// occupancy mask of a super-brick (block of 4x4x4 bricks; bit b = (bx&3) << 4 | (by&3) << 2 | (bz&3)); 0 = no such block
+LI_HD unsigned long long lc_sb_find(const MapDev& M, unsigned long long key) {
+    unsigned h = li_hash(key) & M.sb_mask;
+    for (unsigned i = 0; i <= M.sb_mask; i++) {
+        const unsigned long long k = LC_LDG(&M.sb_keys[h]);
+        if (k == key) return LC_LDG(&M.sb_occ[h]);
+        if (k == LI_EMPTY_KEY) return 0ull;
+        h = (h + 1) & M.sb_mask;
+    }
+    return 0ull;
+}
+
 // Work counters of one query (host checker / cost model only; the device instantiation passes nullptr and COUNT = false).
 struct LcStats {
-    int rounds, bricks, probes, found, cells, cells_scanned, points, inserts;
+    int rounds, supers, probes, found, cells, cells_scanned, points, inserts;
 };
 
 LI_HD float lc_box_d2(float qx, float qy, float qz, float lox, float hix, float loy, float hiy, float loz, float hiz) {
@@ -173,7 +185,23 @@ LI_HD float lc_box_d2(float qx, float qy, float qz, float lox, float hix, float 
     return (ex * ex + ey * ey + ez * ez) * (1.0f - 1e-6f);
 }
 
+// candidate test of the inner loops. KD_TREE::calc_dist (ikd_Tree.cpp:1273-1277): (dx*dx + dy*dy) + dz*dz in f32, no FMA
+#define LC_CANDIDATE(J)                                                  \
+    do {                                                                 \
+        const float4 p_ = LC_LDG(&pool[first + (J)]);                    \
+        const float dx_ = qx - p_.x, dy_ = qy - p_.y, dz_ = qz - p_.z;   \
+        const float d_ = (dx_ * dx_ + dy_ * dy_) + dz_ * dz_;            \
+        if (COUNT) st->points++;                                         \
+        if (d_ < tau) {                                                  \
+            lc_insert(ld, li, d_, (int)(first + (J)));                   \
+            tau = fminf(ld[4], cap5);                                    \
+            if (COUNT) st->inserts++;                                    \
+        }                                                                \
+    } while (0)
+
 // Exact 5-NN of one query. ld / li: ascending squared distances / pool offsets (-1 = missing).
+// Three levels of 4x4x4 occupancy masks: super-brick (4.8 m at ds = 0.15) -> brick (1.2 m) -> cell (0.3 m); only
+// bricks that exist are probed and only occupied cells inside the ball's bounding box are tested.
 template <bool COUNT>
 LI_HD void knn5_cells(const MapDev& M, float rho2, float qx, float qy, float qz, float (&ld)[5], int (&li)[5], LcStats* st) {
 #pragma unroll
@@ -183,11 +211,11 @@ LI_HD void knn5_cells(const MapDev& M, float rho2, float qx, float qy, float qz,
     }
     const float ds = M.ds;
     const float cs = 2.0f * ds;   // cell edge (exact)
-    const float B = 8.0f * ds;
+    const float B = 8.0f * ds;    // brick edge (exact)
     const float lim = (float)(LI_CELL_LIMIT - 16 * 8) * ds;
     if (!(fabsf(qx) < lim && fabsf(qy) < lim && fabsf(qz) < lim)) return;   // also rejects NaN / inf
     // Rounding slack, as in knn5_lockstep: box indices differ from real geometry by <~ |x| 2^-23; every pruning box is
-    // inflated by `margin`, squared bounds carry a (1 - 1e-6) factor, the enumeration range a slack in cells.
+    // inflated by `margin`, squared bounds carry a (1 - 1e-6) factor, the enumeration range a slack in voxels.
     const float l1 = fabsf(qx) + fabsf(qy) + fabsf(qz);
     const float margin = 1e-6f * (l1 + 16.0f * B);
     const float inv_ds = 1.0f / ds;
@@ -199,71 +227,55 @@ LI_HD void knn5_cells(const MapDev& M, float rho2, float qx, float qy, float qz,
         if (COUNT) st->rounds++;
         const bool last = hi2 >= 5.0f;   // the radius bound d2 <= 5 is inclusive
         const float r = sqrtf(fminf(hi2, 5.0f)) * (1.0f + 1e-6f) + margin;
-        // voxel range of the ball's bounding box (conservative), cells = voxels >> 1, bricks = voxels >> 3
+        // voxel range of the ball's bounding box (conservative); cells = voxels >> 1, bricks = voxels >> 3, super-bricks = voxels >> 5
         const int lvx = (int)floorf((qx - r) * inv_ds - slk), hvx = (int)floorf((qx + r) * inv_ds + slk);
         const int lvy = (int)floorf((qy - r) * inv_ds - slk), hvy = (int)floorf((qy + r) * inv_ds + slk);
         const int lvz = (int)floorf((qz - r) * inv_ds - slk), hvz = (int)floorf((qz + r) * inv_ds + slk);
-        const int lcx = lvx >> 1, hcx = hvx >> 1, lcy = lvy >> 1, hcy = hvy >> 1, lcz = lvz >> 1, hcz = hvz >> 1;
         float tau = fminf(ld[4], cap5);
-        for (int kz = lvz >> 3; kz <= (hvz >> 3); kz++) {
-            const float bloz = (float)(kz << 3) * ds - margin, bhiz = (float)((kz + 1) << 3) * ds + margin;
-            const int az = lc_imax(lcz - 4 * kz, 0), bz = lc_imin(hcz - 4 * kz, 3);
-            for (int ky = lvy >> 3; ky <= (hvy >> 3); ky++) {
-                const float bloy = (float)(ky << 3) * ds - margin, bhiy = (float)((ky + 1) << 3) * ds + margin;
-                const int ay = lc_imax(lcy - 4 * ky, 0), by = lc_imin(hcy - 4 * ky, 3);
-                for (int kx = lvx >> 3; kx <= (hvx >> 3); kx++) {
-                    if (COUNT) st->bricks++;
-                    const float blox = (float)(kx << 3) * ds - margin, bhix = (float)((kx + 1) << 3) * ds + margin;
-                    const float db = lc_box_d2(qx, qy, qz, blox, bhix, bloy, bhiy, bloz, bhiz);
-                    // a brick's box distance bounds its cells' from below: necessary conditions only (no lo2 test here)
-                    if (!((last ? db <= 5.0f : db < hi2) && db < ld[4])) continue;
-                    if (COUNT) st->probes++;
-                    unsigned first = 0, count = 0;
-                    const int slot = lc_brick_find(M.ent, M.mask, li_pack_key(kx, ky, kz), first, count);
-                    if (slot < 0 || count == 0u) continue;
-                    if (COUNT) st->found++;
-                    const unsigned short* __restrict__ dir = M.cdir + (size_t)slot * 64;
-                    if (LC_LDG(&dir[0]) == LI_CDIR_UNINDEXED) {
-                        // oversized brick: one unit under the brick-level shell rule
-                        if (db >= lo2) {
-                            for (unsigned j = 0; j < count; j++) {
-                                const float4 p = LC_LDG(&pool[first + j]);
-                                const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
-                                const float d = (dx * dx + dy * dy) + dz * dz;
-                                if (COUNT) st->points++;
-                                if (d < tau) {
-                                    lc_insert(ld, li, d, (int)(first + j));
-                                    tau = fminf(ld[4], cap5);
-                                    if (COUNT) st->inserts++;
-                                }
-                            }
+        for (int sz = lvz >> 5; sz <= (hvz >> 5); sz++) {
+            const unsigned long long mz = lc_mask_z(lc_imax((lvz >> 3) - 4 * sz, 0), lc_imin((hvz >> 3) - 4 * sz, 3));
+            for (int sy = lvy >> 5; sy <= (hvy >> 5); sy++) {
+                const unsigned long long myz = mz & lc_mask_y(lc_imax((lvy >> 3) - 4 * sy, 0), lc_imin((hvy >> 3) - 4 * sy, 3));
+                for (int sx = lvx >> 5; sx <= (hvx >> 5); sx++) {
+                    if (COUNT) st->supers++;
+                    unsigned long long bm = lc_sb_find(M, li_pack_key(sx, sy, sz)) & myz &
+                                            lc_mask_x(lc_imax((lvx >> 3) - 4 * sx, 0), lc_imin((hvx >> 3) - 4 * sx, 3));
+                    while (bm) {
+                        const int b = lc_ctz64(bm);
+                        bm &= bm - 1ull;
+                        const int kx = 4 * sx + (b >> 4), ky = 4 * sy + ((b >> 2) & 3), kz = 4 * sz + (b & 3);
+                        const float db = lc_box_d2(qx, qy, qz, (float)kx * B - margin, (float)(kx + 1) * B + margin, (float)ky * B - margin,
+                                                   (float)(ky + 1) * B + margin, (float)kz * B - margin, (float)(kz + 1) * B + margin);
+                        // a brick's box distance bounds its cells' from below: necessary conditions only (no lo2 test here)
+                        if (!((last ? db <= 5.0f : db < hi2) && db < ld[4])) continue;
+                        if (COUNT) st->probes++;
+                        unsigned first = 0, count = 0;
+                        const int slot = lc_brick_find(M.ent, M.mask, li_pack_key(kx, ky, kz), first, count);
+                        if (slot < 0 || count == 0u) continue;
+                        if (COUNT) st->found++;
+                        const unsigned short* __restrict__ dir = M.cdir + (size_t)slot * 64;
+                        if (LC_LDG(&dir[0]) == LI_CDIR_UNINDEXED) {
+                            // oversized brick: one unit under the brick-level shell rule
+                            if (db >= lo2)
+                                for (unsigned j = 0; j < count; j++) LC_CANDIDATE(j);
+                            continue;
                         }
-                        continue;
-                    }
-                    const int ax = lc_imax(lcx - 4 * kx, 0), bx = lc_imin(hcx - 4 * kx, 3);
-                    unsigned long long m = LC_LDG(&M.cocc[slot]) & lc_mask_x(ax, bx) & lc_mask_y(ay, by) & lc_mask_z(az, bz);
-                    while (m) {
-                        const int c = lc_ctz64(m);
-                        m &= m - 1ull;
-                        if (COUNT) st->cells++;
-                        const int gx = 4 * kx + (c >> 4), gy = 4 * ky + ((c >> 2) & 3), gz = 4 * kz + (c & 3);
-                        const float dc = lc_box_d2(qx, qy, qz, (float)gx * cs - margin, (float)(gx + 1) * cs + margin, (float)gy * cs - margin,
-                                                   (float)(gy + 1) * cs + margin, (float)gz * cs - margin, (float)(gz + 1) * cs + margin);
-                        if (!(dc >= lo2 && (last ? dc <= 5.0f : dc < hi2) && dc < ld[4])) continue;
-                        if (COUNT) st->cells_scanned++;
-                        const unsigned s0 = LC_LDG(&dir[c]);
-                        const unsigned e0 = (c == 63) ? count : (unsigned)LC_LDG(&dir[c + 1]);
-                        for (unsigned j = s0; j < e0; j++) {
-                            const float4 p = LC_LDG(&pool[first + j]);
-                            // KD_TREE::calc_dist (ikd_Tree.cpp:1273-1277): (dx*dx + dy*dy) + dz*dz in f32, no FMA
-                            const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
-                            const float d = (dx * dx + dy * dy) + dz * dz;
-                            if (COUNT) st->points++;
-                            if (d < tau) {
-                                lc_insert(ld, li, d, (int)(first + j));
-                                tau = fminf(ld[4], cap5);
-                                if (COUNT) st->inserts++;
-                            }
+                        unsigned long long m = LC_LDG(&M.cocc[slot]) &
+                                               lc_mask_x(lc_imax((lvx >> 1) - 4 * kx, 0), lc_imin((hvx >> 1) - 4 * kx, 3)) &
+                                               lc_mask_y(lc_imax((lvy >> 1) - 4 * ky, 0), lc_imin((hvy >> 1) - 4 * ky, 3)) &
+                                               lc_mask_z(lc_imax((lvz >> 1) - 4 * kz, 0), lc_imin((hvz >> 1) - 4 * kz, 3));
+                        while (m) {
+                            const int c = lc_ctz64(m);
+                            m &= m - 1ull;
+                            if (COUNT) st->cells++;
+                            const int gx = 4 * kx + (c >> 4), gy = 4 * ky + ((c >> 2) & 3), gz = 4 * kz + (c & 3);
+                            const float dc = lc_box_d2(qx, qy, qz, (float)gx * cs - margin, (float)(gx + 1) * cs + margin, (float)gy * cs - margin,
+                                                       (float)(gy + 1) * cs + margin, (float)gz * cs - margin, (float)(gz + 1) * cs + margin);
+                            if (!(dc >= lo2 && (last ? dc <= 5.0f : dc < hi2) && dc < ld[4])) continue;
+                            if (COUNT) st->cells_scanned++;
+                            const unsigned s0 = LC_LDG(&dir[c]);
+                            const unsigned e0 = (c == 63) ? count : (unsigned)LC_LDG(&dir[c + 1]);
+                            for (unsigned j = s0; j < e0; j++) LC_CANDIDATE(j);
                         }
                     }
                 }
@@ -277,6 +289,35 @@ LI_HD void knn5_cells(const MapDev& M, float rho2, float qx, float qy, float qz,
 }
 
 #ifdef __CUDACC__
+// ---- super-brick table: called by the insert kernels when they CREATE a brick (map_kernels.cuh) -------------
+__device__ __forceinline__ void li_sb_mark(const MapDev& M, unsigned long long brick_key) {
+    if (!M.sb_keys) return;
+    const int kx = (int)(unsigned)(brick_key >> 42) - LI_CELL_LIMIT, ky = (int)((unsigned)(brick_key >> 21) & 0x1fffffu) - LI_CELL_LIMIT,
+              kz = (int)((unsigned)brick_key & 0x1fffffu) - LI_CELL_LIMIT;
+    const unsigned long long key = li_pack_key(kx >> 2, ky >> 2, kz >> 2);
+    const unsigned long long bit = 1ull << (((kx & 3) << 4) | ((ky & 3) << 2) | (kz & 3));
+    unsigned h = li_hash(key) & M.sb_mask;
+    for (unsigned i = 0; i <= M.sb_mask; i++) {
+        unsigned long long k = *reinterpret_cast<volatile unsigned long long*>(&M.sb_keys[h]);
+        if (k == LI_EMPTY_KEY) {
+            k = atomicCAS(&M.sb_keys[h], LI_EMPTY_KEY, key);
+            if (k == LI_EMPTY_KEY) k = key;
+        }
+        if (k == key) {
+            atomicOr(&M.sb_occ[h], bit);
+            return;
+        }
+        h = (h + 1) & M.sb_mask;
+    }
+    atomicOr(&M.counters[CNT_ERR], ERR_HASH_FULL);
+}
+__global__ void k_sb_clear(MapDev M) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > M.sb_mask) return;
+    M.sb_keys[i] = LI_EMPTY_KEY;
+    M.sb_occ[i] = 0ull;
+}
+
 // ---- directory maintenance ---------------------------------------------------------------------------
 // after k_ins_commit / k_ds_compact: the bricks of the batch's touched list (count on the device: fixed grid)
 __global__ void k_cells_refresh_touched(MapDev M) {
@@ -298,8 +339,9 @@ __global__ void k_cells_refresh_all(MapDev M, unsigned slots) {
 #ifndef LI_CELLS_THREADS
 #define LI_CELLS_THREADS 128
 #endif
-template <bool HOST>
-__global__ void __launch_bounds__(LI_CELLS_THREADS) k_knn_cells_scan(MapDev M, ScanDev S, PoseD P, float rho2, const float* __restrict__ raw, int stride) {
+// MINB: resident blocks per SM the kernel is compiled for (6 -> 80 registers, no spills; 8 -> 64 registers, ~10 spilled words)
+template <bool HOST, int MINB>
+__global__ void __launch_bounds__(LI_CELLS_THREADS, MINB) k_knn_cells_scan(MapDev M, ScanDev S, PoseD P, float rho2, const float* __restrict__ raw, int stride) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= S.n) return;
     float bx, by, bz;

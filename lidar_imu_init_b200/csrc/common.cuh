@@ -35,6 +35,11 @@ struct MapDev {
     // 4x4x4 cells (cell = 2x2x2 voxels) and the start offset of every cell inside the slab, which is kept sorted by cell
     unsigned long long* cocc;
     unsigned short* cdir;          // [slots * 64]; cdir[slot*64] == 0xffff: brick not indexed (scan the whole slab)
+    // super-brick table (cells.cuh): open addressing over 4x4x4-brick blocks; sb_occ bit b = brick b of the block was
+    // created at some time (bits are never cleared: a stale bit only costs one brick probe)
+    unsigned long long* sb_keys;
+    unsigned long long* sb_occ;
+    unsigned sb_mask;              // slots - 1
 };
 
 enum { CNT_TOUCHED = 0, CNT_ERR = 1, CNT_LIVE = 2, CNT_BRICKS = 3, CNT_CHANGED = 4, CNT_DROPPED = 5, CNT_NADD = 6, CNT_NNOD = 7, CNT_COUNT = 16 };

@@ -22,6 +22,9 @@
 #include "voxelgrid_kernels.cuh"
 #include "undistort_kernels.cuh"
 
+#ifndef LI_CELLS_MINB_DEFAULT
+#define LI_CELLS_MINB_DEFAULT 6
+#endif
 #ifndef LIINIT_KNN_DEFAULT
 #define LIINIT_KNN_DEFAULT LIINIT_KNN_BRICKS   // what knn_index = 0 selects
 #endif
@@ -89,6 +92,7 @@ struct Ctx {
     float last_ms = 0.f;
     int last_launches = 0;
     int group = 4;
+    int cells_minb = LI_CELLS_MINB_DEFAULT;   // register budget variant of the cells search kernel (developer A/B: LIINIT_CELLS_MINB)
     bool cells = false;   // knn_index = LIINIT_KNN_CELLS: per-brick cell directory + thread-per-point search (cells.cuh)
     float rho2 = 0.09f;   // squared seed radius of the 5-NN search
 };
@@ -232,14 +236,18 @@ void launch_knn_scan(Ctx* c, const PoseD& P) {
 #define LI_PLANE_WAVES 1   // the plane pass runs LI_PLANE_WAVES x (2 blocks per SM); each thread strides over the scan
 #endif
 
-void launch_knn_cells_scan(Ctx* c, const PoseD& P) {
+template <int MINB>
+void launch_knn_cells_scan_t(Ctx* c, const PoseD& P) {
     const int grid = nblk(c->scan_n, LI_CELLS_THREADS);
     if (c->attached) {
-        k_knn_cells_scan<true><<<grid, LI_CELLS_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, c->attached, c->attached_stride);
+        k_knn_cells_scan<true, MINB><<<grid, LI_CELLS_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, c->attached, c->attached_stride);
         c->attached = nullptr;   // the kernel leaves the packed copy in d_body
     } else {
-        k_knn_cells_scan<false><<<grid, LI_CELLS_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, nullptr, 0);
+        k_knn_cells_scan<false, MINB><<<grid, LI_CELLS_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, nullptr, 0);
     }
+}
+void launch_knn_cells_scan(Ctx* c, const PoseD& P) {
+    if (c->cells_minb == 8) launch_knn_cells_scan_t<8>(c, P); else if (c->cells_minb == 4) launch_knn_cells_scan_t<4>(c, P); else launch_knn_cells_scan_t<6>(c, P);
 }
 
 constexpr int TPQ_CH = 32, TPQ_NB = 8;
@@ -384,6 +392,10 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
         }
         // the cell directory is defined for 8x8x8-voxel bricks; another brick size keeps the brick search
         c->cells = (ki == LIINIT_KNN_CELLS) && bs == LI_CELLS_BSHIFT;
+        const char* mb = getenv("LIINIT_CELLS_MINB");
+        if (mb && atoi(mb) == 8) c->cells_minb = 8;
+        if (mb && atoi(mb) == 6) c->cells_minb = 6;
+        if (mb && atoi(mb) == 4) c->cells_minb = 4;
     }
     {
         float cells = cfg->knn_seed_radius_cells > 0.f ? cfg->knn_seed_radius_cells : 2.0f;
@@ -404,9 +416,16 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
     CUC(cudaMalloc(&M.pool_top, sizeof(unsigned long long)));
     M.cocc = nullptr;
     M.cdir = nullptr;
+    M.sb_keys = nullptr;
+    M.sb_occ = nullptr;
+    M.sb_mask = 0;
     if (c->cells) {
         CUC(cudaMalloc(&M.cocc, (size_t)c->hash_slots * sizeof(unsigned long long)));
         CUC(cudaMalloc(&M.cdir, (size_t)c->hash_slots * 64 * sizeof(unsigned short)));
+        // one super-brick per brick in the worst case (scattered points): same slot count as the brick hash
+        M.sb_mask = c->hash_slots - 1;
+        CUC(cudaMalloc(&M.sb_keys, (size_t)c->hash_slots * sizeof(unsigned long long)));
+        CUC(cudaMalloc(&M.sb_occ, (size_t)c->hash_slots * sizeof(unsigned long long)));
     }
     int batch = cfg->max_scan_points > (1 << 20) ? cfg->max_scan_points : (1 << 20);
     c->stage_pts_cap = batch;
@@ -454,6 +473,10 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
     CUC(cudaMemsetAsync(M.pool_top, 0, sizeof(unsigned long long), c->stream));
     k_map_clear<<<nblk(c->hash_slots, 256), 256, 0, c->stream>>>(M.ent, M.aux, c->hash_slots);
     c->launches++;
+    if (c->cells) {
+        k_sb_clear<<<nblk(c->hash_slots, 256), 256, 0, c->stream>>>(M);
+        c->launches++;
+    }
     CUC(cudaGetLastError());
     CUC(cudaStreamSynchronize(c->stream));
     c->S.body = c->d_body;
@@ -472,7 +495,7 @@ int liinit_destroy(liinit_ctx* h) {
     Ctx* c = &h->c;
     cudaSetDevice(c->device);
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
-    cudaFree(c->M.ent); cudaFree(c->M.aux); cudaFree(c->M.pool); cudaFree(c->M.pool_top); cudaFree(c->M.touched_list); cudaFree(c->M.cocc); cudaFree(c->M.cdir);
+    cudaFree(c->M.ent); cudaFree(c->M.aux); cudaFree(c->M.pool); cudaFree(c->M.pool_top); cudaFree(c->M.touched_list); cudaFree(c->M.cocc); cudaFree(c->M.cdir); cudaFree(c->M.sb_keys); cudaFree(c->M.sb_occ);
     cudaFree(c->d_counters); cudaFreeHost(c->h_counters); cudaFree(c->d_stage_raw); cudaFree(c->d_stage_pts);
     cudaFree(c->d_slot_of); cudaFree(c->d_vslot_of); cudaFree(c->d_flag); cudaFree(c->d_ins); cudaFree(c->V.keys); cudaFree(c->V.head); cudaFree(c->d_vg_imin); cudaFree(c->d_vg_block); cudaFree(c->d_vg_misc); cudaFree(c->d_rs_keys); cudaFree(c->d_rs_vals); cudaFree(c->d_rs_hist); cudaFree(c->d_vg_params); cudaFree(c->d_tmin_idx); cudaFree(c->d_poses);
     cudaFree(c->d_body); cudaFree(c->d_world); cudaFree(c->d_near_ids); cudaFree(c->d_selected); cudaFree(c->d_normvec);
@@ -504,6 +527,10 @@ int liinit_map_build(liinit_ctx* h, const float* xyz, int stride, int n) {
     CU(cudaMemsetAsync(c->M.pool_top, 0, sizeof(unsigned long long), c->stream));
     k_map_clear<<<nblk(c->hash_slots, 256), 256, 0, c->stream>>>(c->M.ent, c->M.aux, c->hash_slots);
     c->launches++;
+    if (c->cells) {
+        k_sb_clear<<<nblk(c->hash_slots, 256), 256, 0, c->stream>>>(c->M);
+        c->launches++;
+    }
     c->have_neighbors = false;
     for (long long off = 0; off < n; off += c->stage_pts_cap) {
         int m = (int)((n - off < c->stage_pts_cap) ? (n - off) : c->stage_pts_cap);
@@ -1024,6 +1051,12 @@ int liinit_last_pass_kernel_times(liinit_ctx* h, float* knn_ms, float* plane_ms)
     }
     if (knn_ms) *knn_ms = a;
     if (plane_ms) *plane_ms = b;
+    return LIINIT_OK;
+}
+
+int liinit_knn_index(liinit_ctx* h, int* knn_index) {
+    if (!h || !knn_index) return LIINIT_ERR_INVALID;
+    *knn_index = h->c.cells ? LIINIT_KNN_CELLS : LIINIT_KNN_BRICKS;
     return LIINIT_OK;
 }
 

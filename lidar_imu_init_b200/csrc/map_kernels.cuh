@@ -8,6 +8,7 @@
 // produces, independent of order.
 #pragma once
 #include "common.cuh"
+#include "cells.cuh"   // li_sb_mark: super-brick occupancy of the cell-directory search (no-op unless enabled)
 
 // ---- staging: strided host layout -> float4 -------------------------------------------------------
 __global__ void k_repack(const float* __restrict__ src, int stride, int n, float4* __restrict__ dst) {
@@ -113,7 +114,10 @@ __global__ void k_ins_count(MapDev M, const float4* __restrict__ pts, int n, con
         return;
     }
     slot_of[i] = s;
-    if (created) atomicAdd(&M.counters[CNT_BRICKS], 1);
+    if (created) {
+        atomicAdd(&M.counters[CNT_BRICKS], 1);
+        li_sb_mark(M, key);
+    }
     atomicAdd(&M.aux[s].y, 1u);
     li_touch(M, s);
 }
@@ -242,7 +246,10 @@ __global__ void k_ds_link(MapDev M, VoxTmp V, const float4* __restrict__ pts, in
         atomicOr(&M.counters[CNT_ERR], ERR_HASH_FULL);
         return;
     }
-    if (created) atomicAdd(&M.counters[CNT_BRICKS], 1);
+    if (created) {
+        atomicAdd(&M.counters[CNT_BRICKS], 1);
+        li_sb_mark(M, skey);
+    }
     slot_of[i] = s;
     atomicAdd(&M.aux[s].y, 1u);
     li_touch(M, s);

@@ -49,7 +49,7 @@ def load():
     return _L
 
 
-STAT_NAMES = ("rounds", "bricks", "probes", "found", "cells", "cells_scanned", "points", "inserts")
+STAT_NAMES = ("rounds", "supers", "probes", "found", "cells", "cells_scanned", "points", "inserts")
 
 
 class CellsEmul:

@@ -24,6 +24,7 @@ struct Emul {
     std::vector<float4> pool;
     std::vector<unsigned long long> cocc;
     std::vector<unsigned short> cdir;
+    std::vector<unsigned long long> sb_keys, sb_occ;
     std::vector<int> counters;
     MapDev M{};
     int hash_log2 = 16;
@@ -79,6 +80,22 @@ void layout(Emul* E, bool refresh) {
     E->M.bshift = 3;
     E->M.cocc = E->cocc.data();
     E->M.cdir = E->cdir.data();
+    // super-brick table, as li_sb_mark fills it when bricks are created
+    E->sb_keys.assign(slots, LI_EMPTY_KEY);
+    E->sb_occ.assign(slots, 0ull);
+    E->M.sb_keys = E->sb_keys.data();
+    E->M.sb_occ = E->sb_occ.data();
+    E->M.sb_mask = (unsigned)slots - 1;
+    for (auto& kv : E->bricks) {
+        const unsigned long long bk = kv.first;
+        const int kx = (int)(unsigned)(bk >> 42) - LI_CELL_LIMIT, ky = (int)((unsigned)(bk >> 21) & 0x1fffffu) - LI_CELL_LIMIT,
+                  kz = (int)((unsigned)bk & 0x1fffffu) - LI_CELL_LIMIT;
+        const unsigned long long key = li_pack_key(kx >> 2, ky >> 2, kz >> 2);
+        unsigned h = li_hash(key) & E->M.sb_mask;
+        while (E->sb_keys[h] != LI_EMPTY_KEY && E->sb_keys[h] != key) h = (h + 1) & E->M.sb_mask;
+        E->sb_keys[h] = key;
+        E->sb_occ[h] |= 1ull << (((kx & 3) << 4) | ((ky & 3) << 2) | (kz & 3));
+    }
     size_t off = 0;
     for (auto& kv : E->bricks) {
         unsigned h = li_hash(kv.first) & E->M.mask;

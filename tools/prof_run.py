@@ -11,9 +11,10 @@ ap.add_argument("--brick", type=int, default=0)
 ap.add_argument("--imu", type=int, default=0)
 ap.add_argument("--passes", type=int, default=4)
 ap.add_argument("--rho", type=float, default=0.0)
+ap.add_argument("--index", type=int, default=0)
 a = ap.parse_args()
 c = scenes.make_config("C2", N=a.N, M=a.M)
-g = capi.LiInitGpu(c["ds"], max_map_points=int(a.M * 1.2), max_scan_points=a.N + 10, knn_group_lanes=a.group, brick_cells_log2=a.brick, knn_seed_radius_cells=a.rho)
+g = capi.LiInitGpu(c["ds"], max_map_points=int(a.M * 1.2), max_scan_points=a.N + 10, knn_group_lanes=a.group, brick_cells_log2=a.brick, knn_seed_radius_cells=a.rho, knn_index=a.index)
 g.map_build(c["map_xyz"])
 g.scan_upload(c["body_xyz"])
 p = c["pose_init"]

@@ -288,6 +288,136 @@ LI_HD void knn5_cells(const MapDev& M, float rho2, float qx, float qy, float qz,
     }
 }
 
+// ---- variant 2: growing BOXES instead of shells -----------------------------------------------------------------
+// The per-cell box distance of knn5_cells costs about as many instructions as scanning the ~3 points a cell of a
+// downsampled surface map holds, so here a cell is never tested: round k scans EVERY occupied cell of the voxel box
+// around the ball of radius r_k that was not already inside the box of round k-1 (the previous box is masked out, so no
+// point is seen twice), and only the always-safe bound "unit farther than the current 5th best" prunes bricks and
+// large cells. After round k every map point within r_k of the query has been examined, hence
+//     stop   5 known and d5 <= r_k^2, or r_k^2 >= 5;     next   r^2 = d5 if 5 are known (one closing round) else 4 r^2.
+// bits of the cells (or bricks) of block k whose coordinate on one axis lies in [lo, hi] (global index); 0 if none
+LI_HD unsigned long long lc_range_x(int lo, int hi, int k) {
+    const int a = lc_imax(lo - 4 * k, 0), b = lc_imin(hi - 4 * k, 3);
+    return a <= b ? lc_mask_x(a, b) : 0ull;
+}
+LI_HD unsigned long long lc_range_y(int lo, int hi, int k) {
+    const int a = lc_imax(lo - 4 * k, 0), b = lc_imin(hi - 4 * k, 3);
+    return a <= b ? lc_mask_y(a, b) : 0ull;
+}
+LI_HD unsigned long long lc_range_z(int lo, int hi, int k) {
+    const int a = lc_imax(lo - 4 * k, 0), b = lc_imin(hi - 4 * k, 3);
+    return a <= b ? lc_mask_z(a, b) : 0ull;
+}
+
+#ifndef LI_CELLS_BIG
+#define LI_CELLS_BIG 16   // cells with more points than this are tested against the 5th best before they are scanned
+#endif
+
+template <bool COUNT>
+LI_HD void knn5_boxes(const MapDev& M, float rho2, float qx, float qy, float qz, float (&ld)[5], int (&li)[5], LcStats* st) {
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        ld[i] = INFINITY;
+        li[i] = -1;
+    }
+    const float ds = M.ds;
+    const float cs = 2.0f * ds;   // cell edge (exact)
+    const float B = 8.0f * ds;    // brick edge (exact)
+    const float lim = (float)(LI_CELL_LIMIT - 16 * 8) * ds;
+    if (!(fabsf(qx) < lim && fabsf(qy) < lim && fabsf(qz) < lim)) return;   // also rejects NaN / inf
+    const float l1 = fabsf(qx) + fabsf(qy) + fabsf(qz);
+    const float margin = 1e-6f * (l1 + 16.0f * B);
+    const float inv_ds = 1.0f / ds;
+    const float slk = 0.02f + 4e-7f * l1 * inv_ds;
+    const float cap5 = lc_u2f(0x40a00001u);   // smallest float above 5: d <= 5 <=> d < cap5
+    const float4* __restrict__ pool = M.pool;
+    float hi2 = rho2;
+    // cell box of the previous round (empty before the first)
+    int pcx0 = 1, pcx1 = 0, pcy0 = 1, pcy1 = 0, pcz0 = 1, pcz1 = 0;
+    for (;;) {
+        if (COUNT) st->rounds++;
+        const bool last = hi2 >= 5.0f;
+        const float r = sqrtf(fminf(hi2, 5.0f)) * (1.0f + 1e-6f) + margin;
+        // voxel box around the ball (conservative: every map point within sqrt(hi2) of the query is stored under a voxel
+        // index inside it); cells = voxels >> 1, bricks = voxels >> 3, super-bricks = voxels >> 5
+        const int lvx = (int)floorf((qx - r) * inv_ds - slk), hvx = (int)floorf((qx + r) * inv_ds + slk);
+        const int lvy = (int)floorf((qy - r) * inv_ds - slk), hvy = (int)floorf((qy + r) * inv_ds + slk);
+        const int lvz = (int)floorf((qz - r) * inv_ds - slk), hvz = (int)floorf((qz + r) * inv_ds + slk);
+        // the box never shrinks: keep it a superset of the previous one, so "previous box" = "everything scanned so far"
+        const int cx0 = lc_imin(lvx >> 1, pcx0 <= pcx1 ? pcx0 : (lvx >> 1)), cx1 = lc_imax(hvx >> 1, pcx0 <= pcx1 ? pcx1 : (hvx >> 1));
+        const int cy0 = lc_imin(lvy >> 1, pcy0 <= pcy1 ? pcy0 : (lvy >> 1)), cy1 = lc_imax(hvy >> 1, pcy0 <= pcy1 ? pcy1 : (hvy >> 1));
+        const int cz0 = lc_imin(lvz >> 1, pcz0 <= pcz1 ? pcz0 : (lvz >> 1)), cz1 = lc_imax(hvz >> 1, pcz0 <= pcz1 ? pcz1 : (hvz >> 1));
+        float tau = fminf(ld[4], cap5);
+        for (int sz = cz0 >> 4; sz <= (cz1 >> 4); sz++) {
+            const unsigned long long mz = lc_range_z(cz0 >> 2, cz1 >> 2, sz);
+            for (int sy = cy0 >> 4; sy <= (cy1 >> 4); sy++) {
+                const unsigned long long myz = mz & lc_range_y(cy0 >> 2, cy1 >> 2, sy);
+                for (int sx = cx0 >> 4; sx <= (cx1 >> 4); sx++) {
+                    if (COUNT) st->supers++;
+                    unsigned long long bm = lc_sb_find(M, li_pack_key(sx, sy, sz)) & myz & lc_range_x(cx0 >> 2, cx1 >> 2, sx);
+                    while (bm) {
+                        const int b = lc_ctz64(bm);
+                        bm &= bm - 1ull;
+                        const int kx = 4 * sx + (b >> 4), ky = 4 * sy + ((b >> 2) & 3), kz = 4 * sz + (b & 3);
+                        // cells of this brick inside the current box and not inside the previous one
+                        const unsigned long long want = lc_range_x(cx0, cx1, kx) & lc_range_y(cy0, cy1, ky) & lc_range_z(cz0, cz1, kz);
+                        const unsigned long long seen = lc_range_x(pcx0, pcx1, kx) & lc_range_y(pcy0, pcy1, ky) & lc_range_z(pcz0, pcz1, kz);
+                        if ((want & ~seen) == 0ull) continue;
+                        const float db = lc_box_d2(qx, qy, qz, (float)kx * B - margin, (float)(kx + 1) * B + margin, (float)ky * B - margin,
+                                                   (float)(ky + 1) * B + margin, (float)kz * B - margin, (float)(kz + 1) * B + margin);
+                        if (!(db < tau)) continue;   // nothing in this brick can enter the top 5 (safe at any time: tau only shrinks)
+                        if (COUNT) st->probes++;
+                        unsigned first = 0, count = 0;
+                        const int slot = lc_brick_find(M.ent, M.mask, li_pack_key(kx, ky, kz), first, count);
+                        if (slot < 0 || count == 0u) continue;
+                        if (COUNT) st->found++;
+                        const unsigned short* __restrict__ dir = M.cdir + (size_t)slot * 64;
+                        if (LC_LDG(&dir[0]) == LI_CDIR_UNINDEXED) {
+                            // oversized brick (no directory): one unit; scanned in the first round whose box touches it
+                            if (seen == 0ull)
+                                for (unsigned j = 0; j < count; j++) LC_CANDIDATE(j);
+                            continue;
+                        }
+                        unsigned long long m = LC_LDG(&M.cocc[slot]) & want & ~seen;
+                        while (m) {
+                            const int c = lc_ctz64(m);
+                            m &= m - 1ull;
+                            if (COUNT) st->cells++;
+                            const unsigned s0 = LC_LDG(&dir[c]);
+                            const unsigned e0 = (c == 63) ? count : (unsigned)LC_LDG(&dir[c + 1]);
+                            if (e0 - s0 > (unsigned)LI_CELLS_BIG) {
+                                const int gx = 4 * kx + (c >> 4), gy = 4 * ky + ((c >> 2) & 3), gz = 4 * kz + (c & 3);
+                                const float dc = lc_box_d2(qx, qy, qz, (float)gx * cs - margin, (float)(gx + 1) * cs + margin, (float)gy * cs - margin,
+                                                           (float)(gy + 1) * cs + margin, (float)gz * cs - margin, (float)(gz + 1) * cs + margin);
+                                if (!(dc < tau)) continue;
+                            }
+                            if (COUNT) st->cells_scanned++;
+                            for (unsigned j = s0; j < e0; j++) LC_CANDIDATE(j);
+                        }
+                    }
+                }
+            }
+        }
+        const bool full = li[4] >= 0;
+        if (last || (full && ld[4] <= hi2)) break;
+        pcx0 = cx0; pcx1 = cx1; pcy0 = cy0; pcy1 = cy1; pcz0 = cz0; pcz1 = cz1;
+        hi2 = full ? fminf(ld[4] * (1.0f + 1e-6f), 5.0f) : fminf(4.0f * hi2, 5.0f);
+    }
+}
+
+// which of the two searches the kernels (and the host checker by default) use
+#ifndef LI_CELLS_SEARCH
+#define LI_CELLS_SEARCH 1   // 1 = shells on cells (knn5_cells), 2 = growing boxes (knn5_boxes)
+#endif
+template <bool COUNT>
+LI_HD void knn5_dir(const MapDev& M, float rho2, float qx, float qy, float qz, float (&ld)[5], int (&li)[5], LcStats* st) {
+#if LI_CELLS_SEARCH == 2
+    knn5_boxes<COUNT>(M, rho2, qx, qy, qz, ld, li, st);
+#else
+    knn5_cells<COUNT>(M, rho2, qx, qy, qz, ld, li, st);
+#endif
+}
+
 #ifdef __CUDACC__
 // ---- super-brick table: called by the insert kernels when they CREATE a brick (map_kernels.cuh) -------------
 __device__ __forceinline__ void li_sb_mark(const MapDev& M, unsigned long long brick_key) {
@@ -357,7 +487,7 @@ __global__ void __launch_bounds__(LI_CELLS_THREADS, MINB) k_knn_cells_scan(MapDe
     li_body_to_world(P, bx, by, bz, wx, wy, wz);
     float ld[5];
     int li[5];
-    knn5_cells<false>(M, rho2, wx, wy, wz, ld, li, nullptr);
+    knn5_dir<false>(M, rho2, wx, wy, wz, ld, li, nullptr);
     S.world[q] = make_float4(wx, wy, wz, 0.f);
 #pragma unroll
     for (int k = 0; k < 5; k++) S.near_ids[(size_t)q * 5 + k] = li[k];
@@ -371,7 +501,7 @@ __global__ void __launch_bounds__(LI_CELLS_THREADS) k_knn_cells_queries(MapDev M
     const float4 p = __ldg(&qpts[q]);
     float ld[5];
     int li[5];
-    knn5_cells<false>(M, rho2, p.x, p.y, p.z, ld, li, nullptr);
+    knn5_dir<false>(M, rho2, p.x, p.y, p.z, ld, li, nullptr);
 #pragma unroll
     for (int k = 0; k < 5; k++) {
         ids[(size_t)q * 5 + k] = li[k];

@@ -44,7 +44,7 @@ def load():
         L.emul_destroy.argtypes = [C.c_void_p]
         L.emul_num_bricks.argtypes = [C.c_void_p]
         L.emul_check_directory.argtypes = [C.c_void_p]
-        L.emul_knn.argtypes = [C.c_void_p, _f32, C.c_int, C.c_float, _f32, _f32, _i32, C.c_void_p]
+        L.emul_knn.argtypes = [C.c_void_p, _f32, C.c_int, C.c_float, C.c_int, _f32, _f32, _i32, C.c_void_p]
         _L = L
     return _L
 
@@ -72,14 +72,14 @@ class CellsEmul:
     def num_bricks(self) -> int:
         return self.L.emul_num_bricks(self.h)
 
-    def knn(self, q, rho=0.3, stats=False):
+    def knn(self, q, rho=0.3, stats=False, variant=0):
         q = np.ascontiguousarray(q, np.float32).reshape(-1, 3)
         n = len(q)
         xyz = np.zeros((n, 5, 3), np.float32)
         d2 = np.zeros((n, 5), np.float32)
         cnt = np.zeros(n, np.int32)
         st = np.zeros((n, 8), np.int32) if stats else None
-        self.L.emul_knn(self.h, q, n, np.float32(rho) * np.float32(rho), xyz, d2, cnt, st.ctypes.data_as(C.c_void_p) if stats else None)
+        self.L.emul_knn(self.h, q, n, np.float32(rho) * np.float32(rho), variant, xyz, d2, cnt, st.ctypes.data_as(C.c_void_p) if stats else None)
         return (xyz, d2, cnt, st) if stats else (xyz, d2, cnt)
 
     def close(self):

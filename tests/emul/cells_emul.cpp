@@ -171,8 +171,9 @@ int emul_check_directory(void* h) {
     return bad;
 }
 
-// 5-NN of n queries (packed xyz). out_xyz [n*15], out_d2 [n*5] (-1 = missing), out_cnt [n], stats [n*8] or NULL.
-void emul_knn(void* h, const float* q, int n, float rho2, float* out_xyz, float* out_d2, int* out_cnt, int* stats) {
+// 5-NN of n queries (packed xyz). variant: 0 = the search the kernels are built with, 1 = shells on cells, 2 = growing boxes.
+// out_xyz [n*15], out_d2 [n*5] (-1 = missing), out_cnt [n], stats [n*8] or NULL.
+void emul_knn(void* h, const float* q, int n, float rho2, int variant, float* out_xyz, float* out_d2, int* out_cnt, int* stats) {
     Emul* E = (Emul*)h;
 #pragma omp parallel for schedule(dynamic, 256)
     for (int i = 0; i < n; i++) {
@@ -180,7 +181,9 @@ void emul_knn(void* h, const float* q, int n, float rho2, float* out_xyz, float*
         int li[5];
         LcStats st;
         std::memset(&st, 0, sizeof(st));
-        knn5_cells<true>(E->M, rho2, q[3 * (size_t)i], q[3 * (size_t)i + 1], q[3 * (size_t)i + 2], ld, li, &st);
+        if (variant == 2) knn5_boxes<true>(E->M, rho2, q[3 * (size_t)i], q[3 * (size_t)i + 1], q[3 * (size_t)i + 2], ld, li, &st);
+        else if (variant == 1) knn5_cells<true>(E->M, rho2, q[3 * (size_t)i], q[3 * (size_t)i + 1], q[3 * (size_t)i + 2], ld, li, &st);
+        else knn5_dir<true>(E->M, rho2, q[3 * (size_t)i], q[3 * (size_t)i + 1], q[3 * (size_t)i + 2], ld, li, &st);   // what the kernels run
         int cnt = 0;
         for (int k = 0; k < 5; k++) {
             if (li[k] >= 0) {

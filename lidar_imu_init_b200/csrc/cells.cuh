@@ -176,7 +176,13 @@ LI_HD unsigned long long lc_sb_find(const MapDev& M, unsigned long long key) {
 // Work counters of one query (host checker / cost model only; the device instantiation passes nullptr and COUNT = false).
 struct LcStats {
     int rounds, supers, probes, found, cells, cells_scanned, points, inserts;
+    int* tr;        // optional structure trace (knn5_boxes): -1 round, -2 super-brick, -3 brick + status, -4 cell + points + insert bits
+    int ntr, cap;
 };
+#define LC_TR(v)                                                    \
+    do {                                                            \
+        if (COUNT && st->tr && st->ntr < st->cap) st->tr[st->ntr++] = (v); \
+    } while (0)
 
 LI_HD float lc_box_d2(float qx, float qy, float qz, float lox, float hix, float loy, float hiy, float loz, float hiz) {
     const float ex = fmaxf(0.f, fmaxf(lox - qx, qx - hix));
@@ -336,6 +342,7 @@ LI_HD void knn5_boxes(const MapDev& M, float rho2, float qx, float qy, float qz,
     int pcx0 = 1, pcx1 = 0, pcy0 = 1, pcy1 = 0, pcz0 = 1, pcz1 = 0;
     for (;;) {
         if (COUNT) st->rounds++;
+        LC_TR(-1);
         const bool last = hi2 >= 5.0f;
         const float r = sqrtf(fminf(hi2, 5.0f)) * (1.0f + 1e-6f) + margin;
         // voxel box around the ball (conservative: every map point within sqrt(hi2) of the query is stored under a voxel
@@ -354,6 +361,7 @@ LI_HD void knn5_boxes(const MapDev& M, float rho2, float qx, float qy, float qz,
                 const unsigned long long myz = mz & lc_range_y(cy0 >> 2, cy1 >> 2, sy);
                 for (int sx = cx0 >> 4; sx <= (cx1 >> 4); sx++) {
                     if (COUNT) st->supers++;
+                    LC_TR(-2);
                     unsigned long long bm = lc_sb_find(M, li_pack_key(sx, sy, sz)) & myz & lc_range_x(cx0 >> 2, cx1 >> 2, sx);
                     while (bm) {
                         const int b = lc_ctz64(bm);
@@ -362,15 +370,20 @@ LI_HD void knn5_boxes(const MapDev& M, float rho2, float qx, float qy, float qz,
                         // cells of this brick inside the current box and not inside the previous one
                         const unsigned long long want = lc_range_x(cx0, cx1, kx) & lc_range_y(cy0, cy1, ky) & lc_range_z(cz0, cz1, kz);
                         const unsigned long long seen = lc_range_x(pcx0, pcx1, kx) & lc_range_y(pcy0, pcy1, ky) & lc_range_z(pcz0, pcz1, kz);
+                        LC_TR(-3);
+                        int* trs = (COUNT && st->tr && st->ntr < st->cap) ? &st->tr[st->ntr++] : nullptr;   // brick status
+                        if (trs) *trs = 0;
                         if ((want & ~seen) == 0ull) continue;
                         const float db = lc_box_d2(qx, qy, qz, (float)kx * B - margin, (float)(kx + 1) * B + margin, (float)ky * B - margin,
                                                    (float)(ky + 1) * B + margin, (float)kz * B - margin, (float)(kz + 1) * B + margin);
                         if (!(db < tau)) continue;   // nothing in this brick can enter the top 5 (safe at any time: tau only shrinks)
                         if (COUNT) st->probes++;
+                        if (trs) *trs = 1;
                         unsigned first = 0, count = 0;
                         const int slot = lc_brick_find(M.ent, M.mask, li_pack_key(kx, ky, kz), first, count);
                         if (slot < 0 || count == 0u) continue;
                         if (COUNT) st->found++;
+                        if (trs) *trs = 2;
                         const unsigned short* __restrict__ dir = M.cdir + (size_t)slot * 64;
                         if (LC_LDG(&dir[0]) == LI_CDIR_UNINDEXED) {
                             // oversized brick (no directory): one unit; scanned in the first round whose box touches it
@@ -392,7 +405,17 @@ LI_HD void knn5_boxes(const MapDev& M, float rho2, float qx, float qy, float qz,
                                 if (!(dc < tau)) continue;
                             }
                             if (COUNT) st->cells_scanned++;
-                            for (unsigned j = s0; j < e0; j++) LC_CANDIDATE(j);
+                            LC_TR(-4);
+                            LC_TR((int)(e0 - s0));
+                            const int ins0 = COUNT ? st->inserts : 0;
+                            int* trb = (COUNT && st->tr && st->ntr < st->cap) ? &st->tr[st->ntr++] : nullptr;   // insert bits
+                            if (trb) *trb = 0;
+                            for (unsigned j = s0; j < e0; j++) {
+                                const int before = COUNT ? st->inserts : 0;
+                                LC_CANDIDATE(j);
+                                if (trb && j - s0 < 31 && st->inserts != before) *trb |= 1 << (j - s0);
+                            }
+                            (void)ins0;
                         }
                     }
                 }
@@ -405,18 +428,206 @@ LI_HD void knn5_boxes(const MapDev& M, float rho2, float qx, float qy, float qz,
     }
 }
 
-// which of the two searches the kernels (and the host checker by default) use
-#ifndef LI_CELLS_SEARCH
-#define LI_CELLS_SEARCH 1   // 1 = shells on cells (knn5_cells), 2 = growing boxes (knn5_boxes)
-#endif
-template <bool COUNT>
-LI_HD void knn5_dir(const MapDev& M, float rho2, float qx, float qy, float qz, float (&ld)[5], int (&li)[5], LcStats* st) {
-#if LI_CELLS_SEARCH == 2
-    knn5_boxes<COUNT>(M, rho2, qx, qy, qz, ld, li, st);
+// ---- variant 3: growing boxes, ENUMERATE then STREAM ----------------------------------------------------------------
+// Measured on B200 (profiles/r01_cells): the free-running nested loops of knn5_cells / knn5_boxes keep 5 of 32 lanes
+// busy -- a warp pays, at every nesting level, for the longest trip count among its lanes (tools/cells_cost_model.py
+// reproduces the instruction count from the CPU traces). Here the work of a round is split so that the long loop is FLAT:
+//   A  enumerate: per lane a small state machine walks super-bricks -> bricks (probe, masks) and pushes the point range
+//      (start, count) of every cell to scan into the lane's queue (shared memory on the device);
+//   B  stream: all lanes walk their queues, ONE candidate per lane and iteration -- the trip count is the maximum over
+//      the lanes of their TOTAL candidate count, not a sum of per-cell maxima.
+// Every loop that contains a vote is warp-uniform (LC_ANY = __any_sync over the full warp on the device, the lane's own
+// predicate on the host, where one lane runs alone); a full queue anywhere makes the whole warp drain. The set of
+// candidates a lane evaluates, and their order, does not depend on the other lanes, so results are identical on both
+// sides. Search logic = knn5_boxes.
+#ifdef __CUDA_ARCH__
+#define LC_ANY(p) __any_sync(0xffffffffu, (p))
 #else
-    knn5_cells<COUNT>(M, rho2, qx, qy, qz, ld, li, st);
+#define LC_ANY(p) (p)
 #endif
+
+#ifndef LI_CELLS_QC
+#define LI_CELLS_QC 32   // point ranges a lane can queue before the warp drains
+#endif
+
+struct LcQ {            // this lane's queue: entry i at [i * stride]
+    unsigned* rstart;          // absolute pool offset of the range
+    unsigned short* rcount;    // <= 0xfff0 points (cells of indexed bricks only)
+    int stride;
+};
+
+#define LC_CANDIDATE_ABS(J)                                              \
+    do {                                                                 \
+        const float4 p_ = LC_LDG(&pool[(J)]);                            \
+        const float dx_ = qx - p_.x, dy_ = qy - p_.y, dz_ = qz - p_.z;   \
+        const float d_ = (dx_ * dx_ + dy_ * dy_) + dz_ * dz_;            \
+        if (COUNT) st->points++;                                         \
+        if (d_ < tau) {                                                  \
+            lc_insert(ld, li, d_, (int)(J));                             \
+            tau = fminf(ld[4], cap5);                                    \
+            if (COUNT) st->inserts++;                                    \
+        }                                                                \
+    } while (0)
+
+// phase B: evaluate the nr queued ranges of every lane, one candidate per lane and iteration
+template <bool COUNT>
+LI_HD void lc_drain(const float4* __restrict__ pool, const LcQ& Q, int nr, float qx, float qy, float qz, float cap5, float& tau, float (&ld)[5],
+                    int (&li)[5], LcStats* st) {
+    int ri = 0;
+    unsigned j = 0, e = 0;
+    while (LC_ANY(ri < nr || j < e)) {
+        if (j >= e && ri < nr) {
+            j = Q.rstart[ri * Q.stride];
+            e = j + Q.rcount[ri * Q.stride];
+            ri++;
+        }
+        if (j < e) {
+            LC_CANDIDATE_ABS(j);
+            j++;
+        }
+    }
 }
+
+template <bool COUNT>
+LI_HD void knn5_stream(const MapDev& M, float rho2, bool valid, float qx, float qy, float qz, float (&ld)[5], int (&li)[5], LcStats* st, const LcQ& Q) {
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        ld[i] = INFINITY;
+        li[i] = -1;
+    }
+    const float ds = M.ds;
+    const float cs = 2.0f * ds;   // cell edge (exact)
+    const float B = 8.0f * ds;    // brick edge (exact)
+    const float lim = (float)(LI_CELL_LIMIT - 16 * 8) * ds;
+    bool done = !(valid && fabsf(qx) < lim && fabsf(qy) < lim && fabsf(qz) < lim);   // also rejects NaN / inf
+    if (done) {
+        qx = 0.f; qy = 0.f; qz = 0.f;
+    }
+    const float l1 = fabsf(qx) + fabsf(qy) + fabsf(qz);
+    const float margin = 1e-6f * (l1 + 16.0f * B);
+    const float inv_ds = 1.0f / ds;
+    const float slk = 0.02f + 4e-7f * l1 * inv_ds;
+    const float cap5 = lc_u2f(0x40a00001u);   // smallest float above 5: d <= 5 <=> d < cap5
+    const float4* __restrict__ pool = M.pool;
+    float hi2 = rho2;
+    float tau = cap5;
+    int pcx0 = 1, pcx1 = 0, pcy0 = 1, pcy1 = 0, pcz0 = 1, pcz1 = 0;   // cell box of the previous round (empty before the first)
+    while (LC_ANY(!done)) {
+        const bool need = !done;
+        if (COUNT && need) st->rounds++;
+        const bool last = hi2 >= 5.0f;
+        const float r = sqrtf(fminf(hi2, 5.0f)) * (1.0f + 1e-6f) + margin;
+        const int lvx = (int)floorf((qx - r) * inv_ds - slk), hvx = (int)floorf((qx + r) * inv_ds + slk);
+        const int lvy = (int)floorf((qy - r) * inv_ds - slk), hvy = (int)floorf((qy + r) * inv_ds + slk);
+        const int lvz = (int)floorf((qz - r) * inv_ds - slk), hvz = (int)floorf((qz + r) * inv_ds + slk);
+        const bool hadp = pcx0 <= pcx1;
+        const int cx0 = hadp ? lc_imin(lvx >> 1, pcx0) : (lvx >> 1), cx1 = hadp ? lc_imax(hvx >> 1, pcx1) : (hvx >> 1);
+        const int cy0 = hadp ? lc_imin(lvy >> 1, pcy0) : (lvy >> 1), cy1 = hadp ? lc_imax(hvy >> 1, pcy1) : (hvy >> 1);
+        const int cz0 = hadp ? lc_imin(lvz >> 1, pcz0) : (lvz >> 1), cz1 = hadp ? lc_imax(hvz >> 1, pcz1) : (hvz >> 1);
+        // super-brick lattice of the box, walked with three counters (no division)
+        const int sx0 = cx0 >> 4, sx1 = cx1 >> 4, sy0 = cy0 >> 4, sy1 = cy1 >> 4, sz1 = cz1 >> 4;
+        int sx = sx0, sy = sy0, sz = cz0 >> 4;
+        bool more = need;              // supers left to visit or bricks left in bm
+        unsigned long long bm = 0ull;  // bricks of the current super-brick still to visit
+        int bsx = 0, bsy = 0, bsz = 0; // ... and its coordinates
+        int nr = 0;                    // ranges in this lane's queue
+        while (LC_ANY(more)) {
+            // ---- next brick of this lane (short divergent helper loop over super-bricks without a wanted brick)
+            bool hasb = false;
+            int kx = 0, ky = 0, kz = 0;
+            if (more) {
+                while (bm == 0ull && sz <= sz1) {
+                    if (COUNT) st->supers++;
+                    bm = lc_sb_find(M, li_pack_key(sx, sy, sz)) & lc_range_x(cx0 >> 2, cx1 >> 2, sx) & lc_range_y(cy0 >> 2, cy1 >> 2, sy) &
+                         lc_range_z(cz0 >> 2, cz1 >> 2, sz);
+                    bsx = sx; bsy = sy; bsz = sz;
+                    if (++sx > sx1) {
+                        sx = sx0;
+                        if (++sy > sy1) {
+                            sy = sy0;
+                            ++sz;
+                        }
+                    }
+                }
+                if (bm != 0ull) {
+                    const int b = lc_ctz64(bm);
+                    bm &= bm - 1ull;
+                    kx = 4 * bsx + (b >> 4); ky = 4 * bsy + ((b >> 2) & 3); kz = 4 * bsz + (b & 3);
+                    hasb = true;
+                } else {
+                    more = false;
+                }
+            }
+            // ---- brick step: cells of this brick inside the current box and not inside the previous one
+            unsigned long long m = 0ull;
+            unsigned first = 0, count = 0;
+            const unsigned short* __restrict__ dir = M.cdir;
+            bool whole = false;
+            if (hasb) {
+                const unsigned long long want = lc_range_x(cx0, cx1, kx) & lc_range_y(cy0, cy1, ky) & lc_range_z(cz0, cz1, kz);
+                const unsigned long long seen = hadp ? (lc_range_x(pcx0, pcx1, kx) & lc_range_y(pcy0, pcy1, ky) & lc_range_z(pcz0, pcz1, kz)) : 0ull;
+                if ((want & ~seen) != 0ull) {
+                    const float db = lc_box_d2(qx, qy, qz, (float)kx * B - margin, (float)(kx + 1) * B + margin, (float)ky * B - margin,
+                                               (float)(ky + 1) * B + margin, (float)kz * B - margin, (float)(kz + 1) * B + margin);
+                    if (db < tau) {   // else nothing in this brick can enter the top 5 (safe at any time: tau only shrinks)
+                        if (COUNT) st->probes++;
+                        const int slot = lc_brick_find(M.ent, M.mask, li_pack_key(kx, ky, kz), first, count);
+                        if (slot >= 0 && count > 0u) {
+                            if (COUNT) st->found++;
+                            dir = M.cdir + (size_t)slot * 64;
+                            if (LC_LDG(&dir[0]) == LI_CDIR_UNINDEXED) whole = seen == 0ull;   // no directory: one unit, scanned when first touched
+                            else m = LC_LDG(&M.cocc[slot]) & want & ~seen;
+                        }
+                    }
+                }
+            }
+            if (whole)
+                for (unsigned j = 0; j < count; j++) LC_CANDIDATE_ABS(first + j);
+            // ---- phase A: queue the point ranges of the wanted cells
+            while (LC_ANY(m != 0ull)) {
+                if (m != 0ull) {
+                    const int c = lc_ctz64(m);
+                    m &= m - 1ull;
+                    if (COUNT) st->cells++;
+                    const unsigned s0 = LC_LDG(&dir[c]);
+                    const unsigned e0 = (c == 63) ? count : (unsigned)LC_LDG(&dir[c + 1]);
+                    bool take = true;
+                    if (e0 - s0 > (unsigned)LI_CELLS_BIG) {   // large cell: worth a test against the 5th best
+                        const int gx = 4 * kx + (c >> 4), gy = 4 * ky + ((c >> 2) & 3), gz = 4 * kz + (c & 3);
+                        const float dc = lc_box_d2(qx, qy, qz, (float)gx * cs - margin, (float)(gx + 1) * cs + margin, (float)gy * cs - margin,
+                                                   (float)(gy + 1) * cs + margin, (float)gz * cs - margin, (float)(gz + 1) * cs + margin);
+                        take = dc < tau;
+                    }
+                    if (take) {
+                        if (COUNT) st->cells_scanned++;
+                        Q.rstart[nr * Q.stride] = first + s0;
+                        Q.rcount[nr * Q.stride] = (unsigned short)(e0 - s0);
+                        nr++;
+                    }
+                }
+                if (LC_ANY(nr >= LI_CELLS_QC)) {
+                    lc_drain<COUNT>(pool, Q, nr, qx, qy, qz, cap5, tau, ld, li, st);
+                    nr = 0;
+                }
+            }
+        }
+        lc_drain<COUNT>(pool, Q, nr, qx, qy, qz, cap5, tau, ld, li, st);
+        if (need) {
+            const bool full = li[4] >= 0;
+            if (last || (full && ld[4] <= hi2)) {
+                done = true;
+            } else {
+                pcx0 = cx0; pcx1 = cx1; pcy0 = cy0; pcy1 = cy1; pcz0 = cz0; pcz1 = cz1;
+                hi2 = full ? fminf(ld[4] * (1.0f + 1e-6f), 5.0f) : fminf(4.0f * hi2, 5.0f);
+            }
+        }
+    }
+}
+
+// the three searches: 1 = shells on cells (knn5_cells), 2 = growing boxes (knn5_boxes), 3 = growing boxes, enumerate + stream
+#ifndef LI_CELLS_SEARCH_DEFAULT
+#define LI_CELLS_SEARCH_DEFAULT 3
+#endif
 
 #ifdef __CUDACC__
 // ---- super-brick table: called by the insert kernels when they CREATE a brick (map_kernels.cuh) -------------
@@ -454,6 +665,82 @@ __global__ void k_cells_refresh_touched(MapDev M) {
     const int nt = gridDim.x * blockDim.x, ntouched = M.counters[CNT_TOUCHED];
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ntouched; t += nt) li_cells_refresh_brick(M, (unsigned)M.touched_list[t]);
 }
+// Same job, one WARP per brick (the thread-per-brick version above costs ~0.6 ms per map update at C2: three dependent passes over
+// a slab per thread). Slabs of up to 32 * LI_REFRESH_K points are held in registers: coalesced loads, a shared-memory
+// histogram over the 64 cells, prefix sums by shuffle, then every lane drops its points at cursor[cell]++ -- all loads
+// happen before the first store (__syncwarp), so the permutation is in place. Larger slabs fall back to lane 0 running
+// li_cells_refresh_brick. The order of the points INSIDE a cell is whatever the atomics give (as for appends).
+#ifndef LI_REFRESH_K
+#define LI_REFRESH_K 8
+#endif
+__device__ __forceinline__ void li_cells_refresh_brick_warp(const MapDev& M, unsigned slot, int* cnt /* [64] */, int* cur /* [64] */, int lane) {
+    const uint4 e = M.ent[slot];
+    const unsigned first = e.z, n = e.w;
+    if (n > 32u * LI_REFRESH_K) {
+        if (lane == 0) li_cells_refresh_brick(M, slot);
+        __syncwarp();
+        return;
+    }
+    float4* slab = M.pool + first;
+    float4 p[LI_REFRESH_K];
+    unsigned key[LI_REFRESH_K];
+    cnt[lane] = 0;
+    cnt[lane + 32] = 0;
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < LI_REFRESH_K; k++) {
+        const unsigned j = k * 32 + lane;
+        key[k] = 0xffffffffu;
+        if (j < n) {
+            p[k] = slab[j];
+            key[k] = lc_cell_of(p[k], M.ds);
+            atomicAdd(&cnt[key[k]], 1);
+        }
+    }
+    __syncwarp();
+    // lane l owns cells 2l and 2l+1
+    const int c0 = cnt[2 * lane], c1 = cnt[2 * lane + 1];
+    int incl = c0 + c1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int s0 = incl - (c0 + c1), s1 = s0 + c0;
+    reinterpret_cast<ushort2*>(M.cdir + (size_t)slot * 64)[lane] = make_ushort2((unsigned short)s0, (unsigned short)s1);
+    const unsigned b0 = __ballot_sync(0xffffffffu, c0 > 0), b1 = __ballot_sync(0xffffffffu, c1 > 0);
+    if (lane == 0) {
+        unsigned long long occ = 0ull;   // bit 2l from b0, bit 2l+1 from b1
+#pragma unroll
+        for (int l = 0; l < 32; l++) occ |= ((unsigned long long)((b0 >> l) & 1u) << (2 * l)) | ((unsigned long long)((b1 >> l) & 1u) << (2 * l + 1));
+        M.cocc[slot] = occ;
+    }
+    cur[2 * lane] = s0;
+    cur[2 * lane + 1] = s1;
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < LI_REFRESH_K; k++)
+        if (key[k] != 0xffffffffu) slab[atomicAdd(&cur[key[k]], 1)] = p[k];
+    __syncwarp();
+}
+__global__ void __launch_bounds__(128) k_cells_refresh_touched_warp(MapDev M) {
+    __shared__ int s_cnt[4][64], s_cur[4][64];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int nw = (gridDim.x * blockDim.x) >> 5, ntouched = M.counters[CNT_TOUCHED];
+    for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < ntouched; t += nw)
+        li_cells_refresh_brick_warp(M, (unsigned)M.touched_list[t], s_cnt[wib], s_cur[wib], lane);
+}
+__global__ void __launch_bounds__(128) k_cells_refresh_all_warp(MapDev M, unsigned slots) {
+    __shared__ int s_cnt[4][64], s_cur[4][64];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const unsigned nw = (gridDim.x * blockDim.x) >> 5;
+    for (unsigned i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < slots; i += nw) {
+        const uint4 e = M.ent[i];
+        if (((unsigned long long)e.x | ((unsigned long long)e.y << 32)) == LI_EMPTY_KEY) continue;   // warp-uniform
+        li_cells_refresh_brick_warp(M, i, s_cnt[wib], s_cur[wib], lane);
+    }
+}
+
 // after a box delete (any slab may have been squeezed)
 __global__ void k_cells_refresh_all(MapDev M, unsigned slots) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -466,46 +753,77 @@ __global__ void k_cells_refresh_all(MapDev M, unsigned slots) {
 // ---- search kernel of an ICP pass: world transform + 5-NN, one scan point per thread --------------------
 // HOST = true: the scan is still the caller's page-locked host buffer (liinit_scan_attach_host); consecutive lanes read
 // consecutive points, so for packed xyz a warp pulls one contiguous 384-byte run over PCIe.
+// SEARCH: 1 / 2 / 3 as above. MINB: resident blocks per SM the kernel is compiled for (register budget).
 #ifndef LI_CELLS_THREADS
 #define LI_CELLS_THREADS 128
 #endif
-// MINB: resident blocks per SM the kernel is compiled for (6 -> 80 registers, no spills; 8 -> 64 registers, ~10 spilled words)
-template <bool HOST, int MINB>
+template <int SEARCH>
+__device__ __forceinline__ void li_cells_search(const MapDev& M, float rho2, bool valid, float x, float y, float z, float (&ld)[5], int (&li)[5]) {
+    if constexpr (SEARCH == 3) {
+        __shared__ unsigned s_start[LI_CELLS_QC * LI_CELLS_THREADS];
+        __shared__ unsigned short s_count[LI_CELLS_QC * LI_CELLS_THREADS];
+        LcQ Q;
+        Q.rstart = s_start + threadIdx.x;   // entry i of this lane at [i * blockDim.x]: conflict-free whatever i each lane is at
+        Q.rcount = s_count + threadIdx.x;
+        Q.stride = LI_CELLS_THREADS;
+        knn5_stream<false>(M, rho2, valid, x, y, z, ld, li, nullptr, Q);
+    } else {
+        if (!valid) {
+#pragma unroll
+            for (int i = 0; i < 5; i++) {
+                ld[i] = INFINITY;
+                li[i] = -1;
+            }
+            return;
+        }
+        if constexpr (SEARCH == 2) knn5_boxes<false>(M, rho2, x, y, z, ld, li, nullptr);
+        else knn5_cells<false>(M, rho2, x, y, z, ld, li, nullptr);
+    }
+}
+
+template <bool HOST, int MINB, int SEARCH>
 __global__ void __launch_bounds__(LI_CELLS_THREADS, MINB) k_knn_cells_scan(MapDev M, ScanDev S, PoseD P, float rho2, const float* __restrict__ raw, int stride) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= S.n) return;
-    float bx, by, bz;
-    if (HOST) {
-        const float* s = raw + (size_t)q * stride;
-        bx = s[0]; by = s[1]; bz = s[2];
-        S.body[q] = make_float4(bx, by, bz, 0.f);
-    } else {
-        const float4 b = __ldg(&S.body[q]);
-        bx = b.x; by = b.y; bz = b.z;
+    const bool valid = q < S.n;   // no early exit: the stream search votes over the full warp
+    float bx = 0.f, by = 0.f, bz = 0.f, wx = 0.f, wy = 0.f, wz = 0.f;
+    if (valid) {
+        if (HOST) {
+            const float* s = raw + (size_t)q * stride;
+            bx = s[0]; by = s[1]; bz = s[2];
+            S.body[q] = make_float4(bx, by, bz, 0.f);
+        } else {
+            const float4 b = __ldg(&S.body[q]);
+            bx = b.x; by = b.y; bz = b.z;
+        }
+        li_body_to_world(P, bx, by, bz, wx, wy, wz);
     }
-    float wx, wy, wz;
-    li_body_to_world(P, bx, by, bz, wx, wy, wz);
     float ld[5];
     int li[5];
-    knn5_dir<false>(M, rho2, wx, wy, wz, ld, li, nullptr);
-    S.world[q] = make_float4(wx, wy, wz, 0.f);
+    li_cells_search<SEARCH>(M, rho2, valid, wx, wy, wz, ld, li);
+    if (valid) {
+        S.world[q] = make_float4(wx, wy, wz, 0.f);
 #pragma unroll
-    for (int k = 0; k < 5; k++) S.near_ids[(size_t)q * 5 + k] = li[k];
+        for (int k = 0; k < 5; k++) S.near_ids[(size_t)q * 5 + k] = li[k];
+    }
 }
 
 // ---- stand-alone Nearest_Search for arbitrary world-frame queries -----------------------------------------
+template <int SEARCH>
 __global__ void __launch_bounds__(LI_CELLS_THREADS) k_knn_cells_queries(MapDev M, const float4* __restrict__ qpts, int n, int* __restrict__ ids,
                                                                         float* __restrict__ d2, float rho2) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n) return;
-    const float4 p = __ldg(&qpts[q]);
+    const bool valid = q < n;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) p = __ldg(&qpts[q]);
     float ld[5];
     int li[5];
-    knn5_dir<false>(M, rho2, p.x, p.y, p.z, ld, li, nullptr);
+    li_cells_search<SEARCH>(M, rho2, valid, p.x, p.y, p.z, ld, li);
+    if (valid) {
 #pragma unroll
-    for (int k = 0; k < 5; k++) {
-        ids[(size_t)q * 5 + k] = li[k];
-        d2[(size_t)q * 5 + k] = (li[k] >= 0) ? ld[k] : -1.f;
+        for (int k = 0; k < 5; k++) {
+            ids[(size_t)q * 5 + k] = li[k];
+            d2[(size_t)q * 5 + k] = (li[k] >= 0) ? ld[k] : -1.f;
+        }
     }
 }
 #endif  // __CUDACC__

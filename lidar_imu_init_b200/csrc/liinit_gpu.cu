@@ -92,6 +92,8 @@ struct Ctx {
     float last_ms = 0.f;
     int last_launches = 0;
     int group = 4;
+    int cells_search = LI_CELLS_SEARCH_DEFAULT;   // 1 shells on cells, 2 growing boxes, 3 growing boxes enumerate + stream (developer A/B: LIINIT_CELLS_SEARCH)
+    bool cells_refresh_warp = true;   // directory refresh: warp per brick (false: thread per brick, the version the CPU checker runs)
     int cells_minb = LI_CELLS_MINB_DEFAULT;   // register budget variant of the cells search kernel (developer A/B: LIINIT_CELLS_MINB)
     bool cells = false;   // knn_index = LIINIT_KNN_CELLS: per-brick cell directory + thread-per-point search (cells.cuh)
     float rho2 = 0.09f;   // squared seed radius of the 5-NN search
@@ -155,7 +157,8 @@ int reset_batch_counters(Ctx* c) {
 // cell directory of the bricks the batch touched (after the commit / compaction that fixed their counts)
 void refresh_cells_touched(Ctx* c) {
     if (!c->cells) return;
-    k_cells_refresh_touched<<<c->num_sms * 8, 128, 0, c->stream>>>(c->M);
+    if (c->cells_refresh_warp) k_cells_refresh_touched_warp<<<c->num_sms * 16, 128, 0, c->stream>>>(c->M);
+    else k_cells_refresh_touched<<<c->num_sms * 8, 128, 0, c->stream>>>(c->M);
     c->launches++;
 }
 
@@ -236,18 +239,26 @@ void launch_knn_scan(Ctx* c, const PoseD& P) {
 #define LI_PLANE_WAVES 1   // the plane pass runs LI_PLANE_WAVES x (2 blocks per SM); each thread strides over the scan
 #endif
 
-template <int MINB>
+template <int MINB, int SEARCH>
 void launch_knn_cells_scan_t(Ctx* c, const PoseD& P) {
     const int grid = nblk(c->scan_n, LI_CELLS_THREADS);
     if (c->attached) {
-        k_knn_cells_scan<true, MINB><<<grid, LI_CELLS_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, c->attached, c->attached_stride);
+        k_knn_cells_scan<true, MINB, SEARCH><<<grid, LI_CELLS_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, c->attached, c->attached_stride);
         c->attached = nullptr;   // the kernel leaves the packed copy in d_body
     } else {
-        k_knn_cells_scan<false, MINB><<<grid, LI_CELLS_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, nullptr, 0);
+        k_knn_cells_scan<false, MINB, SEARCH><<<grid, LI_CELLS_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, nullptr, 0);
     }
 }
+template <int SEARCH>
+void launch_knn_cells_scan_s(Ctx* c, const PoseD& P) {
+    if (c->cells_minb == 8) launch_knn_cells_scan_t<8, SEARCH>(c, P);
+    else if (c->cells_minb == 4) launch_knn_cells_scan_t<4, SEARCH>(c, P);
+    else launch_knn_cells_scan_t<6, SEARCH>(c, P);
+}
 void launch_knn_cells_scan(Ctx* c, const PoseD& P) {
-    if (c->cells_minb == 8) launch_knn_cells_scan_t<8>(c, P); else if (c->cells_minb == 4) launch_knn_cells_scan_t<4>(c, P); else launch_knn_cells_scan_t<6>(c, P);
+    if (c->cells_search == 1) launch_knn_cells_scan_s<1>(c, P);
+    else if (c->cells_search == 2) launch_knn_cells_scan_s<2>(c, P);
+    else launch_knn_cells_scan_s<3>(c, P);
 }
 
 constexpr int TPQ_CH = 32, TPQ_NB = 8;
@@ -396,6 +407,10 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
         if (mb && atoi(mb) == 8) c->cells_minb = 8;
         if (mb && atoi(mb) == 6) c->cells_minb = 6;
         if (mb && atoi(mb) == 4) c->cells_minb = 4;
+        const char* rf = getenv("LIINIT_CELLS_REFRESH");
+        if (rf && !strcmp(rf, "thread")) c->cells_refresh_warp = false;
+        const char* cs = getenv("LIINIT_CELLS_SEARCH");
+        if (cs && atoi(cs) >= 1 && atoi(cs) <= 3) c->cells_search = atoi(cs);
     }
     {
         float cells = cfg->knn_seed_radius_cells > 0.f ? cfg->knn_seed_radius_cells : 2.0f;
@@ -581,7 +596,8 @@ int liinit_map_delete_boxes(liinit_ctx* h, const float* boxes, int nbox, int* de
                                                                                           c->d_vg_misc + 6);
     c->launches++;
     if (c->cells) {
-        k_cells_refresh_all<<<nblk(c->hash_slots, 128), 128, 0, c->stream>>>(c->M, c->hash_slots);
+        if (c->cells_refresh_warp) k_cells_refresh_all_warp<<<c->num_sms * 16, 128, 0, c->stream>>>(c->M, c->hash_slots);
+        else k_cells_refresh_all<<<nblk(c->hash_slots, 128), 128, 0, c->stream>>>(c->M, c->hash_slots);
         c->launches++;
     }
     c->have_neighbors = false;   // pool offsets inside the touched slabs moved
@@ -659,7 +675,10 @@ int liinit_map_nearest_search(liinit_ctx* h, const float* q, int stride, int n, 
         CU(cudaMalloc(&d_ids, (size_t)m * 5 * sizeof(int)));
         CU(cudaMalloc(&d_xyz, (size_t)m * 15 * sizeof(float)));
         if (c->cells) {
-            k_knn_cells_queries<<<nblk(m, LI_CELLS_THREADS), LI_CELLS_THREADS, 0, c->stream>>>(c->M, c->d_stage_pts, m, d_ids, c->d_q_d2, c->rho2);
+            const int gq = nblk(m, LI_CELLS_THREADS);
+            if (c->cells_search == 1) k_knn_cells_queries<1><<<gq, LI_CELLS_THREADS, 0, c->stream>>>(c->M, c->d_stage_pts, m, d_ids, c->d_q_d2, c->rho2);
+            else if (c->cells_search == 2) k_knn_cells_queries<2><<<gq, LI_CELLS_THREADS, 0, c->stream>>>(c->M, c->d_stage_pts, m, d_ids, c->d_q_d2, c->rho2);
+            else k_knn_cells_queries<3><<<gq, LI_CELLS_THREADS, 0, c->stream>>>(c->M, c->d_stage_pts, m, d_ids, c->d_q_d2, c->rho2);
         } else if (c->group == 1) {
             int grid = nblk(m, 128);
             if (grid > c->num_sms * 12) grid = c->num_sms * 12;

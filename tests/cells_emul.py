@@ -45,6 +45,8 @@ def load():
         L.emul_num_bricks.argtypes = [C.c_void_p]
         L.emul_check_directory.argtypes = [C.c_void_p]
         L.emul_knn.argtypes = [C.c_void_p, _f32, C.c_int, C.c_float, C.c_int, _f32, _f32, _i32, C.c_void_p]
+        L.emul_trace.restype = C.c_longlong
+        L.emul_trace.argtypes = [C.c_void_p, _f32, C.c_int, C.c_float, _i32, C.c_longlong, np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")]
         _L = L
     return _L
 
@@ -81,6 +83,15 @@ class CellsEmul:
         st = np.zeros((n, 8), np.int32) if stats else None
         self.L.emul_knn(self.h, q, n, np.float32(rho) * np.float32(rho), variant, xyz, d2, cnt, st.ctypes.data_as(C.c_void_p) if stats else None)
         return (xyz, d2, cnt, st) if stats else (xyz, d2, cnt)
+
+    def trace(self, q, rho=0.3, cap_per_query=400):
+        """Structure traces of the growing-boxes search (for the lockstep cost model): (tokens, offsets)."""
+        q = np.ascontiguousarray(q, np.float32).reshape(-1, 3)
+        n = len(q)
+        tr = np.zeros(n * cap_per_query, np.int32)
+        off = np.zeros(n + 1, np.int64)
+        used = self.L.emul_trace(self.h, q, n, np.float32(rho) * np.float32(rho), tr, len(tr), off)
+        return tr[:used], off
 
     def close(self):
         if self.h:

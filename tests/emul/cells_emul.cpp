@@ -7,6 +7,7 @@
 // without a GPU. Nothing under lidar_imu_init_b200/ loads this file; the product has no CPU path.
 //
 // Build: g++ -O2 -std=c++17 -ffp-contract=off -fPIC -shared -I/usr/local/cuda/include cells_emul.cpp -o libcells_emul.so
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -171,7 +172,7 @@ int emul_check_directory(void* h) {
     return bad;
 }
 
-// 5-NN of n queries (packed xyz). variant: 0 = the search the kernels are built with, 1 = shells on cells, 2 = growing boxes.
+// 5-NN of n queries (packed xyz). variant: 0 = the kernels' default, 1 = shells on cells, 2 = growing boxes, 3 = growing boxes (enumerate + stream).
 // out_xyz [n*15], out_d2 [n*5] (-1 = missing), out_cnt [n], stats [n*8] or NULL.
 void emul_knn(void* h, const float* q, int n, float rho2, int variant, float* out_xyz, float* out_d2, int* out_cnt, int* stats) {
     Emul* E = (Emul*)h;
@@ -181,9 +182,18 @@ void emul_knn(void* h, const float* q, int n, float rho2, int variant, float* ou
         int li[5];
         LcStats st;
         std::memset(&st, 0, sizeof(st));
-        if (variant == 2) knn5_boxes<true>(E->M, rho2, q[3 * (size_t)i], q[3 * (size_t)i + 1], q[3 * (size_t)i + 2], ld, li, &st);
-        else if (variant == 1) knn5_cells<true>(E->M, rho2, q[3 * (size_t)i], q[3 * (size_t)i + 1], q[3 * (size_t)i + 2], ld, li, &st);
-        else knn5_dir<true>(E->M, rho2, q[3 * (size_t)i], q[3 * (size_t)i + 1], q[3 * (size_t)i + 2], ld, li, &st);   // what the kernels run
+        const int v = variant ? variant : LI_CELLS_SEARCH_DEFAULT;   // 0 = what the kernels run by default
+        if (v == 3) {
+            unsigned rs[LI_CELLS_QC];
+            unsigned short rc[LI_CELLS_QC];   // one lane alone: its queue is a local array
+            LcQ Q;
+            Q.rstart = rs; Q.rcount = rc; Q.stride = 1;
+            knn5_stream<true>(E->M, rho2, true, q[3 * (size_t)i], q[3 * (size_t)i + 1], q[3 * (size_t)i + 2], ld, li, &st, Q);
+        } else if (v == 2) {
+            knn5_boxes<true>(E->M, rho2, q[3 * (size_t)i], q[3 * (size_t)i + 1], q[3 * (size_t)i + 2], ld, li, &st);
+        } else {
+            knn5_cells<true>(E->M, rho2, q[3 * (size_t)i], q[3 * (size_t)i + 1], q[3 * (size_t)i + 2], ld, li, &st);
+        }
         int cnt = 0;
         for (int k = 0; k < 5; k++) {
             if (li[k] >= 0) {
@@ -199,8 +209,28 @@ void emul_knn(void* h, const float* q, int n, float rho2, int variant, float* ou
             }
         }
         out_cnt[i] = cnt;
-        if (stats) std::memcpy(stats + 8 * (size_t)i, &st, sizeof(st));
+        if (stats) std::memcpy(stats + 8 * (size_t)i, &st, 8 * sizeof(int));
     }
+}
+
+// structure traces of knn5_boxes for the lockstep cost model (tools/cells_cost_model.py): per query a slice of `tr`
+// ([off[i], off[i+1])), tokens as documented at LcStats.
+long long emul_trace(void* h, const float* q, int n, float rho2, int* tr, long long cap, long long* off) {
+    Emul* E = (Emul*)h;
+    long long pos = 0;
+    for (int i = 0; i < n; i++) {
+        float ld[5];
+        int li[5];
+        LcStats st;
+        std::memset(&st, 0, sizeof(st));
+        st.tr = tr + pos;
+        st.cap = (int)std::min<long long>(cap - pos, 1 << 20);
+        knn5_boxes<true>(E->M, rho2, q[3 * (size_t)i], q[3 * (size_t)i + 1], q[3 * (size_t)i + 2], ld, li, &st);
+        off[i] = pos;
+        pos += st.ntr;
+    }
+    off[n] = pos;
+    return pos;
 }
 
 }  // extern "C"

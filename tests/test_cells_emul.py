@@ -23,7 +23,7 @@ def case():
     return scenes.make_config("C2", N=20000, M=200000, open_air_frac=0.02)
 
 
-VARIANTS = [1, 2]   # 1 = shells on cells (knn5_cells), 2 = growing boxes (knn5_boxes); 0 = whichever the kernels are built with
+VARIANTS = [1, 2, 3]   # 1 = shells on cells (knn5_cells), 2 = growing boxes (knn5_boxes), 3 = enumerate + stream (knn5_stream); 0 = the kernels' default
 
 
 @pytest.mark.parametrize("variant", VARIANTS)

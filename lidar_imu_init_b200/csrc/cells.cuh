@@ -469,21 +469,47 @@ struct LcQ {            // this lane's queue: entry i at [i * stride]
         }                                                                \
     } while (0)
 
-// phase B: evaluate the nr queued ranges of every lane, one candidate per lane and iteration
+// phase B: evaluate the nr queued ranges of every lane, LI_CELLS_U candidates per lane and iteration: the loads of a batch are
+// issued back to back before any distance is evaluated (measured with one load per iteration: issue slots 33 % busy, every
+// iteration waits for its own L2 round trip). The order in which a lane sees its candidates is unchanged.
+#ifndef LI_CELLS_U
+#define LI_CELLS_U 4
+#endif
 template <bool COUNT>
 LI_HD void lc_drain(const float4* __restrict__ pool, const LcQ& Q, int nr, float qx, float qy, float qz, float cap5, float& tau, float (&ld)[5],
                     int (&li)[5], LcStats* st) {
     int ri = 0;
     unsigned j = 0, e = 0;
     while (LC_ANY(ri < nr || j < e)) {
-        if (j >= e && ri < nr) {
-            j = Q.rstart[ri * Q.stride];
-            e = j + Q.rcount[ri * Q.stride];
-            ri++;
+        float4 p[LI_CELLS_U];
+        unsigned idx[LI_CELLS_U];
+        bool ok[LI_CELLS_U];
+#pragma unroll
+        for (int u = 0; u < LI_CELLS_U; u++) {
+            if (j >= e && ri < nr) {
+                j = Q.rstart[ri * Q.stride];
+                e = j + Q.rcount[ri * Q.stride];
+                ri++;
+            }
+            ok[u] = j < e;
+            idx[u] = j;
+            if (ok[u]) {
+                p[u] = LC_LDG(&pool[j]);
+                j++;
+            }
         }
-        if (j < e) {
-            LC_CANDIDATE_ABS(j);
-            j++;
+#pragma unroll
+        for (int u = 0; u < LI_CELLS_U; u++) {
+            if (ok[u]) {
+                const float dx_ = qx - p[u].x, dy_ = qy - p[u].y, dz_ = qz - p[u].z;
+                const float d_ = (dx_ * dx_ + dy_ * dy_) + dz_ * dz_;   // KD_TREE::calc_dist association, no FMA
+                if (COUNT) st->points++;
+                if (d_ < tau) {
+                    lc_insert(ld, li, d_, (int)idx[u]);
+                    tau = fminf(ld[4], cap5);
+                    if (COUNT) st->inserts++;
+                }
+            }
         }
     }
 }
@@ -531,11 +557,16 @@ LI_HD void knn5_stream(const MapDev& M, float rho2, bool valid, float qx, float 
         unsigned long long bm = 0ull;  // bricks of the current super-brick still to visit
         int bsx = 0, bsy = 0, bsz = 0; // ... and its coordinates
         int nr = 0;                    // ranges in this lane's queue
-        while (LC_ANY(more)) {
-            // ---- next brick of this lane (short divergent helper loop over super-bricks without a wanted brick)
-            bool hasb = false;
-            int kx = 0, ky = 0, kz = 0;
-            if (more) {
+        // current brick of this lane: wanted cells still to queue (m), slab, directory
+        unsigned long long m = 0ull;
+        unsigned first = 0, count = 0;
+        int kx = 0, ky = 0, kz = 0;
+        const unsigned short* __restrict__ dir = M.cdir;
+        for (;;) {
+            const bool anymore = LC_ANY(more || m != 0ull);
+            // ---- phase A1: a lane whose brick is used up takes its next one
+            if (m == 0ull && more) {
+                // short divergent helper loop over super-bricks without a wanted brick
                 while (bm == 0ull && sz <= sz1) {
                     if (COUNT) st->supers++;
                     bm = lc_sb_find(M, li_pack_key(sx, sy, sz)) & lc_range_x(cx0 >> 2, cx1 >> 2, sx) & lc_range_y(cy0 >> 2, cy1 >> 2, sy) &
@@ -549,42 +580,38 @@ LI_HD void knn5_stream(const MapDev& M, float rho2, bool valid, float qx, float 
                         }
                     }
                 }
-                if (bm != 0ull) {
+                if (bm == 0ull) {
+                    more = false;
+                } else {
                     const int b = lc_ctz64(bm);
                     bm &= bm - 1ull;
                     kx = 4 * bsx + (b >> 4); ky = 4 * bsy + ((b >> 2) & 3); kz = 4 * bsz + (b & 3);
-                    hasb = true;
-                } else {
-                    more = false;
-                }
-            }
-            // ---- brick step: cells of this brick inside the current box and not inside the previous one
-            unsigned long long m = 0ull;
-            unsigned first = 0, count = 0;
-            const unsigned short* __restrict__ dir = M.cdir;
-            bool whole = false;
-            if (hasb) {
-                const unsigned long long want = lc_range_x(cx0, cx1, kx) & lc_range_y(cy0, cy1, ky) & lc_range_z(cz0, cz1, kz);
-                const unsigned long long seen = hadp ? (lc_range_x(pcx0, pcx1, kx) & lc_range_y(pcy0, pcy1, ky) & lc_range_z(pcz0, pcz1, kz)) : 0ull;
-                if ((want & ~seen) != 0ull) {
-                    const float db = lc_box_d2(qx, qy, qz, (float)kx * B - margin, (float)(kx + 1) * B + margin, (float)ky * B - margin,
-                                               (float)(ky + 1) * B + margin, (float)kz * B - margin, (float)(kz + 1) * B + margin);
-                    if (db < tau) {   // else nothing in this brick can enter the top 5 (safe at any time: tau only shrinks)
-                        if (COUNT) st->probes++;
-                        const int slot = lc_brick_find(M.ent, M.mask, li_pack_key(kx, ky, kz), first, count);
-                        if (slot >= 0 && count > 0u) {
-                            if (COUNT) st->found++;
-                            dir = M.cdir + (size_t)slot * 64;
-                            if (LC_LDG(&dir[0]) == LI_CDIR_UNINDEXED) whole = seen == 0ull;   // no directory: one unit, scanned when first touched
-                            else m = LC_LDG(&M.cocc[slot]) & want & ~seen;
+                    // cells of this brick inside the current box and not inside the previous one
+                    const unsigned long long want = lc_range_x(cx0, cx1, kx) & lc_range_y(cy0, cy1, ky) & lc_range_z(cz0, cz1, kz);
+                    const unsigned long long seen = hadp ? (lc_range_x(pcx0, pcx1, kx) & lc_range_y(pcy0, pcy1, ky) & lc_range_z(pcz0, pcz1, kz)) : 0ull;
+                    if ((want & ~seen) != 0ull) {
+                        const float db = lc_box_d2(qx, qy, qz, (float)kx * B - margin, (float)(kx + 1) * B + margin, (float)ky * B - margin,
+                                                   (float)(ky + 1) * B + margin, (float)kz * B - margin, (float)(kz + 1) * B + margin);
+                        if (db < tau) {   // else nothing in this brick can enter the top 5 (safe at any time: tau only shrinks)
+                            if (COUNT) st->probes++;
+                            const int slot = lc_brick_find(M.ent, M.mask, li_pack_key(kx, ky, kz), first, count);
+                            if (slot >= 0 && count > 0u) {
+                                if (COUNT) st->found++;
+                                dir = M.cdir + (size_t)slot * 64;
+                                if (LC_LDG(&dir[0]) == LI_CDIR_UNINDEXED) {
+                                    // no directory (oversized brick): one unit, scanned when the box first touches it
+                                    if (seen == 0ull)
+                                        for (unsigned j = 0; j < count; j++) LC_CANDIDATE_ABS(first + j);
+                                } else {
+                                    m = LC_LDG(&M.cocc[slot]) & want & ~seen;
+                                }
+                            }
                         }
                     }
                 }
             }
-            if (whole)
-                for (unsigned j = 0; j < count; j++) LC_CANDIDATE_ABS(first + j);
-            // ---- phase A: queue the point ranges of the wanted cells
-            while (LC_ANY(m != 0ull)) {
+            // ---- phase A2: queue the point ranges of the wanted cells until some lane's queue is full
+            while (LC_ANY(m != 0ull) && !LC_ANY(nr >= LI_CELLS_QC)) {
                 if (m != 0ull) {
                     const int c = lc_ctz64(m);
                     m &= m - 1ull;
@@ -605,13 +632,14 @@ LI_HD void knn5_stream(const MapDev& M, float rho2, bool valid, float qx, float 
                         nr++;
                     }
                 }
-                if (LC_ANY(nr >= LI_CELLS_QC)) {
-                    lc_drain<COUNT>(pool, Q, nr, qx, qy, qz, cap5, tau, ld, li, st);
-                    nr = 0;
-                }
             }
+            // ---- phase B (the only call site): a full queue somewhere, or nothing left to enumerate
+            if (!anymore || LC_ANY(nr >= LI_CELLS_QC)) {
+                lc_drain<COUNT>(pool, Q, nr, qx, qy, qz, cap5, tau, ld, li, st);
+                nr = 0;
+            }
+            if (!anymore) break;
         }
-        lc_drain<COUNT>(pool, Q, nr, qx, qy, qz, cap5, tau, ld, li, st);
         if (need) {
             const bool full = li[4] >= 0;
             if (last || (full && ld[4] <= hi2)) {

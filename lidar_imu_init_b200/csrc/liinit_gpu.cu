@@ -77,6 +77,7 @@ struct Ctx {
     float4* d_normvec = nullptr;
     int scan_n = 0;
     bool have_neighbors = false;
+    bool scan_fresh = false;   // new scan whose flags / neighbour lists have not been initialised yet (see init_scan_state)
     const float* attached = nullptr;   // device alias of a page-locked host scan not copied yet (liinit_scan_attach_host)
     int attached_stride = 0;
     // reduction
@@ -221,6 +222,17 @@ void materialize_scan(Ctx* c) {
     c->attached = nullptr;
 }
 
+// A new scan starts with nothing selected and no neighbours (Nearest_Points / point_selected_surf at iteration 0). The search
+// pass that normally follows overwrites both arrays for every point of the scan, so the two fills are only issued when
+// something else looks at them first (map_incremental, the download hooks): two stream operations fewer per scan.
+int init_scan_state(Ctx* c) {
+    if (!c->scan_fresh) return LIINIT_OK;
+    CU(cudaMemsetAsync(c->d_selected, 0, (size_t)c->scan_n, c->stream));
+    CU(cudaMemsetAsync(c->d_near_ids, 0xff, (size_t)c->scan_n * 5 * sizeof(int), c->stream));
+    c->scan_fresh = false;
+    return LIINIT_OK;
+}
+
 template <int G>
 void launch_knn_scan(Ctx* c, const PoseD& P) {
     long long threads = (long long)c->scan_n * G;
@@ -302,6 +314,7 @@ int run_pass(Ctx* c, const double* R, const double* p, const double* RLI, const 
         CU(cudaEventRecord(c->evm, c->stream));
         if (imu_en) launch_plane<true, true>(c, P, out); else launch_plane<false, true>(c, P, out);
         c->have_neighbors = true;
+        c->scan_fresh = false;   // the two kernels wrote near_ids / selected for every point of the scan
         c->launches += 2;
         c->last_launches = 2;
         c->last_was_search = true;
@@ -735,11 +748,10 @@ int liinit_scan_upload(liinit_ctx* h, const float* body, int stride, int n) {
         return fail(c, LIINIT_ERR_INVALID, "stride_floats must be 3, 4 or 12");
     }
     // new scan: no neighbours, nothing selected (Nearest_Points / point_selected_surf start over at iteration 0)
-    CU(cudaMemsetAsync(c->d_selected, 0, (size_t)n, c->stream));
-    CU(cudaMemsetAsync(c->d_near_ids, 0xff, (size_t)n * 5 * sizeof(int), c->stream));
     c->scan_n = n;
     c->S.n = n;
     c->have_neighbors = false;
+    c->scan_fresh = true;
     CU(cudaGetLastError());
     return LIINIT_OK;
 }
@@ -757,11 +769,10 @@ int liinit_scan_attach_host(liinit_ctx* h, const float* pinned_body, int stride,
     }
     c->attached = (const float*)at.devicePointer;
     c->attached_stride = stride;
-    CU(cudaMemsetAsync(c->d_selected, 0, (size_t)n, c->stream));
-    CU(cudaMemsetAsync(c->d_near_ids, 0xff, (size_t)n * 5 * sizeof(int), c->stream));
     c->scan_n = n;
     c->S.n = n;
     c->have_neighbors = false;
+    c->scan_fresh = true;
     return LIINIT_OK;
 }
 
@@ -889,11 +900,10 @@ int liinit_raw_downsample(liinit_ctx* h, float leaf_size, int* n_down) {
     if (res[7] & 2) return fail(c, LIINIT_ERR_CAPACITY, "voxel grid: more leaves than max_scan_points");
     const int m = res[6];
     if (m <= 0) return fail(c, LIINIT_ERR_INVALID, "voxel grid: no output points");
-    CU(cudaMemsetAsync(c->d_selected, 0, (size_t)m, c->stream));
-    CU(cudaMemsetAsync(c->d_near_ids, 0xff, (size_t)m * 5 * sizeof(int), c->stream));
     c->scan_n = m;
     c->S.n = m;
     c->have_neighbors = false;
+    c->scan_fresh = true;
     c->attached = nullptr;
     if (n_down) *n_down = m;
     return LIINIT_OK;
@@ -953,6 +963,10 @@ int liinit_scan_download_state(liinit_ctx* h, float* world_xyz, float* near_xyz,
     CU(cudaSetDevice(c->device));
     int n = c->scan_n;
     if (n <= 0) return fail(c, LIINIT_ERR_INVALID, "no scan uploaded");
+    {
+        int r = init_scan_state(c);
+        if (r) return r;
+    }
     CU(cudaStreamSynchronize(c->stream));
     if (world_xyz) {
         std::vector<float4> w(n);
@@ -992,6 +1006,10 @@ int liinit_scan_download_effect(liinit_ctx* h, float* ori_xyz, float* normvec, i
     CU(cudaSetDevice(c->device));
     int n = c->scan_n;
     if (n <= 0) return fail(c, LIINIT_ERR_INVALID, "no scan uploaded");
+    {
+        int r = init_scan_state(c);
+        if (r) return r;
+    }
     CU(cudaStreamSynchronize(c->stream));
     std::vector<unsigned char> sel(n);
     std::vector<float4> nv(n), body(n);
@@ -1021,6 +1039,10 @@ int liinit_map_incremental(liinit_ctx* h, const double* R, const double* p, cons
     int n = c->scan_n;
     if (n <= 0) return fail(c, LIINIT_ERR_INVALID, "no scan uploaded");
     materialize_scan(c);
+    {
+        int r = init_scan_state(c);   // no search pass on this scan yet: every point has "no neighbours" (-> PointToAdd)
+        if (r) return r;
+    }
     PoseD P;
     fill_pose(P, R, p, RLI, TLI);
     static const int zeros[2] = {0, 0};

@@ -187,3 +187,73 @@ def breakdown():
 
 if __name__ == "__main__" and os.environ.get("BREAKDOWN"):
     breakdown()
+
+
+def stream_cost(lanes, QC=32, K=dict(round=130, helper=45, brick=75, probe=30, found=30, cell=35, vote=9, drain0=8, it=35, ins=25)):
+    """enumerate + stream (knn5_stream): warp instructions of one warp (list of parsed queries)"""
+    tot = 150
+    nr_rounds = max(len(q) for q in lanes)
+    for r in range(nr_rounds):
+        act = [q[r] for q in lanes if r < len(q)]
+        tot += K["round"]
+        # per lane: flat list of bricks of the round (super boundaries only add helper iterations)
+        bl = []
+        for a in act:
+            bricks = []
+            for sup in a:
+                for j, b in enumerate(sup):
+                    bricks.append((b, j == 0))   # first brick of a super: the helper loop ran
+            bl.append(bricks)
+        queue = [[] for _ in act]   # queued (npts, bits) per lane
+
+        def drain():
+            nonlocal tot
+            tot += K["drain0"]
+            seqs = []
+            for qq in queue:
+                s = []
+                for npts, bits in qq:
+                    s += [(bits >> j) & 1 for j in range(npts)]
+                seqs.append(s)
+                qq.clear()
+            n = max((len(s) for s in seqs), default=0)
+            for j in range(n):
+                tot += K["it"] + (K["ins"] if any(s[j] for s in seqs if j < len(s)) else 0)
+
+        for step in range(max(len(b) for b in bl) + 1):   # +1: the step in which the last lane finds no more bricks
+            cur = [(i, b[step]) for i, b in enumerate(bl) if step < len(b)]
+            tot += K["helper"] + K["brick"]
+            if any(x[1][0][0] >= 1 for x in cur): tot += K["probe"]
+            f = [(i, x[0]) for i, x in cur if x[0][0] == 2]
+            if f:
+                tot += K["found"]
+                for k in range(max(len(b[1]) for _, b in f)):
+                    tot += K["cell"] + K["vote"]
+                    for i, b in f:
+                        if k < len(b[1]): queue[i].append(b[1][k])
+                    if any(len(qq) >= QC for qq in queue): drain()
+            else:
+                tot += K["vote"]
+        drain()
+    return tot
+
+
+def stream_main():
+    import cells_emul as ce
+    mp = np.load('/tmp/c2_map.npy')
+    E = ce.CellsEmul(mp, 0.15, hash_log2=22)
+    W = int(os.environ.get("WARPS", "1500"))
+    for name in ("pose_init", "pose_gt"):
+        q = np.load(f'/tmp/c2_q_{name}.npy')
+        nw = len(q) // 32
+        pick = np.linspace(0, nw - 1, W).astype(int)
+        idx = (pick[:, None] * 32 + np.arange(32)[None, :]).ravel()
+        tr, off = E.trace(q[idx], rho=0.3)
+        Q = [parse(tr[off[i]:off[i + 1]].tolist()) for i in range(len(idx))]
+        for QC in (16, 32, 64, 10**6):
+            tot = sum(stream_cost(Q[w * 32:(w + 1) * 32], QC) for w in range(W))
+            print(f"{name}: enumerate+stream QC={QC}: {tot/(W*32):.0f} warp-instr/query -> {tot/(W*32)*240000/1e6:.0f} M per pass", flush=True)
+
+
+if __name__ == "__main__" and os.environ.get("STREAM"):
+    stream_main()

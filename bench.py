@@ -46,10 +46,10 @@ def emit(obj):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the search kernel (ncu --set full, cold cache), per index:
-#   1 (bricks, k_knn_scan): 109.96 MB read + 6.61 MB written, profiles/r01_ncu_full_final_metrics.txt
-#   2 (cells, k_knn_cells_scan): filled in from profiles/ once captured (None = not captured yet)
-NCU_DRAM_BYTES_KNN = {1: 116_571_136, 2: None}
-NCU_DRAM_SOURCE = {1: "profiles/r01_ncu_full_final_metrics.txt", 2: "profiles/r01_ncu_cells_metrics.txt"}
+#   1 (bricks, k_knn_scan<4,0>): 110.65 MB read + 7.11 MB written, profiles/r01_ncu_full_final_metrics.txt
+#   2 (cells, k_knn_cells_scan<0,6,3>): 133.67 MB read + 7.93 MB written, profiles/r01_cells/ncu_full_stream_final_metrics.txt
+NCU_DRAM_BYTES_KNN = {1: 117_762_816, 2: 141_602_560}
+NCU_DRAM_SOURCE = {1: "profiles/r01_ncu_full_final_metrics.txt", 2: "profiles/r01_cells/ncu_full_stream_final_metrics.txt"}
 KNN_KERNEL = {1: "k_knn_scan (5-NN search on whole bricks, lockstep lane groups; dominant kernel of the pass)",
               2: "k_knn_cells_scan (5-NN search on the per-brick cell directory, one scan point per thread; dominant kernel of the pass)"}
 ALG_BYTES_PER_POINT = 132  # 16 body + 80 neighbours + 16 normal/residual + 20 ids
@@ -314,7 +314,7 @@ def run_gpu(args, rank, world, local_rank):
                      "algorithmic_bytes_per_launch": ALG_BYTES_PER_POINT * N, "kernel_ms": knn_ms, "plane_kernel_ms": plane_ms,
                      "kernel_ms_l2_warm": knn_warm, "plane_kernel_ms_l2_warm": plane_warm,
                      "note": "traffic = dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel from the ncu --set full capture in "
-                             + NCU_DRAM_SOURCE[kidx] + " (cold cache: ncu flushes between replays), bytes per launch; null = not captured yet"},
+                             + NCU_DRAM_SOURCE[kidx] + " (cold cache: ncu flushes between replays), bytes per launch"},
     }
     # ---- extras (not part of the contract value): the other pass kinds of a real scan -----------------------
     if world == 1:

@@ -22,8 +22,8 @@
 #include "voxelgrid_kernels.cuh"
 #include "undistort_kernels.cuh"
 
-#ifndef LI_CELLS_MINB_DEFAULT
-#define LI_CELLS_MINB_DEFAULT 6
+#ifndef LI_CELLS_MINB
+#define LI_CELLS_MINB 6
 #endif
 #ifndef LIINIT_KNN_DEFAULT
 #define LIINIT_KNN_DEFAULT LIINIT_KNN_BRICKS   // what knn_index = 0 selects
@@ -95,7 +95,6 @@ struct Ctx {
     int group = 4;
     int cells_search = LI_CELLS_SEARCH_DEFAULT;   // 1 shells on cells, 2 growing boxes, 3 growing boxes enumerate + stream (developer A/B: LIINIT_CELLS_SEARCH)
     bool cells_refresh_warp = true;   // directory refresh: warp per brick (false: thread per brick, the version the CPU checker runs)
-    int cells_minb = LI_CELLS_MINB_DEFAULT;   // register budget variant of the cells search kernel (developer A/B: LIINIT_CELLS_MINB)
     bool cells = false;   // knn_index = LIINIT_KNN_CELLS: per-brick cell directory + thread-per-point search (cells.cuh)
     float rho2 = 0.09f;   // squared seed radius of the 5-NN search
 };
@@ -261,16 +260,12 @@ void launch_knn_cells_scan_t(Ctx* c, const PoseD& P) {
         k_knn_cells_scan<false, MINB, SEARCH><<<grid, LI_CELLS_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, nullptr, 0);
     }
 }
-template <int SEARCH>
-void launch_knn_cells_scan_s(Ctx* c, const PoseD& P) {
-    if (c->cells_minb == 8) launch_knn_cells_scan_t<8, SEARCH>(c, P);
-    else if (c->cells_minb == 4) launch_knn_cells_scan_t<4, SEARCH>(c, P);
-    else launch_knn_cells_scan_t<6, SEARCH>(c, P);
-}
+// LI_CELLS_MINB (resident blocks per SM the kernel is compiled for): 6 -> 80 registers; measured against 4 (106 registers, no spills)
+// and 8 (64 registers, 55 spilled words): 0.56 / 0.60 / 0.72 ms at the initial pose (profiles/r01_cells/ab_stream_final.log)
 void launch_knn_cells_scan(Ctx* c, const PoseD& P) {
-    if (c->cells_search == 1) launch_knn_cells_scan_s<1>(c, P);
-    else if (c->cells_search == 2) launch_knn_cells_scan_s<2>(c, P);
-    else launch_knn_cells_scan_s<3>(c, P);
+    if (c->cells_search == 1) launch_knn_cells_scan_t<LI_CELLS_MINB, 1>(c, P);
+    else if (c->cells_search == 2) launch_knn_cells_scan_t<LI_CELLS_MINB, 2>(c, P);
+    else launch_knn_cells_scan_t<LI_CELLS_MINB, 3>(c, P);
 }
 
 constexpr int TPQ_CH = 32, TPQ_NB = 8;
@@ -416,10 +411,6 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
         }
         // the cell directory is defined for 8x8x8-voxel bricks; another brick size keeps the brick search
         c->cells = (ki == LIINIT_KNN_CELLS) && bs == LI_CELLS_BSHIFT;
-        const char* mb = getenv("LIINIT_CELLS_MINB");
-        if (mb && atoi(mb) == 8) c->cells_minb = 8;
-        if (mb && atoi(mb) == 6) c->cells_minb = 6;
-        if (mb && atoi(mb) == 4) c->cells_minb = 4;
         const char* rf = getenv("LIINIT_CELLS_REFRESH");
         if (rf && !strcmp(rf, "thread")) c->cells_refresh_warp = false;
         const char* cs = getenv("LIINIT_CELLS_SEARCH");

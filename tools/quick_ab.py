@@ -9,7 +9,7 @@ import argparse
 ap = argparse.ArgumentParser()
 ap.add_argument("--N", type=int, default=240000)
 ap.add_argument("--M", type=int, default=5000000)
-ap.add_argument("--variants", default="1:0:2:0,2:8:2:3,2:6:2:3,2:4:2:3,2:8:3:3,2:8:1.5:3,2:8:2:2,2:8:2:1")   # index:minb:rho_cells:search
+ap.add_argument("--variants", default="1:0:2:0,2:6:2:3,2:6:3:3,2:6:1.5:3,2:6:2:2,2:6:2:1")   # index:minb:rho_cells:search (minb: only honoured by libraries built with the A/B switch, see git history)
 a = ap.parse_args()
 t = time.time(); c = scenes.make_config("C2", N=a.N, M=a.M); print("gen", round(time.time() - t, 2), flush=True)
 ref = None

@@ -49,6 +49,29 @@ def test_index_knn_matches_oracle(gpu_lib, oracle_mod, small_case, index, rho_ce
     g.close()
 
 
+@pytest.mark.parametrize("search", [1, 2, 3])
+def test_cells_all_loop_shapes(gpu_lib, oracle_mod, small_case, search, monkeypatch):
+    """The three searches over the directory (shells on cells, growing boxes, enumerate + stream) are kept
+    selectable for A/B (LIINIT_CELLS_SEARCH, read when the context is created): all of them must stay exact."""
+    monkeypatch.setenv("LIINIT_CELLS_SEARCH", str(search))
+    c = small_case
+    g = gpu_lib.LiInitGpu(c["ds"], max_map_points=400000, max_scan_points=50000, knn_index=CELLS)
+    g.map_build(c["map_xyz"])
+    om = oracle_mod.OracleMap(c["ds"], _bk(oracle_mod))
+    om.build(c["map_xyz"])
+    q = _world(c["body_xyz"], c["pose_init"])
+    gx, gd, gc = g.nearest_search(q)
+    ox, od, oc, _ = om.knn(q)
+    assert np.array_equal(gc, oc) and np.array_equal(gd, od) and np.array_equal(gx, ox)
+    g.scan_upload(c["body_xyz"][:1000])          # ragged tail: 1000 = 7 blocks of 128 + 104 (idle lanes must keep voting)
+    p = c["pose_init"]
+    H, b, m, _ = g.icp_iterate(p.rot_end, p.pos_end, p.R_LI, p.T_LI, False, True)
+    osc = oracle_mod.OracleScan(c["body_xyz"][:1000])
+    Ho, bo, mo = osc.iterate(om, p.rot_end, p.pos_end, p.R_LI, p.T_LI, False, True)
+    assert m == mo and _relerr(H, Ho) <= REL and _relerr(b, bo) <= REL
+    g.close()
+
+
 @pytest.mark.parametrize("imu_en", [False, True])
 def test_cells_search_and_reuse_pass(gpu_lib, oracle_mod, imu_en):
     c = scenes.make_config("C2", N=20000, M=200000, open_air_frac=0.02, imu_en=imu_en)

@@ -1,18 +1,24 @@
 #!/bin/bash
-# GPU session B: enumerate+stream cells search (warp-per-brick refresh) through the GPU suite, same-box A/B of all variants,
-# bench lines + ncu evidence for BOTH indexes (the brick search at HEAD needs fresh profiles whatever the outcome).
+# One gpurun call that covers a development cycle (about 2.5 minutes of box time on one B200):
+#   /usr/local/graft/bin/gpurun --timeout 600 -- 'bash tools/gpu_session.sh'
+# GPU suite with the cells index forced (the default index is covered by the plain suite), same-box A/B of the search variants
+# (tools/quick_ab.py), bench lines + ncu launch lists + ncu --set full captures for BOTH indexes, sanitizer on the smoke.
+# Everything lands in gpurun_out/; tools/ncu_metrics.py and tools/ncu_lines.py turn the .ncu-rep files into the text kept under profiles/.
 set +e
 mkdir -p gpurun_out
 T0=$SECONDS
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,temperature.gpu --format=csv > gpurun_out/gpu.txt 2>&1
-LIINIT_KNN_INDEX=2 timeout 600 python -m pytest tests -m gpu -x -q --durations=5 > gpurun_out/t_cells.log 2>&1; echo "cells(stream, warp refresh) suite rc=$? t=$((SECONDS-T0))"
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/t_default.log 2>&1; echo "default suite rc=$? t=$((SECONDS-T0))"
+tail -2 gpurun_out/t_default.log
+LIINIT_KNN_INDEX=2 timeout 600 python -m pytest tests -m gpu -x -q --durations=5 > gpurun_out/t_cells.log 2>&1; echo "cells suite rc=$? t=$((SECONDS-T0))"
 tail -2 gpurun_out/t_cells.log
 LIINIT_KNN_INDEX=2 LIINIT_CELLS_REFRESH=thread timeout 300 python -m pytest tests/test_gpu_cells.py tests/test_gpu_parity.py -x -q > gpurun_out/t_cells_threadrefresh.log 2>&1; echo "cells thread-refresh rc=$? t=$((SECONDS-T0))"
 tail -1 gpurun_out/t_cells_threadrefresh.log
 for s in 2 1; do LIINIT_KNN_INDEX=2 LIINIT_CELLS_SEARCH=$s timeout 300 python -m pytest tests/test_gpu_cells.py -x -q > gpurun_out/t_cells_search$s.log 2>&1; echo "cells search=$s rc=$? t=$((SECONDS-T0))"; done
 timeout 300 python tools/quick_ab.py > gpurun_out/ab.log 2>&1; echo "ab rc=$? t=$((SECONDS-T0))"
 grep -v "^gen" gpurun_out/ab.log
-for v in qc16 qc64 t64; do LIINIT_GPU_LIB=build/variants/libliinit_gpu_$v.so timeout 120 python tools/quick_ab.py --variants 2:8:2:3,2:6:2:3 > gpurun_out/ab_$v.log 2>&1; echo "ab $v rc=$? t=$((SECONDS-T0))"; grep -v "^gen" gpurun_out/ab_$v.log; done
+# compile-time variants: build them into build/variants/ (nvcc ... -DLI_CELLS_QC=16 -o build/variants/lib_x.so ...) and probe each with
+#   LIINIT_GPU_LIB=build/variants/lib_x.so python tools/quick_ab.py --variants 2:6:2:3      (tools/probe_variant.py for the brick search)
 timeout 300 python bench.py --knn-index 2 > gpurun_out/bench_cells.json 2> gpurun_out/bench_cells.err; echo "bench cells rc=$? t=$((SECONDS-T0))"
 cut -c1-400 gpurun_out/bench_cells.json
 timeout 300 python bench.py --knn-index 1 > gpurun_out/bench_bricks.json 2> gpurun_out/bench_bricks.err; echo "bench bricks rc=$? t=$((SECONDS-T0))"

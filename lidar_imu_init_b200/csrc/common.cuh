@@ -83,7 +83,7 @@ LI_HD unsigned li_hash(unsigned long long k) {
     return h;
 }
 
-#ifdef __CUDACC__
+#if defined(__CUDACC__) || defined(LI_SIMT_EMUL)   // LI_SIMT_EMUL: tests/emul/simt_shim.h runs the warp-cooperative kernels on the CPU, 32 fibers per warp
 
 // Voxel index exactly as the reference computes it: floor(x / downsample_size) in float
 // (ikd_Tree.cpp:389). IEEE division, no reciprocal shortcut.
@@ -99,6 +99,21 @@ __device__ __forceinline__ float li_dist2(float ax, float ay, float az, float bx
 // Same value, two issue slots fewer: the x and y lanes go through Blackwell's packed fp32 pipe (sub.f32x2 / mul.f32x2 ->
 // FADD2 / FMUL2 on sm_100a; each half is an IEEE round-to-nearest operation, so the result is bit-identical to li_dist2).
 // qxy = {qx, qy} packed by li_pack_f32x2; p.x, p.y arrive adjacent from the 16-byte slab load, so the packing is free.
+#ifdef LI_SIMT_EMUL   // CPU emulation of the kernels: the same values without PTX
+inline unsigned long long li_pack_f32x2(float lo, float hi) {
+    unsigned a, b;
+    memcpy(&a, &lo, 4);
+    memcpy(&b, &hi, 4);
+    return (unsigned long long)a | ((unsigned long long)b << 32);
+}
+inline float li_dist2_packed(unsigned long long qxy, float qz, const float4& p) {
+    const unsigned a = (unsigned)qxy, b = (unsigned)(qxy >> 32);
+    float qx, qy;
+    memcpy(&qx, &a, 4);
+    memcpy(&qy, &b, 4);
+    return li_dist2(qx, qy, qz, p.x, p.y, p.z);
+}
+#else
 __device__ __forceinline__ unsigned long long li_pack_f32x2(float lo, float hi) {
     unsigned long long r;
     asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
@@ -113,6 +128,7 @@ __device__ __forceinline__ float li_dist2_packed(unsigned long long qxy, float q
     float dz = __fsub_rn(qz, p.z);
     return __fadd_rn(__fadd_rn(sx, sy), __fmul_rn(dz, dz));
 }
+#endif
 
 // Lookup only (searches). Returns true and (first,count) when the brick exists.
 __device__ __forceinline__ bool li_brick_find(const uint4* __restrict__ ent, unsigned mask, unsigned long long key,

@@ -123,9 +123,13 @@ __device__ __forceinline__ void group_merge(const float (&ld)[5], const int (&li
 #if LI_SCAN_V2
 // a float the compiler must treat as defined but that costs no instruction (contents: whatever the register held)
 __device__ __forceinline__ float li_stale_float() {
+#ifdef LI_SIMT_EMUL
+    return 0.f;
+#else
     float v;
     asm("" : "=f"(v));
     return v;
+#endif
 }
 template <int G, int U = LI_KNN_U>
 __device__ __forceinline__ void group_scan_pipelined(const float4* __restrict__ pool, unsigned f, unsigned cnt, float qx, float qy, float qz,

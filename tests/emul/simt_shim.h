@@ -1,14 +1,17 @@
-// simt_shim.h -- runs the warp-cooperative CUDA kernels of the product ON THE CPU, unchanged: one warp = 32 fibers
-// (ucontext) scheduled round-robin, every warp intrinsic is a rendezvous. TEST INFRASTRUCTURE (tests/emul), never part
+// simt_shim.h -- runs the CUDA kernels of the product ON THE CPU, unchanged: one thread = one fiber (ucontext), every warp
+// intrinsic and every __syncthreads is a rendezvous. TEST INFRASTRUCTURE (tests/emul), never part
 // of the product: it exists so that the lockstep search kernel (knn_kernels.cuh) -- whose control flow lives in votes
 // and shuffles and therefore cannot be restated lane by lane -- is checked by `-m "not gpu"` tests too.
 //
-// Model: all kernels here call every *_sync intrinsic with the full mask from warp-uniform control flow, so every live
-// lane executes the same sequence of intrinsics. Rendezvous k: a lane deposits its operand in buffer k & 1 and yields to
-// the scheduler; the scheduler resumes the lanes in turn, so when a lane runs again all 32 deposits of rendezvous k are
-// there. Two buffers suffice: rendezvous k + 2 cannot start before every lane has read k. Code between two rendezvous
-// simply runs lane after lane. Arithmetic: the host is compiled with -ffp-contract=off, the library with --fmad=false,
-// both IEEE, so *_rn intrinsics are the plain operators.
+// Model: the kernels call every *_sync intrinsic with the full mask from warp-uniform control flow, so every live lane of
+// a warp executes the same sequence of intrinsics. An intrinsic is a counting barrier over the live lanes of the warp with
+// two exchange buffers (generation parity): a lane deposits its operand, the last one to arrive opens the generation, the
+// others yield to the scheduler until it is open; nobody can start generation k + 2 before everybody has left k + 1, i.e.
+// has read k. __syncthreads is the same barrier over the block. Blocks run one after the other, the threads of a block
+// are resumed round-robin; code between two rendezvous simply runs thread after thread, atomics are plain
+// read-modify-writes (one OS thread), __shared__ is a static. Threads that return from the kernel stop counting.
+// Arithmetic: the host is compiled with -ffp-contract=off, the library with --fmad=false, both IEEE, so *_rn intrinsics
+// are the plain operators.
 #pragma once
 #define LI_SIMT_EMUL 1
 #include <ucontext.h>
@@ -20,36 +23,58 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 using std::isfinite;
-
-#ifndef __launch_bounds__
-#define __launch_bounds__(...)
-#endif
 
 struct SimtDim { unsigned x, y, z; };
 inline SimtDim threadIdx{0, 0, 0}, blockIdx{0, 0, 0}, blockDim{32, 1, 1}, gridDim{1, 1, 1};
 
-struct SimtWarp {
+#ifndef __launch_bounds__
+#define __launch_bounds__(...)
+#endif
+#undef __shared__
+#define __shared__ static   // one block runs at a time and all its fibers live on one OS thread
+
+constexpr int SIMT_MAX_THREADS = 1024;
+struct SimtBlock {
     ucontext_t sched;
-    ucontext_t lane[32];
-    char* stack[32];
-    bool fin[32];
-    uint64_t buf[2][32];
-    unsigned long nsync[32];
-    int cur;
+    ucontext_t th[SIMT_MAX_THREADS];
+    char* stack[SIMT_MAX_THREADS];
+    bool fin[SIMT_MAX_THREADS];
+    int nthreads;
+    int cur;   // thread of the block that is running
+    // warp rendezvous: a counting barrier per warp, two exchange buffers (generation parity)
+    uint64_t buf[SIMT_MAX_THREADS / 32][2][32];
+    int warr[SIMT_MAX_THREADS / 32];
+    unsigned long wgen[SIMT_MAX_THREADS / 32];
+    int wlive[SIMT_MAX_THREADS / 32];
+    // block barrier
+    int barr;
+    unsigned long bgen;
+    int blive;
     unsigned long long rendezvous;   // statistics
 };
-inline SimtWarp g_w;
+inline SimtBlock g_b;
 
-inline uint64_t simt_exchange_begin(uint64_t v) {   // deposit + yield; returns the buffer index to read from
-    const int l = g_w.cur;
-    const unsigned long k = g_w.nsync[l]++;
-    g_w.buf[k & 1][l] = v;
-    g_w.rendezvous++;
-    swapcontext(&g_w.lane[l], &g_w.sched);
-    return k & 1;
+inline void simt_yield() { swapcontext(&g_b.th[g_b.cur], &g_b.sched); }
+
+// deposit v, wait until every live lane of this thread's warp has deposited; returns the buffer to read from
+inline const uint64_t* simt_exchange(uint64_t v) {
+    const int t = g_b.cur, w = t >> 5, l = t & 31;
+    const unsigned long gen = g_b.wgen[w];
+    g_b.buf[w][gen & 1][l] = v;
+    g_b.rendezvous++;
+    if (++g_b.warr[w] >= g_b.wlive[w]) {
+        g_b.warr[w] = 0;
+        g_b.wgen[w]++;
+    } else {
+        while (g_b.wgen[w] == gen) simt_yield();
+    }
+    return g_b.buf[w][gen & 1];
 }
+inline bool simt_lane_live(int l) { return !g_b.fin[(g_b.cur & ~31) + l]; }
+
 template <class T>
 inline uint64_t simt_bits(T v) {
     static_assert(sizeof(T) <= 8, "shuffle operand too wide");
@@ -66,38 +91,52 @@ inline T simt_unbits(uint64_t b) {
 
 template <class T>
 inline T __shfl_sync(unsigned, T v, int src) {
-    const uint64_t k = simt_exchange_begin(simt_bits(v));
-    return simt_unbits<T>(g_w.buf[k][src & 31]);
+    return simt_unbits<T>(simt_exchange(simt_bits(v))[src & 31]);
 }
 template <class T>
 inline T __shfl_xor_sync(unsigned, T v, int o) {
-    const int l = g_w.cur;
-    const uint64_t k = simt_exchange_begin(simt_bits(v));
-    return simt_unbits<T>(g_w.buf[k][(l ^ o) & 31]);
+    const int l = g_b.cur & 31;
+    return simt_unbits<T>(simt_exchange(simt_bits(v))[(l ^ o) & 31]);
 }
 template <class T>
 inline T __shfl_up_sync(unsigned, T v, int o) {
-    const int l = g_w.cur;
-    const uint64_t k = simt_exchange_begin(simt_bits(v));
-    return l >= o ? simt_unbits<T>(g_w.buf[k][l - o]) : v;
+    const int l = g_b.cur & 31;
+    const uint64_t* b = simt_exchange(simt_bits(v));
+    return l >= o ? simt_unbits<T>(b[l - o]) : v;
+}
+template <class T>
+inline T __shfl_down_sync(unsigned, T v, int o) {
+    const int l = g_b.cur & 31;
+    const uint64_t* b = simt_exchange(simt_bits(v));
+    return l + o < 32 ? simt_unbits<T>(b[l + o]) : v;
 }
 inline unsigned __ballot_sync(unsigned, bool p) {
-    const uint64_t k = simt_exchange_begin(p ? 1u : 0u);
+    const uint64_t* b = simt_exchange(p ? 1u : 0u);
     unsigned r = 0;
     for (int i = 0; i < 32; i++)
-        if (!g_w.fin[i] && g_w.buf[k][i]) r |= 1u << i;
+        if (simt_lane_live(i) && b[i]) r |= 1u << i;
     return r;
 }
 inline int __any_sync(unsigned m, bool p) { return __ballot_sync(m, p) != 0u; }
 inline int __all_sync(unsigned m, bool p) { return __ballot_sync(m, !p) == 0u; }
 inline unsigned __reduce_min_sync(unsigned, unsigned v) {
-    const uint64_t k = simt_exchange_begin(v);
+    const uint64_t* b = simt_exchange(v);
     unsigned r = 0xffffffffu;
     for (int i = 0; i < 32; i++)
-        if (!g_w.fin[i] && (unsigned)g_w.buf[k][i] < r) r = (unsigned)g_w.buf[k][i];
+        if (simt_lane_live(i) && (unsigned)b[i] < r) r = (unsigned)b[i];
     return r;
 }
-inline void __syncwarp(unsigned = 0xffffffffu) { (void)simt_exchange_begin(0); }
+inline void __syncwarp(unsigned = 0xffffffffu) { (void)simt_exchange(0); }
+inline void __syncthreads() {
+    const unsigned long gen = g_b.bgen;
+    if (++g_b.barr >= g_b.blive) {
+        g_b.barr = 0;
+        g_b.bgen++;
+    } else {
+        while (g_b.bgen == gen) simt_yield();
+    }
+}
+inline void __threadfence() {}
 
 // ---- scalar device intrinsics -----------------------------------------------------------------------
 inline float __fadd_rn(float a, float b) { return a + b; }
@@ -131,47 +170,59 @@ inline T atomicExch(T* p, T v) { T o = *p; *p = v; return o; }
 template <class T>
 inline T atomicCAS(T* p, T c, T v) { T o = *p; if (o == c) *p = v; return o; }
 
-// ---- running one warp ---------------------------------------------------------------------------------
-typedef void (*SimtLaneFn)(void*);
-struct SimtLaunch { SimtLaneFn fn; void* arg; };
+// ---- running a grid: blocks one after the other, the threads of a block as fibers ------------------------------------
+struct SimtLaunch { void (*fn)(void*); void* arg; };
 inline SimtLaunch g_simt_launch;
 inline void simt_trampoline() {
     g_simt_launch.fn(g_simt_launch.arg);
-    g_w.fin[g_w.cur] = true;   // uc_link brings us back to the scheduler
+    // a thread that leaves the kernel no longer takes part in rendezvous / barriers (as on the device: exited threads do not block)
+    const int t = g_b.cur, w = t >> 5;
+    g_b.fin[t] = true;
+    g_b.wlive[w]--;
+    g_b.blive--;
+    if (g_b.wlive[w] > 0 && g_b.warr[w] >= g_b.wlive[w]) { g_b.warr[w] = 0; g_b.wgen[w]++; }
+    if (g_b.blive > 0 && g_b.barr >= g_b.blive) { g_b.barr = 0; g_b.bgen++; }
 }
-// Runs fn(arg) once per lane of ONE warp (threadIdx.x = 0..31, blockDim.x = 32, the given block of a grid of `nblocks`).
-inline void simt_run_warp(SimtLaneFn fn, void* arg, unsigned block, unsigned nblocks) {
-    const size_t STACK = 256 * 1024;
+// kernel<<<grid, block>>>: fn(arg) is the kernel call with its arguments bound
+inline void simt_launch(unsigned grid, unsigned block, void (*fn)(void*), void* arg) {
+    const size_t STACK = 192 * 1024;
+    if (block == 0 || block > SIMT_MAX_THREADS || (block & 31)) {
+        fprintf(stderr, "simt_shim: block size %u not supported (multiple of 32, <= %d)\n", block, SIMT_MAX_THREADS);
+        abort();
+    }
     g_simt_launch.fn = fn;
     g_simt_launch.arg = arg;
-    blockDim = SimtDim{32, 1, 1};
-    gridDim = SimtDim{nblocks, 1, 1};
-    blockIdx = SimtDim{block, 0, 0};
-    for (int l = 0; l < 32; l++) {
-        if (!g_w.stack[l]) g_w.stack[l] = (char*)malloc(STACK);
-        g_w.fin[l] = false;
-        g_w.nsync[l] = 0;
-        getcontext(&g_w.lane[l]);
-        g_w.lane[l].uc_stack.ss_sp = g_w.stack[l];
-        g_w.lane[l].uc_stack.ss_size = STACK;
-        g_w.lane[l].uc_link = &g_w.sched;
-        makecontext(&g_w.lane[l], simt_trampoline, 0);
-    }
-    for (bool alive = true; alive;) {
-        alive = false;
-        for (int l = 0; l < 32; l++) {
-            if (g_w.fin[l]) continue;
-            g_w.cur = l;
-            threadIdx = SimtDim{(unsigned)l, 0, 0};
-            swapcontext(&g_w.sched, &g_w.lane[l]);
-            if (!g_w.fin[l]) alive = true;
+    blockDim = SimtDim{block, 1, 1};
+    gridDim = SimtDim{grid, 1, 1};
+    g_b.nthreads = (int)block;
+    for (unsigned b = 0; b < grid; b++) {
+        blockIdx = SimtDim{b, 0, 0};
+        g_b.barr = 0; g_b.bgen = 0; g_b.blive = (int)block;
+        for (unsigned w = 0; w < block / 32; w++) { g_b.warr[w] = 0; g_b.wgen[w] = 0; g_b.wlive[w] = 32; }
+        for (unsigned t = 0; t < block; t++) {
+            if (!g_b.stack[t]) g_b.stack[t] = (char*)malloc(STACK);
+            g_b.fin[t] = false;
+            getcontext(&g_b.th[t]);
+            g_b.th[t].uc_stack.ss_sp = g_b.stack[t];
+            g_b.th[t].uc_stack.ss_size = STACK;
+            g_b.th[t].uc_link = &g_b.sched;
+            makecontext(&g_b.th[t], simt_trampoline, 0);
+        }
+        for (bool alive = true; alive;) {
+            alive = false;
+            for (unsigned t = 0; t < block; t++) {
+                if (g_b.fin[t]) continue;
+                g_b.cur = (int)t;
+                threadIdx = SimtDim{t, 0, 0};
+                swapcontext(&g_b.sched, &g_b.th[t]);
+                if (!g_b.fin[t]) alive = true;
+            }
         }
     }
-    // lockstep check: every lane must have gone through the same number of rendezvous
-    for (int l = 1; l < 32; l++)
-        if (g_w.nsync[l] != g_w.nsync[0]) {
-            fprintf(stderr, "simt_shim: lane %d made %lu rendezvous, lane 0 %lu -- control flow around a warp intrinsic is not warp-uniform\n", l,
-                    g_w.nsync[l], g_w.nsync[0]);
-            abort();
-        }
+}
+// bind a kernel call: SIMT_LAUNCH(grid, block, kernel<...>, args...)
+template <class F>
+inline void simt_launch_fn(unsigned grid, unsigned block, F&& f) {
+    auto thunk = [](void* p) { (*static_cast<typename std::remove_reference<F>::type*>(p))(); };
+    simt_launch(grid, block, thunk, (void*)&f);
 }

@@ -25,7 +25,7 @@ def available() -> bool:
 
 def build(force: bool = False) -> str:
     deps = [SRC, os.path.join(HERE, "emul", "simt_shim.h"), os.path.join(HERE, "emul", "emul_map.h")] + \
-           [os.path.join(CSRC, f) for f in ("knn_kernels.cuh", "common.cuh", "cells.cuh")]
+           [os.path.join(CSRC, f) for f in ("knn_kernels.cuh", "icp_kernels.cuh", "common.cuh", "cells.cuh")]
     if force or not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-Wno-attributes", "-Wno-unknown-pragmas",
                                "-I", CUDA_INC, SRC, "-o", LIB])
@@ -44,8 +44,15 @@ def load():
         L.simt_map_destroy.argtypes = [C.c_void_p]
         L.simt_knn_scan.restype = C.c_longlong
         L.simt_knn_scan.argtypes = [C.c_void_p, _f32, C.c_int, _f64, C.c_float, C.c_int, _f32, _f32, _i32]
+        L.simt_icp_pass.argtypes = [C.c_void_p, _f32, C.c_int, _f64, C.c_void_p, C.c_float, C.c_int, C.c_int, _f64, C.c_void_p, _f32, _f32, _i32,
+                                    np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS"), _f32]
         _L = L
     return _L
+
+
+def _pose_vec(pose):
+    return np.ascontiguousarray(np.concatenate([np.asarray(pose.rot_end, np.float64).ravel(), np.asarray(pose.pos_end, np.float64).ravel(),
+                                                np.asarray(pose.R_LI, np.float64).ravel(), np.asarray(pose.T_LI, np.float64).ravel()]))
 
 
 class SimtMap:
@@ -68,6 +75,27 @@ class SimtMap:
         cnt = np.zeros(n, np.int32)
         self.rendezvous = self.L.simt_knn_scan(self.h, body, n, np.ascontiguousarray(P), np.float32(rho) * np.float32(rho), G, world, near, cnt)
         return world, near, cnt
+
+    def icp_pass(self, body, pose, imu_en, pose2=None, rho=0.3, G=4):
+        """Search pass (k_knn_scan + k_icp_plane) and, with pose2, a reuse pass behind it. Returns dict(H, b, m, res_sq, [H2, b2, m2],
+        world, near_xyz, near_cnt, selected, normvec) with H [12,12], b [12] as liinit_icp_iterate delivers them."""
+        body = np.ascontiguousarray(body, np.float32).reshape(-1, 3)
+        n = len(body)
+        out, out2 = np.zeros(160), np.zeros(160)
+        world = np.zeros((n, 3), np.float32)
+        near = np.zeros((n, 5, 3), np.float32)
+        cnt = np.zeros(n, np.int32)
+        sel = np.zeros(n, np.uint8)
+        nv = np.zeros((n, 4), np.float32)
+        P2 = _pose_vec(pose2) if pose2 is not None else None
+        self.L.simt_icp_pass(self.h, body, n, _pose_vec(pose), P2.ctypes.data_as(C.c_void_p) if P2 is not None else None,
+                             np.float32(rho) * np.float32(rho), G, int(bool(imu_en)), out,
+                             out2.ctypes.data_as(C.c_void_p) if P2 is not None else None, world, near, cnt, sel, nv)
+        r = dict(H=out[:144].reshape(12, 12).copy(), b=out[144:156].copy(), res_sq=out[156], m=int(round(out[157])), world=world, near_xyz=near,
+                 near_cnt=cnt, selected=sel, normvec=nv)
+        if P2 is not None:
+            r.update(H2=out2[:144].reshape(12, 12).copy(), b2=out2[144:156].copy(), m2=int(round(out2[157])))
+        return r
 
     def close(self):
         if self.h:

@@ -440,7 +440,7 @@ LI_HD void knn5_boxes(const MapDev& M, float rho2, float qx, float qy, float qz,
 // predicate on the host, where one lane runs alone); a full queue anywhere makes the whole warp drain. The set of
 // candidates a lane evaluates, and their order, does not depend on the other lanes, so results are identical on both
 // sides. Search logic = knn5_boxes.
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) || defined(LI_SIMT_EMUL)   // (the SIMT shim of tests/emul votes over its 32 fibers)
 #define LC_ANY(p) __any_sync(0xffffffffu, (p))
 #else
 #define LC_ANY(p) (p)
@@ -657,7 +657,7 @@ LI_HD void knn5_stream(const MapDev& M, float rho2, bool valid, float qx, float 
 #define LI_CELLS_SEARCH_DEFAULT 3
 #endif
 
-#ifdef __CUDACC__
+#if defined(__CUDACC__) || defined(LI_SIMT_EMUL)
 // ---- super-brick table: called by the insert kernels when they CREATE a brick (map_kernels.cuh) -------------
 __device__ __forceinline__ void li_sb_mark(const MapDev& M, unsigned long long brick_key) {
     if (!M.sb_keys) return;

@@ -10,6 +10,8 @@
 #pragma once
 #ifdef __CUDACC__
 #include <cuda_runtime.h>
+#elif defined(LI_SIMT_EMUL)   // tests/emul/simt_shim.h brings the vector types and constructors (and no CUDA API header)
+#include <vector_types.h>
 #else   // host-only parse (tests/emul: the cell-directory search is compiled for the CPU as its own checker)
 #include <vector_types.h>
 #include <vector_functions.h>

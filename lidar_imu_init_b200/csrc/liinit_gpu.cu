@@ -16,7 +16,9 @@
 #include "common.cuh"
 #include "icp_kernels.cuh"
 #include "knn_kernels.cuh"
+#ifndef LI_SIMT_EMUL   // (the CPU checker of tests/emul leaves out the cp.async-staged thread-per-point variant)
 #include "knn_tpq.cuh"
+#endif
 #include "cells.cuh"
 #include "map_kernels.cuh"
 #include "voxelgrid_kernels.cuh"
@@ -268,6 +270,7 @@ void launch_knn_cells_scan(Ctx* c, const PoseD& P) {
     else launch_knn_cells_scan_t<LI_CELLS_MINB, 3>(c, P);
 }
 
+#ifndef LI_SIMT_EMUL
 constexpr int TPQ_CH = 32, TPQ_NB = 8;
 constexpr size_t TPQ_SMEM = 4 * TpqCfg<TPQ_CH, TPQ_NB>::WARP_TILE_F4 * sizeof(float4);
 
@@ -278,6 +281,7 @@ void launch_knn_scan_tpq(Ctx* c, const PoseD& P) {
     if (grid > cap) grid = cap;
     k_knn_scan_tpq<TPQ_CH, TPQ_NB><<<grid, 128, TPQ_SMEM, c->stream>>>(c->M, c->S, P, c->rho2);
 }
+#endif
 
 template <bool IMU, bool SEARCH>
 void launch_plane(Ctx* c, const PoseD& P, double* out) {
@@ -299,7 +303,9 @@ int run_pass(Ctx* c, const double* R, const double* p, const double* RLI, const 
     if (search) {
         if (c->cells) launch_knn_cells_scan(c, P);
         else switch (c->group) {
+#ifndef LI_SIMT_EMUL
             case 1: launch_knn_scan_tpq(c, P); break;
+#endif
             case 16: launch_knn_scan<16>(c, P); break;
             case 32: launch_knn_scan<32>(c, P); break;
             case 2: launch_knn_scan<2>(c, P); break;
@@ -371,8 +377,10 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
     cudaDeviceProp prop;
     CUC(cudaGetDeviceProperties(&prop, c->device));
     c->num_sms = prop.multiProcessorCount;
+#ifndef LI_SIMT_EMUL
     CUC(cudaFuncSetAttribute(k_knn_scan_tpq<TPQ_CH, TPQ_NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TPQ_SMEM));
     CUC(cudaFuncSetAttribute(k_knn_queries_tpq<TPQ_CH, TPQ_NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TPQ_SMEM));
+#endif
     CUC(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     CUC(cudaEventCreate(&c->ev0));
@@ -683,10 +691,12 @@ int liinit_map_nearest_search(liinit_ctx* h, const float* q, int stride, int n, 
             if (c->cells_search == 1) k_knn_cells_queries<1><<<gq, LI_CELLS_THREADS, 0, c->stream>>>(c->M, c->d_stage_pts, m, d_ids, c->d_q_d2, c->rho2);
             else if (c->cells_search == 2) k_knn_cells_queries<2><<<gq, LI_CELLS_THREADS, 0, c->stream>>>(c->M, c->d_stage_pts, m, d_ids, c->d_q_d2, c->rho2);
             else k_knn_cells_queries<3><<<gq, LI_CELLS_THREADS, 0, c->stream>>>(c->M, c->d_stage_pts, m, d_ids, c->d_q_d2, c->rho2);
+#ifndef LI_SIMT_EMUL
         } else if (c->group == 1) {
             int grid = nblk(m, 128);
             if (grid > c->num_sms * 12) grid = c->num_sms * 12;
             k_knn_queries_tpq<TPQ_CH, TPQ_NB><<<grid, 128, TPQ_SMEM, c->stream>>>(c->M, c->d_stage_pts, m, d_ids, c->d_q_d2, c->rho2);
+#endif
         } else {
             int grid = nblk((long long)m * 8, 256);
             if (grid > c->max_blocks) grid = c->max_blocks;

@@ -15,8 +15,7 @@
 #pragma once
 #define LI_SIMT_EMUL 1
 #include <ucontext.h>
-#include <vector_functions.h>
-#include <vector_types.h>
+#include <vector_types.h>   // the vector structs only (host_defines.h qualifiers come with it); no CUDA API header
 
 #include <cmath>
 #include <cstdint>
@@ -26,6 +25,16 @@
 #include <type_traits>
 
 using std::isfinite;
+
+// the constructors of vector_functions.h that the kernels use
+inline float4 make_float4(float x, float y, float z, float w) { float4 v; v.x = x; v.y = y; v.z = z; v.w = w; return v; }
+inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { uint4 v; v.x = x; v.y = y; v.z = z; v.w = w; return v; }
+inline int4 make_int4(int x, int y, int z, int w) { int4 v; v.x = x; v.y = y; v.z = z; v.w = w; return v; }
+inline float2 make_float2(float x, float y) { float2 v; v.x = x; v.y = y; return v; }
+inline uint2 make_uint2(unsigned x, unsigned y) { uint2 v; v.x = x; v.y = y; return v; }
+inline ushort2 make_ushort2(unsigned short x, unsigned short y) { ushort2 v; v.x = x; v.y = y; return v; }
+inline float3 make_float3(float x, float y, float z) { float3 v; v.x = x; v.y = y; v.z = z; return v; }
+inline int3 make_int3(int x, int y, int z) { int3 v; v.x = x; v.y = y; v.z = z; return v; }
 
 struct SimtDim { unsigned x, y, z; };
 inline SimtDim threadIdx{0, 0, 0}, blockIdx{0, 0, 0}, blockDim{32, 1, 1}, gridDim{1, 1, 1};
@@ -126,6 +135,14 @@ inline unsigned __reduce_min_sync(unsigned, unsigned v) {
         if (simt_lane_live(i) && (unsigned)b[i] < r) r = (unsigned)b[i];
     return r;
 }
+inline unsigned __match_any_sync(unsigned, unsigned v) {
+    const uint64_t* b = simt_exchange(v);
+    unsigned r = 0;
+    for (int i = 0; i < 32; i++)
+        if (simt_lane_live(i) && (unsigned)b[i] == v) r |= 1u << i;
+    return r;
+}
+inline unsigned __activemask() { unsigned r = 0; for (int i = 0; i < 32; i++) if (simt_lane_live(i)) r |= 1u << i; return r; }
 inline void __syncwarp(unsigned = 0xffffffffu) { (void)simt_exchange(0); }
 inline void __syncthreads() {
     const unsigned long gen = g_b.bgen;
@@ -149,6 +166,10 @@ inline double __dmul_rn(double a, double b) { return a * b; }
 inline double __ddiv_rn(double a, double b) { return a / b; }
 inline unsigned __float_as_uint(float f) { return simt_unbits<unsigned>(simt_bits(f)); }
 inline float __uint_as_float(unsigned u) { return simt_unbits<float>(simt_bits(u)); }
+inline int __float_as_int(float f) { return simt_unbits<int>(simt_bits(f)); }
+inline float __int_as_float(int i) { return simt_unbits<float>(simt_bits(i)); }
+inline long long __double_as_longlong(double d) { return simt_unbits<long long>(simt_bits(d)); }
+inline double __longlong_as_double(long long v) { return simt_unbits<double>(simt_bits(v)); }
 inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 inline int __ffsll(long long v) { return __builtin_ffsll(v); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
@@ -161,14 +182,22 @@ inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }
 inline int min(int a, int b) { return a < b ? a : b; }
 inline int max(int a, int b) { return a > b ? a : b; }
 // one OS thread: atomics are plain read-modify-writes
-template <class T>
-inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
-template <class T>
-inline T atomicOr(T* p, T v) { T o = *p; *p = o | v; return o; }
-template <class T>
-inline T atomicExch(T* p, T v) { T o = *p; *p = v; return o; }
-template <class T>
-inline T atomicCAS(T* p, T c, T v) { T o = *p; if (o == c) *p = v; return o; }
+template <class T, class U>
+inline T atomicAdd(T* p, U v) { T o = *p; *p = (T)(o + (T)v); return o; }
+template <class T, class U>
+inline T atomicSub(T* p, U v) { T o = *p; *p = (T)(o - (T)v); return o; }
+template <class T, class U>
+inline T atomicOr(T* p, U v) { T o = *p; *p = (T)(o | (T)v); return o; }
+template <class T, class U>
+inline T atomicAnd(T* p, U v) { T o = *p; *p = (T)(o & (T)v); return o; }
+template <class T, class U>
+inline T atomicExch(T* p, U v) { T o = *p; *p = (T)v; return o; }
+template <class T, class U>
+inline T atomicMin(T* p, U v) { T o = *p; if ((T)v < o) *p = (T)v; return o; }
+template <class T, class U>
+inline T atomicMax(T* p, U v) { T o = *p; if ((T)v > o) *p = (T)v; return o; }
+template <class T, class U, class V>
+inline T atomicCAS(T* p, U c, V v) { T o = *p; if (o == (T)c) *p = (T)v; return o; }
 
 // ---- running a grid: blocks one after the other, the threads of a block as fibers ------------------------------------
 struct SimtLaunch { void (*fn)(void*); void* arg; };

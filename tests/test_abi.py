@@ -36,6 +36,21 @@ def test_product_does_not_reference_oracle():
     assert not bad, bad
 
 
+def test_product_does_not_reference_the_cpu_checkers():
+    """tests/emul (the kernels run on the CPU through a SIMT shim) is test infrastructure as well: no Python module of the package may
+    load it or its libraries, and the built product library must not contain the shim (the sources only carry LI_SIMT_EMUL guards)."""
+    bad = []
+    for dp, _, fs in os.walk(os.path.join(ROOT, "lidar_imu_init_b200")):
+        for f in fs:
+            if f.endswith(".py"):
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                if re.search(r"emul|simt_shim|cuda_shim", txt):
+                    bad.append(os.path.join(dp, f))
+    assert not bad, bad
+    build = open(os.path.join(ROOT, "lidar_imu_init_b200", "_build.py")).read()
+    assert "LI_SIMT_EMUL" not in build and "tests" not in build
+
+
 def test_no_gpu_fails_loudly(gpu_lib):
     try:
         import torch

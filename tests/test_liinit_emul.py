@@ -1,0 +1,284 @@
+"""The product's C-ABI library -- entry points, staging, launch sequences and EVERY kernel -- compiled for the host from its own
+source (tests/emul/make_liinit_emul.py: kernel launches rewritten to the SIMT shim, CUDA runtime to host memory) and checked
+against the oracle with the assertions of the GPU parity tests, at sizes a CPU finishes in seconds. This is a checker of LOGIC for
+`-m "not gpu"` runs (the real proof stays `-m gpu` on the B200); the package itself has no CPU path and never loads this library."""
+import numpy as np
+import pytest
+
+import liinit_emul as le
+from lidar_imu_init_b200 import scenes
+
+pytestmark = pytest.mark.skipif(not le.available(), reason="g++ or the CUDA vector-type headers are missing")
+
+REL = 1e-9
+BRICKS, CELLS = 1, 2
+
+
+def _world(body, p):
+    return (p.rot_end @ (p.R_LI @ body.T.astype(np.float64) + p.T_LI[:, None]) + p.pos_end[:, None]).T.astype(np.float32)
+
+
+def _bk(orc):
+    return 1 if orc.has_ikd() else 0
+
+
+def _relerr(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def _same_set(a, b):
+    return set(map(bytes, np.ascontiguousarray(a, np.float32))) == set(map(bytes, np.ascontiguousarray(b, np.float32)))
+
+
+@pytest.fixture(scope="module")
+def case():
+    return scenes.make_config("C2", N=3000, M=60000, open_air_frac=0.02)
+
+
+@pytest.mark.parametrize("index", [BRICKS, CELLS])
+@pytest.mark.parametrize("imu_en", [False, True])
+def test_emul_search_and_reuse_pass(oracle_mod, imu_en, index):
+    c = scenes.make_config("C2", N=3000, M=60000, open_air_frac=0.02, imu_en=imu_en)
+    p = c["pose_init"]
+    g = le.EmulGpu(c["ds"], max_map_points=150000, max_scan_points=5000, knn_index=index)
+    assert g.knn_index() == index
+    g.map_build(c["map_xyz"])
+    assert g.map_validnum() == len(c["map_xyz"])
+    g.scan_upload(c["body_xyz"])
+    om = oracle_mod.OracleMap(c["ds"], _bk(oracle_mod))
+    om.build(c["map_xyz"])
+    osc = oracle_mod.OracleScan(c["body_xyz"])
+    H, b, m, rs = g.icp_iterate(p.rot_end, p.pos_end, p.R_LI, p.T_LI, imu_en, True)
+    Ho, bo, mo = osc.iterate(om, p.rot_end, p.pos_end, p.R_LI, p.T_LI, imu_en, True)
+    assert m == mo and m > 2500
+    st, so = g.scan_state(), osc.get()
+    for k in ("world", "near_cnt", "near_xyz", "selected"):
+        assert np.array_equal(st[k], so[k]), k
+    sel = so["selected"].astype(bool)
+    assert np.array_equal(st["normvec"][sel], so["normvec"][sel])
+    assert _relerr(H, Ho) <= REL and _relerr(b, bo) <= REL
+    p2 = scenes.perturb_pose(p, 77, dtheta_deg=0.05, dpos=0.01)
+    H2, b2, m2, _ = g.icp_iterate(p2.rot_end, p2.pos_end, p2.R_LI, p2.T_LI, imu_en, False)
+    Ho2, bo2, mo2 = osc.iterate(om, p2.rot_end, p2.pos_end, p2.R_LI, p2.T_LI, imu_en, False)
+    assert m2 == mo2 and _relerr(H2, Ho2) <= REL and _relerr(b2, bo2) <= REL
+    ori, nv = g.scan_effect()
+    sel2 = osc.get()["selected"].astype(bool)
+    assert np.array_equal(ori, c["body_xyz"][sel2]) and np.array_equal(nv, osc.get()["normvec"][sel2])
+    g.close()
+
+
+@pytest.mark.parametrize("index", [BRICKS, CELLS])
+def test_emul_map_updates_match_oracle(oracle_mod, index):
+    """Build, downsample / plain Add_Points batches (incl. a batch hitting voxels that hold several points), map_incremental,
+    a box delete -- live set, counters and searches on the updated map against the verbatim ikd-Tree."""
+    c = scenes.make_config("C2", N=4000, M=40000, open_air_frac=0.02)
+    p, gt = c["pose_init"], c["pose_gt"]
+    g = le.EmulGpu(c["ds"], max_map_points=150000, max_scan_points=6000, knn_index=index, hash_capacity_log2=14)   # (the box delete walks every slot)
+    om = oracle_mod.OracleMap(c["ds"], _bk(oracle_mod))
+    g.map_build(c["map_xyz"])
+    om.build(c["map_xyz"])
+    g.scan_upload(c["body_xyz"])
+    osc = oracle_mod.OracleScan(c["body_xyz"])
+    g.icp_iterate(p.rot_end, p.pos_end, p.R_LI, p.T_LI, False, True)
+    osc.iterate(om, p.rot_end, p.pos_end, p.R_LI, p.T_LI, False, True)
+    na, nn = g.map_incremental(gt.rot_end, gt.pos_end, gt.R_LI, gt.T_LI, c["ds"])
+    _, oa, on, _ = osc.map_incremental(om, gt.rot_end, gt.pos_end, gt.R_LI, gt.T_LI, c["ds"])
+    assert (na, nn) == (oa, on) and g.map_validnum() == om.validnum()
+
+    def same_search(q):
+        gx, gd, gc = g.nearest_search(q)
+        ox, od, oc, _ = om.knn(q)
+        assert np.array_equal(gc, oc) and np.array_equal(gd, od) and np.array_equal(gx, ox)
+
+    q = _world(c["body_xyz"][:1500], gt)
+    same_search(q)
+    new = _world(c["body_xyz"], gt) + np.float32(0.013)
+    for lo, hi, down in ((0, 1500, True), (1500, 2500, False), (1000, 3500, True)):
+        assert g.map_add_points(new[lo:hi], down) == om.add_points(new[lo:hi], down) or not down
+        assert g.map_validnum() == om.validnum()
+        same_search(q)
+    sc = c["scene"]
+    boxes = np.array([[-1, -1, -1, 0.4 * sc.L, sc.W + 1, sc.H + 1]], np.float32)
+    assert g.map_delete_boxes(boxes) == om.delete_boxes(boxes)
+    same_search(q)
+    assert _same_set(g.map_download(), om.flatten())
+    g.map_build(c["map_xyz"][:5000])      # Build replaces the map
+    assert g.map_validnum() == 5000
+    g.close()
+
+
+@pytest.mark.parametrize("search", [1, 2, 3])
+def test_emul_cells_loop_shapes_with_real_votes(oracle_mod, case, search, monkeypatch):
+    """The three searches over the cell directory with 32 lanes voting for real (the single-lane checker of test_cells_emul.py
+    degenerates the votes): queue indexing by thread, warp-wide drains, idle lanes of a ragged last block."""
+    monkeypatch.setenv("LIINIT_CELLS_SEARCH", str(search))
+    c = case
+    g = le.EmulGpu(c["ds"], max_map_points=150000, max_scan_points=5000, knn_index=CELLS)
+    g.map_build(c["map_xyz"])
+    om = oracle_mod.OracleMap(c["ds"], _bk(oracle_mod))
+    om.build(c["map_xyz"])
+    q = _world(c["body_xyz"][:1001], c["pose_init"])
+    gx, gd, gc = g.nearest_search(q)
+    ox, od, oc, _ = om.knn(q)
+    assert np.array_equal(gc, oc) and np.array_equal(gd, od) and np.array_equal(gx, ox)
+    g.close()
+
+
+def test_emul_both_indexes_bit_identical(case):
+    c, p = case, case["pose_init"]
+    outs = []
+    for index in (BRICKS, CELLS):
+        g = le.EmulGpu(c["ds"], max_map_points=150000, max_scan_points=5000, knn_index=index)
+        g.map_build(c["map_xyz"])
+        g.scan_upload(c["body_xyz"][:1500])
+        outs.append((g.icp_iterate(p.rot_end, p.pos_end, p.R_LI, p.T_LI, True, True), g.scan_state()))
+        g.close()
+    (ra, sa), (rb, sb) = outs
+    assert ra[2] == rb[2] and np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1], rb[1])
+    sel = sa["selected"].astype(bool)
+    for k in ("world", "near_cnt", "near_xyz", "selected"):
+        assert np.array_equal(sa[k], sb[k]), k
+    assert np.array_equal(sa["normvec"][sel], sb["normvec"][sel])   # (entries of unselected points are never written)
+
+
+@pytest.mark.parametrize("group", [8, 32])
+def test_emul_group_sizes(oracle_mod, case, group):
+    c, p = case, case["pose_init"]
+    g = le.EmulGpu(c["ds"], max_map_points=150000, max_scan_points=5000, knn_group_lanes=group)
+    g.map_build(c["map_xyz"])
+    g.scan_upload(c["body_xyz"][:1200])
+    om = oracle_mod.OracleMap(c["ds"], _bk(oracle_mod))
+    om.build(c["map_xyz"])
+    osc = oracle_mod.OracleScan(c["body_xyz"][:1200])
+    H, b, m, _ = g.icp_iterate(p.rot_end, p.pos_end, p.R_LI, p.T_LI, False, True)
+    Ho, bo, mo = osc.iterate(om, p.rot_end, p.pos_end, p.R_LI, p.T_LI, False, True)
+    assert m == mo and _relerr(H, Ho) <= REL and np.array_equal(g.scan_state()["near_xyz"], osc.get()["near_xyz"])
+    g.close()
+
+
+def test_emul_lazy_scan_state_and_call_order(oracle_mod, case):
+    """A new scan's flags / neighbour lists are initialised lazily (init_scan_state): every consumer other than the search pass must
+    see "nothing selected, no neighbours"; a reuse pass before any search pass is refused."""
+    c, p = case, case["pose_init"]
+    g = le.EmulGpu(c["ds"], max_map_points=150000, max_scan_points=5000)
+    g.map_build(c["map_xyz"])
+    g.scan_upload(c["body_xyz"][:800])
+    g.icp_iterate(p.rot_end, p.pos_end, p.R_LI, p.T_LI, False, True)          # leaves flags and neighbours of 800 points behind
+    g.scan_upload(c["body_xyz"][100:600])                                       # new scan, nothing run on it yet
+    st = g.scan_state()
+    assert not st["selected"].any() and not st["near_cnt"].any()
+    with pytest.raises(le.EmulError) as e:
+        g.icp_iterate(p.rot_end, p.pos_end, p.R_LI, p.T_LI, False, False)
+    assert e.value.code == -1
+    # map_incremental straight after an upload: no neighbours -> every point is PointToAdd (laserMapping.cpp:528-551)
+    om = oracle_mod.OracleMap(c["ds"], _bk(oracle_mod))
+    om.build(c["map_xyz"])
+    osc = oracle_mod.OracleScan(c["body_xyz"][100:600])
+    na, nn = g.map_incremental(p.rot_end, p.pos_end, p.R_LI, p.T_LI, c["ds"])
+    _, oa, on, _ = osc.map_incremental(om, p.rot_end, p.pos_end, p.R_LI, p.T_LI, c["ds"])
+    assert (na, nn) == (oa, on) == (500, 0) and g.map_validnum() == om.validnum()
+    g.close()
+
+
+def test_emul_attach_voxelgrid_layouts_and_errors(oracle_mod, case):
+    c, p = case, case["pose_init"]
+    g = le.EmulGpu(c["ds"], max_map_points=150000, max_scan_points=5000)
+    g.map_build(c["map_xyz"])
+    body = c["body_xyz"][:1000]
+    g.scan_upload(body)
+    ref = g.icp_iterate(p.rot_end, p.pos_end, p.R_LI, p.T_LI, False, True)
+    for stride in (3, 4, 12):                                                   # point layouts + the in-place host read of the search kernel
+        wide = np.full((len(body), stride), 7.0, np.float32)
+        wide[:, :3] = body
+        g.scan_attach(wide)
+        got = g.icp_iterate(p.rot_end, p.pos_end, p.R_LI, p.T_LI, False, True)
+        assert got[2] == ref[2] and np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1])
+        assert np.array_equal(g.scan_body(), body)
+    # scan voxel grid (PCL VoxelGrid semantics, row N2) against the oracle restatement
+    raw = (body[:, None, :] + np.random.default_rng(3).normal(0, 0.05, (len(body), 4, 3)).astype(np.float32)).reshape(-1, 3)
+    n = g.scan_upload_raw(raw, 0.5)
+    want = oracle_mod.voxel_grid(raw, 0.5)
+    assert n == len(want) and np.array_equal(g.scan_body(), want)
+    # errors are reported, not swallowed
+    with pytest.raises(le.EmulError) as e:
+        g.scan_upload(np.zeros((5001, 3), np.float32))
+    assert e.value.code == -3
+    with pytest.raises(le.EmulError) as e:
+        g.map_build(np.zeros((150001, 3), np.float32))
+    assert e.value.code == -3
+    with pytest.raises(le.EmulError):
+        le.EmulGpu(c["ds"], max_map_points=1000, max_scan_points=100, knn_index=7)
+    g.close()
+
+
+@pytest.mark.parametrize("rho_cells", [1.0, 6.0])
+def test_emul_seed_radius_large_coordinates_and_odd_inputs(oracle_mod, rho_cells):
+    """6 km from the origin (coarse float cells: pruning margins must keep the search exact), any seed radius, non-finite and
+    absurdly far scan points, a 3-point map, an empty map."""
+    c = scenes.make_config("C2", N=1003, M=30000, open_air_frac=0.02)
+    off = np.array([6000.0, -4500.0, 300.0])
+    mp = (c["map_xyz"].astype(np.float64) + off).astype(np.float32)
+    q = (_world(c["body_xyz"], c["pose_init"]).astype(np.float64) + off).astype(np.float32)
+    g = le.EmulGpu(c["ds"], max_map_points=100000, max_scan_points=2000, knn_seed_radius_cells=rho_cells)
+    x, d2, cnt = g.nearest_search(np.zeros((5, 3), np.float32))                 # empty map
+    assert not cnt.any() and np.all(d2 == -1)
+    g.map_build(mp)
+    om = oracle_mod.OracleMap(c["ds"], _bk(oracle_mod))
+    om.build(mp)
+    gx, gd, gc = g.nearest_search(q)
+    ox, od, oc, _ = om.knn(q)
+    assert np.array_equal(gc, oc) and np.array_equal(gd, od) and np.array_equal(gx, ox)
+    p = c["pose_init"]
+    body = c["body_xyz"][:300].copy()
+    body[3] = [np.nan, 0, 0]
+    body[77] = [np.inf, 1, 1]
+    body[299] = [1e30, 0, 0]
+    g.map_build(c["map_xyz"])
+    g.scan_upload(body)
+    H, b, m, _ = g.icp_iterate(p.rot_end, p.pos_end, p.R_LI, p.T_LI, False, True)
+    st = g.scan_state()
+    assert not st["selected"][[3, 77, 299]].any() and np.isfinite(H).all() and np.isfinite(b).all() and m > 200
+    g.map_build(c["map_xyz"][:3])
+    H, b, m, _ = g.icp_iterate(p.rot_end, p.pos_end, p.R_LI, p.T_LI, False, True)   # fewer than 5 map points: nothing selectable
+    assert m == 0 and not H.any()
+    mpn = c["map_xyz"][:1000].copy()
+    mpn[10] = [np.nan, np.nan, np.nan]
+    g.map_build(mpn)
+    assert g.map_validnum() == 999                                               # non-finite map points are dropped at insertion
+    g.close()
+
+
+import glob
+import os
+
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "c*.npz")))
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(g)[:-4] for g in GOLD])
+@pytest.mark.parametrize("index", [BRICKS, CELLS])
+def test_emul_reproduces_golden(path, index):
+    """The committed golden vectors (generated with the reference's verbatim ikd-Tree, tools/make_golden.py) against the kernels run
+    on the CPU -- the same assertions as tests/test_gpu_golden.py, no oracle involved."""
+    G = np.load(path)
+    imu_en, ds = bool(G["imu_en"]), float(G["ds"])
+    pose = lambda a: (a[0:9].reshape(3, 3), a[9:12], a[12:21].reshape(3, 3), a[21:24])
+    g = le.EmulGpu(ds, max_map_points=200000, max_scan_points=10000, knn_index=index, hash_capacity_log2=15)
+    g.map_build(G["map_xyz"])
+    g.scan_upload(G["body_xyz"])
+    H, b, m, _ = g.icp_iterate(*pose(G["pose_init"]), imu_en, True)
+    st = g.scan_state()
+    assert m == int(G["s_m"])
+    for k in ("world", "near_cnt", "near_xyz", "selected"):
+        assert np.array_equal(st[k], G["s_" + k]), k
+    sel = G["s_selected"].astype(bool)
+    assert np.array_equal(st["normvec"][sel], G["s_normvec"][sel])
+    assert _relerr(H, G["s_HtH"]) <= REL and _relerr(b, G["s_Htr"]) <= REL
+    H2, b2, m2, _ = g.icp_iterate(*pose(G["pose_2"]), imu_en, False)
+    assert m2 == int(G["r_m"]) and _relerr(H2, G["r_HtH"]) <= REL and _relerr(b2, G["r_Htr"]) <= REL
+    assert np.array_equal(g.scan_state()["selected"], G["r_selected"])
+    na, nn = g.map_incremental(*pose(G["pose_gt"]), ds)
+    assert (na, nn) == (int(G["mi_n_add"]), int(G["mi_n_nod"]))
+    live = g.map_download()
+    live = live[np.lexsort((live[:, 2], live[:, 1], live[:, 0]))]
+    assert np.array_equal(live, G["mi_live"])
+    g.close()

@@ -835,6 +835,46 @@ __global__ void __launch_bounds__(LI_CELLS_THREADS, MINB) k_knn_cells_scan(MapDe
     }
 }
 
+// Same pass with DYNAMIC scheduling: a persistent grid (MINB blocks per SM), every warp pulls batches of 32 scan points from a ticket
+// counter until the scan is used up. Why: with one block per 128 points a block lives ~300 k cycles (dependent L2 round trips, 24
+// warps per SM), so the last wave of blocks runs on a nearly empty GPU -- SMs were active 61 % of the kernel in the ncu capture of the
+// static version (profiles/r01_cells/ncu_full_stream_final_metrics.txt). With warp-granular batches the tail shrinks to one batch.
+// Checked on the CPU (tests/test_liinit_emul.py); NOT yet measured on a GPU (round-1 GPU budget was spent): opt-in via
+// LIINIT_CELLS_SCHED=dynamic until it has been.
+template <bool HOST, int MINB, int SEARCH>
+__global__ void __launch_bounds__(LI_CELLS_THREADS, MINB) k_knn_cells_scan_dyn(MapDev M, ScanDev S, PoseD P, float rho2, const float* __restrict__ raw, int stride,
+                                                                                unsigned* __restrict__ ticket) {
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(ticket, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= (unsigned)S.n) break;   // warp-uniform
+        const int q = (int)base + lane;
+        const bool valid = q < S.n;
+        float bx = 0.f, by = 0.f, bz = 0.f, wx = 0.f, wy = 0.f, wz = 0.f;
+        if (valid) {
+            if (HOST) {
+                const float* s = raw + (size_t)q * stride;
+                bx = s[0]; by = s[1]; bz = s[2];
+                S.body[q] = make_float4(bx, by, bz, 0.f);
+            } else {
+                const float4 b = __ldg(&S.body[q]);
+                bx = b.x; by = b.y; bz = b.z;
+            }
+            li_body_to_world(P, bx, by, bz, wx, wy, wz);
+        }
+        float ld[5];
+        int li[5];
+        li_cells_search<SEARCH>(M, rho2, valid, wx, wy, wz, ld, li);
+        if (valid) {
+            S.world[q] = make_float4(wx, wy, wz, 0.f);
+#pragma unroll
+            for (int k = 0; k < 5; k++) S.near_ids[(size_t)q * 5 + k] = li[k];
+        }
+    }
+}
+
 // ---- stand-alone Nearest_Search for arbitrary world-frame queries -----------------------------------------
 template <int SEARCH>
 __global__ void __launch_bounds__(LI_CELLS_THREADS) k_knn_cells_queries(MapDev M, const float4* __restrict__ qpts, int n, int* __restrict__ ids,

@@ -96,6 +96,8 @@ struct Ctx {
     int last_launches = 0;
     int group = 4;
     int cells_search = LI_CELLS_SEARCH_DEFAULT;   // 1 shells on cells, 2 growing boxes, 3 growing boxes enumerate + stream (developer A/B: LIINIT_CELLS_SEARCH)
+    bool cells_dynamic = false;       // cells search kernel with warp-granular dynamic scheduling (LIINIT_CELLS_SCHED=dynamic; not yet GPU-measured)
+    unsigned* d_ticket = nullptr;
     bool cells_refresh_warp = true;   // directory refresh: warp per brick (false: thread per brick, the version the CPU checker runs)
     bool cells = false;   // knn_index = LIINIT_KNN_CELLS: per-brick cell directory + thread-per-point search (cells.cuh)
     float rho2 = 0.09f;   // squared seed radius of the 5-NN search
@@ -254,6 +256,17 @@ void launch_knn_scan(Ctx* c, const PoseD& P) {
 
 template <int MINB, int SEARCH>
 void launch_knn_cells_scan_t(Ctx* c, const PoseD& P) {
+    if (c->cells_dynamic) {   // persistent grid, warps pull 32-point batches from a ticket counter (reset in stream order)
+        cudaMemsetAsync(c->d_ticket, 0, sizeof(unsigned), c->stream);
+        const int pgrid = c->num_sms * MINB;
+        if (c->attached) {
+            k_knn_cells_scan_dyn<true, MINB, SEARCH><<<pgrid, LI_CELLS_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, c->attached, c->attached_stride, c->d_ticket);
+            c->attached = nullptr;
+        } else {
+            k_knn_cells_scan_dyn<false, MINB, SEARCH><<<pgrid, LI_CELLS_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, nullptr, 0, c->d_ticket);
+        }
+        return;
+    }
     const int grid = nblk(c->scan_n, LI_CELLS_THREADS);
     if (c->attached) {
         k_knn_cells_scan<true, MINB, SEARCH><<<grid, LI_CELLS_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, c->attached, c->attached_stride);
@@ -419,6 +432,8 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
         }
         // the cell directory is defined for 8x8x8-voxel bricks; another brick size keeps the brick search
         c->cells = (ki == LIINIT_KNN_CELLS) && bs == LI_CELLS_BSHIFT;
+        const char* sd = getenv("LIINIT_CELLS_SCHED");
+        if (sd && !strcmp(sd, "dynamic")) c->cells_dynamic = true;
         const char* rf = getenv("LIINIT_CELLS_REFRESH");
         if (rf && !strcmp(rf, "thread")) c->cells_refresh_warp = false;
         const char* cs = getenv("LIINIT_CELLS_SEARCH");
@@ -453,6 +468,7 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
         M.sb_mask = c->hash_slots - 1;
         CUC(cudaMalloc(&M.sb_keys, (size_t)c->hash_slots * sizeof(unsigned long long)));
         CUC(cudaMalloc(&M.sb_occ, (size_t)c->hash_slots * sizeof(unsigned long long)));
+        CUC(cudaMalloc(&c->d_ticket, sizeof(unsigned)));
     }
     int batch = cfg->max_scan_points > (1 << 20) ? cfg->max_scan_points : (1 << 20);
     c->stage_pts_cap = batch;
@@ -522,7 +538,7 @@ int liinit_destroy(liinit_ctx* h) {
     Ctx* c = &h->c;
     cudaSetDevice(c->device);
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
-    cudaFree(c->M.ent); cudaFree(c->M.aux); cudaFree(c->M.pool); cudaFree(c->M.pool_top); cudaFree(c->M.touched_list); cudaFree(c->M.cocc); cudaFree(c->M.cdir); cudaFree(c->M.sb_keys); cudaFree(c->M.sb_occ);
+    cudaFree(c->M.ent); cudaFree(c->M.aux); cudaFree(c->M.pool); cudaFree(c->M.pool_top); cudaFree(c->M.touched_list); cudaFree(c->M.cocc); cudaFree(c->M.cdir); cudaFree(c->M.sb_keys); cudaFree(c->M.sb_occ); cudaFree(c->d_ticket);
     cudaFree(c->d_counters); cudaFreeHost(c->h_counters); cudaFree(c->d_stage_raw); cudaFree(c->d_stage_pts);
     cudaFree(c->d_slot_of); cudaFree(c->d_vslot_of); cudaFree(c->d_flag); cudaFree(c->d_ins); cudaFree(c->V.keys); cudaFree(c->V.head); cudaFree(c->d_vg_imin); cudaFree(c->d_vg_block); cudaFree(c->d_vg_misc); cudaFree(c->d_rs_keys); cudaFree(c->d_rs_vals); cudaFree(c->d_rs_hist); cudaFree(c->d_vg_params); cudaFree(c->d_tmin_idx); cudaFree(c->d_poses);
     cudaFree(c->d_body); cudaFree(c->d_world); cudaFree(c->d_near_ids); cudaFree(c->d_selected); cudaFree(c->d_normvec);

@@ -124,6 +124,35 @@ def test_emul_cells_loop_shapes_with_real_votes(oracle_mod, case, search, monkey
     g.close()
 
 
+def test_emul_cells_dynamic_scheduling(oracle_mod, case, monkeypatch):
+    """LIINIT_CELLS_SCHED=dynamic: persistent grid, warps pull 32-point batches from a ticket counter. Same pass, bit for bit."""
+    c, p = case, case["pose_init"]
+    outs = []
+    for sched in ("static", "dynamic"):
+        monkeypatch.setenv("LIINIT_CELLS_SCHED", sched)
+        g = le.EmulGpu(c["ds"], max_map_points=150000, max_scan_points=5000, knn_index=CELLS)
+        g.map_build(c["map_xyz"])
+        body = c["body_xyz"][:1777]
+        g.scan_upload(body)
+        r = g.icp_iterate(p.rot_end, p.pos_end, p.R_LI, p.T_LI, False, True)
+        st = g.scan_state()
+        g.scan_attach(np.ascontiguousarray(body))                        # and through the in-place host read
+        r2 = g.icp_iterate(p.rot_end, p.pos_end, p.R_LI, p.T_LI, False, True)
+        assert r2[2] == r[2] and np.array_equal(r2[0], r[0])
+        r3 = g.icp_iterate(p.rot_end, p.pos_end, p.R_LI, p.T_LI, False, True)   # the ticket counter is reset per launch
+        assert r3[2] == r[2] and np.array_equal(r3[0], r[0])
+        outs.append((r, st))
+        g.close()
+    (ra, sa), (rb, sb) = outs
+    assert ra[2] == rb[2] and np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1], rb[1])
+    for k in ("world", "near_cnt", "near_xyz", "selected"):
+        assert np.array_equal(sa[k], sb[k]), k
+    om = oracle_mod.OracleMap(c["ds"], _bk(oracle_mod))
+    om.build(c["map_xyz"])
+    ox, od, oc, _ = om.knn(sa["world"])
+    assert np.array_equal(sb["near_cnt"], oc) and np.array_equal(sb["near_xyz"], ox)
+
+
 def test_emul_both_indexes_bit_identical(case):
     c, p = case, case["pose_init"]
     outs = []

@@ -1,0 +1,44 @@
+"""AddressSanitizer over EVERY kernel and entry point, on the CPU: builds the emulated library (tests/emul/make_liinit_emul.py) with
+-fsanitize=address and drives build / search + reuse pass / map_incremental / Add_Points / box delete / nearest search / voxel grid /
+download through it for both spatial indexes. Complements compute-sanitizer on the GPU (profiles/r01_sanitizer.txt).
+usage:  python tools/emul_asan.py          (re-executes itself with libasan preloaded)"""
+import os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+ASAN_LIB = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+OUT = "/tmp/libliinit_emul_asan.so"
+
+if os.environ.get("LI_EMUL_ASAN_CHILD") != "1":
+    import liinit_emul as le
+    le._mk.build(force=False)            # generates tests/emul/_gen/liinit_gpu_emul.cpp
+    gen = os.path.join(le._mk.GEN, "liinit_gpu_emul.cpp")
+    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-fsanitize=address", "-fno-omit-frame-pointer",
+                           "-Wno-attributes", "-Wno-unknown-pragmas", "-DLI_SIMT_EMUL=1", "-I", le._mk.HERE, "-I", le._mk.CSRC,
+                           "-I", os.path.join(ROOT, "include"), "-I", le._mk.CUDA_INC, gen, "-o", OUT])
+    env = dict(os.environ, LD_PRELOAD=ASAN_LIB, ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0", LI_EMUL_ASAN_CHILD="1")
+    sys.exit(subprocess.call([sys.executable, os.path.abspath(__file__)], env=env))
+
+import numpy as np
+import liinit_emul as le
+from lidar_imu_init_b200 import scenes
+le._mk.build = lambda force=False: OUT
+c = scenes.make_config("C2", N=1500, M=30000, open_air_frac=0.02)
+p, gt = c["pose_init"], c["pose_gt"]
+for index in (1, 2):
+    for search in ((0,) if index == 1 else (1, 2, 3)):
+        os.environ["LIINIT_CELLS_SEARCH"] = str(search or 3)
+        g = le.EmulGpu(c["ds"], max_map_points=100000, max_scan_points=3000, knn_index=index, hash_capacity_log2=14)
+        g.map_build(c["map_xyz"])
+        g.scan_upload(c["body_xyz"])
+        H, b, m, rs = g.icp_iterate(p.rot_end, p.pos_end, p.R_LI, p.T_LI, True, True)
+        g.icp_iterate(p.rot_end, p.pos_end, p.R_LI, p.T_LI, True, False)
+        na, nn = g.map_incremental(gt.rot_end, gt.pos_end, gt.R_LI, gt.T_LI, c["ds"])
+        g.map_add_points(c["body_xyz"][:500] + 50.0, True)
+        g.map_add_points(c["body_xyz"][500:900] + 50.0, False)
+        g.map_delete_boxes(np.array([[-1, -1, -1, 30, 30, 30]], np.float32))
+        g.nearest_search(c["body_xyz"][:300])
+        n = g.scan_upload_raw(np.repeat(c["body_xyz"][:800], 3, 0) + np.random.default_rng(1).normal(0, .05, (2400, 3)).astype(np.float32), 0.5)
+        live = g.map_download()
+        print(f"index {index} search {search}: m={m} map_incremental={na},{nn} voxel-grid leaves={n} live={len(live)}", flush=True)
+        g.close()
+print("emul_asan: no AddressSanitizer report")

@@ -53,6 +53,11 @@ def load():
         L.liinit_scan_download_effect.argtypes = [vp, vp, vp, C.c_int, C.POINTER(C.c_int)]
         L.liinit_map_incremental.argtypes = [vp, _f64, _f64, _f64, _f64, C.c_double, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.liinit_knn_index.argtypes = [vp, C.POINTER(C.c_int)]
+        L.liinit_raw_upload.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int]
+        L.liinit_raw_undistort_cv.argtypes = [vp, _f64, _f64, _f64]
+        L.liinit_raw_undistort_imu.argtypes = [vp, _f64, C.c_int, _f64, _f64, _f64, _f64]
+        L.liinit_raw_download.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int)]
+        L.liinit_raw_downsample.argtypes = [vp, C.c_float, C.POINTER(C.c_int)]
         _L = L
     return _L
 
@@ -161,6 +166,30 @@ class EmulGpu:
         a = _pts(pts)
         n = C.c_int()
         self._ck(self.L.liinit_scan_upload_raw(self.h, a.ctypes.data_as(vp), a.shape[1], len(a), leaf, C.byref(n)))
+        self.scan_n = n.value
+        return n.value
+
+    def raw_upload(self, pts, time_index=-1):
+        a = np.ascontiguousarray(pts, np.float32)
+        self._ck(self.L.liinit_raw_upload(self.h, a.ctypes.data_as(vp), a.shape[1], time_index, len(a)))
+        self.raw_n = len(a)
+
+    def raw_undistort_cv(self, omega, rot_end, vel_end):
+        self._ck(self.L.liinit_raw_undistort_cv(self.h, _c64(omega), _c64(rot_end), _c64(vel_end)))
+
+    def raw_undistort_imu(self, poses, rot_end, pos_end, R_LI, T_LI):
+        P = _c64(poses)
+        self._ck(self.L.liinit_raw_undistort_imu(self.h, P.reshape(-1), len(P), _c64(rot_end), _c64(pos_end), _c64(R_LI), _c64(T_LI)))
+
+    def raw_points(self):
+        out = np.zeros((self.raw_n, 3), np.float32)
+        n = C.c_int()
+        self._ck(self.L.liinit_raw_download(self.h, out.ctypes.data_as(vp), len(out), C.byref(n)))
+        return out[:n.value]
+
+    def raw_downsample(self, leaf):
+        n = C.c_int()
+        self._ck(self.L.liinit_raw_downsample(self.h, leaf, C.byref(n)))
         self.scan_n = n.value
         return n.value
 

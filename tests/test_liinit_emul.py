@@ -311,3 +311,52 @@ def test_emul_reproduces_golden(path, index):
     live = live[np.lexsort((live[:, 2], live[:, 1], live[:, 0]))]
     assert np.array_equal(live, G["mi_live"])
     g.close()
+
+
+def test_emul_raw_front_end(oracle_mod):
+    """Row N3 + N2 on the CPU: both back-propagation loops of IMU_Processing.hpp against the oracle (1 ulp: two libms), then
+    raw points -> CV undistortion -> voxel grid -> search pass, stage by stage."""
+    rng = np.random.default_rng(1)
+    raw = np.zeros((4000, 12), np.float32)                 # pcl::PointXYZINormal layout, curvature (index 9) = time in ms
+    raw[:, :3] = rng.uniform(-30, 30, (4000, 3))
+    raw[:, 9] = rng.uniform(0, 100.0, 4000).astype(np.float32)
+    raw[7, 9] = 0.0
+    ulp_close = lambda a, b: np.all(np.abs(a - b) <= np.spacing(np.maximum(np.abs(a), np.abs(b)).astype(np.float32)))
+    omega, R, v = np.array([0.3, -0.2, 0.5]), scenes.rot_from_rpy(0.1, -0.2, 0.7), np.array([2.0, -1.0, 0.3])
+    g = le.EmulGpu(0.15, max_map_points=1000, max_scan_points=6000)
+    g.raw_upload(raw, time_index=9)
+    g.raw_undistort_cv(omega, R, v)
+    got, want = g.raw_points(), oracle_mod.undistort_cv(raw[:, :3], raw[:, 9], omega, R, v)
+    assert ulp_close(got, want) and np.array_equal(got[int(np.argmin(raw[:, 9]))], raw[int(np.argmin(raw[:, 9])), :3])
+    npose, poses = 22, np.zeros((22, 22))
+    Rk, pos, vel = scenes.rot_from_rpy(0.02, 0.01, 0.3), np.array([5.0, 2.0, 1.0]), np.array([1.5, 0.2, -0.1])
+    for k in range(npose):
+        poses[k, 0] = 0.005 * k
+        poses[k, 1:4], poses[k, 4:7] = rng.normal(0, 0.5, 3), rng.normal(0, 0.3, 3)
+        poses[k, 7:10], poses[k, 10:13], poses[k, 13:22] = vel, pos, Rk.reshape(9)
+        pos, vel, Rk = pos + vel * 0.005, vel + poses[k, 1:4] * 0.005, Rk @ scenes.so3_exp(poses[k, 4:7] * 0.005)
+    R_LI, T_LI = scenes.sample_extrinsic()
+    g.raw_upload(raw, time_index=9)
+    g.raw_undistort_imu(poses, Rk, pos, R_LI, T_LI)
+    assert ulp_close(g.raw_points(), oracle_mod.undistort_imu(raw[:, :3], raw[:, 9], poses, Rk, pos, R_LI, T_LI))
+    g.close()
+    c = scenes.make_config("C2", N=6000, M=40000, open_air_frac=0.0)
+    p = c["pose_init"]
+    raw = np.zeros((len(c["body_xyz"]), 12), np.float32)
+    raw[:, :3] = c["body_xyz"]
+    raw[:, 9] = rng.uniform(0, 20.0, len(raw)).astype(np.float32)
+    g = le.EmulGpu(c["ds"], max_map_points=100000, max_scan_points=8000)
+    g.map_build(c["map_xyz"])
+    g.raw_upload(raw, time_index=9)
+    g.raw_undistort_cv(np.array([0.02, -0.01, 0.05]), p.rot_end, np.array([0.5, 0.1, 0.0]))
+    und = g.raw_points()
+    n = g.raw_downsample(0.2)
+    body, want_body = g.scan_body(), oracle_mod.voxel_grid(und, 0.2)
+    assert n == len(want_body) and np.array_equal(body, want_body)
+    H, b, m, _ = g.icp_iterate(p.rot_end, p.pos_end, p.R_LI, p.T_LI, False, True)
+    om = oracle_mod.OracleMap(c["ds"], _bk(oracle_mod))
+    om.build(c["map_xyz"])
+    sc = oracle_mod.OracleScan(body)
+    Ho, bo, mo = sc.iterate(om, p.rot_end, p.pos_end, p.R_LI, p.T_LI, False, True)
+    assert m == mo and _relerr(H, Ho) <= REL and _relerr(b, bo) <= REL
+    g.close()

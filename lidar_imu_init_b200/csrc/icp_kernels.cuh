@@ -12,6 +12,9 @@
 #ifndef LI_PLANE_MIN_BLOCKS
 #define LI_PLANE_MIN_BLOCKS 2
 #endif
+#ifndef LI_PLANE_PREFETCH
+#define LI_PLANE_PREFETCH 0   // 1: request the inputs of the next grid-stride round before computing the current one (to be measured)
+#endif
 
 // ----------------------------------------------------------------------------------------------
 // Phase 2 math (per scan point, fp64)
@@ -361,6 +364,22 @@ __global__ void __launch_bounds__(256, LI_PLANE_MIN_BLOCKS) k_icp_plane(MapDev M
     for (int k = 0; k < L::K; k++) acc[k] = 0.0;
     const int stride = gridDim.x * blockDim.x;
     const int nround = (S.n + stride - 1) / stride;
+#if LI_PLANE_PREFETCH
+    // software pipeline, one stage: the body point, the flag and the five neighbour ids of round it + 1 are requested before round it
+    // is computed, so that only the neighbour gather (which needs the ids) is an exposed round trip. Same arithmetic, same order.
+    float4 b_n = make_float4(0.f, 0.f, 0.f, 0.f);
+    int id_n[5] = {-1, -1, -1, -1, -1};
+    bool gate_n = false;
+    {
+        const int q0 = blockIdx.x * blockDim.x + threadIdx.x;
+        if (q0 < S.n) {
+            b_n = __ldg(&S.body[q0]);
+            gate_n = SEARCH ? true : (S.selected[q0] != 0);
+#pragma unroll
+            for (int k = 0; k < 5; k++) id_n[k] = S.near_ids[(size_t)q0 * 5 + k];
+        }
+    }
+#endif
     for (int it = 0; it < nround; it++) {
         const int q = it * stride + blockIdx.x * blockDim.x + threadIdx.x;
         double row[L::NC];
@@ -368,16 +387,38 @@ __global__ void __launch_bounds__(256, LI_PLANE_MIN_BLOCKS) k_icp_plane(MapDev M
         bool sel = false;
 #pragma unroll
         for (int i = 0; i < L::NC; i++) row[i] = 0.0;
+#if LI_PLANE_PREFETCH
+        const float4 b = b_n;
+        int id[5];
+#pragma unroll
+        for (int k = 0; k < 5; k++) id[k] = id_n[k];
+        const bool gate = gate_n;
+        {
+            const int qn = q + stride;
+            if (it + 1 < nround && qn < S.n) {
+                b_n = __ldg(&S.body[qn]);
+                gate_n = SEARCH ? true : (S.selected[qn] != 0);
+#pragma unroll
+                for (int k = 0; k < 5; k++) id_n[k] = S.near_ids[(size_t)qn * 5 + k];
+            }
+        }
+#endif
         if (q < S.n) {
+#if !LI_PLANE_PREFETCH
             float4 b = __ldg(&S.body[q]);
+#endif
             float wx, wy, wz;
             li_body_to_world(P, b.x, b.y, b.z, wx, wy, wz);
             if (!SEARCH) S.world[q] = make_float4(wx, wy, wz, 0.f);
+#if !LI_PLANE_PREFETCH
             bool gate = SEARCH ? true : (S.selected[q] != 0);
+#endif
             if (gate) {
+#if !LI_PLANE_PREFETCH
                 int id[5];
 #pragma unroll
                 for (int k = 0; k < 5; k++) id[k] = S.near_ids[(size_t)q * 5 + k];
+#endif
                 if (id[4] >= 0) {
                     float4 nb[5];
 #pragma unroll

@@ -265,9 +265,11 @@ __device__ __forceinline__ void lockstep_scan_found(const float4* __restrict__ p
 //                merge -> (n, g5);  stop if n == 5 and g5 <= hi2 (no unscanned brick can hold a closer point) or hi2 >= 5;
 //                otherwise lo2 = hi2 and hi2 = g5 if 5 are known (one closing step) else 4*hi2 (sparse neighbourhood).
 // The first shell is a guess (rho = seed radius): with a dense map most queries finish in it, the rest need one closing step.
+// thr0: a bound already known for the 5th best (only candidates below it can matter) -- INFINITY unless an earlier stage
+// (the cell-directory first round of the hybrid search, cells.cuh) handed it over.
 template <int G>
 __device__ __forceinline__ void knn5_lockstep(const MapDev& M, float rho2, bool valid, float qx, float qy, float qz, float (&gd)[5],
-                                              int (&gi)[5], int gl, int gbase) {
+                                              int (&gi)[5], int gl, int gbase, float thr0 = INFINITY) {
     float ld[5];
     int li[5];
 #pragma unroll
@@ -307,7 +309,7 @@ __device__ __forceinline__ void knn5_lockstep(const MapDev& M, float rho2, bool 
         const int nxy = nx * ny;
         const int total = need ? nxy * nz : 0;
         const float inv_nxy = 1.0f / (float)nxy, inv_nx = 1.0f / (float)nx;
-        const float thr = (gi[4] >= 0) ? gd[4] : INFINITY;
+        const float thr = (gi[4] >= 0) ? gd[4] : thr0;
         for (int base = 0; __any_sync(LI_FULL, base < total); base += G) {
             const int idx = base + gl;
             const bool want = idx < total;
@@ -393,6 +395,41 @@ k_knn_scan(MapDev M, ScanDev S, PoseD P, float rho2, const float* __restrict__ r
         knn5_lockstep<G>(M, rho2, valid, wx, wy, wz, gd, gi, gl, gbase);
         if (valid && gl == 0) {
             S.world[q] = make_float4(wx, wy, wz, 0.f);
+#pragma unroll
+            for (int k = 0; k < 5; k++) S.near_ids[(size_t)q * 5 + k] = gi[k];
+        }
+    }
+}
+
+// ---- second stage of the hybrid search (cells.cuh): the lockstep search over a LIST of scan points -----------------
+// list[0 .. *list_n): scan points the cell-directory first round did not finish; seed_hi2[q] = squared radius of the first shell
+// (the 5th-best distance found so far when five were found: one closing shell suffices), seed_thr[q] = bound on the 5th best.
+// S.world[q] was written by the first stage. The count lives on the device: fixed grid, grid-stride over the list.
+template <int G>
+__global__ void __launch_bounds__(LI_KNN_THREADS, LI_KNN_MIN_BLOCKS)
+k_knn_scan_list(MapDev M, ScanDev S, const int* __restrict__ list, const int* __restrict__ list_n, const float* __restrict__ seed_hi2,
+                const float* __restrict__ seed_thr) {
+    constexpr int Q = Grp<G>::Q;
+    const int lane = threadIdx.x & 31;
+    const int gl = lane % G, gid = lane / G, gbase = gid * G;
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int n = *list_n;
+    for (int ib = warp_global * Q; ib < n; ib += nwarps * Q) {   // warp-uniform
+        const int i = ib + gid;
+        const bool valid = i < n;
+        const int q = valid ? list[i] : 0;
+        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+        float rho2 = 1.0f, thr0 = INFINITY;
+        if (valid) {
+            w = S.world[q];
+            rho2 = seed_hi2[q];
+            thr0 = seed_thr[q];
+        }
+        float gd[5];
+        int gi[5];
+        knn5_lockstep<G>(M, rho2, valid, w.x, w.y, w.z, gd, gi, gl, gbase, thr0);
+        if (valid && gl == 0) {
 #pragma unroll
             for (int k = 0; k < 5; k++) S.near_ids[(size_t)q * 5 + k] = gi[k];
         }

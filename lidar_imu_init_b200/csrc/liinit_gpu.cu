@@ -96,6 +96,11 @@ struct Ctx {
     int last_launches = 0;
     int group = 4;
     int cells_search = LI_CELLS_SEARCH_DEFAULT;   // 1 shells on cells, 2 growing boxes, 3 growing boxes enumerate + stream (developer A/B: LIINIT_CELLS_SEARCH)
+    bool hybrid = false;              // knn_index = LIINIT_KNN_HYBRID: first box on the cell directory, the rest by the brick search (not yet GPU-measured)
+    int* d_hard_list = nullptr;       // scan points the first stage did not finish
+    int* d_hard_n = nullptr;
+    float* d_seed_hi2 = nullptr;      // per scan point: first-shell radius^2 / 5th-best bound handed to the second stage
+    float* d_seed_thr = nullptr;
     bool cells_dynamic = false;       // cells search kernel with warp-granular dynamic scheduling (LIINIT_CELLS_SCHED=dynamic; not yet GPU-measured)
     unsigned* d_ticket = nullptr;
     bool cells_refresh_warp = true;   // directory refresh: warp per brick (false: thread per brick, the version the CPU checker runs)
@@ -277,7 +282,30 @@ void launch_knn_cells_scan_t(Ctx* c, const PoseD& P) {
 }
 // LI_CELLS_MINB (resident blocks per SM the kernel is compiled for): 6 -> 80 registers; measured against 4 (106 registers, no spills)
 // and 8 (64 registers, 55 spilled words): 0.56 / 0.60 / 0.72 ms at the initial pose (profiles/r01_cells/ab_stream_final.log)
+// hybrid search: k_knn_cells_first for every point, then the lockstep brick search over the list it left (count on the device: fixed grid)
+void launch_knn_hybrid(Ctx* c, const PoseD& P) {
+    cudaMemsetAsync(c->d_hard_n, 0, sizeof(int), c->stream);
+    const int grid = nblk(c->scan_n, LI_CELLS_THREADS);
+    if (c->attached) {
+        k_knn_cells_first<true, LI_CELLS_MINB><<<grid, LI_CELLS_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, c->attached, c->attached_stride, c->d_hard_list,
+                                                                                           c->d_hard_n, c->d_seed_hi2, c->d_seed_thr);
+        c->attached = nullptr;
+    } else {
+        k_knn_cells_first<false, LI_CELLS_MINB><<<grid, LI_CELLS_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, nullptr, 0, c->d_hard_list, c->d_hard_n,
+                                                                                            c->d_seed_hi2, c->d_seed_thr);
+    }
+    int g2 = nblk((long long)c->scan_n * 4, LI_KNN_THREADS);
+    const int cap = c->max_blocks * (256 / LI_KNN_THREADS);
+    if (g2 > cap) g2 = cap;
+    k_knn_scan_list<4><<<g2, LI_KNN_THREADS, 0, c->stream>>>(c->M, c->S, c->d_hard_list, c->d_hard_n, c->d_seed_hi2, c->d_seed_thr);
+    c->launches++;   // (run_pass counts two launches for a search pass; this path has one more)
+}
+
 void launch_knn_cells_scan(Ctx* c, const PoseD& P) {
+    if (c->hybrid) {
+        launch_knn_hybrid(c, P);
+        return;
+    }
     if (c->cells_search == 1) launch_knn_cells_scan_t<LI_CELLS_MINB, 1>(c, P);
     else if (c->cells_search == 2) launch_knn_cells_scan_t<LI_CELLS_MINB, 2>(c, P);
     else launch_knn_cells_scan_t<LI_CELLS_MINB, 3>(c, P);
@@ -426,12 +454,13 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
             const char* e = getenv("LIINIT_KNN_INDEX");
             ki = (e && *e) ? atoi(e) : LIINIT_KNN_DEFAULT;
         }
-        if (ki != LIINIT_KNN_BRICKS && ki != LIINIT_KNN_CELLS) {
-            c->err = "knn_index must be 0, LIINIT_KNN_BRICKS or LIINIT_KNN_CELLS";
+        if (ki != LIINIT_KNN_BRICKS && ki != LIINIT_KNN_CELLS && ki != LIINIT_KNN_HYBRID) {
+            c->err = "knn_index must be 0, LIINIT_KNN_BRICKS, LIINIT_KNN_CELLS or LIINIT_KNN_HYBRID";
             return bail(LIINIT_ERR_INVALID);
         }
         // the cell directory is defined for 8x8x8-voxel bricks; another brick size keeps the brick search
-        c->cells = (ki == LIINIT_KNN_CELLS) && bs == LI_CELLS_BSHIFT;
+        c->cells = (ki == LIINIT_KNN_CELLS || ki == LIINIT_KNN_HYBRID) && bs == LI_CELLS_BSHIFT;
+        c->hybrid = c->cells && ki == LIINIT_KNN_HYBRID;
         const char* sd = getenv("LIINIT_CELLS_SCHED");
         if (sd && !strcmp(sd, "dynamic")) c->cells_dynamic = true;
         const char* rf = getenv("LIINIT_CELLS_REFRESH");
@@ -469,6 +498,12 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
         CUC(cudaMalloc(&M.sb_keys, (size_t)c->hash_slots * sizeof(unsigned long long)));
         CUC(cudaMalloc(&M.sb_occ, (size_t)c->hash_slots * sizeof(unsigned long long)));
         CUC(cudaMalloc(&c->d_ticket, sizeof(unsigned)));
+        if (c->hybrid) {
+            CUC(cudaMalloc(&c->d_hard_list, (size_t)cfg->max_scan_points * sizeof(int)));
+            CUC(cudaMalloc(&c->d_hard_n, sizeof(int)));
+            CUC(cudaMalloc(&c->d_seed_hi2, (size_t)cfg->max_scan_points * sizeof(float)));
+            CUC(cudaMalloc(&c->d_seed_thr, (size_t)cfg->max_scan_points * sizeof(float)));
+        }
     }
     int batch = cfg->max_scan_points > (1 << 20) ? cfg->max_scan_points : (1 << 20);
     c->stage_pts_cap = batch;
@@ -538,7 +573,7 @@ int liinit_destroy(liinit_ctx* h) {
     Ctx* c = &h->c;
     cudaSetDevice(c->device);
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
-    cudaFree(c->M.ent); cudaFree(c->M.aux); cudaFree(c->M.pool); cudaFree(c->M.pool_top); cudaFree(c->M.touched_list); cudaFree(c->M.cocc); cudaFree(c->M.cdir); cudaFree(c->M.sb_keys); cudaFree(c->M.sb_occ); cudaFree(c->d_ticket);
+    cudaFree(c->M.ent); cudaFree(c->M.aux); cudaFree(c->M.pool); cudaFree(c->M.pool_top); cudaFree(c->M.touched_list); cudaFree(c->M.cocc); cudaFree(c->M.cdir); cudaFree(c->M.sb_keys); cudaFree(c->M.sb_occ); cudaFree(c->d_ticket); cudaFree(c->d_hard_list); cudaFree(c->d_hard_n); cudaFree(c->d_seed_hi2); cudaFree(c->d_seed_thr);
     cudaFree(c->d_counters); cudaFreeHost(c->h_counters); cudaFree(c->d_stage_raw); cudaFree(c->d_stage_pts);
     cudaFree(c->d_slot_of); cudaFree(c->d_vslot_of); cudaFree(c->d_flag); cudaFree(c->d_ins); cudaFree(c->V.keys); cudaFree(c->V.head); cudaFree(c->d_vg_imin); cudaFree(c->d_vg_block); cudaFree(c->d_vg_misc); cudaFree(c->d_rs_keys); cudaFree(c->d_rs_vals); cudaFree(c->d_rs_hist); cudaFree(c->d_vg_params); cudaFree(c->d_tmin_idx); cudaFree(c->d_poses);
     cudaFree(c->d_body); cudaFree(c->d_world); cudaFree(c->d_near_ids); cudaFree(c->d_selected); cudaFree(c->d_normvec);
@@ -1114,7 +1149,7 @@ int liinit_last_pass_kernel_times(liinit_ctx* h, float* knn_ms, float* plane_ms)
 
 int liinit_knn_index(liinit_ctx* h, int* knn_index) {
     if (!h || !knn_index) return LIINIT_ERR_INVALID;
-    *knn_index = h->c.cells ? LIINIT_KNN_CELLS : LIINIT_KNN_BRICKS;
+    *knn_index = h->c.hybrid ? LIINIT_KNN_HYBRID : h->c.cells ? LIINIT_KNN_CELLS : LIINIT_KNN_BRICKS;
     return LIINIT_OK;
 }
 

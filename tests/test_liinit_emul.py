@@ -11,7 +11,7 @@ from lidar_imu_init_b200 import scenes
 pytestmark = pytest.mark.skipif(not le.available(), reason="g++ or the CUDA vector-type headers are missing")
 
 REL = 1e-9
-BRICKS, CELLS = 1, 2
+BRICKS, CELLS, HYBRID = 1, 2, 3
 
 
 def _world(body, p):
@@ -35,7 +35,7 @@ def case():
     return scenes.make_config("C2", N=3000, M=60000, open_air_frac=0.02)
 
 
-@pytest.mark.parametrize("index", [BRICKS, CELLS])
+@pytest.mark.parametrize("index", [BRICKS, CELLS, HYBRID])
 @pytest.mark.parametrize("imu_en", [False, True])
 def test_emul_search_and_reuse_pass(oracle_mod, imu_en, index):
     c = scenes.make_config("C2", N=3000, M=60000, open_air_frac=0.02, imu_en=imu_en)
@@ -156,18 +156,22 @@ def test_emul_cells_dynamic_scheduling(oracle_mod, case, monkeypatch):
 def test_emul_both_indexes_bit_identical(case):
     c, p = case, case["pose_init"]
     outs = []
-    for index in (BRICKS, CELLS):
+    for index in (BRICKS, CELLS, HYBRID):
         g = le.EmulGpu(c["ds"], max_map_points=150000, max_scan_points=5000, knn_index=index)
         g.map_build(c["map_xyz"])
         g.scan_upload(c["body_xyz"][:1500])
         outs.append((g.icp_iterate(p.rot_end, p.pos_end, p.R_LI, p.T_LI, True, True), g.scan_state()))
+        g.scan_attach(np.ascontiguousarray(c["body_xyz"][:1500]))      # the in-place host read goes through the same first stage
+        r2 = g.icp_iterate(p.rot_end, p.pos_end, p.R_LI, p.T_LI, True, True)
+        assert r2[2] == outs[-1][0][2] and np.array_equal(r2[0], outs[-1][0][0])
         g.close()
-    (ra, sa), (rb, sb) = outs
-    assert ra[2] == rb[2] and np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1], rb[1])
+    (ra, sa) = outs[0]
     sel = sa["selected"].astype(bool)
-    for k in ("world", "near_cnt", "near_xyz", "selected"):
-        assert np.array_equal(sa[k], sb[k]), k
-    assert np.array_equal(sa["normvec"][sel], sb["normvec"][sel])   # (entries of unselected points are never written)
+    for rb, sb in outs[1:]:
+        assert ra[2] == rb[2] and np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1], rb[1])
+        for k in ("world", "near_cnt", "near_xyz", "selected"):
+            assert np.array_equal(sa[k], sb[k]), k
+        assert np.array_equal(sa["normvec"][sel], sb["normvec"][sel])   # (entries of unselected points are never written)
 
 
 @pytest.mark.parametrize("group", [8, 32])
@@ -284,7 +288,7 @@ GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "c*.np
 
 
 @pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(g)[:-4] for g in GOLD])
-@pytest.mark.parametrize("index", [BRICKS, CELLS])
+@pytest.mark.parametrize("index", [BRICKS, CELLS, HYBRID])
 def test_emul_reproduces_golden(path, index):
     """The committed golden vectors (generated with the reference's verbatim ikd-Tree, tools/make_golden.py) against the kernels run
     on the CPU -- the same assertions as tests/test_gpu_golden.py, no oracle involved."""

@@ -17,8 +17,10 @@ tail -1 gpurun_out/t_cells_threadrefresh.log
 for s in 2 1; do LIINIT_KNN_INDEX=2 LIINIT_CELLS_SEARCH=$s timeout 300 python -m pytest tests/test_gpu_cells.py -x -q > gpurun_out/t_cells_search$s.log 2>&1; echo "cells search=$s rc=$? t=$((SECONDS-T0))"; done
 timeout 300 python tools/quick_ab.py > gpurun_out/ab.log 2>&1; echo "ab rc=$? t=$((SECONDS-T0))"
 grep -v "^gen" gpurun_out/ab.log
-# compile-time variants: build them into build/variants/ (nvcc ... -DLI_CELLS_QC=16 -o build/variants/lib_x.so ...) and probe each with
-#   LIINIT_GPU_LIB=build/variants/lib_x.so python tools/quick_ab.py --variants 2:6:2:3      (tools/probe_variant.py for the brick search)
+# compile-time variants: tools/build_variants.sh (run before gpurun) builds them into build/variants/; each is probed here when present
+for lib in build/variants/*.so; do [ -f "$lib" ] && LIINIT_GPU_LIB=$lib timeout 100 python tools/probe_variant.py 2>/dev/null | tee -a gpurun_out/probe_variants.log; done
+timeout 100 python tools/probe_variant.py 2>/dev/null | tee -a gpurun_out/probe_variants.log
+echo "variant probes t=$((SECONDS-T0))"
 timeout 300 python bench.py --knn-index 2 > gpurun_out/bench_cells.json 2> gpurun_out/bench_cells.err; echo "bench cells rc=$? t=$((SECONDS-T0))"
 cut -c1-400 gpurun_out/bench_cells.json
 timeout 300 python bench.py --knn-index 1 > gpurun_out/bench_bricks.json 2> gpurun_out/bench_bricks.err; echo "bench bricks rc=$? t=$((SECONDS-T0))"

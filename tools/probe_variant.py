@@ -18,6 +18,7 @@ for pose in ("init", "gt"):
     ks = []
     for it in range(12):
         H, b, m, rs = g.icp_iterate(R, p, I, zero, False, True)
-        ks.append(g.last_pass_kernel_times()[0])
-    out.append(f"{pose}: m={m} knn {np.median(ks[3:]):.4f} (min {min(ks):.4f}) trace(HtH)={np.trace(H):.9e}")
+        ks.append(g.last_pass_kernel_times())
+    ks = np.array(ks)
+    out.append(f"{pose}: m={m} knn {np.median(ks[3:, 0]):.4f} (min {ks[:, 0].min():.4f}) plane {np.median(ks[3:, 1]):.4f} trace(HtH)={np.trace(H):.9e}")
 print(" | ".join(out), flush=True)

@@ -9,20 +9,25 @@ import argparse
 ap = argparse.ArgumentParser()
 ap.add_argument("--N", type=int, default=240000)
 ap.add_argument("--M", type=int, default=5000000)
-ap.add_argument("--variants", default="1:0:2:0,2:6:2:3,2:6:3:3,2:6:1.5:3,2:6:2:2,2:6:2:1")   # index:minb:rho_cells:search (minb: only honoured by libraries built with the A/B switch, see git history)
+# index:minb:rho_cells:search[:sched]   index 1 bricks / 2 cells / 3 hybrid; minb only honoured by libraries built with that A/B switch (git history);
+# search 1 shells on cells / 2 growing boxes / 3 enumerate + stream; sched s = one block per 128 points, d = LIINIT_CELLS_SCHED=dynamic
+ap.add_argument("--variants", default="1:0:2:0,2:6:2:3,2:6:2:3:d,3:6:2:3,2:6:2:2,2:6:2:1")
 a = ap.parse_args()
 t = time.time(); c = scenes.make_config("C2", N=a.N, M=a.M); print("gen", round(time.time() - t, 2), flush=True)
 ref = None
 for v in a.variants.split(","):
-    idx, minb, rho, search = v.split(":")
+    f = v.split(":")
+    idx, minb, rho, search = f[:4]
+    sched = f[4] if len(f) > 4 else "s"
     os.environ["LIINIT_CELLS_MINB"] = minb
     os.environ["LIINIT_CELLS_SEARCH"] = search
+    os.environ["LIINIT_CELLS_SCHED"] = "dynamic" if sched == "d" else "static"
     g = capi.LiInitGpu(c["ds"], max_map_points=int(a.M * 1.2), max_scan_points=a.N + 10, knn_index=int(idx), knn_seed_radius_cells=float(rho))
     tb = []
     for rep in range(2):
         t = time.time(); g.map_build(c["map_xyz"]); tb.append(time.time() - t)
     g.scan_upload(c["body_xyz"])
-    line = f"index {idx} minb {minb} rho {rho} search {search}: build {min(tb)*1e3:.1f} ms"
+    line = f"index {idx} minb {minb} rho {rho} search {search} sched {sched}: build {min(tb)*1e3:.1f} ms"
     for pose_name in ("init", "gt"):
         p = c["pose_" + pose_name]
         ks, ps = [], []

@@ -275,6 +275,21 @@ __global__ void k_ds_link(MapDev M, VoxTmp V, const float4* __restrict__ pts, in
 
 // pass D3: one thread per box -- replay the box's new points in batch order (see the state machine above).
 // Existing losers are tombstoned (w = 0xffffffff), ins[i] = 1 marks the new points that end up in the map.
+//
+// Which existing points are "in the box" is decided GEOMETRICALLY, as Search_by_range / Delete_by_range decide it
+// (vertex_min <= x && x < vertex_max per axis, ikd_Tree.cpp:633,980), not by the voxel id a point was filed under: the float boxes
+// [fl(k ds), fl(fl(k ds) + ds)) of neighbouring k do not tile the axis -- they leave one-ulp gaps AND one-ulp overlaps, and a
+// point inside an overlap belongs to both boxes although it is stored under one index only (found by tools/emul_fuzz.py: lattice
+// points 900 m from the origin). Such a point can sit in the adjacent brick when the box touches a brick face, so up to two bricks
+// per axis are looked at -- one in all but ulp cases. (A point shared by two boxes that BOTH receive new points in the same batch
+// is order dependent in the reference's sequential walk; here the two box threads are not ordered. Documented)
+struct DsBox {
+    float mn[3], mx[3];
+};
+__device__ __forceinline__ bool li_in_box(const DsBox& B, const float4& q) {
+    return q.x >= B.mn[0] && q.x < B.mx[0] && q.y >= B.mn[1] && q.y < B.mx[1] && q.z >= B.mn[2] && q.z < B.mx[2];
+}
+
 __global__ void k_ds_replay(MapDev M, VoxTmp V, const float4* __restrict__ pts, const int* __restrict__ next_of,
                             int* __restrict__ ins) {
     unsigned v = blockIdx.x * blockDim.x + threadIdx.x;
@@ -283,25 +298,43 @@ __global__ void k_ds_replay(MapDev M, VoxTmp V, const float4* __restrict__ pts, 
     if (head < 0) return;
     // the box
     float4 ph = pts[head];
-    const int cx = li_cell(ph.x, M.ds), cy = li_cell(ph.y, M.ds), cz = li_cell(ph.z, M.ds);
-    const unsigned vib = li_voxel_in_brick(M, cx, cy, cz);
-    // the brick that holds the box's existing points
-    unsigned first = 0, count = 0;
-    bool have = li_brick_find(M.ent, M.mask, li_pack_key(cx >> M.bshift, cy >> M.bshift, cz >> M.bshift), first, count);
-    // (li_brick_find uses the read-only path; ent is not modified between D2's reserve and this kernel)
+    const int c[3] = {li_cell(ph.x, M.ds), li_cell(ph.y, M.ds), li_cell(ph.z, M.ds)};
+    const int cx = c[0], cy = c[1], cz = c[2];
+    DsBox B;
+    int blo[3], bhi[3];   // range of brick coordinates per axis that can store a point of this box
+    const int bm = (1 << M.bshift) - 1;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const float cf = (float)c[a];
+        B.mn[a] = __fmul_rn(cf, M.ds);
+        B.mx[a] = __fadd_rn(B.mn[a], M.ds);
+        const float mx_prev = __fadd_rn(__fmul_rn(cf - 1.0f, M.ds), M.ds);   // upper end of box c-1
+        const float mn_next = __fmul_rn(cf + 1.0f, M.ds);                    // lower end of box c+1
+        const int b0 = c[a] >> M.bshift;
+        blo[a] = (B.mn[a] < mx_prev && (c[a] & bm) == 0) ? b0 - 1 : b0;      // overlap with box c-1, which lives in the brick below
+        bhi[a] = (B.mx[a] > mn_next && (c[a] & bm) == bm) ? b0 + 1 : b0;     // overlap with box c+1, which lives in the brick above
+    }
+    // existing content of the box: count, the point closest to the box centre (first minimum in visiting order)
     int nE = 0;
     float bd = INFINITY;
-    int bref = -1;          // >= 0: slot j of an existing point; <= -2: new point index -(bref+2)
+    long long bref = -1;    // >= 0: pool offset of an existing point; <= -2: new point index -(bref+2)
     float bxx = 0, byy = 0, bzz = 0;
-    if (have) {
-        for (unsigned j = 0; j < count; j++) {
-            float4 q = M.pool[(size_t)first + j];
-            if (__float_as_uint(q.w) != vib) continue;
-            nE++;
-            float d = li_center_dist_cell(q.x, q.y, q.z, cx, cy, cz, M.ds);
-            if (d < bd) { bd = d; bref = (int)j; bxx = q.x; byy = q.y; bzz = q.z; }
-        }
-    }
+    bool have = false;
+    for (int kz = blo[2]; kz <= bhi[2]; kz++)
+        for (int ky = blo[1]; ky <= bhi[1]; ky++)
+            for (int kx = blo[0]; kx <= bhi[0]; kx++) {
+                unsigned first = 0, count = 0;
+                // (li_brick_find uses the read-only path; ent is not modified between D2's reserve and this kernel)
+                if (!li_brick_find(M.ent, M.mask, li_pack_key(kx, ky, kz), first, count)) continue;
+                have = true;
+                for (unsigned j = 0; j < count; j++) {
+                    float4 q = M.pool[(size_t)first + j];
+                    if (__float_as_uint(q.w) == 0xffffffffu || !li_in_box(B, q)) continue;
+                    nE++;
+                    float d = li_center_dist_cell(q.x, q.y, q.z, cx, cy, cz, M.ds);
+                    if (d < bd) { bd = d; bref = (long long)first + j; bxx = q.x; byy = q.y; bzz = q.z; }
+                }
+            }
     bool modified = false;
     int changed = 0;
     // batch order = ascending index: repeatedly take the smallest index greater than the last one processed
@@ -323,13 +356,9 @@ __global__ void k_ds_replay(MapDev M, VoxTmp V, const float4* __restrict__ pts, 
             if (newwins) {
                 if (bref <= -2) ins[-(bref + 2)] = 0;   // an earlier in-box new point is deleted with the box
                 ins[cur] = 1;
-                int ibx, iby, ibz;
-                bool inbox = li_box_index(p.x, M.ds, cx, ibx) && ibx == cx;
-                inbox = li_box_index(p.y, M.ds, cy, iby) && iby == cy && inbox;
-                inbox = li_box_index(p.z, M.ds, cz, ibz) && ibz == cz && inbox;
-                if (inbox) {
-                    nE = 1; bd = dp; bref = -(cur + 2); bxx = p.x; byy = p.y; bzz = p.z;
-                } else {
+                if (li_in_box(B, p)) {
+                    nE = 1; bd = dp; bref = -((long long)cur + 2); bxx = p.x; byy = p.y; bzz = p.z;
+                } else {   // the new point lies outside its own box (ulp edge): inserted, but no later query of THIS box sees it
                     nE = 0; bd = INFINITY; bref = -1;
                 }
             } else {
@@ -337,23 +366,33 @@ __global__ void k_ds_replay(MapDev M, VoxTmp V, const float4* __restrict__ pts, 
             }
         }
     }
-    if (modified && have) {
-        for (unsigned j = 0; j < count; j++) {
-            float4* qp = &M.pool[(size_t)first + j];
-            if (__float_as_uint(qp->w) == vib && !(nE == 1 && bref == (int)j)) qp->w = __uint_as_float(0xffffffffu);
-        }
-    }
     if (changed) atomicAdd(&M.counters[CNT_CHANGED], changed);
-    // make sure the brick holding tombstones gets compacted
-    if (modified && have) {
-        unsigned h = li_hash(li_pack_key(cx >> M.bshift, cy >> M.bshift, cz >> M.bshift)) & M.mask;
-        for (unsigned t = 0; t <= M.mask; t++) {
-            unsigned long long k = *reinterpret_cast<volatile unsigned long long*>(&M.ent[h]);
-            if (k == li_pack_key(cx >> M.bshift, cy >> M.bshift, cz >> M.bshift)) { li_touch(M, (int)h); break; }
-            if (k == LI_EMPTY_KEY) break;
-            h = (h + 1) & M.mask;
-        }
-    }
+    if (!(modified && have)) return;
+    // the box was deleted at least once: every existing point in it except a surviving best one goes; the bricks that hold tombstones are
+    // put on the touched list so that the compaction squeezes them out
+    for (int kz = blo[2]; kz <= bhi[2]; kz++)
+        for (int ky = blo[1]; ky <= bhi[1]; ky++)
+            for (int kx = blo[0]; kx <= bhi[0]; kx++) {
+                const unsigned long long key = li_pack_key(kx, ky, kz);
+                unsigned first = 0, count = 0;
+                if (!li_brick_find(M.ent, M.mask, key, first, count)) continue;
+                bool any = false;
+                for (unsigned j = 0; j < count; j++) {
+                    float4* qp = &M.pool[(size_t)first + j];
+                    if (__float_as_uint(qp->w) == 0xffffffffu || !li_in_box(B, *qp)) continue;
+                    if (nE == 1 && bref == (long long)first + j) continue;
+                    qp->w = __uint_as_float(0xffffffffu);
+                    any = true;
+                }
+                if (!any) continue;
+                unsigned h = li_hash(key) & M.mask;
+                for (unsigned t = 0; t <= M.mask; t++) {
+                    unsigned long long k = *reinterpret_cast<volatile unsigned long long*>(&M.ent[h]);
+                    if (k == key) { li_touch(M, (int)h); break; }
+                    if (k == LI_EMPTY_KEY) break;
+                    h = (h + 1) & M.mask;
+                }
+            }
 }
 
 // pass D3b: append the new points that survived the replay.

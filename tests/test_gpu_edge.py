@@ -212,3 +212,42 @@ def test_full_baseline_size_properties(gpu_lib, oracle_mod):
     ox, od, oc, _ = om.knn(st["world"][idx])
     assert np.array_equal(oc, st["near_cnt"][idx]) and np.array_equal(ox, st["near_xyz"][idx])
     g.close()
+
+
+def test_downsample_box_membership_is_geometric(gpu_lib, oracle_mod):
+    """The float boxes [fl(k ds), fl(fl(k ds) + ds)) of neighbouring k overlap by one ulp: an existing lattice point belongs to two boxes
+    although it is filed under one voxel id; Add_Points(downsample) must find it from either (ikd_Tree.cpp:633,980). Found by the
+    CPU fuzz (tools/emul_fuzz.py); same scenario as tests/test_liinit_emul.py::test_emul_downsample_box_membership_is_geometric."""
+    def lattice(rng, n, ds, off):
+        k = rng.integers(-40, 40, (n, 3)).astype(np.float32)
+        a = (k * np.float32(ds)).astype(np.float32)
+        j = rng.integers(0, 3, n)
+        a = np.where(j[:, None] == 0, a, np.where(j[:, None] == 1, np.nextafter(a, np.float32(1e9)), np.nextafter(a, np.float32(-1e9))))
+        return (a.astype(np.float64) + off).astype(np.float32)
+
+    def single_box(pts, ds):
+        f, d = np.float32, np.float32(ds)
+        c = np.floor(pts / d).astype(np.float32)
+        bad = np.zeros(len(pts), bool)
+        for a in range(3):
+            for k in (-1, 0, 1):
+                mn = ((c[:, a] + f(k)) * d).astype(f)
+                inside = (pts[:, a] >= mn) & (pts[:, a] < (mn + d).astype(f))
+                bad |= inside if k != 0 else ~inside
+        return np.ascontiguousarray(pts[~bad])
+
+    ds = 0.15
+    for off in (0.0, 900.0):
+        rng = np.random.default_rng(1011)
+        o = off * np.array([1.0, -0.7, 0.1])
+        first = lattice(rng, 3500, ds, o)
+        g = gpu_lib.LiInitGpu(ds, max_map_points=60000, max_scan_points=4000)
+        om = oracle_mod.OracleMap(ds, _bk(oracle_mod))
+        g.map_build(first)
+        om.build(first)
+        for k in range(3):
+            pts = single_box(lattice(rng, 1500, ds, o), ds)
+            assert g.map_add_points(pts, True) == om.add_points(pts, True)
+            assert g.map_validnum() == om.validnum()
+        assert set(map(bytes, g.map_download())) == set(map(bytes, om.flatten()))
+        g.close()

@@ -30,6 +30,28 @@ def _same_set(a, b):
     return set(map(bytes, np.ascontiguousarray(a, np.float32))) == set(map(bytes, np.ascontiguousarray(b, np.float32)))
 
 
+def _lattice_cloud(rng, n, ds, off):
+    """points exactly on the voxel lattice and one ulp on either side of it"""
+    k = rng.integers(-40, 40, (n, 3)).astype(np.float32)
+    a = (k * np.float32(ds)).astype(np.float32)
+    j = rng.integers(0, 3, n)
+    a = np.where(j[:, None] == 0, a, np.where(j[:, None] == 1, np.nextafter(a, np.float32(1e9)), np.nextafter(a, np.float32(-1e9))))
+    return (a.astype(np.float64) + off).astype(np.float32)
+
+
+def _single_box(pts, ds):
+    """keeps the points that lie in the float box of their division cell and in no neighbouring one (deviations)"""
+    f, d = np.float32, np.float32(ds)
+    c = np.floor(pts / d).astype(np.float32)
+    bad = np.zeros(len(pts), bool)
+    for a in range(3):
+        for k in (-1, 0, 1):
+            mn = ((c[:, a] + f(k)) * d).astype(f)
+            inside = (pts[:, a] >= mn) & (pts[:, a] < (mn + d).astype(f))
+            bad |= inside if k != 0 else ~inside
+    return np.ascontiguousarray(pts[~bad])
+
+
 @pytest.fixture(scope="module")
 def case():
     return scenes.make_config("C2", N=3000, M=60000, open_air_frac=0.02)
@@ -363,4 +385,25 @@ def test_emul_raw_front_end(oracle_mod):
     sc = oracle_mod.OracleScan(body)
     Ho, bo, mo = sc.iterate(om, p.rot_end, p.pos_end, p.R_LI, p.T_LI, False, True)
     assert m == mo and _relerr(H, Ho) <= REL and _relerr(b, bo) <= REL
+    g.close()
+
+
+@pytest.mark.parametrize("off", [0.0, 900.0])
+def test_emul_downsample_box_membership_is_geometric(oracle_mod, off):
+    """Regression for a mismatch found by tools/emul_fuzz.py: the float boxes [fl(k ds), fl(fl(k ds) + ds)) of neighbouring k overlap by one
+    ulp, so an EXISTING point on the lattice belongs to two boxes although it is filed under one voxel id; Add_Points(downsample) must find
+    it from either box (Search_by_range / Delete_by_range test coordinates, ikd_Tree.cpp:633,980)."""
+    rng = np.random.default_rng(1011)
+    ds = 0.15
+    o = off * np.array([1.0, -0.7, 0.1])
+    first = _lattice_cloud(rng, 3500, ds, o)
+    g = le.EmulGpu(ds, max_map_points=60000, max_scan_points=4000, hash_capacity_log2=13)
+    om = oracle_mod.OracleMap(ds, _bk(oracle_mod))
+    g.map_build(first)
+    om.build(first)
+    for k in range(3):
+        pts = _single_box(_lattice_cloud(rng, 1500, ds, o), ds)
+        assert g.map_add_points(pts, True) == om.add_points(pts, True)
+        assert g.map_validnum() == om.validnum()
+    assert _same_set(g.map_download(), om.flatten())
     g.close()

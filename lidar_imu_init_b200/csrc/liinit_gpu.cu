@@ -20,6 +20,7 @@
 #include "knn_tpq.cuh"
 #endif
 #include "cells.cuh"
+#include "fused_kernel.cuh"
 #include "map_kernels.cuh"
 #include "voxelgrid_kernels.cuh"
 #include "undistort_kernels.cuh"
@@ -106,6 +107,14 @@ struct Ctx {
     bool cells_refresh_warp = true;   // directory refresh: warp per brick (false: thread per brick, the version the CPU checker runs)
     bool cells = false;   // knn_index = LIINIT_KNN_CELLS: per-brick cell directory + thread-per-point search (cells.cuh)
     float rho2 = 0.09f;   // squared seed radius of the 5-NN search
+    // fused search pass (fused_kernel.cuh): knn_index = LIINIT_KNN_FUSED
+    bool fused = false;
+    int fused_group = 4;              // lanes per scan point (4 or 8)
+    unsigned* d_fticket = nullptr;    // monotone tile ticket (never reset)
+    unsigned fticket_base = 0;        // its value before the next launch
+    double* d_tree_buf = nullptr;     // reduction tree rows
+    unsigned* d_tree_cnt = nullptr;   // reduction tree counters (zero between launches)
+    int fused_grid = 0;
 };
 
 #define CU(call)                                                                                     \
@@ -332,6 +341,26 @@ void launch_plane(Ctx* c, const PoseD& P, double* out) {
     k_icp_plane<IMU, SEARCH><<<grid, 256, 0, c->stream>>>(c->M, c->S, P, c->d_partials, c->d_done, out);
 }
 
+// One launch for the whole search pass (fused_kernel.cuh). The ticket is monotone: every launch consumes ntiles + one terminating
+// ticket per warp, so the next launch's base is known on the host without a reset on the stream.
+template <int G, bool IMU>
+void launch_fused(Ctx* c, const PoseD& P, double* out) {
+    const int ntiles = (c->scan_n + 31) / 32;
+    int grid = c->fused_grid;
+    const int need = nblk(ntiles, LI_FUSED_THREADS / 32);
+    if (grid > need) grid = need;
+    const size_t smem = sizeof(FusedSmem<G>);
+    if (c->attached) {
+        k_icp_fused<G, IMU, true><<<grid, LI_FUSED_THREADS, smem, c->stream>>>(c->M, c->S, P, c->rho2, c->attached, c->attached_stride, c->d_fticket,
+                                                                               c->fticket_base, c->d_tree_buf, c->d_tree_cnt, out);
+        c->attached = nullptr;   // the kernel leaves the packed copy in d_body
+    } else {
+        k_icp_fused<G, IMU, false><<<grid, LI_FUSED_THREADS, smem, c->stream>>>(c->M, c->S, P, c->rho2, nullptr, 0, c->d_fticket, c->fticket_base,
+                                                                                c->d_tree_buf, c->d_tree_cnt, out);
+    }
+    c->fticket_base += (unsigned)ntiles + (unsigned)grid * (LI_FUSED_THREADS / 32);
+}
+
 // out: where the last block of the plane kernel leaves the 160-double result block -- the caller's device buffer
 // (liinit_icp_iterate_device) or the device alias of the context's page-locked host block (liinit_icp_iterate: the
 // kernel writes the 1.28 kB over PCIe itself, no copy operation behind it).
@@ -341,7 +370,19 @@ int run_pass(Ctx* c, const double* R, const double* p, const double* RLI, const 
     PoseD P;
     fill_pose(P, R, p, RLI, TLI);
     CU(cudaEventRecord(c->ev0, c->stream));
-    if (search) {
+    if (search && c->fused) {
+        if (c->fused_group == 8) {
+            if (imu_en) launch_fused<8, true>(c, P, out); else launch_fused<8, false>(c, P, out);
+        } else {
+            if (imu_en) launch_fused<4, true>(c, P, out); else launch_fused<4, false>(c, P, out);
+        }
+        CU(cudaEventRecord(c->evm, c->stream));
+        c->have_neighbors = true;
+        c->scan_fresh = false;
+        c->launches += 1;
+        c->last_launches = 1;
+        c->last_was_search = true;
+    } else if (search) {
         if (c->cells) launch_knn_cells_scan(c, P);
         else switch (c->group) {
 #ifndef LI_SIMT_EMUL
@@ -454,13 +495,20 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
             const char* e = getenv("LIINIT_KNN_INDEX");
             ki = (e && *e) ? atoi(e) : LIINIT_KNN_DEFAULT;
         }
-        if (ki != LIINIT_KNN_BRICKS && ki != LIINIT_KNN_CELLS && ki != LIINIT_KNN_HYBRID) {
-            c->err = "knn_index must be 0, LIINIT_KNN_BRICKS, LIINIT_KNN_CELLS or LIINIT_KNN_HYBRID";
+        if (ki != LIINIT_KNN_BRICKS && ki != LIINIT_KNN_CELLS && ki != LIINIT_KNN_HYBRID && ki != LIINIT_KNN_FUSED) {
+            c->err = "knn_index must be 0, LIINIT_KNN_BRICKS, LIINIT_KNN_CELLS, LIINIT_KNN_HYBRID or LIINIT_KNN_FUSED";
             return bail(LIINIT_ERR_INVALID);
         }
         // the cell directory is defined for 8x8x8-voxel bricks; another brick size keeps the brick search
         c->cells = (ki == LIINIT_KNN_CELLS || ki == LIINIT_KNN_HYBRID) && bs == LI_CELLS_BSHIFT;
         c->hybrid = c->cells && ki == LIINIT_KNN_HYBRID;
+        c->fused = ki == LIINIT_KNN_FUSED;
+        c->fused_group = (cfg->knn_group_lanes == 8) ? 8 : 4;
+        {
+            const char* fg = getenv("LIINIT_FUSED_GROUP");   // developer A/B
+            if (fg && atoi(fg) == 8) c->fused_group = 8;
+            if (fg && atoi(fg) == 4) c->fused_group = 4;
+        }
         const char* sd = getenv("LIINIT_CELLS_SCHED");
         if (sd && !strcmp(sd, "dynamic")) c->cells_dynamic = true;
         const char* rf = getenv("LIINIT_CELLS_REFRESH");
@@ -544,6 +592,31 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
     c->max_blocks = c->num_sms * 16;
     CUC(cudaMalloc(&c->d_partials, (size_t)c->max_blocks * 96 * sizeof(double)));
     CUC(cudaMalloc(&c->d_done, sizeof(unsigned)));
+    if (c->fused) {
+        long long rows = 0, counters = 0;
+        fused_tree_sizes(((long long)ns + 31) / 32, rows, counters);
+        CUC(cudaMalloc(&c->d_tree_buf, (size_t)rows * 96 * sizeof(double)));
+        CUC(cudaMalloc(&c->d_tree_cnt, (size_t)counters * sizeof(unsigned)));
+        CUC(cudaMalloc(&c->d_fticket, sizeof(unsigned)));
+        CUC(cudaMemsetAsync(c->d_tree_cnt, 0, (size_t)counters * sizeof(unsigned), c->stream));
+        CUC(cudaMemsetAsync(c->d_fticket, 0, sizeof(unsigned), c->stream));
+        c->fticket_base = 0;
+#ifndef LI_SIMT_EMUL
+        CUC(cudaFuncSetAttribute(k_icp_fused<4, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<4>)));
+        CUC(cudaFuncSetAttribute(k_icp_fused<4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<4>)));
+        CUC(cudaFuncSetAttribute(k_icp_fused<4, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<4>)));
+        CUC(cudaFuncSetAttribute(k_icp_fused<4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<4>)));
+        CUC(cudaFuncSetAttribute(k_icp_fused<8, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<8>)));
+        CUC(cudaFuncSetAttribute(k_icp_fused<8, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<8>)));
+        CUC(cudaFuncSetAttribute(k_icp_fused<8, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<8>)));
+        CUC(cudaFuncSetAttribute(k_icp_fused<8, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<8>)));
+#endif
+        c->fused_grid = c->num_sms * LI_FUSED_MIN_BLOCKS;
+        {
+            const char* fb = getenv("LIINIT_FUSED_BLOCKS_PER_SM");   // developer A/B
+            if (fb && atoi(fb) >= 1 && atoi(fb) <= 8) c->fused_grid = c->num_sms * atoi(fb);
+        }
+    }
     CUC(cudaHostAlloc(&c->h_out, 160 * sizeof(double), cudaHostAllocMapped));
     CUC(cudaHostGetDevicePointer((void**)&c->h_out_dev, c->h_out, 0));
     CUC(cudaMemsetAsync(c->d_done, 0, sizeof(unsigned), c->stream));
@@ -577,6 +650,7 @@ int liinit_destroy(liinit_ctx* h) {
     cudaFree(c->d_counters); cudaFreeHost(c->h_counters); cudaFree(c->d_stage_raw); cudaFree(c->d_stage_pts);
     cudaFree(c->d_slot_of); cudaFree(c->d_vslot_of); cudaFree(c->d_flag); cudaFree(c->d_ins); cudaFree(c->V.keys); cudaFree(c->V.head); cudaFree(c->d_vg_imin); cudaFree(c->d_vg_block); cudaFree(c->d_vg_misc); cudaFree(c->d_rs_keys); cudaFree(c->d_rs_vals); cudaFree(c->d_rs_hist); cudaFree(c->d_vg_params); cudaFree(c->d_tmin_idx); cudaFree(c->d_poses);
     cudaFree(c->d_body); cudaFree(c->d_world); cudaFree(c->d_near_ids); cudaFree(c->d_selected); cudaFree(c->d_normvec);
+    cudaFree(c->d_tree_buf); cudaFree(c->d_tree_cnt); cudaFree(c->d_fticket);
     cudaFree(c->d_partials); cudaFree(c->d_done); cudaFreeHost(c->h_out); cudaFree(c->d_q_d2);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -1149,7 +1223,7 @@ int liinit_last_pass_kernel_times(liinit_ctx* h, float* knn_ms, float* plane_ms)
 
 int liinit_knn_index(liinit_ctx* h, int* knn_index) {
     if (!h || !knn_index) return LIINIT_ERR_INVALID;
-    *knn_index = h->c.hybrid ? LIINIT_KNN_HYBRID : h->c.cells ? LIINIT_KNN_CELLS : LIINIT_KNN_BRICKS;
+    *knn_index = h->c.fused ? LIINIT_KNN_FUSED : h->c.hybrid ? LIINIT_KNN_HYBRID : h->c.cells ? LIINIT_KNN_CELLS : LIINIT_KNN_BRICKS;
     return LIINIT_OK;
 }
 

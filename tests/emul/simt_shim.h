@@ -135,6 +135,20 @@ inline unsigned __reduce_min_sync(unsigned, unsigned v) {
         if (simt_lane_live(i) && (unsigned)b[i] < r) r = (unsigned)b[i];
     return r;
 }
+inline unsigned __reduce_max_sync(unsigned, unsigned v) {
+    const uint64_t* b = simt_exchange(v);
+    unsigned r = 0u;
+    for (int i = 0; i < 32; i++)
+        if (simt_lane_live(i) && (unsigned)b[i] > r) r = (unsigned)b[i];
+    return r;
+}
+inline unsigned __reduce_add_sync(unsigned, unsigned v) {
+    const uint64_t* b = simt_exchange(v);
+    unsigned r = 0u;
+    for (int i = 0; i < 32; i++)
+        if (simt_lane_live(i)) r += (unsigned)b[i];
+    return r;
+}
 inline unsigned __match_any_sync(unsigned, unsigned v) {
     const uint64_t* b = simt_exchange(v);
     unsigned r = 0;

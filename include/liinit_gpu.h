@@ -33,8 +33,7 @@ extern "C" {
 
 #define LIINIT_KNN_BRICKS 1
 #define LIINIT_KNN_CELLS 2
-#define LIINIT_KNN_HYBRID 3
-#define LIINIT_KNN_FUSED 4
+#define LIINIT_KNN_WARP 5   /* (3 and 4 were the hybrid and the TMA-fused experiments of round 2: measured slower, removed; profiles/r02) */
 
 typedef struct liinit_ctx liinit_ctx;
 
@@ -45,13 +44,12 @@ typedef struct liinit_config {
     int device_id;           /* CUDA device ordinal */
     int brick_cells_log2;    /* voxels per brick edge = 1<<this; 0 -> default (3, i.e. brick edge = 8*ds) */
     int hash_capacity_log2;  /* brick hash slots = 1<<this; 0 -> derived from max_map_points */
-    int knn_group_lanes;     /* lanes cooperating on one scan point in the 5-NN kernel: 1 (thread per point, smem-staged), 4, 8, 16 or 32; 0 -> default (4) */
+    int knn_group_lanes;     /* lanes cooperating on one scan point in the lockstep 5-NN kernel: 2, 4, 8, 16 or 32; 0 -> default (4) */
     float knn_seed_radius_cells; /* first search shell of the 5-NN kernel, in map voxels (radius = this * filter_size_map); 0 -> default (2) */
-    int knn_index;           /* spatial index the 5-NN kernel searches: LIINIT_KNN_BRICKS (lockstep groups over whole bricks, knn_group_lanes applies),
+    int knn_index;           /* how the 5-NN kernel searches the brick hash: LIINIT_KNN_BRICKS (lockstep groups of knn_group_lanes lanes over whole bricks),
                                 LIINIT_KNN_CELLS (thread per scan point over the per-brick cell directory; needs brick_cells_log2 = 3),
-                                LIINIT_KNN_HYBRID (first box on the cell directory, unfinished points finished by the brick search),
-                                LIINIT_KNN_FUSED (brick index; ONE kernel per search pass: 5-NN over TMA-staged slab chunks + plane fit +
-                                Jacobian + reduction, knn_group_lanes 4 or 8); 0 -> default */
+                                LIINIT_KNN_WARP (one WARP per scan point: rings of the home brick, bricks walked nearest first, candidates
+                                through a shared-memory list; writes the Nearest_Points copies itself, knn_wq.cuh); 0 -> default */
     int reserved[6];
 } liinit_config;
 

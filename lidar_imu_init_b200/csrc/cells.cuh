@@ -879,62 +879,6 @@ __global__ void __launch_bounds__(LI_CELLS_THREADS, MINB) k_knn_cells_scan_dyn(M
     }
 }
 
-// ---- HYBRID search, first stage: one box of the cell directory for every scan point ------------------------------------
-// (knn_index = LIINIT_KNN_HYBRID; checked on the CPU, tests/test_liinit_emul.py; not yet measured on a GPU.) A point whose five
-// neighbours lie within the first box is finished here (25-35 candidates instead of ~180); the others are appended to `list`
-// (warp-aggregated) with what the box learned -- the 5th-best distance as radius and threshold of ONE closing shell when five
-// were found -- and the lockstep brick search (k_knn_scan_list, knn_kernels.cuh) finishes them: displaced points are where whole
-// bricks are the right granularity.
-template <bool HOST, int MINB>
-__global__ void __launch_bounds__(LI_CELLS_THREADS, MINB) k_knn_cells_first(MapDev M, ScanDev S, PoseD P, float rho2, const float* __restrict__ raw, int stride,
-                                                                             int* __restrict__ list, int* __restrict__ list_n, float* __restrict__ seed_hi2,
-                                                                             float* __restrict__ seed_thr) {
-    __shared__ unsigned s_start[LI_CELLS_QC * LI_CELLS_THREADS];
-    __shared__ unsigned short s_count[LI_CELLS_QC * LI_CELLS_THREADS];
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    const bool valid = q < S.n;
-    float bx = 0.f, by = 0.f, bz = 0.f, wx = 0.f, wy = 0.f, wz = 0.f;
-    if (valid) {
-        if (HOST) {
-            const float* s = raw + (size_t)q * stride;
-            bx = s[0]; by = s[1]; bz = s[2];
-            S.body[q] = make_float4(bx, by, bz, 0.f);
-        } else {
-            const float4 b = __ldg(&S.body[q]);
-            bx = b.x; by = b.y; bz = b.z;
-        }
-        li_body_to_world(P, bx, by, bz, wx, wy, wz);
-    }
-    float ld[5];
-    int li[5];
-    LcQ Q;
-    Q.rstart = s_start + threadIdx.x;
-    Q.rcount = s_count + threadIdx.x;
-    Q.stride = LI_CELLS_THREADS;
-    const bool fin = knn5_stream<false, true>(M, rho2, valid, wx, wy, wz, ld, li, nullptr, Q);
-    if (valid) {
-        S.world[q] = make_float4(wx, wy, wz, 0.f);
-        if (fin) {
-#pragma unroll
-            for (int k = 0; k < 5; k++) S.near_ids[(size_t)q * 5 + k] = li[k];
-        } else {
-            const bool full = li[4] >= 0;
-            // five known: every point that can still matter is closer than d5 -> first (and only) shell of radius sqrt(d5), threshold just above d5
-            seed_hi2[q] = full ? fminf(ld[4] * (1.0f + 1e-6f), 5.0f) : fminf(4.0f * rho2, 5.0f);
-            seed_thr[q] = full ? __uint_as_float(__float_as_uint(ld[4]) + 1u) : INFINITY;
-        }
-    }
-    const unsigned todo = __ballot_sync(0xffffffffu, valid && !fin);
-    if (todo) {
-        const int leader = __ffs(todo) - 1;
-        int base = 0;
-        if (lane == leader) base = atomicAdd(list_n, __popc(todo));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (valid && !fin) list[base + __popc(todo & ((1u << lane) - 1u))] = q;
-    }
-}
-
 // ---- stand-alone Nearest_Search for arbitrary world-frame queries -----------------------------------------
 template <int SEARCH>
 __global__ void __launch_bounds__(LI_CELLS_THREADS) k_knn_cells_queries(MapDev M, const float4* __restrict__ qpts, int n, int* __restrict__ ids,

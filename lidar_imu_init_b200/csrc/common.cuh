@@ -59,7 +59,8 @@ struct PoseD {
 struct ScanDev {
     float4* body;           // feats_down_body (xyz, w unused)
     float4* world;          // feats_down_world
-    int* near_ids;          // [N*5] pool offsets, -1 = missing (Nearest_Points)
+    int* near_ids;          // [N*5] pool offsets, -1 = missing: hand-over from the id-writing search kernels to the plane pass of the same search pass
+    float4* near_xyz;       // [N*5] Nearest_Points (laserMapping.cpp:107) as COPIES of the map points (xyz; w = 1 found, 0 missing rank)
     unsigned char* selected;  // point_selected_surf
     float4* normvec;        // (nx,ny,nz,pd2) f32
     int n;

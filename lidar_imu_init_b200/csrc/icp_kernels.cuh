@@ -12,9 +12,6 @@
 #ifndef LI_PLANE_MIN_BLOCKS
 #define LI_PLANE_MIN_BLOCKS 2
 #endif
-#ifndef LI_PLANE_PREFETCH
-#define LI_PLANE_PREFETCH 0   // 1: request the inputs of the next grid-stride round before computing the current one (to be measured)
-#endif
 
 // ----------------------------------------------------------------------------------------------
 // Phase 2 math (per scan point, fp64)
@@ -333,7 +330,7 @@ __device__ __forceinline__ void block_finish(const double (&acc)[AccLayout<IMU>:
 
 // Order the 5 neighbours as PointType_CMP does (ikd_Tree.h:57-60): ascending distance, distances closer than
 // 1e-10 are ties broken by smaller x. The search already delivers ascending distances, only ties can move.
-__device__ __forceinline__ bool tie_order(float4 (&nb)[5], int (&id)[5], float (&d)[5]) {
+__device__ __forceinline__ bool tie_order(float4 (&nb)[5], float (&d)[5]) {
     bool moved = false;
 #pragma unroll
     for (int pass = 0; pass < 4; pass++) {
@@ -341,7 +338,6 @@ __device__ __forceinline__ bool tie_order(float4 (&nb)[5], int (&id)[5], float (
         for (int k = 0; k < 4 - pass; k++) {
             if (fabsf(d[k] - d[k + 1]) < 1e-10f && nb[k + 1].x < nb[k].x) {
                 float4 tq = nb[k]; nb[k] = nb[k + 1]; nb[k + 1] = tq;
-                int ti = id[k]; id[k] = id[k + 1]; id[k + 1] = ti;
                 float td = d[k]; d[k] = d[k + 1]; d[k + 1] = td;
                 moved = true;
             }
@@ -351,10 +347,17 @@ __device__ __forceinline__ bool tie_order(float4 (&nb)[5], int (&id)[5], float (
 }
 
 // ---- plane / residual / Jacobian / reduction pass -----------------------------------------------------
-// SEARCH = true : runs right after k_knn_scan of the same pass; the selection gate is "5 neighbours found"
+// The pass works on S.near_xyz, the device copy of Nearest_Points (laserMapping.cpp:107): five float4 per scan point, w = 1
+// for a neighbour that exists, 0 for a missing rank. They are COPIES of the map points, as in the reference, so reuse passes and
+// map_incremental keep working on them whatever happens to the map in between (Add_Points, box deletes, slab moves).
+// SEARCH = true : runs right after the search kernel of the same pass; the selection gate is "5 neighbours found"
 //                 (laserMapping.cpp:981-984; d2[4] <= 5 holds by construction of the search).
+//                 FROM_IDS = true : the search kernel left pool offsets in S.near_ids (lockstep / cell-directory searches): gather
+//                                   them here and write S.near_xyz;
+//                 FROM_IDS = false: the search kernel wrote S.near_xyz itself (knn_wq.cuh).
+//                 Either way the PointType_CMP tie order is applied here and S.near_xyz holds the ordered neighbours afterwards.
 // SEARCH = false: reuse pass (nearest_search_en == false, :989-994): previous flag and stored neighbours.
-template <bool IMU, bool SEARCH>
+template <bool IMU, bool SEARCH, bool FROM_IDS>
 __global__ void __launch_bounds__(256, LI_PLANE_MIN_BLOCKS) k_icp_plane(MapDev M, ScanDev S, PoseD P, double* __restrict__ partials,
                                                    unsigned* __restrict__ done_counter, double* __restrict__ out160) {
     typedef AccLayout<IMU> L;
@@ -364,22 +367,6 @@ __global__ void __launch_bounds__(256, LI_PLANE_MIN_BLOCKS) k_icp_plane(MapDev M
     for (int k = 0; k < L::K; k++) acc[k] = 0.0;
     const int stride = gridDim.x * blockDim.x;
     const int nround = (S.n + stride - 1) / stride;
-#if LI_PLANE_PREFETCH
-    // software pipeline, one stage: the body point, the flag and the five neighbour ids of round it + 1 are requested before round it
-    // is computed, so that only the neighbour gather (which needs the ids) is an exposed round trip. Same arithmetic, same order.
-    float4 b_n = make_float4(0.f, 0.f, 0.f, 0.f);
-    int id_n[5] = {-1, -1, -1, -1, -1};
-    bool gate_n = false;
-    {
-        const int q0 = blockIdx.x * blockDim.x + threadIdx.x;
-        if (q0 < S.n) {
-            b_n = __ldg(&S.body[q0]);
-            gate_n = SEARCH ? true : (S.selected[q0] != 0);
-#pragma unroll
-            for (int k = 0; k < 5; k++) id_n[k] = S.near_ids[(size_t)q0 * 5 + k];
-        }
-    }
-#endif
     for (int it = 0; it < nround; it++) {
         const int q = it * stride + blockIdx.x * blockDim.x + threadIdx.x;
         double row[L::NC];
@@ -387,56 +374,48 @@ __global__ void __launch_bounds__(256, LI_PLANE_MIN_BLOCKS) k_icp_plane(MapDev M
         bool sel = false;
 #pragma unroll
         for (int i = 0; i < L::NC; i++) row[i] = 0.0;
-#if LI_PLANE_PREFETCH
-        const float4 b = b_n;
-        int id[5];
-#pragma unroll
-        for (int k = 0; k < 5; k++) id[k] = id_n[k];
-        const bool gate = gate_n;
-        {
-            const int qn = q + stride;
-            if (it + 1 < nround && qn < S.n) {
-                b_n = __ldg(&S.body[qn]);
-                gate_n = SEARCH ? true : (S.selected[qn] != 0);
-#pragma unroll
-                for (int k = 0; k < 5; k++) id_n[k] = S.near_ids[(size_t)qn * 5 + k];
-            }
-        }
-#endif
         if (q < S.n) {
-#if !LI_PLANE_PREFETCH
-            float4 b = __ldg(&S.body[q]);
-#endif
-            float wx, wy, wz;
-            li_body_to_world(P, b.x, b.y, b.z, wx, wy, wz);
-            if (!SEARCH) S.world[q] = make_float4(wx, wy, wz, 0.f);
-#if !LI_PLANE_PREFETCH
-            bool gate = SEARCH ? true : (S.selected[q] != 0);
-#endif
-            if (gate) {
-#if !LI_PLANE_PREFETCH
+            const float4 b = __ldg(&S.body[q]);
+            const bool gate = SEARCH ? true : (S.selected[q] != 0);
+            float4 nb[5];
+            if (SEARCH && FROM_IDS) {
                 int id[5];
 #pragma unroll
                 for (int k = 0; k < 5; k++) id[k] = S.near_ids[(size_t)q * 5 + k];
-#endif
-                if (id[4] >= 0) {
-                    float4 nb[5];
 #pragma unroll
-                    for (int k = 0; k < 5; k++) nb[k] = __ldg(&M.pool[id[k]]);
-                    if (SEARCH) {
-                        float d[5];
-#pragma unroll
-                        for (int k = 0; k < 5; k++) d[k] = li_dist2(wx, wy, wz, nb[k].x, nb[k].y, nb[k].z);
-                        bool moved = tie_order(nb, id, d);
-                        if (moved) {
-#pragma unroll
-                            for (int k = 0; k < 5; k++) S.near_ids[(size_t)q * 5 + k] = id[k];
-                        }
+                for (int k = 0; k < 5; k++) {
+                    nb[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (id[k] >= 0) {
+                        nb[k] = __ldg(&M.pool[id[k]]);
+                        nb[k].w = 1.0f;
                     }
-                    float4 nvec;
-                    sel = plane_and_row<IMU>(P, b.x, b.y, b.z, wx, wy, wz, nb, nvec, row, r);
-                    if (sel) S.normvec[q] = nvec;
                 }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 5; k++) nb[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (gate) {
+#pragma unroll
+                    for (int k = 0; k < 5; k++) nb[k] = S.near_xyz[(size_t)q * 5 + k];
+                }
+            }
+            float wx, wy, wz;
+            li_body_to_world(P, b.x, b.y, b.z, wx, wy, wz);
+            if (!SEARCH) S.world[q] = make_float4(wx, wy, wz, 0.f);
+            bool moved = false;
+            if (gate && nb[4].w != 0.f) {
+                if (SEARCH) {
+                    float d[5];
+#pragma unroll
+                    for (int k = 0; k < 5; k++) d[k] = li_dist2(wx, wy, wz, nb[k].x, nb[k].y, nb[k].z);
+                    moved = tie_order(nb, d);
+                }
+                float4 nvec;
+                sel = plane_and_row<IMU>(P, b.x, b.y, b.z, wx, wy, wz, nb, nvec, row, r);
+                if (sel) S.normvec[q] = nvec;
+            }
+            if (SEARCH && (FROM_IDS || moved)) {
+#pragma unroll
+                for (int k = 0; k < 5; k++) S.near_xyz[(size_t)q * 5 + k] = nb[k];
             }
             S.selected[q] = sel ? 1 : 0;
         }

@@ -401,41 +401,6 @@ k_knn_scan(MapDev M, ScanDev S, PoseD P, float rho2, const float* __restrict__ r
     }
 }
 
-// ---- second stage of the hybrid search (cells.cuh): the lockstep search over a LIST of scan points -----------------
-// list[0 .. *list_n): scan points the cell-directory first round did not finish; seed_hi2[q] = squared radius of the first shell
-// (the 5th-best distance found so far when five were found: one closing shell suffices), seed_thr[q] = bound on the 5th best.
-// S.world[q] was written by the first stage. The count lives on the device: fixed grid, grid-stride over the list.
-template <int G>
-__global__ void __launch_bounds__(LI_KNN_THREADS, LI_KNN_MIN_BLOCKS)
-k_knn_scan_list(MapDev M, ScanDev S, const int* __restrict__ list, const int* __restrict__ list_n, const float* __restrict__ seed_hi2,
-                const float* __restrict__ seed_thr) {
-    constexpr int Q = Grp<G>::Q;
-    const int lane = threadIdx.x & 31;
-    const int gl = lane % G, gid = lane / G, gbase = gid * G;
-    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    const int n = *list_n;
-    for (int ib = warp_global * Q; ib < n; ib += nwarps * Q) {   // warp-uniform
-        const int i = ib + gid;
-        const bool valid = i < n;
-        const int q = valid ? list[i] : 0;
-        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-        float rho2 = 1.0f, thr0 = INFINITY;
-        if (valid) {
-            w = S.world[q];
-            rho2 = seed_hi2[q];
-            thr0 = seed_thr[q];
-        }
-        float gd[5];
-        int gi[5];
-        knn5_lockstep<G>(M, rho2, valid, w.x, w.y, w.z, gd, gi, gl, gbase, thr0);
-        if (valid && gl == 0) {
-#pragma unroll
-            for (int k = 0; k < 5; k++) S.near_ids[(size_t)q * 5 + k] = gi[k];
-        }
-    }
-}
-
 // ---- stand-alone Nearest_Search for arbitrary world-frame queries --------------------------------------
 template <int G>
 __global__ void __launch_bounds__(256) k_knn_queries(MapDev M, const float4* __restrict__ qpts, int n, int* __restrict__ ids,

@@ -16,11 +16,8 @@
 #include "common.cuh"
 #include "icp_kernels.cuh"
 #include "knn_kernels.cuh"
-#ifndef LI_SIMT_EMUL   // (the CPU checker of tests/emul leaves out the cp.async-staged thread-per-point variant)
-#include "knn_tpq.cuh"
-#endif
 #include "cells.cuh"
-#include "fused_kernel.cuh"
+#include "knn_wq.cuh"
 #include "map_kernels.cuh"
 #include "voxelgrid_kernels.cuh"
 #include "undistort_kernels.cuh"
@@ -76,10 +73,11 @@ struct Ctx {
     float4* d_body = nullptr;
     float4* d_world = nullptr;
     int* d_near_ids = nullptr;
+    float4* d_near_xyz = nullptr;
     unsigned char* d_selected = nullptr;
     float4* d_normvec = nullptr;
     int scan_n = 0;
-    bool have_neighbors = false;
+    bool have_neighbors = false;   // a search pass has filled near_xyz for the resident scan (point copies: map updates do not invalidate them)
     bool scan_fresh = false;   // new scan whose flags / neighbour lists have not been initialised yet (see init_scan_state)
     const float* attached = nullptr;   // device alias of a page-locked host scan not copied yet (liinit_scan_attach_host)
     int attached_stride = 0;
@@ -97,24 +95,16 @@ struct Ctx {
     int last_launches = 0;
     int group = 4;
     int cells_search = LI_CELLS_SEARCH_DEFAULT;   // 1 shells on cells, 2 growing boxes, 3 growing boxes enumerate + stream (developer A/B: LIINIT_CELLS_SEARCH)
-    bool hybrid = false;              // knn_index = LIINIT_KNN_HYBRID: first box on the cell directory, the rest by the brick search (not yet GPU-measured)
-    int* d_hard_list = nullptr;       // scan points the first stage did not finish
-    int* d_hard_n = nullptr;
-    float* d_seed_hi2 = nullptr;      // per scan point: first-shell radius^2 / 5th-best bound handed to the second stage
-    float* d_seed_thr = nullptr;
     bool cells_dynamic = false;       // cells search kernel with warp-granular dynamic scheduling (LIINIT_CELLS_SCHED=dynamic; not yet GPU-measured)
     unsigned* d_ticket = nullptr;
     bool cells_refresh_warp = true;   // directory refresh: warp per brick (false: thread per brick, the version the CPU checker runs)
     bool cells = false;   // knn_index = LIINIT_KNN_CELLS: per-brick cell directory + thread-per-point search (cells.cuh)
     float rho2 = 0.09f;   // squared seed radius of the 5-NN search
-    // fused search pass (fused_kernel.cuh): knn_index = LIINIT_KNN_FUSED
-    bool fused = false;
-    int fused_group = 4;              // lanes per scan point (4 or 8)
+    // warp-per-scan-point search (knn_wq.cuh): knn_index = LIINIT_KNN_WARP
+    bool wq = false;
+    int wq_grid = 0;
     unsigned* d_fticket = nullptr;    // monotone tile ticket (never reset)
     unsigned fticket_base = 0;        // its value before the next launch
-    double* d_tree_buf = nullptr;     // reduction tree rows
-    unsigned* d_tree_cnt = nullptr;   // reduction tree counters (zero between launches)
-    int fused_grid = 0;
 };
 
 #define CU(call)                                                                                     \
@@ -245,7 +235,7 @@ void materialize_scan(Ctx* c) {
 int init_scan_state(Ctx* c) {
     if (!c->scan_fresh) return LIINIT_OK;
     CU(cudaMemsetAsync(c->d_selected, 0, (size_t)c->scan_n, c->stream));
-    CU(cudaMemsetAsync(c->d_near_ids, 0xff, (size_t)c->scan_n * 5 * sizeof(int), c->stream));
+    CU(cudaMemsetAsync(c->d_near_xyz, 0, (size_t)c->scan_n * 5 * sizeof(float4), c->stream));   // w = 0: no neighbour at any rank
     c->scan_fresh = false;
     return LIINIT_OK;
 }
@@ -291,74 +281,36 @@ void launch_knn_cells_scan_t(Ctx* c, const PoseD& P) {
 }
 // LI_CELLS_MINB (resident blocks per SM the kernel is compiled for): 6 -> 80 registers; measured against 4 (106 registers, no spills)
 // and 8 (64 registers, 55 spilled words): 0.56 / 0.60 / 0.72 ms at the initial pose (profiles/r01_cells/ab_stream_final.log)
-// hybrid search: k_knn_cells_first for every point, then the lockstep brick search over the list it left (count on the device: fixed grid)
-void launch_knn_hybrid(Ctx* c, const PoseD& P) {
-    cudaMemsetAsync(c->d_hard_n, 0, sizeof(int), c->stream);
-    const int grid = nblk(c->scan_n, LI_CELLS_THREADS);
-    if (c->attached) {
-        k_knn_cells_first<true, LI_CELLS_MINB><<<grid, LI_CELLS_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, c->attached, c->attached_stride, c->d_hard_list,
-                                                                                           c->d_hard_n, c->d_seed_hi2, c->d_seed_thr);
-        c->attached = nullptr;
-    } else {
-        k_knn_cells_first<false, LI_CELLS_MINB><<<grid, LI_CELLS_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, nullptr, 0, c->d_hard_list, c->d_hard_n,
-                                                                                            c->d_seed_hi2, c->d_seed_thr);
-    }
-    int g2 = nblk((long long)c->scan_n * 4, LI_KNN_THREADS);
-    const int cap = c->max_blocks * (256 / LI_KNN_THREADS);
-    if (g2 > cap) g2 = cap;
-    k_knn_scan_list<4><<<g2, LI_KNN_THREADS, 0, c->stream>>>(c->M, c->S, c->d_hard_list, c->d_hard_n, c->d_seed_hi2, c->d_seed_thr);
-    c->launches++;   // (run_pass counts two launches for a search pass; this path has one more)
-}
-
 void launch_knn_cells_scan(Ctx* c, const PoseD& P) {
-    if (c->hybrid) {
-        launch_knn_hybrid(c, P);
-        return;
-    }
     if (c->cells_search == 1) launch_knn_cells_scan_t<LI_CELLS_MINB, 1>(c, P);
     else if (c->cells_search == 2) launch_knn_cells_scan_t<LI_CELLS_MINB, 2>(c, P);
     else launch_knn_cells_scan_t<LI_CELLS_MINB, 3>(c, P);
 }
-
-#ifndef LI_SIMT_EMUL
-constexpr int TPQ_CH = 32, TPQ_NB = 8;
-constexpr size_t TPQ_SMEM = 4 * TpqCfg<TPQ_CH, TPQ_NB>::WARP_TILE_F4 * sizeof(float4);
-
-void launch_knn_scan_tpq(Ctx* c, const PoseD& P) {
-    materialize_scan(c);
-    int grid = nblk(c->scan_n, 128);
-    int cap = c->num_sms * 12;
-    if (grid > cap) grid = cap;
-    k_knn_scan_tpq<TPQ_CH, TPQ_NB><<<grid, 128, TPQ_SMEM, c->stream>>>(c->M, c->S, P, c->rho2);
-}
-#endif
 
 template <bool IMU, bool SEARCH>
 void launch_plane(Ctx* c, const PoseD& P, double* out) {
     // one wave of 256-thread blocks (2 resident per SM at ~100-130 registers), grid-stride over the scan
     int grid = nblk(c->scan_n, 256);
     if (grid > c->num_sms * 2 * LI_PLANE_WAVES) grid = c->num_sms * 2 * LI_PLANE_WAVES;
-    k_icp_plane<IMU, SEARCH><<<grid, 256, 0, c->stream>>>(c->M, c->S, P, c->d_partials, c->d_done, out);
+    // the id-writing searches hand pool offsets over (gathered here); the warp search wrote the neighbour copies itself
+    if (SEARCH && !c->wq) k_icp_plane<IMU, SEARCH, true><<<grid, 256, 0, c->stream>>>(c->M, c->S, P, c->d_partials, c->d_done, out);
+    else k_icp_plane<IMU, SEARCH, false><<<grid, 256, 0, c->stream>>>(c->M, c->S, P, c->d_partials, c->d_done, out);
 }
 
-// One launch for the whole search pass (fused_kernel.cuh). The ticket is monotone: every launch consumes ntiles + one terminating
-// ticket per warp, so the next launch's base is known on the host without a reset on the stream.
-template <int G, bool IMU>
-void launch_fused(Ctx* c, const PoseD& P, double* out) {
-    const int ntiles = (c->scan_n + 31) / 32;
-    int grid = c->fused_grid;
-    const int need = nblk(ntiles, LI_FUSED_THREADS / 32);
+// Warp-per-scan-point search (knn_wq.cuh): tiles of LI_WQ_TILE points behind a monotone ticket: every launch consumes ntiles + one
+// terminating ticket per warp, so the next launch's base is known on the host without a reset on the stream.
+void launch_knn_wq(Ctx* c, const PoseD& P) {
+    const int ntiles = (c->scan_n + LI_WQ_TILE - 1) / LI_WQ_TILE;
+    int grid = c->wq_grid;
+    const int need = nblk(ntiles, LI_WQ_THREADS / 32);
     if (grid > need) grid = need;
-    const size_t smem = sizeof(FusedSmem<G>);
     if (c->attached) {
-        k_icp_fused<G, IMU, true><<<grid, LI_FUSED_THREADS, smem, c->stream>>>(c->M, c->S, P, c->rho2, c->attached, c->attached_stride, c->d_fticket,
-                                                                               c->fticket_base, c->d_tree_buf, c->d_tree_cnt, out);
+        k_knn_wq<true><<<grid, LI_WQ_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, c->attached, c->attached_stride, c->d_fticket, c->fticket_base);
         c->attached = nullptr;   // the kernel leaves the packed copy in d_body
     } else {
-        k_icp_fused<G, IMU, false><<<grid, LI_FUSED_THREADS, smem, c->stream>>>(c->M, c->S, P, c->rho2, nullptr, 0, c->d_fticket, c->fticket_base,
-                                                                                c->d_tree_buf, c->d_tree_cnt, out);
+        k_knn_wq<false><<<grid, LI_WQ_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, nullptr, 0, c->d_fticket, c->fticket_base);
     }
-    c->fticket_base += (unsigned)ntiles + (unsigned)grid * (LI_FUSED_THREADS / 32);
+    c->fticket_base += (unsigned)ntiles + (unsigned)grid * (LI_WQ_THREADS / 32);
 }
 
 // out: where the last block of the plane kernel leaves the 160-double result block -- the caller's device buffer
@@ -370,24 +322,10 @@ int run_pass(Ctx* c, const double* R, const double* p, const double* RLI, const 
     PoseD P;
     fill_pose(P, R, p, RLI, TLI);
     CU(cudaEventRecord(c->ev0, c->stream));
-    if (search && c->fused) {
-        if (c->fused_group == 8) {
-            if (imu_en) launch_fused<8, true>(c, P, out); else launch_fused<8, false>(c, P, out);
-        } else {
-            if (imu_en) launch_fused<4, true>(c, P, out); else launch_fused<4, false>(c, P, out);
-        }
-        CU(cudaEventRecord(c->evm, c->stream));
-        c->have_neighbors = true;
-        c->scan_fresh = false;
-        c->launches += 1;
-        c->last_launches = 1;
-        c->last_was_search = true;
-    } else if (search) {
-        if (c->cells) launch_knn_cells_scan(c, P);
+    if (search) {
+        if (c->wq) launch_knn_wq(c, P);
+        else if (c->cells) launch_knn_cells_scan(c, P);
         else switch (c->group) {
-#ifndef LI_SIMT_EMUL
-            case 1: launch_knn_scan_tpq(c, P); break;
-#endif
             case 16: launch_knn_scan<16>(c, P); break;
             case 32: launch_knn_scan<32>(c, P); break;
             case 2: launch_knn_scan<2>(c, P); break;
@@ -459,10 +397,6 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
     cudaDeviceProp prop;
     CUC(cudaGetDeviceProperties(&prop, c->device));
     c->num_sms = prop.multiProcessorCount;
-#ifndef LI_SIMT_EMUL
-    CUC(cudaFuncSetAttribute(k_knn_scan_tpq<TPQ_CH, TPQ_NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TPQ_SMEM));
-    CUC(cudaFuncSetAttribute(k_knn_queries_tpq<TPQ_CH, TPQ_NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TPQ_SMEM));
-#endif
     CUC(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     CUC(cudaEventCreate(&c->ev0));
@@ -486,7 +420,7 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
         return bail(LIINIT_ERR_INVALID);
     }
     c->hash_slots = 1u << hl;
-    c->group = (cfg->knn_group_lanes == 1 || cfg->knn_group_lanes == 2 || cfg->knn_group_lanes == 4 || cfg->knn_group_lanes == 8 || cfg->knn_group_lanes == 16 || cfg->knn_group_lanes == 32) ? cfg->knn_group_lanes : 4;
+    c->group = (cfg->knn_group_lanes == 2 || cfg->knn_group_lanes == 4 || cfg->knn_group_lanes == 8 || cfg->knn_group_lanes == 16 || cfg->knn_group_lanes == 32) ? cfg->knn_group_lanes : 4;
 
     {
         int ki = cfg->knn_index;
@@ -495,20 +429,13 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
             const char* e = getenv("LIINIT_KNN_INDEX");
             ki = (e && *e) ? atoi(e) : LIINIT_KNN_DEFAULT;
         }
-        if (ki != LIINIT_KNN_BRICKS && ki != LIINIT_KNN_CELLS && ki != LIINIT_KNN_HYBRID && ki != LIINIT_KNN_FUSED) {
-            c->err = "knn_index must be 0, LIINIT_KNN_BRICKS, LIINIT_KNN_CELLS, LIINIT_KNN_HYBRID or LIINIT_KNN_FUSED";
+        if (ki != LIINIT_KNN_BRICKS && ki != LIINIT_KNN_CELLS && ki != LIINIT_KNN_WARP) {
+            c->err = "knn_index must be 0, LIINIT_KNN_BRICKS, LIINIT_KNN_CELLS or LIINIT_KNN_WARP";
             return bail(LIINIT_ERR_INVALID);
         }
         // the cell directory is defined for 8x8x8-voxel bricks; another brick size keeps the brick search
-        c->cells = (ki == LIINIT_KNN_CELLS || ki == LIINIT_KNN_HYBRID) && bs == LI_CELLS_BSHIFT;
-        c->hybrid = c->cells && ki == LIINIT_KNN_HYBRID;
-        c->fused = ki == LIINIT_KNN_FUSED;
-        c->fused_group = (cfg->knn_group_lanes == 8) ? 8 : 4;
-        {
-            const char* fg = getenv("LIINIT_FUSED_GROUP");   // developer A/B
-            if (fg && atoi(fg) == 8) c->fused_group = 8;
-            if (fg && atoi(fg) == 4) c->fused_group = 4;
-        }
+        c->cells = ki == LIINIT_KNN_CELLS && bs == LI_CELLS_BSHIFT;
+        c->wq = ki == LIINIT_KNN_WARP;
         const char* sd = getenv("LIINIT_CELLS_SCHED");
         if (sd && !strcmp(sd, "dynamic")) c->cells_dynamic = true;
         const char* rf = getenv("LIINIT_CELLS_REFRESH");
@@ -546,12 +473,6 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
         CUC(cudaMalloc(&M.sb_keys, (size_t)c->hash_slots * sizeof(unsigned long long)));
         CUC(cudaMalloc(&M.sb_occ, (size_t)c->hash_slots * sizeof(unsigned long long)));
         CUC(cudaMalloc(&c->d_ticket, sizeof(unsigned)));
-        if (c->hybrid) {
-            CUC(cudaMalloc(&c->d_hard_list, (size_t)cfg->max_scan_points * sizeof(int)));
-            CUC(cudaMalloc(&c->d_hard_n, sizeof(int)));
-            CUC(cudaMalloc(&c->d_seed_hi2, (size_t)cfg->max_scan_points * sizeof(float)));
-            CUC(cudaMalloc(&c->d_seed_thr, (size_t)cfg->max_scan_points * sizeof(float)));
-        }
     }
     int batch = cfg->max_scan_points > (1 << 20) ? cfg->max_scan_points : (1 << 20);
     c->stage_pts_cap = batch;
@@ -587,34 +508,20 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
     CUC(cudaMalloc(&c->d_body, (size_t)ns * sizeof(float4)));
     CUC(cudaMalloc(&c->d_world, (size_t)ns * sizeof(float4)));
     CUC(cudaMalloc(&c->d_near_ids, (size_t)batch * 5 * sizeof(int)));
+    CUC(cudaMalloc(&c->d_near_xyz, (size_t)ns * 5 * sizeof(float4)));
     CUC(cudaMalloc(&c->d_selected, (size_t)ns));
     CUC(cudaMalloc(&c->d_normvec, (size_t)ns * sizeof(float4)));
     c->max_blocks = c->num_sms * 16;
     CUC(cudaMalloc(&c->d_partials, (size_t)c->max_blocks * 96 * sizeof(double)));
     CUC(cudaMalloc(&c->d_done, sizeof(unsigned)));
-    if (c->fused) {
-        long long rows = 0, counters = 0;
-        fused_tree_sizes(((long long)ns + 31) / 32, rows, counters);
-        CUC(cudaMalloc(&c->d_tree_buf, (size_t)rows * 96 * sizeof(double)));
-        CUC(cudaMalloc(&c->d_tree_cnt, (size_t)counters * sizeof(unsigned)));
+    if (c->wq) {
         CUC(cudaMalloc(&c->d_fticket, sizeof(unsigned)));
-        CUC(cudaMemsetAsync(c->d_tree_cnt, 0, (size_t)counters * sizeof(unsigned), c->stream));
         CUC(cudaMemsetAsync(c->d_fticket, 0, sizeof(unsigned), c->stream));
         c->fticket_base = 0;
-#ifndef LI_SIMT_EMUL
-        CUC(cudaFuncSetAttribute(k_icp_fused<4, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<4>)));
-        CUC(cudaFuncSetAttribute(k_icp_fused<4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<4>)));
-        CUC(cudaFuncSetAttribute(k_icp_fused<4, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<4>)));
-        CUC(cudaFuncSetAttribute(k_icp_fused<4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<4>)));
-        CUC(cudaFuncSetAttribute(k_icp_fused<8, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<8>)));
-        CUC(cudaFuncSetAttribute(k_icp_fused<8, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<8>)));
-        CUC(cudaFuncSetAttribute(k_icp_fused<8, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<8>)));
-        CUC(cudaFuncSetAttribute(k_icp_fused<8, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<8>)));
-#endif
-        c->fused_grid = c->num_sms * LI_FUSED_MIN_BLOCKS;
+        c->wq_grid = c->num_sms * LI_WQ_MIN_BLOCKS;
         {
-            const char* fb = getenv("LIINIT_FUSED_BLOCKS_PER_SM");   // developer A/B
-            if (fb && atoi(fb) >= 1 && atoi(fb) <= 8) c->fused_grid = c->num_sms * atoi(fb);
+            const char* fb = getenv("LIINIT_WQ_BLOCKS_PER_SM");   // developer A/B
+            if (fb && atoi(fb) >= 1 && atoi(fb) <= 16) c->wq_grid = c->num_sms * atoi(fb);
         }
     }
     CUC(cudaHostAlloc(&c->h_out, 160 * sizeof(double), cudaHostAllocMapped));
@@ -633,6 +540,7 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
     c->S.body = c->d_body;
     c->S.world = c->d_world;
     c->S.near_ids = c->d_near_ids;
+    c->S.near_xyz = c->d_near_xyz;
     c->S.selected = c->d_selected;
     c->S.normvec = c->d_normvec;
     c->S.n = 0;
@@ -646,11 +554,11 @@ int liinit_destroy(liinit_ctx* h) {
     Ctx* c = &h->c;
     cudaSetDevice(c->device);
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
-    cudaFree(c->M.ent); cudaFree(c->M.aux); cudaFree(c->M.pool); cudaFree(c->M.pool_top); cudaFree(c->M.touched_list); cudaFree(c->M.cocc); cudaFree(c->M.cdir); cudaFree(c->M.sb_keys); cudaFree(c->M.sb_occ); cudaFree(c->d_ticket); cudaFree(c->d_hard_list); cudaFree(c->d_hard_n); cudaFree(c->d_seed_hi2); cudaFree(c->d_seed_thr);
+    cudaFree(c->M.ent); cudaFree(c->M.aux); cudaFree(c->M.pool); cudaFree(c->M.pool_top); cudaFree(c->M.touched_list); cudaFree(c->M.cocc); cudaFree(c->M.cdir); cudaFree(c->M.sb_keys); cudaFree(c->M.sb_occ); cudaFree(c->d_ticket);
     cudaFree(c->d_counters); cudaFreeHost(c->h_counters); cudaFree(c->d_stage_raw); cudaFree(c->d_stage_pts);
     cudaFree(c->d_slot_of); cudaFree(c->d_vslot_of); cudaFree(c->d_flag); cudaFree(c->d_ins); cudaFree(c->V.keys); cudaFree(c->V.head); cudaFree(c->d_vg_imin); cudaFree(c->d_vg_block); cudaFree(c->d_vg_misc); cudaFree(c->d_rs_keys); cudaFree(c->d_rs_vals); cudaFree(c->d_rs_hist); cudaFree(c->d_vg_params); cudaFree(c->d_tmin_idx); cudaFree(c->d_poses);
-    cudaFree(c->d_body); cudaFree(c->d_world); cudaFree(c->d_near_ids); cudaFree(c->d_selected); cudaFree(c->d_normvec);
-    cudaFree(c->d_tree_buf); cudaFree(c->d_tree_cnt); cudaFree(c->d_fticket);
+    cudaFree(c->d_body); cudaFree(c->d_world); cudaFree(c->d_near_ids); cudaFree(c->d_near_xyz); cudaFree(c->d_selected); cudaFree(c->d_normvec);
+    cudaFree(c->d_fticket);
     cudaFree(c->d_partials); cudaFree(c->d_done); cudaFreeHost(c->h_out); cudaFree(c->d_q_d2);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -683,7 +591,7 @@ int liinit_map_build(liinit_ctx* h, const float* xyz, int stride, int n) {
         k_sb_clear<<<nblk(c->hash_slots, 256), 256, 0, c->stream>>>(c->M);
         c->launches++;
     }
-    c->have_neighbors = false;
+    // (the retained Nearest_Points are copies: a reuse pass / map_incremental after a map change works on them as in the reference)
     for (long long off = 0; off < n; off += c->stage_pts_cap) {
         int m = (int)((n - off < c->stage_pts_cap) ? (n - off) : c->stage_pts_cap);
         int r = stage_points(c, xyz + (size_t)off * stride, stride, m);
@@ -702,7 +610,6 @@ int liinit_map_add_points(liinit_ctx* h, const float* xyz, int stride, int n, in
     if (!h || (!xyz && n > 0) || n < 0) return LIINIT_ERR_INVALID;
     Ctx* c = &h->c;
     CU(cudaSetDevice(c->device));
-    c->have_neighbors = false;   // pool offsets may move
     int total = 0;
     for (long long off = 0; off < n; off += c->stage_pts_cap) {
         int m = (int)((n - off < c->stage_pts_cap) ? (n - off) : c->stage_pts_cap);
@@ -737,7 +644,6 @@ int liinit_map_delete_boxes(liinit_ctx* h, const float* boxes, int nbox, int* de
         else k_cells_refresh_all<<<nblk(c->hash_slots, 128), 128, 0, c->stream>>>(c->M, c->hash_slots);
         c->launches++;
     }
-    c->have_neighbors = false;   // pool offsets inside the touched slabs moved
     CU(cudaGetLastError());
     int cnt = 0;
     CU(cudaMemcpyAsync(&cnt, c->d_vg_misc + 6, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -811,24 +717,23 @@ int liinit_map_nearest_search(liinit_ctx* h, const float* q, int stride, int n, 
         float* d_xyz = nullptr;
         CU(cudaMalloc(&d_ids, (size_t)m * 5 * sizeof(int)));
         CU(cudaMalloc(&d_xyz, (size_t)m * 15 * sizeof(float)));
-        if (c->cells) {
+        if (c->wq) {
+            int gq = nblk((long long)m * 32, LI_WQ_THREADS);
+            if (gq > c->num_sms * 8) gq = c->num_sms * 8;
+            k_knn_wq_queries<<<gq, LI_WQ_THREADS, 0, c->stream>>>(c->M, c->d_stage_pts, m, d_ids, d_xyz, c->d_q_d2, c->rho2);
+        } else if (c->cells) {
             const int gq = nblk(m, LI_CELLS_THREADS);
             if (c->cells_search == 1) k_knn_cells_queries<1><<<gq, LI_CELLS_THREADS, 0, c->stream>>>(c->M, c->d_stage_pts, m, d_ids, c->d_q_d2, c->rho2);
             else if (c->cells_search == 2) k_knn_cells_queries<2><<<gq, LI_CELLS_THREADS, 0, c->stream>>>(c->M, c->d_stage_pts, m, d_ids, c->d_q_d2, c->rho2);
             else k_knn_cells_queries<3><<<gq, LI_CELLS_THREADS, 0, c->stream>>>(c->M, c->d_stage_pts, m, d_ids, c->d_q_d2, c->rho2);
-#ifndef LI_SIMT_EMUL
-        } else if (c->group == 1) {
-            int grid = nblk(m, 128);
-            if (grid > c->num_sms * 12) grid = c->num_sms * 12;
-            k_knn_queries_tpq<TPQ_CH, TPQ_NB><<<grid, 128, TPQ_SMEM, c->stream>>>(c->M, c->d_stage_pts, m, d_ids, c->d_q_d2, c->rho2);
-#endif
         } else {
             int grid = nblk((long long)m * 8, 256);
             if (grid > c->max_blocks) grid = c->max_blocks;
             k_knn_queries<8><<<grid, 256, 0, c->stream>>>(c->M, c->d_stage_pts, m, d_ids, c->d_q_d2, c->rho2);
         }
-        k_gather_xyz<<<nblk((long long)m * 5, 256), 256, 0, c->stream>>>(c->M.pool, d_ids, (long long)m * 5, d_xyz);
-        c->launches += 2;
+        if (!c->wq) k_gather_xyz<<<nblk((long long)m * 5, 256), 256, 0, c->stream>>>(c->M.pool, d_ids, (long long)m * 5, d_xyz);
+        c->launches += c->wq ? 1 : 2;
+        CU(cudaGetLastError());
         CU(cudaMemcpyAsync(ids.data() + (size_t)off * 5, d_ids, (size_t)m * 5 * 4, cudaMemcpyDeviceToHost, c->stream));
         if (out_xyz) CU(cudaMemcpyAsync(out_xyz + (size_t)off * 15, d_xyz, (size_t)m * 15 * 4, cudaMemcpyDeviceToHost, c->stream));
         if (out_d2) CU(cudaMemcpyAsync(out_d2 + (size_t)off * 5, c->d_q_d2, (size_t)m * 5 * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -1101,25 +1006,22 @@ int liinit_scan_download_state(liinit_ctx* h, float* world_xyz, float* near_xyz,
             world_xyz[3 * (size_t)i] = w[i].x; world_xyz[3 * (size_t)i + 1] = w[i].y; world_xyz[3 * (size_t)i + 2] = w[i].z;
         }
     }
-    if (near_xyz || near_cnt) {
-        std::vector<int> ids((size_t)n * 5);
-        CU(cudaMemcpy(ids.data(), c->d_near_ids, (size_t)n * 5 * 4, cudaMemcpyDeviceToHost));
-        if (near_xyz) {
-            float* d_xyz = nullptr;
-            CU(cudaMalloc(&d_xyz, (size_t)n * 15 * sizeof(float)));
-            k_gather_xyz<<<nblk((long long)n * 5, 256), 256, 0, c->stream>>>(c->M.pool, c->d_near_ids, (long long)n * 5, d_xyz);
-            c->launches++;
-            CU(cudaMemcpyAsync(near_xyz, d_xyz, (size_t)n * 15 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-            CU(cudaStreamSynchronize(c->stream));
-            cudaFree(d_xyz);
-        }
-        if (near_cnt)
-            for (int i = 0; i < n; i++) {
-                int cnt = 0;
-                for (int k = 0; k < 5; k++)
-                    if (ids[(size_t)i * 5 + k] >= 0) cnt++;
-                near_cnt[i] = cnt;
+    if (near_xyz || near_cnt) {   // Nearest_Points: the device keeps them as point copies (ScanDev::near_xyz, w = 1 found / 0 missing)
+        std::vector<float4> nb((size_t)n * 5);
+        CU(cudaMemcpy(nb.data(), c->d_near_xyz, (size_t)n * 5 * sizeof(float4), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < n; i++) {
+            int cnt = 0;
+            for (int k = 0; k < 5; k++) {
+                const float4& e = nb[(size_t)i * 5 + k];
+                const bool ok = e.w != 0.f;
+                if (ok) cnt++;
+                if (near_xyz) {
+                    float* o = near_xyz + 3 * ((size_t)i * 5 + k);
+                    o[0] = ok ? e.x : 0.f; o[1] = ok ? e.y : 0.f; o[2] = ok ? e.z : 0.f;
+                }
             }
+            if (near_cnt) near_cnt[i] = cnt;
+        }
     }
     if (selected) CU(cudaMemcpy(selected, c->d_selected, (size_t)n, cudaMemcpyDeviceToHost));
     if (normvec) CU(cudaMemcpy(normvec, c->d_normvec, (size_t)n * 16, cudaMemcpyDeviceToHost));
@@ -1173,7 +1075,7 @@ int liinit_map_incremental(liinit_ctx* h, const double* R, const double* p, cons
     fill_pose(P, R, p, RLI, TLI);
     static const int zeros[2] = {0, 0};
     CU(cudaMemcpyAsync(c->d_counters + CNT_NADD, zeros, 2 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    k_incr_classify<<<nblk(n, 256), 256, 0, c->stream>>>(c->M, P, c->d_body, n, c->d_near_ids, ds, flg_EKF_inited, c->d_world,
+    k_incr_classify<<<nblk(n, 256), 256, 0, c->stream>>>(c->M, P, c->d_body, n, c->d_near_xyz, ds, flg_EKF_inited, c->d_world,
                                                         c->d_flag);
     c->launches++;
     CU(cudaGetLastError());
@@ -1183,7 +1085,6 @@ int liinit_map_incremental(liinit_ctx* h, const double* R, const double* p, cons
     if (r) return r;
     r = plain_insert(c, c->d_world, n, c->d_flag, 2);
     if (r) return r;
-    c->have_neighbors = false;   // pool offsets may have moved; iteration 0 of the next scan searches anyway
     r = fetch_counters(c);
     if (r) return r;
     if (n_add) *n_add = c->h_counters[CNT_NADD];
@@ -1223,7 +1124,7 @@ int liinit_last_pass_kernel_times(liinit_ctx* h, float* knn_ms, float* plane_ms)
 
 int liinit_knn_index(liinit_ctx* h, int* knn_index) {
     if (!h || !knn_index) return LIINIT_ERR_INVALID;
-    *knn_index = h->c.fused ? LIINIT_KNN_FUSED : h->c.hybrid ? LIINIT_KNN_HYBRID : h->c.cells ? LIINIT_KNN_CELLS : LIINIT_KNN_BRICKS;
+    *knn_index = h->c.wq ? LIINIT_KNN_WARP : h->c.cells ? LIINIT_KNN_CELLS : LIINIT_KNN_BRICKS;
     return LIINIT_OK;
 }
 

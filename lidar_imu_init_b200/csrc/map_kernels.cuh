@@ -517,8 +517,9 @@ __global__ void k_map_flatten(MapDev M, unsigned slots, float* __restrict__ out,
 
 // ---- map_incremental classification (laserMapping.cpp:516-559) ------------------------------------
 // flag[i]: 0 = skip, 1 = PointToAdd (downsample insert), 2 = PointNoNeedDownsample (plain insert).
-// world[i] = pointBodyToWorld(body[i]) with the FINAL state (:523). near_ids: retained from the last search.
-__global__ void k_incr_classify(MapDev M, PoseD P, const float4* __restrict__ body, int n, const int* __restrict__ near_ids,
+// world[i] = pointBodyToWorld(body[i]) with the FINAL state (:523). near_xyz: Nearest_Points retained from the last search pass
+// (copies of the map points, w = 1 / 0 = found / missing rank) -- valid whatever happened to the map since, as in the reference.
+__global__ void k_incr_classify(MapDev M, PoseD P, const float4* __restrict__ body, int n, const float4* __restrict__ near_xyz,
                                 double ds, int flg_EKF_inited, float4* __restrict__ world, int* __restrict__ flag) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -526,12 +527,12 @@ __global__ void k_incr_classify(MapDev M, PoseD P, const float4* __restrict__ bo
     float wx, wy, wz;
     li_body_to_world(P, b.x, b.y, b.z, wx, wy, wz);
     world[i] = make_float4(wx, wy, wz, 0.f);
-    int ids[5];
+    float4 nb[5];
     int cnt = 0;
 #pragma unroll
     for (int j = 0; j < 5; j++) {
-        ids[j] = near_ids[(size_t)i * 5 + j];
-        if (ids[j] >= 0) cnt++;
+        nb[j] = near_xyz[(size_t)i * 5 + j];
+        if (nb[j].w != 0.f) cnt++;
     }
     int f = 1;
     if (cnt > 0 && flg_EKF_inited) {
@@ -540,7 +541,7 @@ __global__ void k_incr_classify(MapDev M, PoseD P, const float4* __restrict__ bo
         float my = (float)__dadd_rn(__dmul_rn(floor(__ddiv_rn((double)wy, ds)), ds), __dmul_rn(0.5, ds));
         float mz = (float)__dadd_rn(__dmul_rn(floor(__ddiv_rn((double)wz, ds)), ds), __dmul_rn(0.5, ds));
         float dist = li_dist2(wx, wy, wz, mx, my, mz);
-        float4 n0 = M.pool[ids[0]];
+        float4 n0 = nb[0];
         double half = 0.5 * ds;
         if ((double)fabsf(__fsub_rn(n0.x, mx)) > half && (double)fabsf(__fsub_rn(n0.y, my)) > half &&
             (double)fabsf(__fsub_rn(n0.z, mz)) > half) {
@@ -549,11 +550,7 @@ __global__ void k_incr_classify(MapDev M, PoseD P, const float4* __restrict__ bo
             if (cnt >= 5) {
 #pragma unroll
                 for (int j = 0; j < 5; j++) {
-                    float4 q = M.pool[ids[j]];
-                    if (li_dist2(q.x, q.y, q.z, mx, my, mz) < dist) {
-                        f = 0;
-                        break;
-                    }
+                    if (li_dist2(nb[j].x, nb[j].y, nb[j].z, mx, my, mz) < dist) f = 0;
                 }
             }
         }
@@ -562,4 +559,3 @@ __global__ void k_incr_classify(MapDev M, PoseD P, const float4* __restrict__ bo
     if (f == 1) atomicAdd(&M.counters[CNT_NADD], 1);
     if (f == 2) atomicAdd(&M.counters[CNT_NNOD], 1);
 }
-

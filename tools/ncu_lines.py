@@ -1,11 +1,13 @@
 """Attribute ncu per-instruction counters (SASS source page) to CUDA source lines via nvdisasm -g line info.
-usage: python tools/ncu_lines.py <report.ncu-rep> <kernel regex> <mangled-name-prefix> [top]"""
+usage: python tools/ncu_lines.py <report.ncu-rep> <kernel regex> <mangled-name-prefix> [top]
+env NCU_LINES_CUBIN=<cubin> NCU_LINES_SRC=<dir>: use an already built cubin / source directory (a report captured from an older tree)"""
 import csv, re, subprocess, sys, collections, os
 rep, kre, mangled = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-cub = "/tmp/liinit_lines.cubin"
-subprocess.check_call(["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "--fmad=false", "-cubin", "-o", cub,
+cub = os.environ.get("NCU_LINES_CUBIN", "/tmp/liinit_lines.cubin")
+if "NCU_LINES_CUBIN" not in os.environ:
+    subprocess.check_call(["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "--fmad=false", "-cubin", "-o", cub,
                        os.path.join(root, "lidar_imu_init_b200/csrc/liinit_gpu.cu")])
 sass = subprocess.run(["nvdisasm", "-g", "-c", cub], capture_output=True, text=True).stdout.splitlines()
 lines = []  # per instruction: (file, line)
@@ -41,7 +43,7 @@ tot = sum(a[0] for a in agg.values()); tots = sum(a[2] for a in agg.values())
 src_cache = {}
 def src(f, ln):
     if f not in src_cache:
-        p = os.path.join(root, "lidar_imu_init_b200/csrc", f)
+        p = os.path.join(os.environ.get("NCU_LINES_SRC", os.path.join(root, "lidar_imu_init_b200/csrc")), f)
         src_cache[f] = open(p).read().splitlines() if os.path.exists(p) else []
     s = src_cache[f]
     return s[ln - 1].strip()[:90] if 0 < ln <= len(s) else ""

@@ -1,18 +1,24 @@
 #!/usr/bin/env python
 """bench.py -- ICP measurement-model throughput on B200 (BASELINE.json metric).
 
-A "step" is ONE search pass of the hot path over one scan: body->world transform, exact 5-NN in the device
+A "step" is ONE search pass of the hot path over one frame: body->world transform, exact 5-NN in the device
 map, plane fit, point-to-plane residual, Jacobian row, HtH / Htr reduced and delivered to the host
-(laserMapping.cpp:959-1080). Workload: BASELINE.json configs[1] (C2): 240k-point scan vs 5M-point map,
-synthetic (lidar_imu_init_b200/scenes.py), initial pose = ground truth (+) 0.5 deg / 5 cm.
+(laserMapping.cpp:959-1080). Workloads (synthetic, lidar_imu_init_b200/scenes.py; initial pose = ground truth (+) 0.5 deg / 5 cm,
+SURVEY.md 8d), selected with --config:
 
-  value  : points*iters/s, scan resident in HBM, timed on the device (CUDA events around each step on the
+  C2 (default, the configuration the metric is quoted on): 240k-point Avia-shaped scan vs 5M-point map.
+       N > 1: WEAK scaling -- a frame of N x 240k points; the map is replicated, every rank uploads the frame, the library
+       cuts it into N slots and sums the accumulators over the ranks inside liinit_icp_iterate (NCCL, behind the C-ABI).
+  C3   130k-point spinning scan (det_range 100 m) vs 10M-point map.
+  C4   260k-point scans, map grown 5M -> 50M points by timed Add_Points(downsample) batches (+ a timed box delete), then the
+       search pass against the grown map.
+  C5   one 2M-point frame vs the 5M-point map; N > 1: STRONG scaling, slots of 2M / N points.
+
+  value  : points*iters/s, frame resident in HBM, timed on the device (CUDA events around each step on the
            stream the kernels run on; L2 flushed between steps by a 256 MiB memset outside the events).
-  e2e    : same metric through the C-ABI with HOST buffers: every step hands the pinned host scan to the library
-           (liinit_scan_attach_host: the search kernel reads it over PCIe; the staged liinit_scan_upload variant is
-           timed next to it) and reads HtH/Htr back (liinit_icp_iterate).
-  N > 1  : weak scaling -- every rank holds a replica of the map and its own 240k-point shard of an
-           N*240k-point frame; one NCCL all-reduce of the 160-double accumulator per step.
+  e2e    : same metric through the C-ABI with HOST buffers: every step hands the pinned host frame to the library
+           (N = 1: liinit_scan_attach_host, the search kernel reads it over PCIe; N > 1: liinit_scan_upload; the staged
+           variant is timed next to it) and reads HtH/Htr back (liinit_icp_iterate).
   --impl reference : the reference's CPU path (verbatim ikd-Tree from oracle/_ref + the restated OpenMP loop)
            on the host cores, same metric/config, each step a bounded sample of the scan.
 
@@ -45,16 +51,28 @@ def emit(obj):
         sys.stdout.flush()
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the search kernel (ncu --set full, cold cache), per index:
-#   1 (bricks, k_knn_scan<4,0>): 110.65 MB read + 7.11 MB written, profiles/r01_ncu_full_final_metrics.txt
-#   2 (cells, k_knn_cells_scan<0,6,3>): 133.67 MB read + 7.93 MB written, profiles/r01_cells/ncu_full_stream_final_metrics.txt
-NCU_DRAM_BYTES_KNN = {1: 117_762_816, 2: 141_602_560}
-NCU_DRAM_SOURCE = {1: "profiles/r01_ncu_full_final_metrics.txt", 2: "profiles/r01_cells/ncu_full_stream_final_metrics.txt"}
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the search kernel on C2 (ncu --set full, cold cache), per index
+NCU_DRAM_BYTES_KNN = {1: 117_762_816, 2: 141_602_560, 5: 115_708_928}
+NCU_DRAM_SOURCE = {1: "profiles/r01_ncu_full_final_metrics.txt", 2: "profiles/r01_cells/ncu_full_stream_final_metrics.txt",
+                   5: "profiles/r02/ncu_full_wq_v1_metrics.txt"}
 KNN_KERNEL = {1: "k_knn_scan (5-NN search on whole bricks, lockstep lane groups; dominant kernel of the pass)",
-              2: "k_knn_cells_scan (5-NN search on the per-brick cell directory, one scan point per thread; dominant kernel of the pass)"}
+              2: "k_knn_cells_scan (5-NN search on the per-brick cell directory, one scan point per thread; dominant kernel of the pass)",
+              5: "k_knn_wq (5-NN search on whole bricks, one warp per scan point; dominant kernel of the pass)"}
+KNN_NAME = {1: "bricks", 2: "cells", 5: "warp"}
 ALG_BYTES_PER_POINT = 132  # 16 body + 80 neighbours + 16 normal/residual + 20 ids
-METRIC = "ICP points*iters/s (search pass), 240k-pt scan vs 5M-pt map"
 UNIT = "points*iters/s"
+
+# name: (scan points per GPU-frame, map points, det_range, workload string, metric string)
+CONFIGS = {
+    "C2": (240_000, 5_000_000, 450.0, "C2: 240k-pt Avia-shaped scan vs 5M-pt map (BASELINE.json configs[1]), search pass",
+           "ICP points*iters/s (search pass), 240k-pt scan vs 5M-pt map"),
+    "C3": (130_000, 10_000_000, 100.0, "C3: 130k-pt spinning scan vs 10M-pt map (BASELINE.json configs[2]), search pass",
+           "ICP points*iters/s (search pass), 130k-pt scan vs 10M-pt map"),
+    "C4": (260_000, 50_000_000, 150.0, "C4: 260k-pt scans, map grown 5M -> 50M pts by Add_Points batches + box delete (BASELINE.json configs[3]), "
+           "search pass against the grown map", "ICP points*iters/s (search pass), 260k-pt scan vs map grown to 50M pts"),
+    "C5": (2_000_000, 5_000_000, 450.0, "C5: one 2M-pt frame vs 5M-pt map, scan points sharded over the GPUs (BASELINE.json configs[4]), search pass",
+           "ICP points*iters/s (search pass), 2M-pt frame vs 5M-pt map"),
+}
 
 
 def _peaks():
@@ -115,43 +133,101 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def make_workload(rank: int, n_scan: int, n_map: int):
+def make_workload(cfg: str, world: int, n_scan: int, n_map: int):
+    """Scene + map + the WHOLE frame (every rank generates the same one) + poses. C2 at N > 1: N scans of n_scan points of the same
+    scene and pose (different seeds) back to back -- slot r of the library's cut is scan r."""
     from lidar_imu_init_b200 import scenes
-    c = scenes.make_config("C2", seed=1, N=n_scan, M=n_map)
-    if rank > 0:  # another shard of the same frame: same scene/map/pose, different scan points
-        c["body_xyz"] = scenes.scan_points(c["scene"], c["pose_gt"], n_scan, seed=2 + 1000 * rank, det_range=450.0, sigma=0.01,
-                                           open_air_frac=0.01, order="voxel")
+    det = CONFIGS[cfg][2]
+    if cfg == "C4":
+        return make_c4(n_scan, n_map)
+    c = scenes.make_config("C2", seed=1, N=n_scan, M=n_map)   # ("C2" = the generic box scene generator; sizes come from the arguments)
+    if det != 450.0:
+        c["body_xyz"] = scenes.scan_points(c["scene"], c["pose_gt"], n_scan, seed=2, det_range=det, sigma=0.01, open_air_frac=0.01, order="voxel")
+    if cfg == "C2" and world > 1:
+        parts = [c["body_xyz"]]
+        for r in range(1, world):
+            parts.append(scenes.scan_points(c["scene"], c["pose_gt"], n_scan, seed=2 + 1000 * r, det_range=det, sigma=0.01, open_air_frac=0.01,
+                                            order="voxel"))
+        c["body_xyz"] = np.ascontiguousarray(np.concatenate(parts, 0))
     return c
 
 
+def make_c4(n_scan: int, n_map: int):
+    """C4: a long hall whose map points are ordered along x, so that Add_Points batches in that order are a sensor walking through it."""
+    from lidar_imu_init_b200 import scenes
+    ds = 0.15
+    scene = scenes.scene_for_points(n_map, ds, aspect=(1200.0, 160.0, 20.0))
+    mp = scenes.map_points(scene, ds, n_map, seed=1)
+    mp = np.ascontiguousarray(mp[np.argsort(mp[:, 0], kind="stable")])
+    gt = scenes.default_sensor_pose(scene)
+    gt.pos_end[0] = 0.5 * scene.L
+    body = scenes.scan_points(scene, gt, n_scan, seed=2, det_range=150.0, sigma=0.01, open_air_frac=0.01, order="voxel")
+    return dict(scene=scene, map_xyz=mp, body_xyz=body, pose_gt=gt, pose_init=scenes.perturb_pose(gt, 3), ds=ds, imu_en=False, name="C4")
+
+
+def config_dict(cfg: str, n_scan: int, n_map: int, ds: float):
+    """The workload description BOTH arms print (same keys, same values: the driver compares them)."""
+    return {"workload": CONFIGS[cfg][3], "scan_points": n_scan, "map_points": n_map, "filter_size_map": ds, "imu_en": False,
+            "initial_pose": "ground truth (+) 0.5 deg / 5 cm", "open_air_frac": 0.01, "scan_order": "voxel-grid order"}
+
+
 # ------------------------------------------------------------------------------------------------------
-def cpu_reference_pass(c, sample_points: int, threads: int, reps: int, warm: int):
+def _interleave_memory():
+    """set_mempolicy(MPOL_INTERLEAVE, all nodes): the verbatim ikd-Tree is built by one thread -- without this its 0.9 GB of nodes
+    land on one NUMA node and the 128-thread search arm measures that node's memory controller (1.2e6 .. 7.5e6 points*iters/s box to
+    box in round 1). Best effort."""
+    try:
+        import ctypes
+        nodes = [int(d[4:]) for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()]
+        if len(nodes) < 2:
+            return "single NUMA node"
+        mask = ctypes.c_ulong(sum(1 << n for n in nodes))
+        libc = ctypes.CDLL(None, use_errno=True)
+        rc = libc.syscall(238, 3, ctypes.byref(mask), ctypes.c_ulong(max(nodes) + 2))   # SYS_set_mempolicy, MPOL_INTERLEAVE
+        return f"interleaved over {len(nodes)} NUMA nodes" if rc == 0 else f"set_mempolicy failed (errno {ctypes.get_errno()})"
+    except Exception as e:
+        return f"unavailable ({e!r})"
+
+
+def _cpu_env():
+    # read by libgomp when the oracle library is loaded: one thread per core, spread over the sockets, no migration
+    os.environ.setdefault("OMP_PROC_BIND", "spread")
+    os.environ.setdefault("OMP_PLACES", "cores")
+
+
+def cpu_reference_pass(c, sample_points: int, threads: int, reps: int, warm: int, om=None):
     """Time the CPU path (oracle) on a bounded sample of the scan against the full map."""
     from oracle import oracle as orc
     kind = "reference" if orc.has_ikd() else "port"
-    om = orc.OracleMap(c["ds"], 1 if orc.has_ikd() else 0)
-    t0 = time.time()
-    om.build(c["map_xyz"])
-    build_s = time.time() - t0
+    build_s = 0.0
+    if om is None:
+        om = orc.OracleMap(c["ds"], 1 if orc.has_ikd() else 0)
+        t0 = time.time()
+        om.build(c["map_xyz"])
+        build_s = time.time() - t0
     step = max(1, len(c["body_xyz"]) // sample_points)
     body = np.ascontiguousarray(c["body_xyz"][::step][:sample_points])
     sc = orc.OracleScan(body)
     p = c["pose_init"]
     ts = []
+    res = None
     for i in range(warm + reps):
         t = time.perf_counter()
-        sc.iterate(om, p.rot_end, p.pos_end, p.R_LI, p.T_LI, c["imu_en"], True, nthreads=threads)
+        res = sc.iterate(om, p.rot_end, p.pos_end, p.R_LI, p.T_LI, c["imu_en"], True, nthreads=threads)
         dt = time.perf_counter() - t
         if i >= warm:
             ts.append(dt)
-    return dict(kind=kind, n=len(body), times=ts, build_s=build_s, om=om, sc=sc)
+    return dict(kind=kind, n=len(body), times=ts, build_s=build_s, om=om, sc=sc, result=res)
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
+    _cpu_env()
+    numa = _interleave_memory()
     threads = os.cpu_count() or 1
-    c = make_workload(0, args.scan_points, args.map_points)
+    cfg = args.config
+    c = make_workload(cfg if cfg != "C4" else "C2", 1, args.scan_points, min(args.map_points, 10_000_000))
     # size the per-step sample so that steps+warmup stay within ~2 minutes
     probe = cpu_reference_pass(c, 12000, threads, 1, 1)
     per_pt = probe["times"][0] / probe["n"]
@@ -168,17 +244,25 @@ def run_reference(args, rank, world):
         sc.iterate(om, p.rot_end, p.pos_end, p.R_LI, p.T_LI, False, True, nthreads=threads)
         if i >= args.warmup:
             ts.append(time.perf_counter() - t)
-    ms = 1e3 * float(np.mean(ts))
+    ms = 1e3 * float(np.median(ts))
     val = len(body) / (ms * 1e-3)
-    sample = f"{len(body)} of {args.scan_points} scan points per step vs the full {args.map_points}-point map, search pass, {threads} OpenMP threads"
+    v3 = None
+    if threads > 3:
+        t3 = []
+        for i in range(3):
+            t = time.perf_counter()
+            sc.iterate(om, p.rot_end, p.pos_end, p.R_LI, p.T_LI, False, True, nthreads=3)
+            t3.append(time.perf_counter() - t)
+        v3 = len(body) / float(np.median(t3[1:]))
+    sample = (f"{len(body)} of {args.scan_points} scan points per step vs the full {len(c['map_xyz'])}-point map, search pass, {threads} OpenMP threads "
+              f"(OMP_PROC_BIND={os.environ.get('OMP_PROC_BIND')}, OMP_PLACES={os.environ.get('OMP_PLACES')}, tree memory {numa}), median of the steps")
     out = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 kNN / f64 plane+Jacobian",
-        "data": "synthetic", "iters_per_s": val / args.scan_points,
-        "config": {"workload": "C2: 240k-pt Avia-shaped scan vs 5M-pt map (BASELINE.json configs[1]), search pass", "scan_points": args.scan_points,
-                   "map_points": args.map_points, "filter_size_map": c["ds"], "sample_points_per_step": len(body)},
+        "impl": "reference", "metric": CONFIGS[cfg][4], "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if cfg == "C5" else "weak", "vs_baseline": None,
+        "dtype": "f32 kNN / f64 plane+Jacobian", "data": "synthetic", "iters_per_s": val / args.scan_points,
+        "config": config_dict(cfg, args.scan_points, args.map_points, c["ds"]),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": probe["kind"], "sample": sample,
-                         "build_s": probe["build_s"]},
+                         "build_s": probe["build_s"], "value_mp_proc_num_3": v3, "ms_per_step_all": [1e3 * t for t in ts]},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -186,6 +270,36 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------------
+def grow_map_c4(g, c, n_start: int, batch: int):
+    """C4: Build(first n_start points) then Add_Points(downsample) batches to the end of the hall, each timed (wall clock incl. the H2D
+    of the batch); one Delete_Point_Boxes over the first 40 m of the hall at the end."""
+    import torch
+    mp = c["map_xyz"]
+    t0 = time.time()
+    g.map_build(mp[:n_start])
+    build_s = time.time() - t0
+    ts, sizes = [], []
+    for lo in range(n_start, len(mp), batch):
+        b = mp[lo:lo + batch]
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        g.map_add_points(b, True)
+        ts.append((time.perf_counter() - t) * 1e3)
+        sizes.append(len(b))
+    n_before = g.map_validnum()
+    sc = c["scene"]
+    boxes = np.array([[-1.0, -1.0, -1.0, 40.0, sc.W + 1.0, sc.H + 1.0]], np.float32)
+    torch.cuda.synchronize()
+    t = time.perf_counter()
+    n_del = g.map_delete_boxes(boxes)
+    del_ms = (time.perf_counter() - t) * 1e3
+    return {"build_points": n_start, "map_build_s": build_s, "add_batches": len(ts), "points_per_batch": batch, "add_ms_median": float(np.median(ts)) if ts else None,
+            "add_ms_max": float(np.max(ts)) if ts else None, "add_points_per_s": float(np.sum(sizes) / (np.sum(ts) * 1e-3)) if ts else None,
+            "map_points_after_growth": n_before, "delete_boxes_ms": del_ms, "deleted_points": int(n_del), "map_points_final": g.map_validnum(),
+            "map_stats": g.map_stats(), "note": "Add_Points(downsample_on) batches of new surface, wall clock per call incl. H2D and the counters' D2H; "
+                                                "one Delete_Point_Boxes over the first 40 m of the hall"}
+
+
 def run_gpu(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -197,45 +311,47 @@ def run_gpu(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    cfg = args.config
+    strong = cfg == "C5"
 
-    c = make_workload(rank, args.scan_points, args.map_points)
-    N = len(c["body_xyz"])
+    c = make_workload(cfg, world, args.scan_points, args.map_points)
+    NF = len(c["body_xyz"])                       # points of the whole frame
     p = c["pose_init"]
-    g = capi.LiInitGpu(c["ds"], max_map_points=int(args.map_points * 1.2) + 1000, max_scan_points=N + 16, device_id=local_rank,
+    g = capi.LiInitGpu(c["ds"], max_map_points=int(args.map_points * 1.2) + 1000, max_scan_points=NF + 16, device_id=local_rank,
                        knn_group_lanes=args.group, brick_cells_log2=args.brick, knn_index=args.knn_index)
     kidx = g.knn_index()
     stream = torch.cuda.Stream(device=dev)
     g.set_stream(stream.cuda_stream)
-    t0 = time.time()
-    g.map_build(c["map_xyz"])
-    build_s = time.time() - t0
-    # pinned host scan (packed xyz: 12 bytes per point cross PCIe, the device widens to float4) for the e2e path
+    sharding.attach_comm(g, rank, world)          # N > 1: NCCL communicator INSIDE the library (liinit_comm_init)
+    growth = None
+    if cfg == "C4":
+        growth = grow_map_c4(g, c, 5_000_000 if args.map_points >= 10_000_000 else args.map_points // 10, args.scan_points)
+        build_s = growth["map_build_s"]
+    else:
+        t0 = time.time()
+        g.map_build(c["map_xyz"])
+        build_s = time.time() - t0
+    # pinned host frame (packed xyz: 12 bytes per point cross PCIe, the device widens to float4) for the e2e path
     body4 = torch.from_numpy(np.ascontiguousarray(c["body_xyz"], dtype=np.float32)).pin_memory()
     SCAN_STRIDE = 3
-    g.scan_upload_ptr(body4.data_ptr(), SCAN_STRIDE, N)
-    d_out = torch.zeros(160, dtype=torch.float64, device=dev)
-    h_out = torch.zeros(160, dtype=torch.float64).pin_memory()
+    g.scan_upload_ptr(body4.data_ptr(), SCAN_STRIDE, NF)
+    N = g.comm_info()["shard_n"]                  # points this rank processes
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def step_resident():
-        """scan resident: one search pass; results on the host at return"""
-        if world == 1:
-            return g.icp_iterate(p.rot_end, p.pos_end, p.R_LI, p.T_LI, False, True)
-        g.icp_iterate_device(p.rot_end, p.pos_end, p.R_LI, p.T_LI, False, True, d_out.data_ptr())
-        sharding.allreduce_accumulators(d_out)
-        h_out.copy_(d_out, non_blocking=True)
-        stream.synchronize()
-        return h_out
+        """frame resident: one search pass; results (summed over the ranks inside the library when N > 1) on the host at return"""
+        return g.icp_iterate(p.rot_end, p.pos_end, p.R_LI, p.T_LI, False, True)
 
     def step_e2e():
-        # liinit_scan_attach_host: the search kernel pulls the pinned host scan over PCIe itself (N*12 bytes, inside the
-        # timed region) and the 160-double result block comes back to the host before the call returns
-        g.scan_attach_ptr(body4.data_ptr(), SCAN_STRIDE, N)
+        # N = 1: liinit_scan_attach_host -- the search kernel pulls the pinned host scan over PCIe itself (NF*12 bytes, inside the timed
+        # region); N > 1: the frame is copied (every rank needs all of it for the map update). The 160-double result block comes back to
+        # the host before the call returns.
+        g.scan_attach_ptr(body4.data_ptr(), SCAN_STRIDE, NF)
         return step_resident()
 
     def step_e2e_staged():
         # same step through liinit_scan_upload (cudaMemcpyAsync + repack in front of the search), for comparison
-        g.scan_upload_ptr(body4.data_ptr(), SCAN_STRIDE, N)
+        g.scan_upload_ptr(body4.data_ptr(), SCAN_STRIDE, NF)
         return step_resident()
 
     def timed(fn, steps, warmup, do_flush):
@@ -272,7 +388,7 @@ def run_gpu(args, rank, world, local_rank):
     warm_ms, _, knn_warm, plane_warm = timed(step_resident, args.steps, 1, False)
     e2e_ms, _, _, _ = timed(step_e2e, args.steps, args.warmup, True)
     e2e_staged_ms, _, _, _ = timed(step_e2e_staged, args.steps, args.warmup, True)
-    g.scan_upload_ptr(body4.data_ptr(), SCAN_STRIDE, N)
+    g.scan_upload_ptr(body4.data_ptr(), SCAN_STRIDE, NF)
     clocks = sampler.stop()
 
     def maxr(x):
@@ -284,40 +400,59 @@ def run_gpu(args, rank, world, local_rank):
 
     tot_ms, warm_ms, e2e_ms, e2e_staged_ms = maxr(tot_ms), maxr(warm_ms), maxr(e2e_ms), maxr(e2e_staged_ms)
     ms_step = tot_ms / args.steps
-    total_points = N * world
-    value = total_points / (ms_step * 1e-3)
-    e2e_val = total_points / (e2e_ms / args.steps * 1e-3)
+    value = NF / (ms_step * 1e-3)
+    e2e_val = NF / (e2e_ms / args.steps * 1e-3)
     peak, peak_src = _peaks()
     ach = ALG_BYTES_PER_POINT * N / (knn_ms * 1e-3) / 1e9
-    # sanity of the result the timed steps produced
-    res = step_resident()
-    m_sel = int(res[2]) if world == 1 else int(round(float(h_out[157])))
+    # the result the timed steps produce (same call, same stream as the timed loops)
+    with torch.cuda.stream(stream):
+        H, b, m_sel, rs = step_resident()
+    multi = None
+    if world > 1:
+        # the reduction verified on hardware, every run: sum of the ranks' OWN blocks (fetched through liinit_comm_last_local,
+        # gathered over torch.distributed) against what liinit_icp_iterate returned on this rank
+        loc = g.comm_last_local()
+        box = [None] * world
+        dist.all_gather_object(box, loc)
+        tot = np.sum(np.stack(box, 0), 0)
+        red = np.concatenate([H.reshape(-1), b, [rs, float(m_sel)]])
+        multi = {"m_sum_of_ranks": int(round(tot[157])), "m_reduced": int(m_sel), "m_per_rank": [int(round(x[157])) for x in box],
+                 "rel_err_HtH_vs_rank_sum": float(np.abs(red[:144] - tot[:144]).max() / np.abs(tot[:144]).max()),
+                 "rel_err_Htr_vs_rank_sum": float(np.abs(red[144:156] - tot[144:156]).max() / np.abs(tot[144:156]).max()),
+                 "collective": "ncclAllReduce(160 f64) inside liinit_icp_iterate (liinit_comm_init; NCCL dlopen()ed by the library)"}
 
+    conf = config_dict(cfg, args.scan_points, args.map_points, c["ds"])
     out = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 kNN / f64 plane+Jacobian", "data": "synthetic",
-        "iters_per_s": 1e3 / ms_step, "iters_per_s_l2_warm": 1e3 / (warm_ms / args.steps),
-        "config": {"workload": "C2: 240k-pt Avia-shaped scan vs 5M-pt map (BASELINE.json configs[1]), search pass; "
-                               + ("1 GPU" if world == 1 else f"{world} GPUs, map replicated, one 240k-pt shard per rank, NCCL all-reduce of 160 f64"),
-                   "scan_points_per_gpu": N, "map_points": args.map_points, "filter_size_map": c["ds"], "imu_en": False,
-                   "initial_pose": "ground truth (+) 0.5 deg / 5 cm", "open_air_frac": 0.01, "scan_order": "voxel-grid order",
-                   "l2": "flushed between timed steps (256 MiB memset outside the events)", "knn_index": {1: "bricks", 2: "cells"}[kidx],
-                   "knn_group_lanes": (args.group or 4) if kidx == 1 else None, "brick_cells_log2": args.brick or 3, "selected_points": m_sel, "map_build_s": build_s},
-        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(N * 12 + 192), "d2h_bytes_per_step": 160 * 8,
+        "metric": CONFIGS[cfg][4], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32 kNN / f64 plane+Jacobian",
+        "data": "synthetic", "iters_per_s": 1e3 / ms_step, "iters_per_s_l2_warm": 1e3 / (warm_ms / args.steps),
+        "config": conf,
+        "details": {"frame_points": NF, "points_per_gpu": N,
+                    "parallelism": "1 GPU" if world == 1 else (f"{world} GPUs, map replicated, frame of {NF} points cut into {world} slots by the library, "
+                                                               "accumulators summed over the ranks inside liinit_icp_iterate (NCCL)"),
+                    "l2": "flushed between timed steps (256 MiB memset outside the events)", "knn_index": KNN_NAME[kidx],
+                    "knn_group_lanes": (args.group or 4) if kidx == 1 else None, "brick_cells_log2": args.brick or 3,
+                    "selected_points": int(m_sel), "map_build_s": build_s, "map_points_live": g.map_validnum()},
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(NF * 12 + 192), "d2h_bytes_per_step": 160 * 8,
                 "ms_per_step": e2e_ms / args.steps,
-                "host_input": "pinned packed xyz, read by the search kernel over PCIe (liinit_scan_attach_host, no staging copy)",
+                "host_input": ("pinned packed xyz, read by the search kernel over PCIe (liinit_scan_attach_host, no staging copy)" if world == 1 else
+                               "pinned packed xyz of the whole frame, copied to every rank's device (liinit_scan_attach_host at N > 1 copies)"),
                 "ms_per_step_staged_copy": e2e_staged_ms / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": KNN_KERNEL[kidx], "achieved": ach, "peak": peak,
-                     "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src, "traffic": NCU_DRAM_BYTES_KNN[kidx],
+                     "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src, "traffic": NCU_DRAM_BYTES_KNN[kidx] if cfg == "C2" else None,
                      "algorithmic_bytes_per_launch": ALG_BYTES_PER_POINT * N, "kernel_ms": knn_ms, "plane_kernel_ms": plane_ms,
                      "kernel_ms_l2_warm": knn_warm, "plane_kernel_ms_l2_warm": plane_warm,
                      "note": "traffic = dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel from the ncu --set full capture in "
-                             + NCU_DRAM_SOURCE[kidx] + " (cold cache: ncu flushes between replays), bytes per launch"},
+                             + NCU_DRAM_SOURCE[kidx] + " (C2, cold cache: ncu flushes between replays), bytes per launch"},
     }
+    if multi:
+        out["multi_gpu_check"] = multi
+    if growth:
+        out["map_growth"] = growth
     # ---- extras (not part of the contract value): the other pass kinds of a real scan -----------------------
-    if world == 1:
+    if world == 1 and cfg != "C4":
         try:
             from lidar_imu_init_b200 import host
             rts = []
@@ -327,7 +462,7 @@ def run_gpu(args, rank, world, local_rank):
             st0 = host.state_from_pose(p.rot_end, p.pos_end, p.R_LI, p.T_LI)
             sus = []
             for _ in range(5):
-                g.scan_upload_ptr(body4.data_ptr(), SCAN_STRIDE, N)
+                g.scan_upload_ptr(body4.data_ptr(), SCAN_STRIDE, NF)
                 t0 = time.perf_counter()
                 _, ss = host.scan_update(g, st0, 5, False)
                 sus.append((time.perf_counter() - t0) * 1e3)
@@ -341,18 +476,27 @@ def run_gpu(args, rank, world, local_rank):
                              "scan_update_iterations": ss["iterations"], "scan_update_search_passes": ss["search_passes"],
                              "map_incremental_ms": mi_ms, "map_incremental_added": [na, nn],
                              "note": "scan_update = liinit_scan_update (host C++ IESKF loop, max_iteration 5) on the resident scan, wall clock; "
-                                     "map_incremental = classification + both inserts for the 240k-point scan, wall clock"}
+                                     "map_incremental = classification + both inserts for the frame, wall clock"}
         except Exception as e:
             out["extras"] = {"error": repr(e)}
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu and cfg != "C4":
+        _cpu_env()
+        numa = _interleave_memory()
         threads = os.cpu_count() or 1
         try:
-            r = cpu_reference_pass(c, min(N, args.cpu_sample), threads, 3, 1)
+            r = cpu_reference_pass(c, min(NF, args.cpu_sample), threads, 3, 1)
             v = r["n"] / float(np.median(r["times"]))
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": r["kind"],
-                                   "sample": f"search pass over {r['n']} of {N} scan points vs the full {args.map_points}-pt map "
-                                             f"(verbatim ikd-Tree Build {r['build_s']:.1f}s excluded), median of 3", "iters_per_s": v / N}
-            r3 = cpu_reference_pass(c, min(N, args.cpu_sample), min(3, threads), 2, 1) if threads > 3 else None
+                                   "sample": f"search pass over {r['n']} of {NF} scan points vs the full {args.map_points}-pt map "
+                                             f"(verbatim ikd-Tree Build {r['build_s']:.1f}s excluded; OMP_PROC_BIND={os.environ.get('OMP_PROC_BIND')}, "
+                                             f"tree memory {numa}), median of 3", "iters_per_s": v / NF}
+            if r["n"] == NF:
+                # full-size parity for free: the oracle just evaluated the very pass the GPU was timed on
+                Ho, bo, mo = r["result"]
+                out["parity"] = {"checked_against": "oracle (verbatim ikd-Tree + restated loop), the whole frame, same pose",
+                                 "m_gpu": int(m_sel), "m_oracle": int(mo), "m_equal": bool(int(m_sel) == int(mo)),
+                                 "rel_err_HtH": float(np.abs(H - Ho).max() / np.abs(Ho).max()), "rel_err_Htr": float(np.abs(b - bo).max() / np.abs(bo).max())}
+            r3 = cpu_reference_pass(c, min(NF, args.cpu_sample, 60000), min(3, threads), 2, 1, om=r["om"]) if threads > 3 else None
             if r3:
                 out["cpu_baseline"]["value_mp_proc_num_3"] = r3["n"] / float(np.median(r3["times"]))
         except Exception as e:  # the oracle is test infrastructure; its absence must not hide the GPU number
@@ -376,14 +520,17 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--scan-points", type=int, default=240_000)
-    ap.add_argument("--map-points", type=int, default=5_000_000)
+    ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
+    ap.add_argument("--scan-points", type=int, default=0, help="0 = the configuration's size")
+    ap.add_argument("--map-points", type=int, default=0, help="0 = the configuration's size")
     ap.add_argument("--group", type=int, default=0)
     ap.add_argument("--brick", type=int, default=0)
-    ap.add_argument("--knn-index", type=int, default=0, help="0 = library default, 1 = bricks (lockstep groups), 2 = cells (cell directory)")
+    ap.add_argument("--knn-index", type=int, default=0, help="0 = library default, 1 = bricks (lockstep groups), 2 = cells (cell directory), 5 = warp per point")
     ap.add_argument("--cpu-sample", type=int, default=240_000)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    args.scan_points = args.scan_points or CONFIGS[args.config][0]
+    args.map_points = args.map_points or CONFIGS[args.config][1]
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

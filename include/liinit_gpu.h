@@ -122,8 +122,9 @@ int liinit_scan_download_body(liinit_ctx* h, float* xyz, int cap_points, int* n)
 int liinit_icp_iterate(liinit_ctx* h, const double rot_end[9], const double pos_end[3], const double R_LI[9],
                        const double T_LI[3], int imu_en, int nearest_search_en, double HtH[144], double Htr[12], int* m,
                        double* res_sq);
-/* Same pass, results left on the device for a collective: d_out = device pointer to 160 doubles
- * [HtH 144 | Htr 12 | res_sq | m | pad 2], written on the context's stream; no host synchronisation. */
+/* Same pass, results left on the device: d_out = device pointer to 160 doubles
+ * [HtH 144 | Htr 12 | res_sq | m | pad 2], written on the context's stream; no host synchronisation.
+ * With a communicator attached (liinit_comm_init) both forms return the SUM over the ranks. */
 int liinit_icp_iterate_device(liinit_ctx* h, const double rot_end[9], const double pos_end[3], const double R_LI[9],
                               const double T_LI[3], int imu_en, int nearest_search_en, double* d_out160);
 /* laserCloudOri / corr_normvect after compaction (laserMapping.cpp:1013-1020; published at :625-636):
@@ -139,13 +140,33 @@ int liinit_scan_download_state(liinit_ctx* h, float* world_xyz, float* near_xyz,
 int liinit_map_incremental(liinit_ctx* h, const double rot_end[9], const double pos_end[3], const double R_LI[9],
                            const double T_LI[3], double ds, int flg_EKF_inited, int* n_add, int* n_no_downsample);
 
+/* multi-GPU (the reference is single-process, its only parallelism the OpenMP loop laserMapping.cpp:964-968) --------
+ * One process (or thread) per GPU, one context each. The map is REPLICATED: every rank makes the same map calls with the same data.
+ * The scan is SHARDED: every rank uploads the same whole frame, the library cuts it into nranks equal slots and the search / plane
+ * kernels of a rank work on its slot only. The one exchange of the path -- the sum of [HtH 144 | Htr 12 | res_sq | m] over the ranks
+ * (one ncclAllReduce of 160 doubles over NVLink on the context's stream) -- happens INSIDE liinit_icp_iterate / _device, so the
+ * host-side IESKF loop (liinit_scan_update, liinit_host.h) is unchanged and every rank ends a scan with the same state.
+ * liinit_map_incremental and the download hooks first all-gather the per-point results (Nearest_Points copies, flags, normals) of the
+ * other ranks' slots, then every rank applies the whole frame's update to its replica: collective calls, same order on every rank.
+ * NCCL is loaded with dlopen("libnccl.so.2") when the first of these functions is called; single-GPU use never touches it. */
+#define LIINIT_COMM_ID_BYTES 128
+/* ncclGetUniqueId: call on ONE rank, hand the 128 bytes to the others through whatever channel the application has. */
+int liinit_comm_unique_id(void* id128);
+/* ncclCommInitRank on the context's device; collective over the nranks contexts. LIINIT_ERR_CUDA if NCCL is missing. */
+int liinit_comm_init(liinit_ctx* h, const void* id128, int nranks, int rank);
+/* This rank's OWN accumulator block of the last pass (before the sum), 160 doubles to the host: lets an application / the bench
+ * verify the reduction (sum of the ranks' blocks == what liinit_icp_iterate returned). */
+int liinit_comm_last_local(liinit_ctx* h, double* out160);
+/* nranks / rank of the context and the slot [shard_lo, shard_lo + shard_n) of the resident frame this rank works on. */
+int liinit_comm_info(liinit_ctx* h, int* nranks, int* rank, int* shard_lo, int* shard_n);
+
 /* instrumentation (the reference has none around this loop) ---- */
 /* Device time in milliseconds of the kernels of the last liinit_icp_iterate* call (CUDA events on the context's
  * stream) and the number of kernel launches it made. */
 int liinit_last_pass_timing(liinit_ctx* h, float* kernel_ms, int* launches);
 /* Per-kernel device times of the last pass: the 5-NN kernel (0 for a reuse pass) and the plane/Jacobian/reduction kernel. */
 int liinit_last_pass_kernel_times(liinit_ctx* h, float* knn_ms, float* plane_ms);
-/* The spatial index this context searches (LIINIT_KNN_BRICKS / LIINIT_KNN_CELLS / LIINIT_KNN_HYBRID / LIINIT_KNN_FUSED) after defaults were resolved. */
+/* The spatial index this context searches (LIINIT_KNN_BRICKS / LIINIT_KNN_CELLS / LIINIT_KNN_WARP) after defaults were resolved. */
 int liinit_knn_index(liinit_ctx* h, int* knn_index);
 /* Cumulative number of kernels launched by this context. */
 int liinit_launch_count(liinit_ctx* h, long long* launches);

@@ -44,7 +44,7 @@ def gpu_sources():
 def build_gpu(force: bool = False, verbose: bool = False) -> str:
     srcs = gpu_sources()
     if force or _newer(GPU_LIB, srcs):
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", GPU_LIB, os.path.join(CSRC, "liinit_gpu.cu")]
+        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", GPU_LIB, os.path.join(CSRC, "liinit_gpu.cu"), "-ldl"]
         subprocess.check_call(cmd)
     return GPU_LIB
 

@@ -37,6 +37,7 @@ SYMBOLS = [
     "liinit_raw_download", "liinit_raw_downsample",
     "liinit_icp_iterate", "liinit_icp_iterate_device", "liinit_scan_download_effect", "liinit_scan_download_state",
     "liinit_map_incremental", "liinit_last_pass_timing", "liinit_last_pass_kernel_times", "liinit_launch_count", "liinit_map_stats", "liinit_knn_index",
+    "liinit_comm_unique_id", "liinit_comm_init", "liinit_comm_info", "liinit_comm_last_local",
 ]
 
 
@@ -87,6 +88,10 @@ def load():
     L.liinit_launch_count.argtypes = [vp, C.POINTER(C.c_longlong)]
     L.liinit_knn_index.argtypes = [vp, C.POINTER(C.c_int)]
     L.liinit_map_stats.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+    L.liinit_comm_unique_id.argtypes = [vp]
+    L.liinit_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.liinit_comm_last_local.argtypes = [vp, _f64]
+    L.liinit_comm_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     for s in SYMBOLS:
         getattr(L, s).restype = getattr(L, s).restype if s == "liinit_last_error" else C.c_int
     _LIB = L
@@ -289,6 +294,34 @@ class LiInitGpu:
         a, b = C.c_float(0), C.c_float(0)
         self._ck(self.L.liinit_last_pass_kernel_times(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    # ---- multi-GPU: the all-reduce of the accumulators and the gathers of per-point results live behind the C-ABI ----
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """ncclGetUniqueId through the library (call on one rank, distribute the 128 bytes)."""
+        L = load()
+        buf = C.create_string_buffer(128)
+        rc = L.liinit_comm_unique_id(buf)
+        if rc != 0:
+            raise LiInitError(rc, (L.liinit_last_error(None) or b"").decode())
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, nranks: int, rank: int):
+        """Collective: attach this context to an nranks-wide communicator. From then on icp_iterate returns the sum over the
+        ranks and every rank works on its slot of the uploaded frame."""
+        assert len(unique_id) == 128
+        buf = C.create_string_buffer(unique_id, 128)
+        self._ck(self.L.liinit_comm_init(self.h, buf, int(nranks), int(rank)))
+
+    def comm_last_local(self):
+        out = np.zeros(160)
+        self._ck(self.L.liinit_comm_last_local(self.h, out))
+        return out
+
+    def comm_info(self):
+        a, b, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        self._ck(self.L.liinit_comm_info(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return dict(nranks=a.value, rank=b.value, shard_lo=c.value, shard_n=d.value)
 
     def knn_index(self) -> int:
         """1 = LIINIT_KNN_BRICKS (lockstep groups over whole bricks), 2 = LIINIT_KNN_CELLS (cell directory, thread per point)."""

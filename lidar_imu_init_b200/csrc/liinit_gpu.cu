@@ -5,6 +5,10 @@
 #include "../../include/liinit_gpu.h"
 
 #include <cuda_runtime.h>
+#ifndef LI_SIMT_EMUL
+#include <dlfcn.h>
+#include <nccl.h>   // types only: the library is dlopen()ed when a communicator is asked for (no link-time dependency)
+#endif
 
 #include <cmath>
 #include <cstdio>
@@ -32,6 +36,50 @@
 namespace {
 
 thread_local std::string g_create_error;
+
+#ifndef LI_SIMT_EMUL
+// NCCL entry points, resolved at run time from libnccl.so.2 (the copy the process already has -- e.g. the one a PyTorch host
+// application loaded -- or the system one). A single-GPU deployment never touches it.
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    std::string err;
+};
+NcclApi* nccl_api() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api.lib ? &api : nullptr;
+    tried = true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+        api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (api.lib) break;
+    }
+    if (!api.lib) {
+        api.err = std::string("dlopen(libnccl.so.2): ") + dlerror();
+        return nullptr;
+    }
+    bool ok = true;
+    auto sym = [&](const char* n) { void* f = dlsym(api.lib, n); if (!f) { ok = false; api.err = std::string("missing NCCL symbol ") + n; } return f; };
+    api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+    api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+    api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+    api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
+    api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+    if (!ok) {
+        dlclose(api.lib);
+        api.lib = nullptr;
+        return nullptr;
+    }
+    return &api;
+}
+#endif
 
 struct Ctx {
     liinit_config cfg;
@@ -76,7 +124,17 @@ struct Ctx {
     float4* d_near_xyz = nullptr;
     unsigned char* d_selected = nullptr;
     float4* d_normvec = nullptr;
-    int scan_n = 0;
+    int scan_n = 0;                // points of the resident scan (the whole frame)
+    // multi-GPU: the map is replicated, every rank holds the whole frame and PROCESSES the shard
+    // [shard_lo, shard_lo + S.n) of it; one all-reduce of the 160-double block per pass, inside liinit_icp_iterate*
+    int nranks = 1, rank = 0;
+    int shard_lo = 0;
+#ifndef LI_SIMT_EMUL
+    ncclComm_t comm = nullptr;
+#endif
+    double* d_acc = nullptr;       // the rank's own accumulator block (N > 1) ...
+    double* d_red = nullptr;       // ... and its sum over the ranks
+    bool state_gathered = true;    // per-point results of the other ranks' shards are present on this device
     bool have_neighbors = false;   // a search pass has filled near_xyz for the resident scan (point copies: map updates do not invalidate them)
     bool scan_fresh = false;   // new scan whose flags / neighbour lists have not been initialised yet (see init_scan_state)
     const float* attached = nullptr;   // device alias of a page-locked host scan not copied yet (liinit_scan_attach_host)
@@ -240,14 +298,36 @@ int init_scan_state(Ctx* c) {
     return LIINIT_OK;
 }
 
+// A new frame of n points is resident (or attached): this rank's shard is [rank * cnt, rank * cnt + cnt) clipped to n with
+// cnt = ceil(n / nranks) -- equal-sized slots, so that the per-point results can be all-gathered in place.
+void set_scan(Ctx* c, int n) {
+    c->scan_n = n;
+    const int cnt = (n + c->nranks - 1) / c->nranks;
+    int lo = c->rank * cnt;
+    if (lo > n) lo = n;
+    int hi = lo + cnt;
+    if (hi > n) hi = n;
+    c->shard_lo = lo;
+    c->S.body = c->d_body + lo;
+    c->S.world = c->d_world + lo;
+    c->S.near_ids = c->d_near_ids + (size_t)lo * 5;
+    c->S.near_xyz = c->d_near_xyz + (size_t)lo * 5;
+    c->S.selected = c->d_selected + lo;
+    c->S.normvec = c->d_normvec + lo;
+    c->S.n = hi - lo;
+    c->have_neighbors = false;
+    c->scan_fresh = true;
+    c->state_gathered = c->nranks == 1;
+}
+
 template <int G>
 void launch_knn_scan(Ctx* c, const PoseD& P) {
-    long long threads = (long long)c->scan_n * G;
+    long long threads = (long long)c->S.n * G;
     int grid = nblk(threads, LI_KNN_THREADS);
     int cap = c->max_blocks * (256 / LI_KNN_THREADS);
     if (grid > cap) grid = cap;
     if (c->attached) {
-        k_knn_scan<G, true><<<grid, LI_KNN_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, c->attached, c->attached_stride);
+        k_knn_scan<G, true><<<grid, LI_KNN_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, c->attached, c->attached_stride);   // (N > 1 never gets here: attach materialises the frame)
         c->attached = nullptr;   // the kernel leaves the packed copy in d_body
     } else {
         k_knn_scan<G, false><<<grid, LI_KNN_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, nullptr, 0);
@@ -271,7 +351,7 @@ void launch_knn_cells_scan_t(Ctx* c, const PoseD& P) {
         }
         return;
     }
-    const int grid = nblk(c->scan_n, LI_CELLS_THREADS);
+    const int grid = nblk(c->S.n, LI_CELLS_THREADS);
     if (c->attached) {
         k_knn_cells_scan<true, MINB, SEARCH><<<grid, LI_CELLS_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, c->attached, c->attached_stride);
         c->attached = nullptr;   // the kernel leaves the packed copy in d_body
@@ -290,7 +370,7 @@ void launch_knn_cells_scan(Ctx* c, const PoseD& P) {
 template <bool IMU, bool SEARCH>
 void launch_plane(Ctx* c, const PoseD& P, double* out) {
     // one wave of 256-thread blocks (2 resident per SM at ~100-130 registers), grid-stride over the scan
-    int grid = nblk(c->scan_n, 256);
+    int grid = nblk(c->S.n, 256);
     if (grid > c->num_sms * 2 * LI_PLANE_WAVES) grid = c->num_sms * 2 * LI_PLANE_WAVES;
     // the id-writing searches hand pool offsets over (gathered here); the warp search wrote the neighbour copies itself
     if (SEARCH && !c->wq) k_icp_plane<IMU, SEARCH, true><<<grid, 256, 0, c->stream>>>(c->M, c->S, P, c->d_partials, c->d_done, out);
@@ -300,7 +380,7 @@ void launch_plane(Ctx* c, const PoseD& P, double* out) {
 // Warp-per-scan-point search (knn_wq.cuh): tiles of LI_WQ_TILE points behind a monotone ticket: every launch consumes ntiles + one
 // terminating ticket per warp, so the next launch's base is known on the host without a reset on the stream.
 void launch_knn_wq(Ctx* c, const PoseD& P) {
-    const int ntiles = (c->scan_n + LI_WQ_TILE - 1) / LI_WQ_TILE;
+    const int ntiles = (c->S.n + LI_WQ_TILE - 1) / LI_WQ_TILE;
     int grid = c->wq_grid;
     const int need = nblk(ntiles, LI_WQ_THREADS / 32);
     if (grid > need) grid = need;
@@ -321,6 +401,8 @@ int run_pass(Ctx* c, const double* R, const double* p, const double* RLI, const 
     if (!search && !c->have_neighbors) return fail(c, LIINIT_ERR_INVALID, "reuse pass before any search pass");
     PoseD P;
     fill_pose(P, R, p, RLI, TLI);
+    double* const final_out = out;
+    if (c->nranks > 1) out = c->d_acc;   // this rank's block; the sum over the ranks goes to final_out below
     CU(cudaEventRecord(c->ev0, c->stream));
     if (search) {
         if (c->wq) launch_knn_wq(c, P);
@@ -347,6 +429,44 @@ int run_pass(Ctx* c, const double* R, const double* p, const double* RLI, const 
     }
     CU(cudaEventRecord(c->ev1, c->stream));
     CU(cudaGetLastError());
+    c->state_gathered = c->nranks == 1;
+#ifndef LI_SIMT_EMUL
+    if (c->nranks > 1) {
+        // the one exchange of the path: sum of [HtH 144 | Htr 12 | res_sq | m | pad 2] over the ranks, on the
+        // context's stream, then to wherever the caller wants the block (page-locked host block or its own device buffer)
+        NcclApi* N = nccl_api();
+        ncclResult_t nr = N->AllReduce(c->d_acc, c->d_red, 160, ncclDouble, ncclSum, c->comm, c->stream);
+        if (nr != ncclSuccess) return fail(c, LIINIT_ERR_CUDA, std::string("ncclAllReduce: ") + N->GetErrorString(nr));
+        CU(cudaMemcpyAsync(final_out, c->d_red, 160 * sizeof(double), cudaMemcpyDefault, c->stream));
+    }
+#endif
+    return LIINIT_OK;
+}
+
+#ifndef LI_SIMT_EMUL
+// In-place all-gather of one per-point array (elem bytes per point) over the equal-sized shard slots.
+int gather_array(Ctx* c, void* base, size_t elem) {
+    NcclApi* N = nccl_api();
+    const int cnt = (c->scan_n + c->nranks - 1) / c->nranks;
+    const size_t bytes = (size_t)cnt * elem;
+    ncclResult_t nr = N->AllGather((const char*)base + (size_t)c->rank * bytes, base, bytes, ncclChar, c->comm, c->stream);
+    if (nr != ncclSuccess) return fail(c, LIINIT_ERR_CUDA, std::string("ncclAllGather: ") + N->GetErrorString(nr));
+    return LIINIT_OK;
+}
+#endif
+
+// N > 1: bring the other ranks' per-point results (Nearest_Points, flags, normals, world points) onto this device. Collective:
+// every rank makes the same call (liinit_map_incremental and the download hooks do).
+int gather_scan_state(Ctx* c) {
+    if (c->state_gathered) return LIINIT_OK;
+#ifndef LI_SIMT_EMUL
+    int r;
+    if ((r = gather_array(c, c->d_near_xyz, 5 * sizeof(float4)))) return r;
+    if ((r = gather_array(c, c->d_selected, 1))) return r;
+    if ((r = gather_array(c, c->d_normvec, sizeof(float4)))) return r;
+    if ((r = gather_array(c, c->d_world, sizeof(float4)))) return r;
+#endif
+    c->state_gathered = true;
     return LIINIT_OK;
 }
 
@@ -504,7 +624,9 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
         CUC(cudaMalloc(&c->d_tmin_idx, 8));
         CUC(cudaMalloc(&c->d_poses, 4096 * LI_POSE6D_DOUBLES * sizeof(double)));
     }
-    int ns = cfg->max_scan_points;
+    int ns = cfg->max_scan_points + 64;   // (+ slack: equal-sized shard slots of a frame cut over up to 64 ranks)
+    CUC(cudaMalloc(&c->d_acc, 160 * sizeof(double)));
+    CUC(cudaMalloc(&c->d_red, 160 * sizeof(double)));
     CUC(cudaMalloc(&c->d_body, (size_t)ns * sizeof(float4)));
     CUC(cudaMalloc(&c->d_world, (size_t)ns * sizeof(float4)));
     CUC(cudaMalloc(&c->d_near_ids, (size_t)batch * 5 * sizeof(int)));
@@ -558,7 +680,10 @@ int liinit_destroy(liinit_ctx* h) {
     cudaFree(c->d_counters); cudaFreeHost(c->h_counters); cudaFree(c->d_stage_raw); cudaFree(c->d_stage_pts);
     cudaFree(c->d_slot_of); cudaFree(c->d_vslot_of); cudaFree(c->d_flag); cudaFree(c->d_ins); cudaFree(c->V.keys); cudaFree(c->V.head); cudaFree(c->d_vg_imin); cudaFree(c->d_vg_block); cudaFree(c->d_vg_misc); cudaFree(c->d_rs_keys); cudaFree(c->d_rs_vals); cudaFree(c->d_rs_hist); cudaFree(c->d_vg_params); cudaFree(c->d_tmin_idx); cudaFree(c->d_poses);
     cudaFree(c->d_body); cudaFree(c->d_world); cudaFree(c->d_near_ids); cudaFree(c->d_near_xyz); cudaFree(c->d_selected); cudaFree(c->d_normvec);
-    cudaFree(c->d_fticket);
+    cudaFree(c->d_fticket); cudaFree(c->d_acc); cudaFree(c->d_red);
+#ifndef LI_SIMT_EMUL
+    if (c->comm) { NcclApi* N = nccl_api(); if (N) N->CommDestroy(c->comm); c->comm = nullptr; }
+#endif
     cudaFree(c->d_partials); cudaFree(c->d_done); cudaFreeHost(c->h_out); cudaFree(c->d_q_d2);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -779,10 +904,7 @@ int liinit_scan_upload(liinit_ctx* h, const float* body, int stride, int n) {
         return fail(c, LIINIT_ERR_INVALID, "stride_floats must be 3, 4 or 12");
     }
     // new scan: no neighbours, nothing selected (Nearest_Points / point_selected_surf start over at iteration 0)
-    c->scan_n = n;
-    c->S.n = n;
-    c->have_neighbors = false;
-    c->scan_fresh = true;
+    set_scan(c, n);
     CU(cudaGetLastError());
     return LIINIT_OK;
 }
@@ -800,10 +922,11 @@ int liinit_scan_attach_host(liinit_ctx* h, const float* pinned_body, int stride,
     }
     c->attached = (const float*)at.devicePointer;
     c->attached_stride = stride;
-    c->scan_n = n;
-    c->S.n = n;
-    c->have_neighbors = false;
-    c->scan_fresh = true;
+    set_scan(c, n);
+    if (c->nranks > 1) {   // every rank needs the whole frame on the device (map_incremental): copy it now
+        materialize_scan(c);
+        CU(cudaGetLastError());
+    }
     return LIINIT_OK;
 }
 
@@ -931,10 +1054,7 @@ int liinit_raw_downsample(liinit_ctx* h, float leaf_size, int* n_down) {
     if (res[7] & 2) return fail(c, LIINIT_ERR_CAPACITY, "voxel grid: more leaves than max_scan_points");
     const int m = res[6];
     if (m <= 0) return fail(c, LIINIT_ERR_INVALID, "voxel grid: no output points");
-    c->scan_n = m;
-    c->S.n = m;
-    c->have_neighbors = false;
-    c->scan_fresh = true;
+    set_scan(c, m);
     c->attached = nullptr;
     if (n_down) *n_down = m;
     return LIINIT_OK;
@@ -997,6 +1117,8 @@ int liinit_scan_download_state(liinit_ctx* h, float* world_xyz, float* near_xyz,
     {
         int r = init_scan_state(c);
         if (r) return r;
+        r = gather_scan_state(c);
+        if (r) return r;
     }
     CU(cudaStreamSynchronize(c->stream));
     if (world_xyz) {
@@ -1037,6 +1159,8 @@ int liinit_scan_download_effect(liinit_ctx* h, float* ori_xyz, float* normvec, i
     {
         int r = init_scan_state(c);
         if (r) return r;
+        r = gather_scan_state(c);
+        if (r) return r;
     }
     CU(cudaStreamSynchronize(c->stream));
     std::vector<unsigned char> sel(n);
@@ -1069,6 +1193,9 @@ int liinit_map_incremental(liinit_ctx* h, const double* R, const double* p, cons
     materialize_scan(c);
     {
         int r = init_scan_state(c);   // no search pass on this scan yet: every point has "no neighbours" (-> PointToAdd)
+        if (r) return r;
+        // N > 1: the Nearest_Points of the other ranks' shards; then every rank applies the WHOLE frame's update to its replica
+        r = gather_scan_state(c);
         if (r) return r;
     }
     PoseD P;
@@ -1119,6 +1246,73 @@ int liinit_last_pass_kernel_times(liinit_ctx* h, float* knn_ms, float* plane_ms)
     }
     if (knn_ms) *knn_ms = a;
     if (plane_ms) *plane_ms = b;
+    return LIINIT_OK;
+}
+
+// ---- multi-GPU -----------------------------------------------------------------------
+int liinit_comm_unique_id(void* id128) {
+    if (!id128) return LIINIT_ERR_INVALID;
+#ifdef LI_SIMT_EMUL
+    return LIINIT_ERR_INVALID;
+#else
+    NcclApi* N = nccl_api();
+    if (!N) {
+        g_create_error = "NCCL is not available (dlopen libnccl.so.2 failed)";
+        return LIINIT_ERR_CUDA;
+    }
+    static_assert(sizeof(ncclUniqueId) == LIINIT_COMM_ID_BYTES, "ncclUniqueId size");
+    ncclUniqueId id;
+    ncclResult_t nr = N->GetUniqueId(&id);
+    if (nr != ncclSuccess) {
+        g_create_error = std::string("ncclGetUniqueId: ") + N->GetErrorString(nr);
+        return LIINIT_ERR_CUDA;
+    }
+    memcpy(id128, &id, sizeof(id));
+    return LIINIT_OK;
+#endif
+}
+
+int liinit_comm_init(liinit_ctx* h, const void* id128, int nranks, int rank) {
+    if (!h || !id128 || nranks < 1 || nranks > 64 || rank < 0 || rank >= nranks) return LIINIT_ERR_INVALID;
+    Ctx* c = &h->c;
+#ifdef LI_SIMT_EMUL
+    return fail(c, LIINIT_ERR_INVALID, "no communicator in the CPU checker");
+#else
+    CU(cudaSetDevice(c->device));
+    if (c->comm) return fail(c, LIINIT_ERR_INVALID, "communicator already attached");
+    NcclApi* N = nccl_api();
+    if (!N) return fail(c, LIINIT_ERR_CUDA, "NCCL is not available (dlopen libnccl.so.2 failed)");
+    CU(cudaStreamSynchronize(c->stream));
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    ncclResult_t nr = N->CommInitRank(&c->comm, nranks, id, rank);
+    if (nr != ncclSuccess) {
+        c->comm = nullptr;
+        return fail(c, LIINIT_ERR_CUDA, std::string("ncclCommInitRank: ") + N->GetErrorString(nr));
+    }
+    c->nranks = nranks;
+    c->rank = rank;
+    if (c->scan_n > 0) set_scan(c, c->scan_n);   // re-cut a frame that is already resident
+    return LIINIT_OK;
+#endif
+}
+
+int liinit_comm_last_local(liinit_ctx* h, double* out160) {
+    if (!h || !out160) return LIINIT_ERR_INVALID;
+    Ctx* c = &h->c;
+    if (c->nranks <= 1) return fail(c, LIINIT_ERR_INVALID, "no communicator attached");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpy(out160, c->d_acc, 160 * sizeof(double), cudaMemcpyDeviceToHost));
+    return LIINIT_OK;
+}
+
+int liinit_comm_info(liinit_ctx* h, int* nranks, int* rank, int* shard_lo, int* shard_n) {
+    if (!h) return LIINIT_ERR_INVALID;
+    if (nranks) *nranks = h->c.nranks;
+    if (rank) *rank = h->c.rank;
+    if (shard_lo) *shard_lo = h->c.shard_lo;
+    if (shard_n) *shard_n = h->c.S.n;
     return LIINIT_OK;
 }
 

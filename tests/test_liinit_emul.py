@@ -407,3 +407,34 @@ def test_emul_downsample_box_membership_is_geometric(oracle_mod, off):
         assert g.map_validnum() == om.validnum()
     assert _same_set(g.map_download(), om.flatten())
     g.close()
+
+
+@pytest.mark.parametrize("index", [BRICKS, WARP])
+def test_emul_nearest_points_are_copies(oracle_mod, index):
+    """Nearest_Points are COPIES of the map points in the reference (laserMapping.cpp:107,980): a reuse pass and map_incremental after
+    the map changed (box delete, Add_Points -- slabs compacted, points moved) must still work on what the last search found. (Round 1
+    kept pool offsets and silently classified against whatever had moved there.)"""
+    c = scenes.make_config("C2", N=3000, M=40000, open_air_frac=0.02)
+    p, gt = c["pose_init"], c["pose_gt"]
+    g = le.EmulGpu(c["ds"], max_map_points=150000, max_scan_points=5000, knn_index=index, hash_capacity_log2=14)
+    om = oracle_mod.OracleMap(c["ds"], _bk(oracle_mod))
+    g.map_build(c["map_xyz"])
+    om.build(c["map_xyz"])
+    g.scan_upload(c["body_xyz"])
+    osc = oracle_mod.OracleScan(c["body_xyz"])
+    g.icp_iterate(p.rot_end, p.pos_end, p.R_LI, p.T_LI, False, True)
+    osc.iterate(om, p.rot_end, p.pos_end, p.R_LI, p.T_LI, False, True)
+    sc = c["scene"]
+    boxes = np.array([[-1, -1, -1, 0.5 * sc.L, sc.W + 1, sc.H + 1]], np.float32)
+    assert g.map_delete_boxes(boxes) == om.delete_boxes(boxes)
+    extra = _world(c["body_xyz"][:800], gt) + np.float32(0.021)
+    assert g.map_add_points(extra, True) == om.add_points(extra, True)
+    # reuse pass on the stored neighbours
+    H, b, m, _ = g.icp_iterate(gt.rot_end, gt.pos_end, gt.R_LI, gt.T_LI, False, False)
+    Ho, bo, mo = osc.iterate(om, gt.rot_end, gt.pos_end, gt.R_LI, gt.T_LI, False, False)
+    assert m == mo and _relerr(H, Ho) <= REL and _relerr(b, bo) <= REL
+    na, nn = g.map_incremental(gt.rot_end, gt.pos_end, gt.R_LI, gt.T_LI, c["ds"])
+    _, oa, on, _ = osc.map_incremental(om, gt.rot_end, gt.pos_end, gt.R_LI, gt.T_LI, c["ds"])
+    assert (na, nn) == (oa, on) and g.map_validnum() == om.validnum()
+    assert _same_set(g.map_download(), om.flatten())
+    g.close()

@@ -19,6 +19,9 @@ def test_shard_bounds_partition():
                 assert lo == prev and hi >= lo
                 prev = hi
             assert prev == n
+            sizes = [sharding.shard_bounds(n, r, world)[1] - sharding.shard_bounds(n, r, world)[0] for r in range(world)]
+            cnt = -(-n // world)
+            assert all(s <= cnt for s in sizes) and all(sharding.shard_bounds(n, r, world)[0] == min(r * cnt, n) for r in range(world))   # equal slots
     with pytest.raises(ValueError):
         sharding.shard_bounds(10, 2, 2)
 

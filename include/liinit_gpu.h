@@ -70,6 +70,11 @@ int liinit_map_add_points(liinit_ctx* h, const float* xyz, int stride_floats, in
  * laserMapping.cpp:260-305 but never passes it on). boxes: nbox x {min x,y,z, max x,y,z} (BoxPointType, ikd_Tree.h:63-66);
  * a point is deleted iff min <= p < max on every axis (:633). deleted: number of points removed. */
 int liinit_map_delete_boxes(liinit_ctx* h, const float* boxes, int nbox, int* deleted);
+/* Housekeeping the kd-tree does by rebuilding (ikd_Tree.cpp:586-606): slabs abandoned by growth and points removed by box deletes
+ * are given back -- live points are re-inserted into a cleared pool, empty bricks leave the hash. Called automatically by
+ * liinit_map_add_points / liinit_map_incremental when the pool allocator is in its last quarter and at least half of it is dead;
+ * the live set is unchanged. */
+int liinit_map_compact(liinit_ctx* h);
 /* KD_TREE::validnum / size (ikd_Tree.cpp:71-88,120-137; laserMapping.cpp:932-933,1142): live points. */
 int liinit_map_validnum(liinit_ctx* h, int* n);
 int liinit_map_size(liinit_ctx* h, int* n);
@@ -139,6 +144,10 @@ int liinit_scan_download_state(liinit_ctx* h, float* world_xyz, float* near_xyz,
  * sizes of PointToAdd / PointNoNeedDownsample. */
 int liinit_map_incremental(liinit_ctx* h, const double rot_end[9], const double pos_end[3], const double R_LI[9],
                            const double T_LI[3], double ds, int flg_EKF_inited, int* n_add, int* n_no_downsample);
+
+/* Test hook: esti_plane<double>(pabcd, points, 0.1) (include/common_lib.h:236-269) of the device for n independent neighbour sets.
+ * nb_xyz [n*15] = five xyz per set (f32), pabcd [n*4] = (nx, ny, nz, d), valid [n]. The very function the plane pass calls. */
+int liinit_debug_esti_plane(liinit_ctx* h, const float* nb_xyz, int n, double* pabcd, unsigned char* valid);
 
 /* multi-GPU (the reference is single-process, its only parallelism the OpenMP loop laserMapping.cpp:964-968) --------
  * One process (or thread) per GPU, one context each. The map is REPLICATED: every rank makes the same map calls with the same data.

@@ -33,11 +33,11 @@ _i32 = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 
 SYMBOLS = [
     "liinit_create", "liinit_destroy", "liinit_last_error", "liinit_set_stream", "liinit_map_build", "liinit_map_add_points", "liinit_map_delete_boxes",
-    "liinit_map_validnum", "liinit_map_size", "liinit_map_download", "liinit_map_nearest_search", "liinit_scan_upload", "liinit_scan_attach_host", "liinit_scan_upload_raw", "liinit_scan_download_body", "liinit_raw_upload", "liinit_raw_undistort_cv", "liinit_raw_undistort_imu",
+    "liinit_map_compact", "liinit_map_validnum", "liinit_map_size", "liinit_map_download", "liinit_map_nearest_search", "liinit_scan_upload", "liinit_scan_attach_host", "liinit_scan_upload_raw", "liinit_scan_download_body", "liinit_raw_upload", "liinit_raw_undistort_cv", "liinit_raw_undistort_imu",
     "liinit_raw_download", "liinit_raw_downsample",
     "liinit_icp_iterate", "liinit_icp_iterate_device", "liinit_scan_download_effect", "liinit_scan_download_state",
     "liinit_map_incremental", "liinit_last_pass_timing", "liinit_last_pass_kernel_times", "liinit_launch_count", "liinit_map_stats", "liinit_knn_index",
-    "liinit_comm_unique_id", "liinit_comm_init", "liinit_comm_info", "liinit_comm_last_local",
+    "liinit_comm_unique_id", "liinit_comm_init", "liinit_comm_info", "liinit_comm_last_local", "liinit_debug_esti_plane",
 ]
 
 
@@ -65,6 +65,7 @@ def load():
     L.liinit_map_build.argtypes = [vp, vp, C.c_int, C.c_int]
     L.liinit_map_add_points.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
     L.liinit_map_delete_boxes.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int)]
+    L.liinit_map_compact.argtypes = [vp]
     L.liinit_map_validnum.argtypes = [vp, C.POINTER(C.c_int)]
     L.liinit_map_size.argtypes = [vp, C.POINTER(C.c_int)]
     L.liinit_map_download.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int)]
@@ -90,6 +91,7 @@ def load():
     L.liinit_map_stats.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     L.liinit_comm_unique_id.argtypes = [vp]
     L.liinit_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.liinit_debug_esti_plane.argtypes = [vp, vp, C.c_int, vp, vp]
     L.liinit_comm_last_local.argtypes = [vp, _f64]
     L.liinit_comm_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     for s in SYMBOLS:
@@ -163,9 +165,17 @@ class LiInitGpu:
         self._ck(self.L.liinit_map_delete_boxes(self.h, _ptr(b), len(b), C.byref(d)))
         return d.value
 
+    def map_compact(self):
+        self._ck(self.L.liinit_map_compact(self.h))
+
     def map_validnum(self) -> int:
         n = C.c_int(0)
         self._ck(self.L.liinit_map_validnum(self.h, C.byref(n)))
+        return n.value
+
+    def map_size(self) -> int:
+        n = C.c_int(0)
+        self._ck(self.L.liinit_map_size(self.h, C.byref(n)))
         return n.value
 
     def map_download(self):
@@ -294,6 +304,14 @@ class LiInitGpu:
         a, b = C.c_float(0), C.c_float(0)
         self._ck(self.L.liinit_last_pass_kernel_times(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def debug_esti_plane(self, nb):
+        """esti_plane of the device for neighbour sets nb [n, 5, 3] -> (pabcd [n, 4] f64, valid [n] bool)"""
+        a = np.ascontiguousarray(nb, np.float32).reshape(-1, 15)
+        out = np.zeros((len(a), 4))
+        ok = np.zeros(len(a), np.uint8)
+        self._ck(self.L.liinit_debug_esti_plane(self.h, _ptr(a), len(a), _ptr(out), _ptr(ok)))
+        return out, ok.astype(bool)
 
     # ---- multi-GPU: the all-reduce of the accumulators and the gathers of per-point results live behind the C-ABI ----
     @staticmethod

@@ -208,11 +208,26 @@ int liinit_scan_update(liinit_ctx* h, liinit_state* state, int max_iter, int imu
     return LIINIT_OK;
 }
 
+// Exp(ang_vel, dt) (so3_math.h:39-59): gated on the angular VELOCITY (|w| > 1e-7), not on the angle like Exp(v1, v2, v3) (:61-80,
+// |v| > 1e-5) -- for 1e-7 < |w| < 1e-5 / dt the two differ (identity vs a small rotation). The un-distortion kernel uses the same
+// form (li_so3_exp_dt, undistort_kernels.cuh).
+static void so3_exp_dt(const double w[3], double dt, double R[9]) {
+    const double n = std::sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+    for (int i = 0; i < 9; i++) R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    if (!(n > 0.0000001)) return;
+    const double a[3] = {w[0] / n, w[1] / n, w[2] / n};
+    const double K[9] = {0, -a[2], a[1], a[2], 0, -a[0], -a[1], a[0], 0};
+    double KK[9];
+    mul33(K, K, KK);
+    const double ang = n * dt, sn = std::sin(ang), cs = 1.0 - std::cos(ang);
+    for (int i = 0; i < 9; i++) R[i] += sn * K[i] + cs * KK[i];
+}
+
 void liinit_propagate_cv(liinit_state* s, double dt, const double* cov_gyr_scale, const double* cov_acc_scale) {
     // F is the identity except three 3x3 blocks, so F cov F^T touches rows / columns 0:6 only:
     //   rows 0:3 <- E rows 0:3 + dt rows 15:18 ; rows 3:6 <- rows 3:6 + dt rows 12:15 ; then the same on the columns.
-    double w[3] = {-s->bias_g[0] * dt, -s->bias_g[1] * dt, -s->bias_g[2] * dt}, E[9];
-    liinit_so3_exp(w, E);
+    double E[9];
+    so3_exp_dt(s->bias_g, -dt, E);   // Exp(state_inout.bias_g, -dt) (IMU_Processing.hpp:226)
     std::vector<double> T(D * D);
     double* P = s->cov;
     for (int c = 0; c < D; c++) {
@@ -231,8 +246,8 @@ void liinit_propagate_cv(liinit_state* s, double dt, const double* cov_gyr_scale
         P[(15 + i) * D + 15 + i] += cov_gyr_scale[i] * dt * dt;
         P[(12 + i) * D + 12 + i] += cov_acc_scale[i] * dt * dt;
     }
-    double wf[3] = {s->bias_g[0] * dt, s->bias_g[1] * dt, s->bias_g[2] * dt}, Ef[9], R[9];
-    liinit_so3_exp(wf, Ef);
+    double Ef[9], R[9];
+    so3_exp_dt(s->bias_g, dt, Ef);   // Exp(state_inout.bias_g, dt) (IMU_Processing.hpp:239)
     mul33(s->rot_end, Ef, R);
     std::memcpy(s->rot_end, R, sizeof(R));
     for (int i = 0; i < 3; i++) s->pos_end[i] += s->vel_end[i] * dt;

@@ -60,7 +60,7 @@ __device__ __forceinline__ void lsq5x3(double (&A)[5][3], double (&x)[3]) {
                 p = j;
             }
         }
-        if (best < thresh) {
+        if (best < thresh * (double)(5 - k)) {   // Eigen: biggest_col_sq_norm < threshold_helper * (rows - k)
             rank = k;
             continue;
         }
@@ -133,6 +133,44 @@ __device__ __forceinline__ void lsq5x3(double (&A)[5][3], double (&x)[3]) {
     x[2] = (p0 == 2) ? y0 : ((p1 == 2) ? y1 : y2);
 }
 
+// esti_plane<double>(pca_result, point, 0.1f) (common_lib.h:236-269): plane (pa, pb, pc, pd) through the five neighbours
+// (uncentred f32 -> f64 rows, A x = -1), unit normal; valid iff every neighbour lies within 0.1 of it.
+__device__ __forceinline__ bool esti_plane_d(const float4 (&nb)[5], double& pa, double& pb, double& pc, double& pd) {
+    double A[5][3];
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+        A[j][0] = (double)nb[j].x;
+        A[j][1] = (double)nb[j].y;
+        A[j][2] = (double)nb[j].z;
+    }
+    double nv[3];
+    lsq5x3(A, nv);
+    double nn = sqrt(nv[0] * nv[0] + nv[1] * nv[1] + nv[2] * nv[2]);
+    pa = nv[0] / nn; pb = nv[1] / nn; pc = nv[2] / nn; pd = 1.0 / nn;
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+        double e = fabs(pa * (double)nb[j].x + pb * (double)nb[j].y + pc * (double)nb[j].z + pd);
+        if (!(e <= 0.1)) ok = false;    // reference: reject if > threshold (NaN also rejects via !(<=)... see note)
+    }
+    // note: the reference tests `fabs(..) > threshold -> return false`; a NaN plane passes that test there and is
+    // rejected later by `s > 0.9` being false. Both forms reject NaN; finite cases are identical.
+    return ok;
+}
+
+// test hook (liinit_debug_esti_plane): esti_plane for n independent neighbour sets
+__global__ void k_debug_esti_plane(const float* __restrict__ nb_xyz, int n, double* __restrict__ pabcd, unsigned char* __restrict__ valid) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 nb[5];
+#pragma unroll
+    for (int j = 0; j < 5; j++) nb[j] = make_float4(nb_xyz[(size_t)i * 15 + 3 * j], nb_xyz[(size_t)i * 15 + 3 * j + 1], nb_xyz[(size_t)i * 15 + 3 * j + 2], 1.f);
+    double pa, pb, pc, pd;
+    const bool ok = esti_plane_d(nb, pa, pb, pc, pd);
+    pabcd[(size_t)i * 4] = pa; pabcd[(size_t)i * 4 + 1] = pb; pabcd[(size_t)i * 4 + 2] = pc; pabcd[(size_t)i * 4 + 3] = pd;
+    valid[i] = ok ? 1 : 0;
+}
+
 // Number of accumulators: upper triangle of HtH + Htr + sum r^2 + count, padded to a multiple of 32.
 template <bool IMU>
 struct AccLayout {
@@ -153,26 +191,8 @@ __device__ __forceinline__ bool plane_and_row(const PoseD& P, float bxf, float b
 #pragma unroll
     for (int i = 0; i < L::NC; i++) row[i] = 0.0;
     r = 0.0;
-    double A[5][3];
-#pragma unroll
-    for (int j = 0; j < 5; j++) {
-        A[j][0] = (double)nb[j].x;
-        A[j][1] = (double)nb[j].y;
-        A[j][2] = (double)nb[j].z;
-    }
-    double nv[3];
-    lsq5x3(A, nv);
-    double nn = sqrt(nv[0] * nv[0] + nv[1] * nv[1] + nv[2] * nv[2]);
-    double pa = nv[0] / nn, pb = nv[1] / nn, pc = nv[2] / nn, pd = 1.0 / nn;
-    bool ok = true;
-#pragma unroll
-    for (int j = 0; j < 5; j++) {
-        double e = fabs(pa * (double)nb[j].x + pb * (double)nb[j].y + pc * (double)nb[j].z + pd);
-        if (!(e <= 0.1)) ok = false;    // reference: reject if > threshold (NaN also rejects via !(<=)... see note)
-    }
-    // note: the reference tests `fabs(..) > threshold -> return false`; a NaN plane passes that test there and is
-    // rejected later by `s > 0.9` being false. Both forms reject NaN; finite cases are identical.
-    if (!ok) return false;
+    double pa, pb, pc, pd;
+    if (!esti_plane_d(nb, pa, pb, pc, pd)) return false;
     float pd2 = (float)(pa * (double)wx + pb * (double)wy + pc * (double)wz + pd);
     double bx = (double)bxf, by = (double)byf, bz = (double)bzf;
     double pn = sqrt(bx * bx + by * by + bz * bz);

@@ -96,6 +96,7 @@ struct Ctx {
     unsigned hash_slots = 0;
     int* d_counters = nullptr;
     int* h_counters = nullptr;   // pinned
+    unsigned long long* h_pool_top = nullptr;   // pinned: the bump allocator's value after the last map update
     // staging
     float* d_stage_raw = nullptr;   // strided host layout
     size_t stage_raw_floats = 0;
@@ -201,14 +202,21 @@ int stage_points(Ctx* c, const float* xyz, int stride, int n) {
 
 int fetch_counters(Ctx* c) {
     CU(cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(int) * CNT_COUNT, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->h_pool_top, c->M.pool_top, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return LIINIT_OK;
 }
 
+// Capacity errors are reported ONCE, to the call that hit them: the bits are cleared on the device so that the calls after a box
+// delete / a compaction are judged on their own (they used to stay set until the next Build).
 int check_map_err(Ctx* c) {
     int e = c->h_counters[CNT_ERR];
+    if (e & (ERR_HASH_FULL | ERR_POOL_FULL)) {
+        cudaMemsetAsync(c->d_counters + CNT_ERR, 0, sizeof(int), c->stream);
+        c->h_counters[CNT_ERR] = 0;
+    }
     if (e & ERR_HASH_FULL) return fail(c, LIINIT_ERR_CAPACITY, "brick hash table full (raise hash_capacity_log2 / max_map_points)");
-    if (e & ERR_POOL_FULL) return fail(c, LIINIT_ERR_CAPACITY, "map point pool full (raise max_map_points)");
+    if (e & ERR_POOL_FULL) return fail(c, LIINIT_ERR_CAPACITY, "map point pool full (raise max_map_points, or liinit_map_compact after deletes)");
     return LIINIT_OK;
 }
 
@@ -600,6 +608,8 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
     CUC(cudaMalloc(&c->d_counters, sizeof(int) * CNT_COUNT));
     M.counters = c->d_counters;
     CUC(cudaMallocHost(&c->h_counters, sizeof(int) * CNT_COUNT));
+    CUC(cudaMallocHost(&c->h_pool_top, sizeof(unsigned long long)));
+    *c->h_pool_top = 0;
     c->stage_raw_floats = (size_t)batch * 12;
     CUC(cudaMalloc(&c->d_stage_raw, c->stage_raw_floats * 4));
     CUC(cudaMalloc(&c->d_stage_pts, (size_t)batch * sizeof(float4)));
@@ -677,7 +687,7 @@ int liinit_destroy(liinit_ctx* h) {
     cudaSetDevice(c->device);
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     cudaFree(c->M.ent); cudaFree(c->M.aux); cudaFree(c->M.pool); cudaFree(c->M.pool_top); cudaFree(c->M.touched_list); cudaFree(c->M.cocc); cudaFree(c->M.cdir); cudaFree(c->M.sb_keys); cudaFree(c->M.sb_occ); cudaFree(c->d_ticket);
-    cudaFree(c->d_counters); cudaFreeHost(c->h_counters); cudaFree(c->d_stage_raw); cudaFree(c->d_stage_pts);
+    cudaFree(c->d_counters); cudaFreeHost(c->h_counters); cudaFreeHost(c->h_pool_top); cudaFree(c->d_stage_raw); cudaFree(c->d_stage_pts);
     cudaFree(c->d_slot_of); cudaFree(c->d_vslot_of); cudaFree(c->d_flag); cudaFree(c->d_ins); cudaFree(c->V.keys); cudaFree(c->V.head); cudaFree(c->d_vg_imin); cudaFree(c->d_vg_block); cudaFree(c->d_vg_misc); cudaFree(c->d_rs_keys); cudaFree(c->d_rs_vals); cudaFree(c->d_rs_hist); cudaFree(c->d_vg_params); cudaFree(c->d_tmin_idx); cudaFree(c->d_poses);
     cudaFree(c->d_body); cudaFree(c->d_world); cudaFree(c->d_near_ids); cudaFree(c->d_near_xyz); cudaFree(c->d_selected); cudaFree(c->d_normvec);
     cudaFree(c->d_fticket); cudaFree(c->d_acc); cudaFree(c->d_red);
@@ -731,10 +741,75 @@ int liinit_map_build(liinit_ctx* h, const float* xyz, int stride, int n) {
     return check_map_err(c);
 }
 
+}  // extern "C"
+
+namespace {
+// Slabs only ever grow from the bump allocator and a brick emptied by deletes keeps its slab and its hash slot: a sliding local map
+// (Add_Points ahead, Delete_Point_Boxes behind) would run the pool dry although few points are alive. Compaction = flatten the live
+// points, clear hash + pool, re-insert them (the Build path): every brick gets one tight slab, empty bricks disappear.
+int compact_map(Ctx* c) {
+    int r = fetch_counters(c);
+    if (r) return r;
+    const int live = c->h_counters[CNT_LIVE];
+    float4* d_tmp = nullptr;
+    int* d_n = nullptr;
+    if (live > 0) {
+        CU(cudaMalloc(&d_tmp, (size_t)live * sizeof(float4)));
+        if (cudaMalloc(&d_n, sizeof(int)) != cudaSuccess) {
+            cudaFree(d_tmp);
+            return fail(c, LIINIT_ERR_CUDA, "cudaMalloc (compact)");
+        }
+        cudaMemsetAsync(d_n, 0, sizeof(int), c->stream);
+        k_map_flatten4<<<nblk((long long)c->hash_slots * 32, 256), 256, 0, c->stream>>>(c->M, c->hash_slots, d_tmp, live, d_n);
+        c->launches++;
+    }
+    cudaMemsetAsync(c->d_counters, 0, sizeof(int) * CNT_COUNT, c->stream);
+    cudaMemsetAsync(c->M.pool_top, 0, sizeof(unsigned long long), c->stream);
+    k_map_clear<<<nblk(c->hash_slots, 256), 256, 0, c->stream>>>(c->M.ent, c->M.aux, c->hash_slots);
+    c->launches++;
+    if (c->cells) {
+        k_sb_clear<<<nblk(c->hash_slots, 256), 256, 0, c->stream>>>(c->M);
+        c->launches++;
+    }
+    r = LIINIT_OK;
+    for (long long off = 0; off < live && r == LIINIT_OK; off += c->stage_pts_cap) {
+        const int m = (int)((live - off < c->stage_pts_cap) ? (live - off) : c->stage_pts_cap);
+        r = plain_insert(c, d_tmp + off, m, nullptr, 0);
+    }
+    if (r == LIINIT_OK) r = fetch_counters(c);
+    cudaFree(d_tmp);
+    cudaFree(d_n);
+    if (r) return r;
+    return check_map_err(c);
+}
+
+// Before an update of up to `incoming` points: compact when the allocator is in its last quarter and at least half of what it
+// handed out is dead (abandoned slabs, deleted points).
+int maybe_compact(Ctx* c, long long incoming) {
+    const unsigned long long top = *c->h_pool_top, cap = c->M.pool_cap;
+    const long long live = c->h_counters[CNT_LIVE];
+    if (top + (unsigned long long)(3 * incoming) + (1ull << 16) > cap - cap / 4 && (unsigned long long)(2 * live) < top) return compact_map(c);
+    return LIINIT_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int liinit_map_compact(liinit_ctx* h) {
+    if (!h) return LIINIT_ERR_INVALID;
+    Ctx* c = &h->c;
+    CU(cudaSetDevice(c->device));
+    return compact_map(c);
+}
+
 int liinit_map_add_points(liinit_ctx* h, const float* xyz, int stride, int n, int downsample_on, int* added) {
     if (!h || (!xyz && n > 0) || n < 0) return LIINIT_ERR_INVALID;
     Ctx* c = &h->c;
     CU(cudaSetDevice(c->device));
+    {
+        int r = maybe_compact(c, n);
+        if (r) return r;
+    }
     int total = 0;
     for (long long off = 0; off < n; off += c->stage_pts_cap) {
         int m = (int)((n - off < c->stage_pts_cap) ? (n - off) : c->stage_pts_cap);
@@ -1198,6 +1273,10 @@ int liinit_map_incremental(liinit_ctx* h, const double* R, const double* p, cons
         r = gather_scan_state(c);
         if (r) return r;
     }
+    {
+        int r = maybe_compact(c, n);
+        if (r) return r;
+    }
     PoseD P;
     fill_pose(P, R, p, RLI, TLI);
     static const int zeros[2] = {0, 0};
@@ -1247,6 +1326,31 @@ int liinit_last_pass_kernel_times(liinit_ctx* h, float* knn_ms, float* plane_ms)
     if (knn_ms) *knn_ms = a;
     if (plane_ms) *plane_ms = b;
     return LIINIT_OK;
+}
+
+int liinit_debug_esti_plane(liinit_ctx* h, const float* nb_xyz, int n, double* pabcd, unsigned char* valid) {
+    if (!h || !nb_xyz || !pabcd || !valid || n < 0) return LIINIT_ERR_INVALID;
+    Ctx* c = &h->c;
+    CU(cudaSetDevice(c->device));
+    if (n == 0) return LIINIT_OK;
+    float* d_in = nullptr;
+    double* d_out = nullptr;
+    unsigned char* d_ok = nullptr;
+    int rc = LIINIT_OK;
+    if (cudaMalloc(&d_in, (size_t)n * 15 * 4) != cudaSuccess || cudaMalloc(&d_out, (size_t)n * 32) != cudaSuccess || cudaMalloc(&d_ok, (size_t)n) != cudaSuccess) {
+        rc = fail(c, LIINIT_ERR_CUDA, "cudaMalloc (debug_esti_plane)");
+    } else {
+        cudaMemcpyAsync(d_in, nb_xyz, (size_t)n * 15 * 4, cudaMemcpyHostToDevice, c->stream);
+        k_debug_esti_plane<<<nblk(n, 128), 128, 0, c->stream>>>(d_in, n, d_out, d_ok);
+        c->launches++;
+        cudaMemcpyAsync(pabcd, d_out, (size_t)n * 32, cudaMemcpyDeviceToHost, c->stream);
+        cudaMemcpyAsync(valid, d_ok, (size_t)n, cudaMemcpyDeviceToHost, c->stream);
+        cudaError_t e = cudaStreamSynchronize(c->stream);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) rc = fail(c, LIINIT_ERR_CUDA, std::string("debug_esti_plane: ") + cudaGetErrorString(e));
+    }
+    cudaFree(d_in); cudaFree(d_out); cudaFree(d_ok);
+    return rc;
 }
 
 // ---- multi-GPU -----------------------------------------------------------------------

@@ -142,6 +142,7 @@ __global__ void k_ins_reserve(MapDev M) {
             if (lane == 0) {
                 atomicOr(&M.counters[CNT_ERR], ERR_POOL_FULL);
                 M.aux[s].y = 0u;   // nothing will be appended to this brick
+                atomicAdd(M.pool_top, (unsigned long long)(-(long long)ncap));   // give the failed reservation back: later, smaller ones may still fit
             }
             continue;
         }
@@ -511,6 +512,26 @@ __global__ void k_map_flatten(MapDev M, unsigned slots, float* __restrict__ out,
             out[3 * (size_t)o] = q.x;
             out[3 * (size_t)o + 1] = q.y;
             out[3 * (size_t)o + 2] = q.z;
+        }
+    }
+}
+
+// live points as float4 {x, y, z, 0} (liinit_map_compact re-inserts them into a cleared pool)
+__global__ void k_map_flatten4(MapDev M, unsigned slots, float4* __restrict__ out, int cap, int* __restrict__ out_n) {
+    int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if ((unsigned)w >= slots) return;
+    uint4 e = M.ent[w];
+    unsigned long long k = (unsigned long long)e.x | ((unsigned long long)e.y << 32);
+    if (k == LI_EMPTY_KEY || e.w == 0u) return;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(out_n, (int)e.w);
+    base = __shfl_sync(LI_FULL, base, 0);
+    for (unsigned j = lane; j < e.w; j += 32) {
+        int o = base + (int)j;
+        if (o < cap) {
+            float4 q = M.pool[(size_t)e.z + j];
+            q.w = 0.f;
+            out[o] = q;
         }
     }
 }

@@ -31,6 +31,7 @@ class LidarOdometry:
         self.data_accum_finished = False
         self.move_start_time = 0.0
         self.stats = None
+        self.imu_en = False
 
     def push_imu(self, omg, acc, t, mean_acc_norm=9.81):
         """imu_cbk in LO mode (:428-430)."""
@@ -51,13 +52,12 @@ class LidarOdometry:
         if not self.map_ready:                              # :921-931
             if len(body_xyz) > 5:
                 world = (R @ (RLI @ body_xyz.T.astype(np.float64) + TLI[:, None]) + p[:, None]).T.astype(np.float32)
-                self.g.map_build(world)
+                self._map_build(world)
                 self.map_ready = True
             return self.state
-        self.g.scan_upload(body_xyz)
-        self.state, self.stats = host.scan_update(self.g, self.state, self.max_iteration, False)   # :936-1134
+        self.state, self.stats = self._scan_update(body_xyz, self.state)   # :936-1134
         R, p, RLI, TLI = host.state_pose(self.state)
-        self.g.map_incremental(R, p, RLI, TLI, self.ds)     # :1140
+        self._map_incremental(R, p, RLI, TLI)               # :1140
         if not self.data_accum_start and np.linalg.norm(p) > 0.05:   # :1145-1149
             self.data_accum_start = True
             self.move_start_time = t_end
@@ -68,6 +68,32 @@ class LidarOdometry:
             ok, _ = self.calib.data_sufficiency(self.frame_num, bias_g, self.orig_odom_freq, self.cut_frame_num)
             self.data_accum_finished = ok
         return self.state
+
+    # the three calls into the hot path; a test substitutes the CPU oracle here to drive the SAME loop from the other side
+    def _map_build(self, world):
+        self.g.map_build(world)
+
+    def _scan_update(self, body_xyz, state):
+        self.g.scan_upload(body_xyz)
+        return host.scan_update(self.g, state, self.max_iteration, self.imu_en)
+
+    def _map_incremental(self, R, p, RLI, TLI):
+        self.g.map_incremental(R, p, RLI, TLI, self.ds)
+
+    def hand_over(self, res):
+        """laserMapping.cpp:1198-1222 after LI_Initialization: the pose is re-expressed in the IMU frame with the calibrated extrinsic,
+        gravity / biases are taken over and the filter continues with the 12-column Jacobian (imu_en = true)."""
+        R, p, _, _ = host.state_pose(self.state)
+        R_LI, T_LI = np.asarray(res["R_LI"], float).reshape(3, 3), np.asarray(res["T_LI"], float)
+        s = self.state
+        s[12:21] = R_LI.reshape(9)                          # offset_R_L_I = Init_LI->get_R_LI() (:1204)
+        s[21:24] = T_LI                                     # offset_T_L_I (:1205)
+        s[9:12] = p - R @ R_LI.T @ T_LI                     # pos_end = -rot_end * R_LI^T * T_LI + pos_end (:1206)
+        s[0:9] = (R @ R_LI.T).reshape(9)                    # rot_end = rot_end * R_LI^T (:1207)
+        s[33:36] = np.asarray(res["grav_L0"], float)        # gravity (:1208)
+        s[27:30] = np.asarray(res["gyro_bias"], float)      # bias_g (:1209)
+        s[30:33] = np.asarray(res["acc_bias"], float)       # bias_a (:1210)
+        self.imu_en = True
 
     def initialize(self, timediff_imu_wrt_lidar: float = 0.0):
         """LI_Initialization on what has been accumulated (:1198); returns the calibration dict of calib.LiCalib."""

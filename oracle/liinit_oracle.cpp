@@ -536,7 +536,7 @@ static void lsq_5x3_colpiv(const double Ain[5][3], const double bin[5], double x
             cn[j] = s;
             if (s > best) { best = s; p = j; }
         }
-        if (best < thresh) { rank = k; break; }
+        if (best < thresh * (double)(5 - k)) { rank = k; break; }   // Eigen: biggest_col_sq_norm < threshold_helper * (rows - k)
         if (p != k) {
             for (int i = 0; i < 5; i++) std::swap(A[i][k], A[i][p]);
             std::swap(perm[k], perm[p]);

@@ -41,6 +41,8 @@ def load():
         L.liinit_map_build.argtypes = [vp, vp, C.c_int, C.c_int]
         L.liinit_map_add_points.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
         L.liinit_map_delete_boxes.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int)]
+        L.liinit_map_compact.argtypes = [vp]
+        L.liinit_map_stats.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
         L.liinit_map_validnum.argtypes = [vp, C.POINTER(C.c_int)]
         L.liinit_map_download.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int)]
         L.liinit_map_nearest_search.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, vp, vp, vp]
@@ -58,6 +60,7 @@ def load():
         L.liinit_raw_undistort_imu.argtypes = [vp, _f64, C.c_int, _f64, _f64, _f64, _f64]
         L.liinit_raw_download.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int)]
         L.liinit_raw_downsample.argtypes = [vp, C.c_float, C.POINTER(C.c_int)]
+        L.liinit_debug_esti_plane.argtypes = [vp, vp, C.c_int, vp, vp]
         _L = L
     return _L
 
@@ -140,6 +143,21 @@ class EmulGpu:
         m = C.c_int()
         self._ck(self.L.liinit_map_download(self.h, out.ctypes.data_as(vp), len(out), C.byref(m)))
         return out[:m.value]
+
+    def map_compact(self):
+        self._ck(self.L.liinit_map_compact(self.h))
+
+    def map_stats(self):
+        b, sl, pu, pc = C.c_int(0), C.c_int(0), C.c_longlong(0), C.c_longlong(0)
+        self._ck(self.L.liinit_map_stats(self.h, C.byref(b), C.byref(sl), C.byref(pu), C.byref(pc)))
+        return dict(bricks=b.value, hash_slots=sl.value, pool_used=pu.value, pool_cap=pc.value)
+
+    def debug_esti_plane(self, nb):
+        a = np.ascontiguousarray(nb, np.float32).reshape(-1, 15)
+        out = np.zeros((len(a), 4))
+        ok = np.zeros(len(a), np.uint8)
+        self._ck(self.L.liinit_debug_esti_plane(self.h, a.ctypes.data_as(vp), len(a), out.ctypes.data_as(vp), ok.ctypes.data_as(vp)))
+        return out, ok.astype(bool)
 
     def nearest_search(self, q):
         q = _pts(q)

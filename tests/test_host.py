@@ -93,3 +93,25 @@ def test_propagate_cv_matches_dense_formula():
     assert np.allclose(o[0:9].reshape(3, 3), s[0:9].reshape(3, 3) @ so3_exp(s[27:30] * dt), atol=1e-15)
     assert np.allclose(o[9:12], s[9:12] + s[24:27] * dt)
     assert np.array_equal(o[12:36], s[12:36])
+
+
+def test_propagate_cv_small_angular_velocity_follows_exp_of_velocity():
+    """Exp(ang_vel, dt) (so3_math.h:39-59) is gated on |ang_vel| > 1e-7, not on the angle: with |bias_g| = 5e-5 rad/s and dt = 0.02 s the
+    angle 1e-6 is below the 1e-5 gate of Exp(v1, v2, v3) but the reference still rotates (IMU_Processing.hpp:225-226,239)."""
+    from lidar_imu_init_b200 import _build, host
+    _build.build_host()
+    s = host.state_init()
+    w = np.array([3e-5, -4e-5, 0.0])
+    s[27:30] = w
+    dt = 0.02
+    out = host.propagate_cv(s, dt)
+    R = out[0:9].reshape(3, 3)
+    ang = np.linalg.norm(w) * dt
+    k = w / np.linalg.norm(w)
+    K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    want = np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * K @ K
+    assert not np.array_equal(R, np.eye(3))
+    assert np.abs(R - want).max() < 1e-15
+    # below the velocity gate: identity
+    s[27:30] = np.array([5e-8, 0.0, 0.0])
+    assert np.array_equal(host.propagate_cv(s, dt)[0:9].reshape(3, 3), np.eye(3))

@@ -438,3 +438,45 @@ def test_emul_nearest_points_are_copies(oracle_mod, index):
     assert (na, nn) == (oa, on) and g.map_validnum() == om.validnum()
     assert _same_set(g.map_download(), om.flatten())
     g.close()
+
+
+def test_emul_map_compact_gives_dead_storage_back(oracle_mod):
+    """liinit_map_compact after growth + box deletes: abandoned slabs and emptied bricks are released (pool_used, bricks shrink), the
+    live set and every search stay what the verbatim ikd-Tree has; capacity errors are reported once, not forever."""
+    c = scenes.make_config("C2", N=2500, M=40000, open_air_frac=0.0)
+    gt = c["pose_gt"]
+    g = le.EmulGpu(c["ds"], max_map_points=60000, max_scan_points=4000, hash_capacity_log2=14)
+    om = oracle_mod.OracleMap(c["ds"], _bk(oracle_mod))
+    g.map_build(c["map_xyz"][:20000])
+    om.build(c["map_xyz"][:20000])
+    for lo in range(20000, 40000, 5000):           # growth: slabs are re-allocated, old ones abandoned
+        g.map_add_points(c["map_xyz"][lo:lo + 5000], False)
+        om.add_points(c["map_xyz"][lo:lo + 5000], False)
+        assert g.map_validnum() == om.validnum()
+    sc = c["scene"]
+    boxes = np.array([[-1, -1, -1, 0.6 * sc.L, sc.W + 1, sc.H + 1]], np.float32)
+    assert g.map_delete_boxes(boxes) == om.delete_boxes(boxes)
+    before = g.map_stats()
+    live = g.map_validnum()
+    g.map_compact()
+    after = g.map_stats()
+    assert g.map_validnum() == live == om.validnum()
+    assert after["pool_used"] < 0.6 * before["pool_used"] and after["bricks"] < before["bricks"]
+    assert after["pool_used"] < 2.2 * live + 16 * after["bricks"]
+    assert _same_set(g.map_download(), om.flatten())
+    q = _world(c["body_xyz"], gt)
+    gx, gd, gc = g.nearest_search(q)
+    ox, od, oc, _ = om.knn(q)
+    assert np.array_equal(gc, oc) and np.array_equal(gd, od) and np.array_equal(gx, ox)
+    new = q[:1500] + np.float32(0.017)
+    assert g.map_add_points(new, True) == om.add_points(new, True) and g.map_validnum() == om.validnum()
+    g.close()
+    # a capacity error is reported to the call that hit it and does not stick
+    g = le.EmulGpu(c["ds"], max_map_points=3000, max_scan_points=100, hash_capacity_log2=10)   # 1024 hash slots
+    far = (np.arange(3000, dtype=np.float32)[:, None] * np.float32(7.0)) * np.ones((1, 3), np.float32)   # one brick per point
+    with pytest.raises(le.EmulError):
+        g.map_build(far)
+    g.map_build(c["map_xyz"][:500])
+    assert g.map_validnum() == 500
+    assert g.map_add_points(c["map_xyz"][500:600], False) == 100
+    g.close()

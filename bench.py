@@ -52,13 +52,11 @@ def emit(obj):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the search kernel on C2 (ncu --set full, cold cache), per index
-NCU_DRAM_BYTES_KNN = {1: 117_762_816, 2: 141_602_560, 5: 115_708_928}
-NCU_DRAM_SOURCE = {1: "profiles/r01_ncu_full_final_metrics.txt", 2: "profiles/r01_cells/ncu_full_stream_final_metrics.txt",
-                   5: "profiles/r02/ncu_full_wq_v1_metrics.txt"}
+NCU_DRAM_BYTES_KNN = {1: 117_762_816, 2: 141_602_560}
+NCU_DRAM_SOURCE = {1: "profiles/r01_ncu_full_final_metrics.txt", 2: "profiles/r01_cells/ncu_full_stream_final_metrics.txt"}
 KNN_KERNEL = {1: "k_knn_scan (5-NN search on whole bricks, lockstep lane groups; dominant kernel of the pass)",
-              2: "k_knn_cells_scan (5-NN search on the per-brick cell directory, one scan point per thread; dominant kernel of the pass)",
-              5: "k_knn_wq (5-NN search on whole bricks, one warp per scan point; dominant kernel of the pass)"}
-KNN_NAME = {1: "bricks", 2: "cells", 5: "warp"}
+              2: "k_knn_cells_scan (5-NN search on the per-brick cell directory, one scan point per thread; dominant kernel of the pass)"}
+KNN_NAME = {1: "bricks", 2: "cells"}
 ALG_BYTES_PER_POINT = 132  # 16 body + 80 neighbours + 16 normal/residual + 20 ids
 UNIT = "points*iters/s"
 
@@ -431,7 +429,7 @@ def run_gpu(args, rank, world, local_rank):
                     "parallelism": "1 GPU" if world == 1 else (f"{world} GPUs, map replicated, frame of {NF} points cut into {world} slots by the library, "
                                                                "accumulators summed over the ranks inside liinit_icp_iterate (NCCL)"),
                     "l2": "flushed between timed steps (256 MiB memset outside the events)", "knn_index": KNN_NAME[kidx],
-                    "knn_group_lanes": (args.group or 4) if kidx == 1 else None, "brick_cells_log2": args.brick or 3,
+                    "knn_group_lanes": (args.group or "auto (by frame size: 4 lanes beyond 170k points per GPU)") if kidx == 1 else None, "brick_cells_log2": args.brick or 3,
                     "selected_points": int(m_sel), "map_build_s": build_s, "map_points_live": g.map_validnum()},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(NF * 12 + 192), "d2h_bytes_per_step": 160 * 8,
                 "ms_per_step": e2e_ms / args.steps,
@@ -525,7 +523,7 @@ def main():
     ap.add_argument("--map-points", type=int, default=0, help="0 = the configuration's size")
     ap.add_argument("--group", type=int, default=0)
     ap.add_argument("--brick", type=int, default=0)
-    ap.add_argument("--knn-index", type=int, default=0, help="0 = library default, 1 = bricks (lockstep groups), 2 = cells (cell directory), 5 = warp per point")
+    ap.add_argument("--knn-index", type=int, default=0, help="0 = library default, 1 = bricks (lockstep groups), 2 = cells (cell directory)")
     ap.add_argument("--cpu-sample", type=int, default=240_000)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

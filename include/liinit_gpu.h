@@ -33,7 +33,7 @@ extern "C" {
 
 #define LIINIT_KNN_BRICKS 1
 #define LIINIT_KNN_CELLS 2
-#define LIINIT_KNN_WARP 5   /* (3 and 4 were the hybrid and the TMA-fused experiments of round 2: measured slower, removed; profiles/r02) */
+/* (3, 4, 5 were the hybrid, TMA-fused and warp-per-point searches of round 2: measured slower, removed; profiles/r02) */
 
 typedef struct liinit_ctx liinit_ctx;
 
@@ -44,12 +44,11 @@ typedef struct liinit_config {
     int device_id;           /* CUDA device ordinal */
     int brick_cells_log2;    /* voxels per brick edge = 1<<this; 0 -> default (3, i.e. brick edge = 8*ds) */
     int hash_capacity_log2;  /* brick hash slots = 1<<this; 0 -> derived from max_map_points */
-    int knn_group_lanes;     /* lanes cooperating on one scan point in the lockstep 5-NN kernel: 2, 4, 8, 16 or 32; 0 -> default (4) */
+    int knn_group_lanes;     /* lanes cooperating on one scan point in the lockstep 5-NN kernel: 2, 4, 8, 16 or 32; 0 -> chosen per pass from the frame
+                                size (32 lanes up to 20k points ... 4 lanes beyond 170k: small frames need the latency, large ones the throughput) */
     float knn_seed_radius_cells; /* first search shell of the 5-NN kernel, in map voxels (radius = this * filter_size_map); 0 -> default (2) */
-    int knn_index;           /* how the 5-NN kernel searches the brick hash: LIINIT_KNN_BRICKS (lockstep groups of knn_group_lanes lanes over whole bricks),
-                                LIINIT_KNN_CELLS (thread per scan point over the per-brick cell directory; needs brick_cells_log2 = 3),
-                                LIINIT_KNN_WARP (one WARP per scan point: rings of the home brick, bricks walked nearest first, candidates
-                                through a shared-memory list; writes the Nearest_Points copies itself, knn_wq.cuh); 0 -> default */
+    int knn_index;           /* how the 5-NN kernel searches the brick hash: LIINIT_KNN_BRICKS (lockstep groups of knn_group_lanes lanes over whole bricks)
+                                or LIINIT_KNN_CELLS (thread per scan point over the per-brick cell directory; needs brick_cells_log2 = 3); 0 -> default */
     int reserved[6];
 } liinit_config;
 
@@ -175,7 +174,7 @@ int liinit_comm_info(liinit_ctx* h, int* nranks, int* rank, int* shard_lo, int* 
 int liinit_last_pass_timing(liinit_ctx* h, float* kernel_ms, int* launches);
 /* Per-kernel device times of the last pass: the 5-NN kernel (0 for a reuse pass) and the plane/Jacobian/reduction kernel. */
 int liinit_last_pass_kernel_times(liinit_ctx* h, float* knn_ms, float* plane_ms);
-/* The spatial index this context searches (LIINIT_KNN_BRICKS / LIINIT_KNN_CELLS / LIINIT_KNN_WARP) after defaults were resolved. */
+/* The spatial index this context searches (LIINIT_KNN_BRICKS / LIINIT_KNN_CELLS) after defaults were resolved. */
 int liinit_knn_index(liinit_ctx* h, int* knn_index);
 /* Cumulative number of kernels launched by this context. */
 int liinit_launch_count(liinit_ctx* h, long long* launches);

@@ -21,7 +21,6 @@
 #include "icp_kernels.cuh"
 #include "knn_kernels.cuh"
 #include "cells.cuh"
-#include "knn_wq.cuh"
 #include "map_kernels.cuh"
 #include "voxelgrid_kernels.cuh"
 #include "undistort_kernels.cuh"
@@ -32,6 +31,7 @@
 #ifndef LIINIT_KNN_DEFAULT
 #define LIINIT_KNN_DEFAULT LIINIT_KNN_BRICKS   // what knn_index = 0 selects
 #endif
+
 
 namespace {
 
@@ -159,11 +159,6 @@ struct Ctx {
     bool cells_refresh_warp = true;   // directory refresh: warp per brick (false: thread per brick, the version the CPU checker runs)
     bool cells = false;   // knn_index = LIINIT_KNN_CELLS: per-brick cell directory + thread-per-point search (cells.cuh)
     float rho2 = 0.09f;   // squared seed radius of the 5-NN search
-    // warp-per-scan-point search (knn_wq.cuh): knn_index = LIINIT_KNN_WARP
-    bool wq = false;
-    int wq_grid = 0;
-    unsigned* d_fticket = nullptr;    // monotone tile ticket (never reset)
-    unsigned fticket_base = 0;        // its value before the next launch
 };
 
 #define CU(call)                                                                                     \
@@ -176,6 +171,17 @@ struct Ctx {
     } while (0)
 
 inline int nblk(long long n, int t) { return (int)((n + t - 1) / t); }
+
+// per-call device scratch that is released on every return path (the CU() macro returns early on a CUDA error)
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t count) { return cudaMalloc(&p, count * sizeof(T)); }
+};
 
 int fail(Ctx* c, int code, const std::string& msg) {
     c->err = msg;
@@ -328,6 +334,17 @@ void set_scan(Ctx* c, int n) {
     c->state_gathered = c->nranks == 1;
 }
 
+// Lanes per scan point when the caller left knn_group_lanes = 0. A warp works on 32/G points at once and lives as long as its slowest
+// one: 4 lanes give the best throughput once every SM holds several such batches, but a small frame then occupies a fraction of the
+// GPU for a long batch time. Measured on one B200 (C2 scene, both poses, profiles/r02/probe_frame_size_vs_group_lanes.log):
+//   2k points: 0.049 ms at G = 4, 0.015 ms at G = 32;   30k: 0.076 / 0.052 (G = 16);   120k: 0.150 / 0.117 (G = 8);   240k: 0.199 (G = 4).
+int group_for(int n) {
+    if (n <= 20000) return 32;
+    if (n <= 45000) return 16;
+    if (n <= 170000) return 8;
+    return 4;
+}
+
 template <int G>
 void launch_knn_scan(Ctx* c, const PoseD& P) {
     long long threads = (long long)c->S.n * G;
@@ -380,25 +397,8 @@ void launch_plane(Ctx* c, const PoseD& P, double* out) {
     // one wave of 256-thread blocks (2 resident per SM at ~100-130 registers), grid-stride over the scan
     int grid = nblk(c->S.n, 256);
     if (grid > c->num_sms * 2 * LI_PLANE_WAVES) grid = c->num_sms * 2 * LI_PLANE_WAVES;
-    // the id-writing searches hand pool offsets over (gathered here); the warp search wrote the neighbour copies itself
-    if (SEARCH && !c->wq) k_icp_plane<IMU, SEARCH, true><<<grid, 256, 0, c->stream>>>(c->M, c->S, P, c->d_partials, c->d_done, out);
-    else k_icp_plane<IMU, SEARCH, false><<<grid, 256, 0, c->stream>>>(c->M, c->S, P, c->d_partials, c->d_done, out);
-}
-
-// Warp-per-scan-point search (knn_wq.cuh): tiles of LI_WQ_TILE points behind a monotone ticket: every launch consumes ntiles + one
-// terminating ticket per warp, so the next launch's base is known on the host without a reset on the stream.
-void launch_knn_wq(Ctx* c, const PoseD& P) {
-    const int ntiles = (c->S.n + LI_WQ_TILE - 1) / LI_WQ_TILE;
-    int grid = c->wq_grid;
-    const int need = nblk(ntiles, LI_WQ_THREADS / 32);
-    if (grid > need) grid = need;
-    if (c->attached) {
-        k_knn_wq<true><<<grid, LI_WQ_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, c->attached, c->attached_stride, c->d_fticket, c->fticket_base);
-        c->attached = nullptr;   // the kernel leaves the packed copy in d_body
-    } else {
-        k_knn_wq<false><<<grid, LI_WQ_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, nullptr, 0, c->d_fticket, c->fticket_base);
-    }
-    c->fticket_base += (unsigned)ntiles + (unsigned)grid * (LI_WQ_THREADS / 32);
+    // search pass: the search kernel handed pool offsets over (gathered here, left in S.near_xyz as copies); reuse pass: the copies
+    k_icp_plane<IMU, SEARCH, SEARCH><<<grid, 256, 0, c->stream>>>(c->M, c->S, P, c->d_partials, c->d_done, out);
 }
 
 // out: where the last block of the plane kernel leaves the 160-double result block -- the caller's device buffer
@@ -413,9 +413,8 @@ int run_pass(Ctx* c, const double* R, const double* p, const double* RLI, const 
     if (c->nranks > 1) out = c->d_acc;   // this rank's block; the sum over the ranks goes to final_out below
     CU(cudaEventRecord(c->ev0, c->stream));
     if (search) {
-        if (c->wq) launch_knn_wq(c, P);
-        else if (c->cells) launch_knn_cells_scan(c, P);
-        else switch (c->group) {
+        if (c->cells) launch_knn_cells_scan(c, P);
+        else switch (c->group ? c->group : group_for(c->S.n)) {
             case 16: launch_knn_scan<16>(c, P); break;
             case 32: launch_knn_scan<32>(c, P); break;
             case 2: launch_knn_scan<2>(c, P); break;
@@ -548,7 +547,12 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
         return bail(LIINIT_ERR_INVALID);
     }
     c->hash_slots = 1u << hl;
-    c->group = (cfg->knn_group_lanes == 2 || cfg->knn_group_lanes == 4 || cfg->knn_group_lanes == 8 || cfg->knn_group_lanes == 16 || cfg->knn_group_lanes == 32) ? cfg->knn_group_lanes : 4;
+    // lanes per scan point of the lockstep search: fixed by the caller, or (0) chosen per pass from the frame size (group_for)
+    c->group = (cfg->knn_group_lanes == 2 || cfg->knn_group_lanes == 4 || cfg->knn_group_lanes == 8 || cfg->knn_group_lanes == 16 || cfg->knn_group_lanes == 32) ? cfg->knn_group_lanes : 0;
+    {
+        const char* ge = getenv("LIINIT_KNN_GROUP");   // developer A/B
+        if (ge && (atoi(ge) == 2 || atoi(ge) == 4 || atoi(ge) == 8 || atoi(ge) == 16 || atoi(ge) == 32)) c->group = atoi(ge);
+    }
 
     {
         int ki = cfg->knn_index;
@@ -557,13 +561,12 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
             const char* e = getenv("LIINIT_KNN_INDEX");
             ki = (e && *e) ? atoi(e) : LIINIT_KNN_DEFAULT;
         }
-        if (ki != LIINIT_KNN_BRICKS && ki != LIINIT_KNN_CELLS && ki != LIINIT_KNN_WARP) {
-            c->err = "knn_index must be 0, LIINIT_KNN_BRICKS, LIINIT_KNN_CELLS or LIINIT_KNN_WARP";
+        if (ki != LIINIT_KNN_BRICKS && ki != LIINIT_KNN_CELLS) {
+            c->err = "knn_index must be 0, LIINIT_KNN_BRICKS or LIINIT_KNN_CELLS";
             return bail(LIINIT_ERR_INVALID);
         }
         // the cell directory is defined for 8x8x8-voxel bricks; another brick size keeps the brick search
         c->cells = ki == LIINIT_KNN_CELLS && bs == LI_CELLS_BSHIFT;
-        c->wq = ki == LIINIT_KNN_WARP;
         const char* sd = getenv("LIINIT_CELLS_SCHED");
         if (sd && !strcmp(sd, "dynamic")) c->cells_dynamic = true;
         const char* rf = getenv("LIINIT_CELLS_REFRESH");
@@ -646,16 +649,6 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
     c->max_blocks = c->num_sms * 16;
     CUC(cudaMalloc(&c->d_partials, (size_t)c->max_blocks * 96 * sizeof(double)));
     CUC(cudaMalloc(&c->d_done, sizeof(unsigned)));
-    if (c->wq) {
-        CUC(cudaMalloc(&c->d_fticket, sizeof(unsigned)));
-        CUC(cudaMemsetAsync(c->d_fticket, 0, sizeof(unsigned), c->stream));
-        c->fticket_base = 0;
-        c->wq_grid = c->num_sms * LI_WQ_MIN_BLOCKS;
-        {
-            const char* fb = getenv("LIINIT_WQ_BLOCKS_PER_SM");   // developer A/B
-            if (fb && atoi(fb) >= 1 && atoi(fb) <= 16) c->wq_grid = c->num_sms * atoi(fb);
-        }
-    }
     CUC(cudaHostAlloc(&c->h_out, 160 * sizeof(double), cudaHostAllocMapped));
     CUC(cudaHostGetDevicePointer((void**)&c->h_out_dev, c->h_out, 0));
     CUC(cudaMemsetAsync(c->d_done, 0, sizeof(unsigned), c->stream));
@@ -690,7 +683,7 @@ int liinit_destroy(liinit_ctx* h) {
     cudaFree(c->d_counters); cudaFreeHost(c->h_counters); cudaFreeHost(c->h_pool_top); cudaFree(c->d_stage_raw); cudaFree(c->d_stage_pts);
     cudaFree(c->d_slot_of); cudaFree(c->d_vslot_of); cudaFree(c->d_flag); cudaFree(c->d_ins); cudaFree(c->V.keys); cudaFree(c->V.head); cudaFree(c->d_vg_imin); cudaFree(c->d_vg_block); cudaFree(c->d_vg_misc); cudaFree(c->d_rs_keys); cudaFree(c->d_rs_vals); cudaFree(c->d_rs_hist); cudaFree(c->d_vg_params); cudaFree(c->d_tmin_idx); cudaFree(c->d_poses);
     cudaFree(c->d_body); cudaFree(c->d_world); cudaFree(c->d_near_ids); cudaFree(c->d_near_xyz); cudaFree(c->d_selected); cudaFree(c->d_normvec);
-    cudaFree(c->d_fticket); cudaFree(c->d_acc); cudaFree(c->d_red);
+    cudaFree(c->d_acc); cudaFree(c->d_red);
 #ifndef LI_SIMT_EMUL
     if (c->comm) { NcclApi* N = nccl_api(); if (N) N->CommDestroy(c->comm); c->comm = nullptr; }
 #endif
@@ -751,15 +744,16 @@ int compact_map(Ctx* c) {
     int r = fetch_counters(c);
     if (r) return r;
     const int live = c->h_counters[CNT_LIVE];
+    DevBuf<float4> btmp;
+    DevBuf<int> bn;
     float4* d_tmp = nullptr;
     int* d_n = nullptr;
     if (live > 0) {
-        CU(cudaMalloc(&d_tmp, (size_t)live * sizeof(float4)));
-        if (cudaMalloc(&d_n, sizeof(int)) != cudaSuccess) {
-            cudaFree(d_tmp);
-            return fail(c, LIINIT_ERR_CUDA, "cudaMalloc (compact)");
-        }
-        cudaMemsetAsync(d_n, 0, sizeof(int), c->stream);
+        CU(btmp.alloc((size_t)live));
+        CU(bn.alloc(1));
+        d_tmp = btmp.p;
+        d_n = bn.p;
+        CU(cudaMemsetAsync(d_n, 0, sizeof(int), c->stream));
         k_map_flatten4<<<nblk((long long)c->hash_slots * 32, 256), 256, 0, c->stream>>>(c->M, c->hash_slots, d_tmp, live, d_n);
         c->launches++;
     }
@@ -776,9 +770,8 @@ int compact_map(Ctx* c) {
         const int m = (int)((live - off < c->stage_pts_cap) ? (live - off) : c->stage_pts_cap);
         r = plain_insert(c, d_tmp + off, m, nullptr, 0);
     }
-    if (r == LIINIT_OK) r = fetch_counters(c);
-    cudaFree(d_tmp);
-    cudaFree(d_n);
+    if (r == LIINIT_OK) r = fetch_counters(c);   // (synchronises: the scratch may go)
+    else cudaStreamSynchronize(c->stream);
     if (r) return r;
     return check_map_err(c);
 }
@@ -884,20 +877,21 @@ int liinit_map_download(liinit_ctx* h, float* xyz, int cap, int* n) {
     if (!h || !n || cap < 0) return LIINIT_ERR_INVALID;
     Ctx* c = &h->c;
     CU(cudaSetDevice(c->device));
-    float* d_out = nullptr;
-    int* d_n = nullptr;
-    CU(cudaMalloc(&d_out, (size_t)(cap > 0 ? cap : 1) * 12));
-    CU(cudaMalloc(&d_n, 4));
+    DevBuf<float> out;
+    DevBuf<int> dn;
+    CU(out.alloc((size_t)(cap > 0 ? cap : 1) * 3));
+    CU(dn.alloc(1));
+    float* d_out = out.p;
+    int* d_n = dn.p;
     CU(cudaMemsetAsync(d_n, 0, 4, c->stream));
     k_map_flatten<<<nblk((long long)c->hash_slots * 32, 256), 256, 0, c->stream>>>(c->M, c->hash_slots, d_out, cap, d_n);
     c->launches++;
+    CU(cudaGetLastError());
     int cnt = 0;
     CU(cudaMemcpyAsync(&cnt, d_n, 4, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     int m = cnt < cap ? cnt : cap;
     if (m > 0 && xyz) CU(cudaMemcpy(xyz, d_out, (size_t)m * 12, cudaMemcpyDeviceToHost));
-    cudaFree(d_out);
-    cudaFree(d_n);
     *n = cnt;
     return LIINIT_OK;
 }
@@ -913,15 +907,13 @@ int liinit_map_nearest_search(liinit_ctx* h, const float* q, int stride, int n, 
         int m = (int)((n - off < c->stage_pts_cap) ? (n - off) : c->stage_pts_cap);
         int r = stage_points(c, q + (size_t)off * stride, stride, m);
         if (r) return r;
-        int* d_ids = nullptr;
-        float* d_xyz = nullptr;
-        CU(cudaMalloc(&d_ids, (size_t)m * 5 * sizeof(int)));
-        CU(cudaMalloc(&d_xyz, (size_t)m * 15 * sizeof(float)));
-        if (c->wq) {
-            int gq = nblk((long long)m * 32, LI_WQ_THREADS);
-            if (gq > c->num_sms * 8) gq = c->num_sms * 8;
-            k_knn_wq_queries<<<gq, LI_WQ_THREADS, 0, c->stream>>>(c->M, c->d_stage_pts, m, d_ids, d_xyz, c->d_q_d2, c->rho2);
-        } else if (c->cells) {
+        DevBuf<int> bids;
+        DevBuf<float> bxyz;
+        CU(bids.alloc((size_t)m * 5));
+        CU(bxyz.alloc((size_t)m * 15));
+        int* d_ids = bids.p;
+        float* d_xyz = bxyz.p;
+        if (c->cells) {
             const int gq = nblk(m, LI_CELLS_THREADS);
             if (c->cells_search == 1) k_knn_cells_queries<1><<<gq, LI_CELLS_THREADS, 0, c->stream>>>(c->M, c->d_stage_pts, m, d_ids, c->d_q_d2, c->rho2);
             else if (c->cells_search == 2) k_knn_cells_queries<2><<<gq, LI_CELLS_THREADS, 0, c->stream>>>(c->M, c->d_stage_pts, m, d_ids, c->d_q_d2, c->rho2);
@@ -931,15 +923,13 @@ int liinit_map_nearest_search(liinit_ctx* h, const float* q, int stride, int n, 
             if (grid > c->max_blocks) grid = c->max_blocks;
             k_knn_queries<8><<<grid, 256, 0, c->stream>>>(c->M, c->d_stage_pts, m, d_ids, c->d_q_d2, c->rho2);
         }
-        if (!c->wq) k_gather_xyz<<<nblk((long long)m * 5, 256), 256, 0, c->stream>>>(c->M.pool, d_ids, (long long)m * 5, d_xyz);
-        c->launches += c->wq ? 1 : 2;
+        k_gather_xyz<<<nblk((long long)m * 5, 256), 256, 0, c->stream>>>(c->M.pool, d_ids, (long long)m * 5, d_xyz);
+        c->launches += 2;
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(ids.data() + (size_t)off * 5, d_ids, (size_t)m * 5 * 4, cudaMemcpyDeviceToHost, c->stream));
         if (out_xyz) CU(cudaMemcpyAsync(out_xyz + (size_t)off * 15, d_xyz, (size_t)m * 15 * 4, cudaMemcpyDeviceToHost, c->stream));
         if (out_d2) CU(cudaMemcpyAsync(out_d2 + (size_t)off * 5, c->d_q_d2, (size_t)m * 5 * 4, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
-        cudaFree(d_ids);
-        cudaFree(d_xyz);
     }
     for (int i = 0; i < n; i++) {
         int cnt = 0;
@@ -1422,7 +1412,7 @@ int liinit_comm_info(liinit_ctx* h, int* nranks, int* rank, int* shard_lo, int* 
 
 int liinit_knn_index(liinit_ctx* h, int* knn_index) {
     if (!h || !knn_index) return LIINIT_ERR_INVALID;
-    *knn_index = h->c.wq ? LIINIT_KNN_WARP : h->c.cells ? LIINIT_KNN_CELLS : LIINIT_KNN_BRICKS;
+    *knn_index = h->c.cells ? LIINIT_KNN_CELLS : LIINIT_KNN_BRICKS;
     return LIINIT_OK;
 }
 

@@ -30,7 +30,7 @@ def small_case():
     return scenes.make_config("C2", N=20000, M=200000, open_air_frac=0.02)
 
 
-@pytest.mark.parametrize("group", [1, 8])
+@pytest.mark.parametrize("group", [0, 8])
 def test_knn_matches_oracle(gpu_lib, oracle_mod, small_case, group):
     c = small_case
     g = gpu_lib.LiInitGpu(c["ds"], max_map_points=400000, max_scan_points=50000, knn_group_lanes=group)
@@ -49,7 +49,7 @@ def test_knn_matches_oracle(gpu_lib, oracle_mod, small_case, group):
 
 
 @pytest.mark.parametrize("imu_en", [False, True])
-@pytest.mark.parametrize("tile", [1, 4, 8, 32])
+@pytest.mark.parametrize("tile", [0, 2, 4, 8, 16, 32])
 def test_search_and_reuse_pass(gpu_lib, oracle_mod, imu_en, tile):
     c = scenes.make_config("C2", N=20000, M=200000, open_air_frac=0.02, imu_en=imu_en)
     p = c["pose_init"]

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Compile-time variants of the library for a same-box A/B (run HERE before gpurun: nvcc cross-compiles without a GPU; build/ travels with the snapshot).
-#   LIINIT_GPU_LIB=build/variants/lib_wq_mb6.so python tools/probe_knn.py --variants 5:0:3:0
+#   LIINIT_GPU_LIB=build/variants/lib_x.so python tools/probe_knn.py --variants 1:0:3:0
 # usage: tools/build_variants.sh name1="-DFLAG=1 -DX=2" name2="..."
 set -e
 cd "$(dirname "$0")/.."

@@ -1,5 +1,5 @@
 """Developer A/B on one box: search-pass variants on the C2 scene (cached in /tmp), warm L2.
-  [LIINIT_GPU_LIB=build/variants/x.so] python tools/probe_knn.py --variants 1:4:3:0,5:0:3:0,5:0:3:19
+  [LIINIT_GPU_LIB=build/variants/x.so] python tools/probe_knn.py --variants 1:4:3:0,1:8:3:0,2:0:3:0
 variant = knn_index:group:brick_cells_log2:hash_capacity_log2 (0 = default). Prints the search kernel / plane kernel ms (CUDA events
 inside the library) at the initial and at the converged pose and checks that every variant leaves the same per-point state
 (neighbours, flags, normals) as the first one and HtH within 1e-12."""
@@ -8,7 +8,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from lidar_imu_init_b200 import capi
 ap = argparse.ArgumentParser()
-ap.add_argument("--variants", default="1:4:3:0,5:0:3:0")
+ap.add_argument("--variants", default="1:0:3:0,1:4:3:0,1:8:3:0")
 ap.add_argument("--N", type=int, default=240000)
 ap.add_argument("--M", type=int, default=5000000)
 ap.add_argument("--config", default="C2")

@@ -417,7 +417,7 @@ def run_gpu(args, rank, world, local_rank):
         multi = {"m_sum_of_ranks": int(round(tot[157])), "m_reduced": int(m_sel), "m_per_rank": [int(round(x[157])) for x in box],
                  "rel_err_HtH_vs_rank_sum": float(np.abs(red[:144] - tot[:144]).max() / np.abs(tot[:144]).max()),
                  "rel_err_Htr_vs_rank_sum": float(np.abs(red[144:156] - tot[144:156]).max() / np.abs(tot[144:156]).max()),
-                 "collective": "ncclAllReduce(160 f64) inside liinit_icp_iterate (liinit_comm_init; NCCL dlopen()ed by the library)"}
+                 "collective": "sum of 160 f64 over the ranks inside liinit_icp_iterate: " + g.comm_mode()}
 
     conf = config_dict(cfg, args.scan_points, args.map_points, c["ds"])
     out = {
@@ -427,7 +427,7 @@ def run_gpu(args, rank, world, local_rank):
         "config": conf,
         "details": {"frame_points": NF, "points_per_gpu": N,
                     "parallelism": "1 GPU" if world == 1 else (f"{world} GPUs, map replicated, frame of {NF} points cut into {world} slots by the library, "
-                                                               "accumulators summed over the ranks inside liinit_icp_iterate (NCCL)"),
+                                                               "accumulators summed over the ranks inside liinit_icp_iterate (" + g.comm_mode() + ")"),
                     "l2": "flushed between timed steps (256 MiB memset outside the events)", "knn_index": KNN_NAME[kidx],
                     "knn_group_lanes": (args.group or "auto (by frame size: 4 lanes beyond 170k points per GPU)") if kidx == 1 else None, "brick_cells_log2": args.brick or 3,
                     "selected_points": int(m_sel), "map_build_s": build_s, "map_points_live": g.map_validnum()},

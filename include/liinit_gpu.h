@@ -156,7 +156,12 @@ int liinit_debug_esti_plane(liinit_ctx* h, const float* nb_xyz, int n, double* p
  * host-side IESKF loop (liinit_scan_update, liinit_host.h) is unchanged and every rank ends a scan with the same state.
  * liinit_map_incremental and the download hooks first all-gather the per-point results (Nearest_Points copies, flags, normals) of the
  * other ranks' slots, then every rank applies the whole frame's update to its replica: collective calls, same order on every rank.
- * NCCL is loaded with dlopen("libnccl.so.2") when the first of these functions is called; single-GPU use never touches it. */
+ * NCCL is loaded with dlopen("libnccl.so.2") when the first of these functions is called; single-GPU use never touches it.
+ * How the sum travels: with one process per GPU on an NVLink node, liinit_comm_init maps every rank's 2.6 kB exchange buffer into every
+ * process (CUDA IPC) and the LAST BLOCK of the plane kernel does the collective itself -- peer stores of its 160 doubles into every rank's
+ * buffer, a system-scope flag, a spin on the other ranks' flags, a rank-ordered sum (bit-identical on every rank): no extra launch, no
+ * NCCL kernel. If any rank cannot map its peers (ranks as threads of one process, no peer access) or LIINIT_COMM_MODE=nccl is set, all
+ * ranks use ncclAllReduce on the context's stream instead. NCCL always carries the set-up and the all-gathers of per-point results. */
 #define LIINIT_COMM_ID_BYTES 128
 /* ncclGetUniqueId: call on ONE rank, hand the 128 bytes to the others through whatever channel the application has. */
 int liinit_comm_unique_id(void* id128);
@@ -165,6 +170,8 @@ int liinit_comm_init(liinit_ctx* h, const void* id128, int nranks, int rank);
 /* This rank's OWN accumulator block of the last pass (before the sum), 160 doubles to the host: lets an application / the bench
  * verify the reduction (sum of the ranks' blocks == what liinit_icp_iterate returned). */
 int liinit_comm_last_local(liinit_ctx* h, double* out160);
+/* 1 if the accumulators are summed over peer memory inside the plane kernel, 0 if by ncclAllReduce (or no communicator). */
+int liinit_comm_mode(liinit_ctx* h, int* peer_memory);
 /* nranks / rank of the context and the slot [shard_lo, shard_lo + shard_n) of the resident frame this rank works on. */
 int liinit_comm_info(liinit_ctx* h, int* nranks, int* rank, int* shard_lo, int* shard_n);
 

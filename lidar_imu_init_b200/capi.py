@@ -37,7 +37,7 @@ SYMBOLS = [
     "liinit_raw_download", "liinit_raw_downsample",
     "liinit_icp_iterate", "liinit_icp_iterate_device", "liinit_scan_download_effect", "liinit_scan_download_state",
     "liinit_map_incremental", "liinit_last_pass_timing", "liinit_last_pass_kernel_times", "liinit_launch_count", "liinit_map_stats", "liinit_knn_index",
-    "liinit_comm_unique_id", "liinit_comm_init", "liinit_comm_info", "liinit_comm_last_local", "liinit_debug_esti_plane",
+    "liinit_comm_unique_id", "liinit_comm_init", "liinit_comm_info", "liinit_comm_last_local", "liinit_comm_mode", "liinit_debug_esti_plane",
 ]
 
 
@@ -93,6 +93,7 @@ def load():
     L.liinit_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
     L.liinit_debug_esti_plane.argtypes = [vp, vp, C.c_int, vp, vp]
     L.liinit_comm_last_local.argtypes = [vp, _f64]
+    L.liinit_comm_mode.argtypes = [vp, C.POINTER(C.c_int)]
     L.liinit_comm_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     for s in SYMBOLS:
         getattr(L, s).restype = getattr(L, s).restype if s == "liinit_last_error" else C.c_int
@@ -330,6 +331,11 @@ class LiInitGpu:
         assert len(unique_id) == 128
         buf = C.create_string_buffer(unique_id, 128)
         self._ck(self.L.liinit_comm_init(self.h, buf, int(nranks), int(rank)))
+
+    def comm_mode(self) -> str:
+        v = C.c_int(0)
+        self._ck(self.L.liinit_comm_mode(self.h, C.byref(v)))
+        return "peer memory (fused in the plane kernel)" if v.value else "ncclAllReduce"
 
     def comm_last_local(self):
         out = np.zeros(160)

@@ -288,12 +288,56 @@ __device__ __forceinline__ void warp_accumulate(const double (&row)[AccLayout<IM
     }
 }
 
+// ---- multi-GPU: the sum over the ranks INSIDE the reduction's last block, over NVLink peer memory --------------------------
+// Every rank owns an exchange buffer [2 phases][nranks][160 doubles] + flags [2][nranks], mapped into every other rank's address
+// space (CUDA IPC, liinit_comm_init). The last block of a rank's plane kernel stores its 160-double block into slot `rank` of EVERY
+// rank's buffer (peer stores over NVLink), publishes it with a system-scope flag = pass sequence number, waits until all nranks slots
+// of its OWN buffer carry that number and sums them in rank order -- the same order on every rank, so all ranks hold bit-identical
+// sums (as with ncclAllReduce) and the result does not depend on arrival order. Two phases (seq & 1): a rank can only be one pass ahead
+// of the slowest one, because finishing pass s needs everybody's block of pass s.
+// No extra launch, no NCCL kernel, no host involvement: the collective costs one NVLink round trip at the tail of the kernel that
+// produced its input ("fused at the tail of the kernel").
+#define LI_MAX_RANKS 64
+struct XchgTable {
+    double* blocks[LI_MAX_RANKS];       // rank r's buffer as seen from THIS device
+    unsigned* flags[LI_MAX_RANKS];
+    double* local;                      // where this rank's own block is kept for liinit_comm_last_local
+    int nranks, rank;
+};
+
+__device__ __forceinline__ void li_st_release_sys(unsigned* p, unsigned v) {
+#ifdef LI_SIMT_EMUL
+    *p = v;
+#else
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#endif
+}
+__device__ __forceinline__ unsigned li_ld_acquire_sys(const unsigned* p) {
+#ifdef LI_SIMT_EMUL
+    return *p;
+#else
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+#endif
+}
+__device__ __forceinline__ double li_ld_volatile_f64(const double* p) {
+#ifdef LI_SIMT_EMUL
+    return *p;
+#else
+    double v;
+    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+#endif
+}
+
 // Block-level accumulation + deterministic grid reduction.
 //   acc[K]: this lane's running sums (value index 32*k + lane). partials: [gridDim.x][V]. out160: final layout
 //   [HtH 144 | Htr 12 | res_sq | m | 0 0].
 template <bool IMU>
 __device__ __forceinline__ void block_finish(const double (&acc)[AccLayout<IMU>::K], double* __restrict__ partials,
-                                             unsigned* __restrict__ done_counter, double* __restrict__ out160) {
+                                             unsigned* __restrict__ done_counter, double* __restrict__ out160,
+                                             const XchgTable* __restrict__ X = nullptr, unsigned seq = 0u) {
     typedef AccLayout<IMU> L;
     __shared__ double spart[8][L::V];
     __shared__ bool s_last;
@@ -328,6 +372,7 @@ __device__ __forceinline__ void block_finish(const double (&acc)[AccLayout<IMU>:
         if (lane == 0) s_tot[v] = s;
     }
     __syncthreads();
+    __shared__ double s_out[160];
     for (int o = threadIdx.x; o < 160; o += blockDim.x) {
         int src = -1;
         if (o < 144) {
@@ -342,7 +387,34 @@ __device__ __forceinline__ void block_finish(const double (&acc)[AccLayout<IMU>:
         } else if (o == 157) {
             src = L::NT + L::NC + 1;
         }
-        out160[o] = (src >= 0) ? s_tot[src] : 0.0;
+        s_out[o] = (src >= 0) ? s_tot[src] : 0.0;
+    }
+    __syncthreads();
+    if (X == nullptr) {
+        for (int o = threadIdx.x; o < 160; o += blockDim.x) out160[o] = s_out[o];
+    } else {
+        // the one exchange of the path, fused here (see XchgTable)
+        const int nr = X->nranks, me = X->rank;
+        const int ph = (int)(seq & 1u);
+        for (int t = threadIdx.x; t < nr * 160; t += blockDim.x) {
+            const int r = t / 160, i = t - r * 160;
+            X->blocks[r][(size_t)(ph * nr + me) * 160 + i] = s_out[i];     // peer store (NVLink); r == me: local
+        }
+        for (int o = threadIdx.x; o < 160; o += blockDim.x) X->local[o] = s_out[o];
+        __threadfence_system();
+        __syncthreads();
+        if ((int)threadIdx.x < nr) li_st_release_sys(X->flags[threadIdx.x] + ph * nr + me, seq);
+        if ((int)threadIdx.x < nr) {
+            const unsigned* f = X->flags[me] + ph * nr + threadIdx.x;
+            while (li_ld_acquire_sys(f) != seq) {
+            }
+        }
+        __syncthreads();
+        for (int o = threadIdx.x; o < 160; o += blockDim.x) {
+            double s = 0.0;
+            for (int r = 0; r < nr; r++) s += li_ld_volatile_f64(X->blocks[me] + (size_t)(ph * nr + r) * 160 + o);   // rank order: identical on every rank
+            out160[o] = s;
+        }
     }
     if (threadIdx.x == 0) *done_counter = 0u;
 }
@@ -379,7 +451,8 @@ __device__ __forceinline__ bool tie_order(float4 (&nb)[5], float (&d)[5]) {
 // SEARCH = false: reuse pass (nearest_search_en == false, :989-994): previous flag and stored neighbours.
 template <bool IMU, bool SEARCH, bool FROM_IDS>
 __global__ void __launch_bounds__(256, LI_PLANE_MIN_BLOCKS) k_icp_plane(MapDev M, ScanDev S, PoseD P, double* __restrict__ partials,
-                                                   unsigned* __restrict__ done_counter, double* __restrict__ out160) {
+                                                   unsigned* __restrict__ done_counter, double* __restrict__ out160,
+                                                   const XchgTable* __restrict__ X, unsigned seq) {
     typedef AccLayout<IMU> L;
     const int lane = threadIdx.x & 31;
     double acc[L::K];
@@ -441,5 +514,5 @@ __global__ void __launch_bounds__(256, LI_PLANE_MIN_BLOCKS) k_icp_plane(MapDev M
         }
         warp_accumulate<IMU>(row, r, sel, lane, acc);
     }
-    block_finish<IMU>(acc, partials, done_counter, out160);
+    block_finish<IMU>(acc, partials, done_counter, out160, X, seq);
 }

@@ -134,7 +134,13 @@ struct Ctx {
     ncclComm_t comm = nullptr;
 #endif
     double* d_acc = nullptr;       // the rank's own accumulator block (N > 1) ...
-    double* d_red = nullptr;       // ... and its sum over the ranks
+    double* d_red = nullptr;       // ... and its sum over the ranks (NCCL mode)
+    // peer-memory mode (default when CUDA IPC between the ranks works): the sum happens in the last block of the plane kernel
+    bool comm_p2p = false;
+    void* d_xbuf = nullptr;        // this rank's exchange buffer: [2][nranks][160] doubles + [2][nranks] flags
+    XchgTable* d_xtab = nullptr;   // every rank's buffer as mapped into this process
+    void* peer_map[LI_MAX_RANKS] = {nullptr};   // what cudaIpcOpenMemHandle returned (closed in liinit_destroy)
+    unsigned xseq = 0;             // pass sequence number (identical on every rank: the passes are collective)
     bool state_gathered = true;    // per-point results of the other ranks' shards are present on this device
     bool have_neighbors = false;   // a search pass has filled near_xyz for the resident scan (point copies: map updates do not invalidate them)
     bool scan_fresh = false;   // new scan whose flags / neighbour lists have not been initialised yet (see init_scan_state)
@@ -397,8 +403,10 @@ void launch_plane(Ctx* c, const PoseD& P, double* out) {
     // one wave of 256-thread blocks (2 resident per SM at ~100-130 registers), grid-stride over the scan
     int grid = nblk(c->S.n, 256);
     if (grid > c->num_sms * 2 * LI_PLANE_WAVES) grid = c->num_sms * 2 * LI_PLANE_WAVES;
+    if (grid < 1) grid = 1;   // (an empty slot of a multi-GPU frame still takes part in the exchange)
     // search pass: the search kernel handed pool offsets over (gathered here, left in S.near_xyz as copies); reuse pass: the copies
-    k_icp_plane<IMU, SEARCH, SEARCH><<<grid, 256, 0, c->stream>>>(c->M, c->S, P, c->d_partials, c->d_done, out);
+    const XchgTable* X = (c->nranks > 1 && c->comm_p2p) ? c->d_xtab : nullptr;
+    k_icp_plane<IMU, SEARCH, SEARCH><<<grid, 256, 0, c->stream>>>(c->M, c->S, P, c->d_partials, c->d_done, out, X, c->xseq);
 }
 
 // out: where the last block of the plane kernel leaves the 160-double result block -- the caller's device buffer
@@ -410,10 +418,13 @@ int run_pass(Ctx* c, const double* R, const double* p, const double* RLI, const 
     PoseD P;
     fill_pose(P, R, p, RLI, TLI);
     double* const final_out = out;
-    if (c->nranks > 1) out = c->d_acc;   // this rank's block; the sum over the ranks goes to final_out below
+    if (c->nranks > 1 && !c->comm_p2p) out = c->d_acc;   // NCCL mode: this rank's block; the sum over the ranks goes to final_out below
+    if (c->nranks > 1) c->xseq++;                          // peer-memory mode: the plane kernel's last block sums over the ranks itself
     CU(cudaEventRecord(c->ev0, c->stream));
     if (search) {
-        if (c->cells) launch_knn_cells_scan(c, P);
+        if (c->S.n == 0) {
+            // an empty slot (more ranks than points): nothing to search
+        } else if (c->cells) launch_knn_cells_scan(c, P);
         else switch (c->group ? c->group : group_for(c->S.n)) {
             case 16: launch_knn_scan<16>(c, P); break;
             case 32: launch_knn_scan<32>(c, P); break;
@@ -438,7 +449,7 @@ int run_pass(Ctx* c, const double* R, const double* p, const double* RLI, const 
     CU(cudaGetLastError());
     c->state_gathered = c->nranks == 1;
 #ifndef LI_SIMT_EMUL
-    if (c->nranks > 1) {
+    if (c->nranks > 1 && !c->comm_p2p) {
         // the one exchange of the path: sum of [HtH 144 | Htr 12 | res_sq | m | pad 2] over the ranks, on the
         // context's stream, then to wherever the caller wants the block (page-locked host block or its own device buffer)
         NcclApi* N = nccl_api();
@@ -685,6 +696,10 @@ int liinit_destroy(liinit_ctx* h) {
     cudaFree(c->d_body); cudaFree(c->d_world); cudaFree(c->d_near_ids); cudaFree(c->d_near_xyz); cudaFree(c->d_selected); cudaFree(c->d_normvec);
     cudaFree(c->d_acc); cudaFree(c->d_red);
 #ifndef LI_SIMT_EMUL
+    for (int r = 0; r < LI_MAX_RANKS; r++)
+        if (c->peer_map[r]) cudaIpcCloseMemHandle(c->peer_map[r]);
+    cudaFree(c->d_xtab);
+    cudaFree(c->d_xbuf);
     if (c->comm) { NcclApi* N = nccl_api(); if (N) N->CommDestroy(c->comm); c->comm = nullptr; }
 #endif
     cudaFree(c->d_partials); cudaFree(c->d_done); cudaFreeHost(c->h_out); cudaFree(c->d_q_d2);
@@ -1387,6 +1402,78 @@ int liinit_comm_init(liinit_ctx* h, const void* id128, int nranks, int rank) {
     c->nranks = nranks;
     c->rank = rank;
     if (c->scan_n > 0) set_scan(c, c->scan_n);   // re-cut a frame that is already resident
+    // ---- peer-memory exchange (one process per GPU on one NVLink node): every rank's buffer mapped into every process through CUDA IPC.
+    // If any rank cannot set it up (same process, no peer access, LIINIT_COMM_MODE=nccl), ALL ranks stay on ncclAllReduce.
+    c->comm_p2p = false;
+    if (nranks > 1) {
+        const char* mode = getenv("LIINIT_COMM_MODE");
+        int ok = !(mode && !strcmp(mode, "nccl")) ? 1 : 0;
+        const size_t blk_bytes = (size_t)2 * nranks * 160 * sizeof(double), flag_bytes = (size_t)2 * nranks * sizeof(unsigned);
+        cudaIpcMemHandle_t mine;
+        memset(&mine, 0, sizeof(mine));
+        if (ok && (cudaMalloc(&c->d_xbuf, blk_bytes + flag_bytes) != cudaSuccess || cudaMemset(c->d_xbuf, 0, blk_bytes + flag_bytes) != cudaSuccess ||
+                   cudaIpcGetMemHandle(&mine, c->d_xbuf) != cudaSuccess)) {
+            ok = 0;
+            cudaGetLastError();
+        }
+        // all-gather of the 64-byte handles (+ a 4-byte "fine so far" word) through the communicator that now exists
+        const size_t rec = sizeof(cudaIpcMemHandle_t) + 8;
+        DevBuf<unsigned char> dh;
+        std::vector<unsigned char> hh(rec * nranks, 0);
+        if (dh.alloc(rec * nranks) != cudaSuccess) return fail(c, LIINIT_ERR_CUDA, "cudaMalloc (comm handles)");
+        memcpy(hh.data() + rec * rank, &mine, sizeof(mine));
+        memcpy(hh.data() + rec * rank + sizeof(mine), &ok, sizeof(int));
+        CU(cudaMemcpy(dh.p + rec * rank, hh.data() + rec * rank, rec, cudaMemcpyHostToDevice));
+        nr = N->AllGather(dh.p + rec * rank, dh.p, rec, ncclChar, c->comm, c->stream);
+        if (nr != ncclSuccess) return fail(c, LIINIT_ERR_CUDA, std::string("ncclAllGather (comm handles): ") + N->GetErrorString(nr));
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaMemcpy(hh.data(), dh.p, rec * nranks, cudaMemcpyDeviceToHost));
+        for (int r = 0; r < nranks; r++) {
+            int okr = 0;
+            memcpy(&okr, hh.data() + rec * r + sizeof(mine), sizeof(int));
+            ok = ok && okr;
+        }
+        XchgTable T;
+        memset(&T, 0, sizeof(T));
+        if (ok) {
+            for (int r = 0; r < nranks && ok; r++) {
+                void* base = c->d_xbuf;
+                if (r != rank) {
+                    cudaIpcMemHandle_t hr;
+                    memcpy(&hr, hh.data() + rec * r, sizeof(hr));
+                    if (cudaIpcOpenMemHandle(&base, hr, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                        ok = 0;
+                        cudaGetLastError();
+                        break;
+                    }
+                    c->peer_map[r] = base;
+                }
+                T.blocks[r] = (double*)base;
+                T.flags[r] = (unsigned*)((unsigned char*)base + blk_bytes);
+            }
+        }
+        // second agreement: did every rank open every handle? (sum of the failures over the ranks)
+        {
+            DevBuf<double> dv;
+            if (dv.alloc(1) != cudaSuccess) return fail(c, LIINIT_ERR_CUDA, "cudaMalloc (comm agreement)");
+            double bad = ok ? 0.0 : 1.0;
+            CU(cudaMemcpy(dv.p, &bad, sizeof(double), cudaMemcpyHostToDevice));
+            nr = N->AllReduce(dv.p, dv.p, 1, ncclDouble, ncclSum, c->comm, c->stream);
+            if (nr != ncclSuccess) return fail(c, LIINIT_ERR_CUDA, std::string("ncclAllReduce (comm agreement): ") + N->GetErrorString(nr));
+            CU(cudaStreamSynchronize(c->stream));
+            CU(cudaMemcpy(&bad, dv.p, sizeof(double), cudaMemcpyDeviceToHost));
+            ok = bad == 0.0;
+        }
+        if (ok) {
+            T.local = c->d_acc;
+            T.nranks = nranks;
+            T.rank = rank;
+            CU(cudaMalloc(&c->d_xtab, sizeof(XchgTable)));
+            CU(cudaMemcpy(c->d_xtab, &T, sizeof(T), cudaMemcpyHostToDevice));
+            c->comm_p2p = true;
+            c->xseq = 0;
+        }
+    }
     return LIINIT_OK;
 #endif
 }
@@ -1398,6 +1485,12 @@ int liinit_comm_last_local(liinit_ctx* h, double* out160) {
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaMemcpy(out160, c->d_acc, 160 * sizeof(double), cudaMemcpyDeviceToHost));
+    return LIINIT_OK;
+}
+
+int liinit_comm_mode(liinit_ctx* h, int* peer_memory) {
+    if (!h || !peer_memory) return LIINIT_ERR_INVALID;
+    *peer_memory = (h->c.nranks > 1 && h->c.comm_p2p) ? 1 : 0;
     return LIINIT_OK;
 }
 

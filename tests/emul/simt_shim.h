@@ -168,6 +168,7 @@ inline void __syncthreads() {
     }
 }
 inline void __threadfence() {}
+inline void __threadfence_system() {}
 
 // ---- scalar device intrinsics -----------------------------------------------------------------------
 inline float __fadd_rn(float a, float b) { return a + b; }

@@ -341,9 +341,8 @@ def run_gpu(args, rank, world, local_rank):
         return g.icp_iterate(p.rot_end, p.pos_end, p.R_LI, p.T_LI, False, True)
 
     def step_e2e():
-        # N = 1: liinit_scan_attach_host -- the search kernel pulls the pinned host scan over PCIe itself (NF*12 bytes, inside the timed
-        # region); N > 1: the frame is copied (every rank needs all of it for the map update). The 160-double result block comes back to
-        # the host before the call returns.
+        # liinit_scan_attach_host -- the search kernel pulls this rank's slot of the pinned host frame over PCIe itself (N*12 bytes per
+        # rank, inside the timed region); the 160-double result block comes back to the host before the call returns.
         g.scan_attach_ptr(body4.data_ptr(), SCAN_STRIDE, NF)
         return step_resident()
 
@@ -431,10 +430,11 @@ def run_gpu(args, rank, world, local_rank):
                     "l2": "flushed between timed steps (256 MiB memset outside the events)", "knn_index": KNN_NAME[kidx],
                     "knn_group_lanes": (args.group or "auto (by frame size: 4 lanes beyond 170k points per GPU)") if kidx == 1 else None, "brick_cells_log2": args.brick or 3,
                     "selected_points": int(m_sel), "map_build_s": build_s, "map_points_live": g.map_validnum()},
-        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(NF * 12 + 192), "d2h_bytes_per_step": 160 * 8,
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(N * 12 + 192), "d2h_bytes_per_step": 160 * 8,
                 "ms_per_step": e2e_ms / args.steps,
                 "host_input": ("pinned packed xyz, read by the search kernel over PCIe (liinit_scan_attach_host, no staging copy)" if world == 1 else
-                               "pinned packed xyz of the whole frame, copied to every rank's device (liinit_scan_attach_host at N > 1 copies)"),
+                               "pinned packed xyz of the whole frame; every rank's search kernel reads ITS SLOT over PCIe (liinit_scan_attach_host; the "
+                               "other slots would be copied when map_incremental or a download needs the whole frame)"),
                 "ms_per_step_staged_copy": e2e_staged_ms / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks,

@@ -146,6 +146,7 @@ struct Ctx {
     bool scan_fresh = false;   // new scan whose flags / neighbour lists have not been initialised yet (see init_scan_state)
     const float* attached = nullptr;   // device alias of a page-locked host scan not copied yet (liinit_scan_attach_host)
     int attached_stride = 0;
+    bool attached_slot_done = false;   // N > 1: this rank's slot has been pulled in by its search kernel, the other slots are still on the host
     // reduction
     double* d_partials = nullptr;
     unsigned* d_done = nullptr;
@@ -302,9 +303,23 @@ void fill_pose(PoseD& P, const double* R, const double* p, const double* RLI, co
 // An attached host scan that something other than the search kernel needs: pull it into d_body now.
 void materialize_scan(Ctx* c) {
     if (!c->attached) return;
-    k_repack<<<nblk(c->scan_n, 256), 256, 0, c->stream>>>(c->attached, c->attached_stride, c->scan_n, c->d_body);
-    c->launches++;
+    if (c->attached_slot_done) {   // only what the search kernel did not read: the other ranks' slots [0, lo) and [lo + S.n, n)
+        const int lo = c->shard_lo, hi = c->shard_lo + c->S.n;
+        if (lo > 0) {
+            k_repack<<<nblk(lo, 256), 256, 0, c->stream>>>(c->attached, c->attached_stride, lo, c->d_body);
+            c->launches++;
+        }
+        if (hi < c->scan_n) {
+            k_repack<<<nblk(c->scan_n - hi, 256), 256, 0, c->stream>>>(c->attached + (size_t)hi * c->attached_stride, c->attached_stride, c->scan_n - hi,
+                                                                       c->d_body + hi);
+            c->launches++;
+        }
+    } else {
+        k_repack<<<nblk(c->scan_n, 256), 256, 0, c->stream>>>(c->attached, c->attached_stride, c->scan_n, c->d_body);
+        c->launches++;
+    }
     c->attached = nullptr;
+    c->attached_slot_done = false;
 }
 
 // A new scan starts with nothing selected and no neighbours (Nearest_Points / point_selected_surf at iteration 0). The search
@@ -351,15 +366,25 @@ int group_for(int n) {
     return 4;
 }
 
+// The search kernel of a pass reads an attached host frame in place: its own slot only. With one rank that is the whole frame and
+// nothing is left to copy; with several the rest stays on the host until somebody needs the whole frame (materialize_scan).
+const float* attached_slot(Ctx* c) {
+    return (c->attached && !c->attached_slot_done) ? c->attached + (size_t)c->shard_lo * c->attached_stride : nullptr;
+}
+void attached_slot_read(Ctx* c) {
+    if (c->nranks > 1 && c->S.n < c->scan_n) c->attached_slot_done = true;
+    else c->attached = nullptr;
+}
+
 template <int G>
 void launch_knn_scan(Ctx* c, const PoseD& P) {
     long long threads = (long long)c->S.n * G;
     int grid = nblk(threads, LI_KNN_THREADS);
     int cap = c->max_blocks * (256 / LI_KNN_THREADS);
     if (grid > cap) grid = cap;
-    if (c->attached) {
-        k_knn_scan<G, true><<<grid, LI_KNN_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, c->attached, c->attached_stride);   // (N > 1 never gets here: attach materialises the frame)
-        c->attached = nullptr;   // the kernel leaves the packed copy in d_body
+    if (const float* raw = attached_slot(c)) {
+        k_knn_scan<G, true><<<grid, LI_KNN_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, raw, c->attached_stride);
+        attached_slot_read(c);   // the kernel leaves the packed copy in d_body
     } else {
         k_knn_scan<G, false><<<grid, LI_KNN_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, nullptr, 0);
     }
@@ -374,18 +399,18 @@ void launch_knn_cells_scan_t(Ctx* c, const PoseD& P) {
     if (c->cells_dynamic) {   // persistent grid, warps pull 32-point batches from a ticket counter (reset in stream order)
         cudaMemsetAsync(c->d_ticket, 0, sizeof(unsigned), c->stream);
         const int pgrid = c->num_sms * MINB;
-        if (c->attached) {
-            k_knn_cells_scan_dyn<true, MINB, SEARCH><<<pgrid, LI_CELLS_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, c->attached, c->attached_stride, c->d_ticket);
-            c->attached = nullptr;
+        if (const float* raw = attached_slot(c)) {
+            k_knn_cells_scan_dyn<true, MINB, SEARCH><<<pgrid, LI_CELLS_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, raw, c->attached_stride, c->d_ticket);
+            attached_slot_read(c);
         } else {
             k_knn_cells_scan_dyn<false, MINB, SEARCH><<<pgrid, LI_CELLS_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, nullptr, 0, c->d_ticket);
         }
         return;
     }
     const int grid = nblk(c->S.n, LI_CELLS_THREADS);
-    if (c->attached) {
-        k_knn_cells_scan<true, MINB, SEARCH><<<grid, LI_CELLS_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, c->attached, c->attached_stride);
-        c->attached = nullptr;   // the kernel leaves the packed copy in d_body
+    if (const float* raw = attached_slot(c)) {
+        k_knn_cells_scan<true, MINB, SEARCH><<<grid, LI_CELLS_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, raw, c->attached_stride);
+        attached_slot_read(c);   // the kernel leaves the packed copy in d_body
     } else {
         k_knn_cells_scan<false, MINB, SEARCH><<<grid, LI_CELLS_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, nullptr, 0);
     }
@@ -972,6 +997,7 @@ int liinit_scan_upload(liinit_ctx* h, const float* body, int stride, int n) {
     CU(cudaSetDevice(c->device));
     if (n > c->cfg.max_scan_points) return fail(c, LIINIT_ERR_CAPACITY, "n exceeds max_scan_points");
     c->attached = nullptr;
+    c->attached_slot_done = false;
     if (stride == 4) {
         CU(cudaMemcpyAsync(c->d_body, body, (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
     } else if (stride == 3 || stride == 12) {
@@ -1002,11 +1028,8 @@ int liinit_scan_attach_host(liinit_ctx* h, const float* pinned_body, int stride,
     }
     c->attached = (const float*)at.devicePointer;
     c->attached_stride = stride;
-    set_scan(c, n);
-    if (c->nranks > 1) {   // every rank needs the whole frame on the device (map_incremental): copy it now
-        materialize_scan(c);
-        CU(cudaGetLastError());
-    }
+    c->attached_slot_done = false;
+    set_scan(c, n);   // (N > 1: the search kernel reads this rank's slot in place; the rest is copied when map_incremental / a download needs it)
     return LIINIT_OK;
 }
 
@@ -1236,6 +1259,7 @@ int liinit_scan_download_effect(liinit_ctx* h, float* ori_xyz, float* normvec, i
     CU(cudaSetDevice(c->device));
     int n = c->scan_n;
     if (n <= 0) return fail(c, LIINIT_ERR_INVALID, "no scan uploaded");
+    materialize_scan(c);
     {
         int r = init_scan_state(c);
         if (r) return r;

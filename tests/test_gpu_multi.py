@@ -46,6 +46,16 @@ def _run(g, c, out):
     st0 = host.state_from_pose(p.rot_end, p.pos_end, p.R_LI, p.T_LI)
     st1, info = host.scan_update(g, st0, 5, True)      # liinit_scan_update: the C++ IESKF loop over the C-ABI
     out.update(state=np.array(st1[:24]), iters=info["iterations"])
+    # the same frame handed over as page-locked host memory: the search kernel reads this rank's slot in place, the rest arrives when
+    # map_incremental needs the whole frame
+    import torch
+    pinned = torch.from_numpy(np.ascontiguousarray(c["body_xyz"], np.float32)).pin_memory()
+    g.scan_attach_ptr(pinned.data_ptr(), 3, len(c["body_xyz"]))
+    Ha, ba, ma, _ = g.icp_iterate(p.rot_end, p.pos_end, p.R_LI, p.T_LI, True, True)
+    assert ma == m and np.array_equal(Ha, H) and np.array_equal(ba, b)
+    sta = g.scan_state()
+    for k in ("world", "near_xyz", "near_cnt", "selected", "normvec"):
+        assert np.array_equal(sta[k], st[k]), k
     na, nn = g.map_incremental(gt.rot_end, gt.pos_end, gt.R_LI, gt.T_LI, c["ds"])
     out.update(na=na, nn=nn, valid=g.map_validnum(), live=np.sort(g.map_download().view([("x", "f4"), ("y", "f4"), ("z", "f4")]).ravel()))
 

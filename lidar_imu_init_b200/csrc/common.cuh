@@ -171,6 +171,39 @@ __device__ __forceinline__ int li_brick_find_or_insert(uint4* ent, unsigned mask
     return -1;
 }
 
+// Sort a singly linked list of point indices (head, next[] = -1 terminated) ASCENDING by index, in place: bottom-up merge sort on the
+// links, O(k log k) steps and no extra storage. The per-leaf / per-box lists of the voxel grid and of Add_Points(downsample) are pushed
+// by atomicExch in arrival order; their points must be visited in INPUT order (sequential float sums, sequential box replay). The first
+// versions found "the next smallest index" by walking the whole list for every element: k^2 steps in one thread, seconds for the
+// thousands of points a near-sensor leaf of a 2M-point raw scan can hold (advisor finding, round 1).
+__device__ __forceinline__ int li_list_sort_ascending(int head, int* __restrict__ next) {
+    if (head < 0 || next[head] < 0) return head;
+    for (int width = 1;; width <<= 1) {
+        int cur = head, tail = -1, new_head = -1, merges = 0;
+        while (cur >= 0) {
+            merges++;
+            int a = cur, asz = 0, b = cur;
+            for (int i = 0; i < width && b >= 0; i++) {   // b = first node of the second run
+                b = next[b];
+                asz++;
+            }
+            int bsz = width;
+            while (asz > 0 || (bsz > 0 && b >= 0)) {
+                int pick;
+                if (asz == 0) { pick = b; b = next[b]; bsz--; }
+                else if (bsz == 0 || b < 0 || a < b) { pick = a; a = next[a]; asz--; }
+                else { pick = b; b = next[b]; bsz--; }
+                if (tail >= 0) next[tail] = pick; else new_head = pick;
+                tail = pick;
+            }
+            cur = b;
+        }
+        next[tail] = -1;
+        head = new_head;
+        if (merges <= 1) return head;
+    }
+}
+
 // pointBodyToWorld (laserMapping.cpp:209-220): double math without contraction, float store.
 __device__ __forceinline__ void li_body_to_world(const PoseD& P, float bx, float by, float bz, float& wx, float& wy, float& wz) {
     double x = (double)bx, y = (double)by, z = (double)bz;

@@ -291,7 +291,7 @@ __device__ __forceinline__ bool li_in_box(const DsBox& B, const float4& q) {
     return q.x >= B.mn[0] && q.x < B.mx[0] && q.y >= B.mn[1] && q.y < B.mx[1] && q.z >= B.mn[2] && q.z < B.mx[2];
 }
 
-__global__ void k_ds_replay(MapDev M, VoxTmp V, const float4* __restrict__ pts, const int* __restrict__ next_of,
+__global__ void k_ds_replay(MapDev M, VoxTmp V, const float4* __restrict__ pts, int* __restrict__ next_of,
                             int* __restrict__ ins) {
     unsigned v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v > V.mask) return;
@@ -338,14 +338,8 @@ __global__ void k_ds_replay(MapDev M, VoxTmp V, const float4* __restrict__ pts, 
             }
     bool modified = false;
     int changed = 0;
-    // batch order = ascending index: repeatedly take the smallest index greater than the last one processed
-    int last = -1;
-    for (;;) {
-        int cur = 0x7fffffff;
-        for (int t = head; t >= 0; t = next_of[t])
-            if (t > last && t < cur) cur = t;
-        if (cur == 0x7fffffff) break;
-        last = cur;
+    // batch order = ascending index: the box's list is sorted once (merge sort on the links), then replayed in one walk
+    for (int cur = li_list_sort_ascending(head, next_of); cur >= 0; cur = next_of[cur]) {
         float4 p = pts[cur];
         float dp = li_center_dist_cell(p.x, p.y, p.z, cx, cy, cz, M.ds);
         bool newwins = !(nE > 0 && bd < dp);

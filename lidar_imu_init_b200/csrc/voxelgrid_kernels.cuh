@@ -133,7 +133,7 @@ __global__ void k_vg_collect(VoxTmp V, const int* __restrict__ imin, unsigned* _
 
 // one thread per leaf, leaves in ascending leaf index (PCL's output order): sum the leaf's points in input order
 __global__ void k_vg_centroid_sorted(const float4* __restrict__ pts, const unsigned* __restrict__ reps, const int* __restrict__ count,
-                                     const int* __restrict__ slot_of, VoxTmp V, const int* __restrict__ next_of, float4* __restrict__ out,
+                                     const int* __restrict__ slot_of, VoxTmp V, int* __restrict__ next_of, float4* __restrict__ out,
                                      int out_cap, int* __restrict__ err) {
     int pos = blockIdx.x * blockDim.x + threadIdx.x;
     if (pos >= *count) return;
@@ -141,15 +141,11 @@ __global__ void k_vg_centroid_sorted(const float4* __restrict__ pts, const unsig
         atomicOr(err, 2);
         return;
     }
-    int head = V.head[slot_of[reps[pos]]];
+    // ascending input index: the leaf's list is sorted once (merge sort on the links), then summed in one walk
+    const int head = li_list_sort_ascending(V.head[slot_of[reps[pos]]], next_of);
     float sx = 0.f, sy = 0.f, sz = 0.f;
-    int cnt = 0, last = -1;
-    for (;;) {   // ascending input index: repeatedly take the smallest index greater than the last one
-        int cur = 0x7fffffff;
-        for (int t = head; t >= 0; t = next_of[t])
-            if (t > last && t < cur) cur = t;
-        if (cur == 0x7fffffff) break;
-        last = cur;
+    int cnt = 0;
+    for (int cur = head; cur >= 0; cur = next_of[cur]) {
         float4 p = pts[cur];
         sx = __fadd_rn(sx, p.x);
         sy = __fadd_rn(sy, p.y);

@@ -393,10 +393,21 @@ k_knn_scan(MapDev M, ScanDev S, PoseD P, float rho2, const float* __restrict__ r
         float gd[5];
         int gi[5];
         knn5_lockstep<G>(M, rho2, valid, wx, wy, wz, gd, gi, gl, gbase);
-        if (valid && gl == 0) {
-            S.world[q] = make_float4(wx, wy, wz, 0.f);
+        if (valid) {
+            if (gl == 0) S.world[q] = make_float4(wx, wy, wz, 0.f);
+            // Nearest_Points as COPIES (ScanDev::near_xyz; w = 1 found, 0 missing rank): the group's lanes share the five gathers --
+            // the slabs were read a moment ago, these are cache hits -- and the plane kernel of this pass needs no pool offsets
 #pragma unroll
-            for (int k = 0; k < 5; k++) S.near_ids[(size_t)q * 5 + k] = gi[k];
+            for (int k = 0; k < 5; k++) {
+                if (k % G == gl) {
+                    float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (gi[k] >= 0) {
+                        e = __ldg(&M.pool[gi[k]]);
+                        e.w = 1.0f;
+                    }
+                    S.near_xyz[(size_t)q * 5 + k] = e;
+                }
+            }
         }
     }
 }

@@ -429,9 +429,11 @@ void launch_plane(Ctx* c, const PoseD& P, double* out) {
     int grid = nblk(c->S.n, 256);
     if (grid > c->num_sms * 2 * LI_PLANE_WAVES) grid = c->num_sms * 2 * LI_PLANE_WAVES;
     if (grid < 1) grid = 1;   // (an empty slot of a multi-GPU frame still takes part in the exchange)
-    // search pass: the search kernel handed pool offsets over (gathered here, left in S.near_xyz as copies); reuse pass: the copies
     const XchgTable* X = (c->nranks > 1 && c->comm_p2p) ? c->d_xtab : nullptr;
-    k_icp_plane<IMU, SEARCH, SEARCH><<<grid, 256, 0, c->stream>>>(c->M, c->S, P, c->d_partials, c->d_done, out, X, c->xseq);
+    // the lockstep search leaves the neighbour copies in S.near_xyz itself; the cell-directory search hands pool offsets over, which
+    // the plane kernel of that pass gathers (and leaves as copies); a reuse pass reads the copies
+    if (SEARCH && c->cells) k_icp_plane<IMU, SEARCH, true><<<grid, 256, 0, c->stream>>>(c->M, c->S, P, c->d_partials, c->d_done, out, X, c->xseq);
+    else k_icp_plane<IMU, SEARCH, false><<<grid, 256, 0, c->stream>>>(c->M, c->S, P, c->d_partials, c->d_done, out, X, c->xseq);
 }
 
 // out: where the last block of the plane kernel leaves the 160-double result block -- the caller's device buffer

@@ -33,6 +33,8 @@ struct MapDev {
     int bshift;                    // log2(voxels per brick edge)
     int* touched_list;             // hash slots touched by the current update batch
     int* counters;                 // [0]=touched_n [1]=err flags [2]=n_live [3]=n_bricks [4]=changed voxels [5]=dropped pts
+    int* brick_slots;              // hash slot of every brick ever created, in creation order [counters[CNT_BRICKS]]: whole-map kernels
+                                   // (box delete, flatten, directory refresh) walk the bricks, not the (mostly empty) table
     // cell directory (cells.cuh; only with knn_index = cells, else null): per hash slot the occupancy mask of the brick's
     // 4x4x4 cells (cell = 2x2x2 voxels) and the start offset of every cell inside the slab, which is kept sorted by cell
     unsigned long long* cocc;
@@ -176,6 +178,15 @@ __device__ __forceinline__ int li_brick_find_or_insert(uint4* ent, unsigned mask
 // by atomicExch in arrival order; their points must be visited in INPUT order (sequential float sums, sequential box replay). The first
 // versions found "the next smallest index" by walking the whole list for every element: k^2 steps in one thread, seconds for the
 // thousands of points a near-sensor leaf of a 2M-point raw scan can hold (advisor finding, round 1).
+// true when the list holds more than `limit` nodes (walks at most limit + 1 of them)
+__device__ __forceinline__ bool li_list_longer_than(int head, const int* __restrict__ next, int limit) {
+    int k = 0;
+    for (int t = head; t >= 0; t = next[t])
+        if (++k > limit) return true;
+    return false;
+}
+#define LI_LIST_SELECT_MAX 8   // up to this many nodes "next smallest index" by repeated walks is cheaper than sorting the links (no stores)
+
 __device__ __forceinline__ int li_list_sort_ascending(int head, int* __restrict__ next) {
     if (head < 0 || next[head] < 0) return head;
     for (int width = 1;; width <<= 1) {

@@ -626,6 +626,7 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
     if (pool > 0x7fffff00ull) pool = 0x7fffff00ull;   // ids are int32 pool offsets
     M.pool_cap = pool;
     CUC(cudaMalloc(&M.ent, (size_t)c->hash_slots * sizeof(uint4)));
+    CUC(cudaMalloc(&M.brick_slots, (size_t)c->hash_slots * sizeof(int)));
     CUC(cudaMalloc(&M.aux, (size_t)c->hash_slots * sizeof(uint4)));
     CUC(cudaMalloc(&M.pool, (size_t)pool * sizeof(float4)));
     CUC(cudaMalloc(&M.pool_top, sizeof(unsigned long long)));
@@ -717,7 +718,7 @@ int liinit_destroy(liinit_ctx* h) {
     Ctx* c = &h->c;
     cudaSetDevice(c->device);
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
-    cudaFree(c->M.ent); cudaFree(c->M.aux); cudaFree(c->M.pool); cudaFree(c->M.pool_top); cudaFree(c->M.touched_list); cudaFree(c->M.cocc); cudaFree(c->M.cdir); cudaFree(c->M.sb_keys); cudaFree(c->M.sb_occ); cudaFree(c->d_ticket);
+    cudaFree(c->M.ent); cudaFree(c->M.brick_slots); cudaFree(c->M.aux); cudaFree(c->M.pool); cudaFree(c->M.pool_top); cudaFree(c->M.touched_list); cudaFree(c->M.cocc); cudaFree(c->M.cdir); cudaFree(c->M.sb_keys); cudaFree(c->M.sb_occ); cudaFree(c->d_ticket);
     cudaFree(c->d_counters); cudaFreeHost(c->h_counters); cudaFreeHost(c->h_pool_top); cudaFree(c->d_stage_raw); cudaFree(c->d_stage_pts);
     cudaFree(c->d_slot_of); cudaFree(c->d_vslot_of); cudaFree(c->d_flag); cudaFree(c->d_ins); cudaFree(c->V.keys); cudaFree(c->V.head); cudaFree(c->d_vg_imin); cudaFree(c->d_vg_block); cudaFree(c->d_vg_misc); cudaFree(c->d_rs_keys); cudaFree(c->d_rs_vals); cudaFree(c->d_rs_hist); cudaFree(c->d_vg_params); cudaFree(c->d_tmin_idx); cudaFree(c->d_poses);
     cudaFree(c->d_body); cudaFree(c->d_world); cudaFree(c->d_near_ids); cudaFree(c->d_near_xyz); cudaFree(c->d_selected); cudaFree(c->d_normvec);
@@ -796,7 +797,7 @@ int compact_map(Ctx* c) {
         d_tmp = btmp.p;
         d_n = bn.p;
         CU(cudaMemsetAsync(d_n, 0, sizeof(int), c->stream));
-        k_map_flatten4<<<nblk((long long)c->hash_slots * 32, 256), 256, 0, c->stream>>>(c->M, c->hash_slots, d_tmp, live, d_n);
+        k_map_flatten4<<<nblk((long long)c->h_counters[CNT_BRICKS] * 32, 256), 256, 0, c->stream>>>(c->M, c->hash_slots, d_tmp, live, d_n);
         c->launches++;
     }
     cudaMemsetAsync(c->d_counters, 0, sizeof(int) * CNT_COUNT, c->stream);
@@ -871,7 +872,12 @@ int liinit_map_delete_boxes(liinit_ctx* h, const float* boxes, int nbox, int* de
     if ((size_t)nbox * 6 > c->stage_raw_floats) return fail(c, LIINIT_ERR_CAPACITY, "too many boxes");
     CU(cudaMemcpyAsync(c->d_stage_raw, boxes, (size_t)nbox * 6 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemsetAsync(c->d_vg_misc + 6, 0, sizeof(int), c->stream));
-    k_map_delete_boxes<<<nblk((long long)c->hash_slots * 32, 256), 256, 0, c->stream>>>(c->M, c->hash_slots, c->d_stage_raw, nbox,
+    {   // bricks created so far (the counters are fetched at the end of every map update)
+        int r = fetch_counters(c);
+        if (r) return r;
+    }
+    if (c->h_counters[CNT_BRICKS] <= 0) return LIINIT_OK;
+    k_map_delete_boxes<<<nblk((long long)c->h_counters[CNT_BRICKS] * 32, 256), 256, 0, c->stream>>>(c->M, c->hash_slots, c->d_stage_raw, nbox,
                                                                                           c->d_vg_misc + 6);
     c->launches++;
     if (c->cells) {
@@ -926,7 +932,12 @@ int liinit_map_download(liinit_ctx* h, float* xyz, int cap, int* n) {
     float* d_out = out.p;
     int* d_n = dn.p;
     CU(cudaMemsetAsync(d_n, 0, 4, c->stream));
-    k_map_flatten<<<nblk((long long)c->hash_slots * 32, 256), 256, 0, c->stream>>>(c->M, c->hash_slots, d_out, cap, d_n);
+    {
+        int r = fetch_counters(c);
+        if (r) return r;
+    }
+    if (c->h_counters[CNT_BRICKS] > 0)
+        k_map_flatten<<<nblk((long long)c->h_counters[CNT_BRICKS] * 32, 256), 256, 0, c->stream>>>(c->M, c->hash_slots, d_out, cap, d_n);
     c->launches++;
     CU(cudaGetLastError());
     int cnt = 0;

@@ -115,7 +115,7 @@ __global__ void k_ins_count(MapDev M, const float4* __restrict__ pts, int n, con
     }
     slot_of[i] = s;
     if (created) {
-        atomicAdd(&M.counters[CNT_BRICKS], 1);
+        M.brick_slots[atomicAdd(&M.counters[CNT_BRICKS], 1)] = s;
         li_sb_mark(M, key);
     }
     atomicAdd(&M.aux[s].y, 1u);
@@ -248,7 +248,7 @@ __global__ void k_ds_link(MapDev M, VoxTmp V, const float4* __restrict__ pts, in
         return;
     }
     if (created) {
-        atomicAdd(&M.counters[CNT_BRICKS], 1);
+        M.brick_slots[atomicAdd(&M.counters[CNT_BRICKS], 1)] = s;
         li_sb_mark(M, skey);
     }
     slot_of[i] = s;
@@ -338,8 +338,24 @@ __global__ void k_ds_replay(MapDev M, VoxTmp V, const float4* __restrict__ pts, 
             }
     bool modified = false;
     int changed = 0;
-    // batch order = ascending index: the box's list is sorted once (merge sort on the links), then replayed in one walk
-    for (int cur = li_list_sort_ascending(head, next_of); cur >= 0; cur = next_of[cur]) {
+    // batch order = ascending index. Short lists (the usual box: one to three new points): repeatedly take the smallest index greater than
+    // the last one, no stores; long lists: the links are sorted once (merge sort), then replayed in one walk
+    const bool sorted_walk = li_list_longer_than(head, next_of, LI_LIST_SELECT_MAX);
+    if (sorted_walk) head = li_list_sort_ascending(head, next_of);
+    int last = -1, walk = head;
+    for (;;) {
+        int cur;
+        if (sorted_walk) {
+            cur = walk;
+            if (cur < 0) break;
+            walk = next_of[cur];
+        } else {
+            cur = 0x7fffffff;
+            for (int t = head; t >= 0; t = next_of[t])
+                if (t > last && t < cur) cur = t;
+            if (cur == 0x7fffffff) break;
+            last = cur;
+        }
         float4 p = pts[cur];
         float dp = li_center_dist_cell(p.x, p.y, p.z, cx, cy, cz, M.ds);
         bool newwins = !(nE > 0 && bd < dp);
@@ -448,8 +464,9 @@ __global__ void k_ds_compact(MapDev M) {
 // vertex_min <= c && vertex_max > c on every axis (:633). One warp per hash slot: tombstone-free in-place squeeze.
 __global__ void k_map_delete_boxes(MapDev M, unsigned slots, const float* __restrict__ boxes /* n x {min xyz, max xyz} */, int nbox,
                                    int* __restrict__ deleted) {
-    int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if ((unsigned)w >= slots) return;
+    int wb = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (wb >= M.counters[CNT_BRICKS]) return;   // `slots` = an upper bound of the brick count (the grid is sized by the host)
+    const int w = M.brick_slots[wb];
     uint4 e = M.ent[w];
     unsigned long long k = (unsigned long long)e.x | ((unsigned long long)e.y << 32);
     if (k == LI_EMPTY_KEY || e.w == 0u) return;
@@ -491,8 +508,9 @@ __global__ void k_gather_xyz(const float4* __restrict__ pool, const int* __restr
 
 // ---- flatten -------------------------------------------------------------------------------------
 __global__ void k_map_flatten(MapDev M, unsigned slots, float* __restrict__ out, int cap, int* __restrict__ out_n) {
-    int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if ((unsigned)w >= slots) return;
+    int wb = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (wb >= M.counters[CNT_BRICKS]) return;   // `slots` = an upper bound of the brick count (the grid is sized by the host)
+    const int w = M.brick_slots[wb];
     uint4 e = M.ent[w];
     unsigned long long k = (unsigned long long)e.x | ((unsigned long long)e.y << 32);
     if (k == LI_EMPTY_KEY || e.w == 0u) return;
@@ -512,8 +530,9 @@ __global__ void k_map_flatten(MapDev M, unsigned slots, float* __restrict__ out,
 
 // live points as float4 {x, y, z, 0} (liinit_map_compact re-inserts them into a cleared pool)
 __global__ void k_map_flatten4(MapDev M, unsigned slots, float4* __restrict__ out, int cap, int* __restrict__ out_n) {
-    int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if ((unsigned)w >= slots) return;
+    int wb = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (wb >= M.counters[CNT_BRICKS]) return;   // `slots` = an upper bound of the brick count (the grid is sized by the host)
+    const int w = M.brick_slots[wb];
     uint4 e = M.ent[w];
     unsigned long long k = (unsigned long long)e.x | ((unsigned long long)e.y << 32);
     if (k == LI_EMPTY_KEY || e.w == 0u) return;

@@ -141,16 +141,34 @@ __global__ void k_vg_centroid_sorted(const float4* __restrict__ pts, const unsig
         atomicOr(err, 2);
         return;
     }
-    // ascending input index: the leaf's list is sorted once (merge sort on the links), then summed in one walk
-    const int head = li_list_sort_ascending(V.head[slot_of[reps[pos]]], next_of);
+    // ascending input index. Short lists (the usual leaf): repeatedly take the smallest index greater than the last one -- k^2 loads but no
+    // stores; long lists (near-sensor leaves of a dense raw scan): sort the links once (merge sort), then one walk
+    int head = V.head[slot_of[reps[pos]]];
     float sx = 0.f, sy = 0.f, sz = 0.f;
     int cnt = 0;
-    for (int cur = head; cur >= 0; cur = next_of[cur]) {
-        float4 p = pts[cur];
-        sx = __fadd_rn(sx, p.x);
-        sy = __fadd_rn(sy, p.y);
-        sz = __fadd_rn(sz, p.z);
-        cnt++;
+    if (li_list_longer_than(head, next_of, LI_LIST_SELECT_MAX)) {
+        head = li_list_sort_ascending(head, next_of);
+        for (int cur = head; cur >= 0; cur = next_of[cur]) {
+            float4 p = pts[cur];
+            sx = __fadd_rn(sx, p.x);
+            sy = __fadd_rn(sy, p.y);
+            sz = __fadd_rn(sz, p.z);
+            cnt++;
+        }
+    } else {
+        int last = -1;
+        for (;;) {
+            int cur = 0x7fffffff;
+            for (int t = head; t >= 0; t = next_of[t])
+                if (t > last && t < cur) cur = t;
+            if (cur == 0x7fffffff) break;
+            last = cur;
+            float4 p = pts[cur];
+            sx = __fadd_rn(sx, p.x);
+            sy = __fadd_rn(sy, p.y);
+            sz = __fadd_rn(sz, p.z);
+            cnt++;
+        }
     }
     float c = (float)cnt;
     out[pos] = make_float4(__fdiv_rn(sx, c), __fdiv_rn(sy, c), __fdiv_rn(sz, c), 0.f);

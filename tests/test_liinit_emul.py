@@ -480,3 +480,32 @@ def test_emul_map_compact_gives_dead_storage_back(oracle_mod):
     assert g.map_validnum() == 500
     assert g.map_add_points(c["map_xyz"][500:600], False) == 100
     g.close()
+
+
+def test_emul_long_index_lists_are_walked_in_input_order(oracle_mod):
+    """Leaves / downsample boxes that hold MANY points of a batch (long per-leaf lists: the links are merge-sorted once instead of being
+    walked k times): the voxel-grid centroids -- sequential float sums in input order -- and the Add_Points(downsample) replay must still
+    equal the oracle's bit for bit."""
+    rng = np.random.default_rng(99)
+    # raw cloud: three leaves of 0.5 m with 700 / 90 / 9 points, plus scattered ones
+    dense = [np.array([2.25, 1.25, 0.25]) + rng.uniform(-0.24, 0.24, (700, 3)), np.array([-3.25, 0.75, 1.25]) + rng.uniform(-0.24, 0.24, (90, 3)),
+             np.array([5.75, -2.25, 0.75]) + rng.uniform(-0.24, 0.24, (9, 3))]
+    raw = np.concatenate(dense + [rng.uniform(-8, 8, (1500, 3))], 0).astype(np.float32)
+    raw = np.ascontiguousarray(raw[rng.permutation(len(raw))])
+    g = le.EmulGpu(0.15, max_map_points=60000, max_scan_points=4000, hash_capacity_log2=12)
+    n = g.scan_upload_raw(raw, 0.5)
+    want = oracle_mod.voxel_grid(raw, 0.5)
+    assert n == len(want) and np.array_equal(g.scan_body(), want)
+    # downsample insert: 40 + 12 + 3 new points falling into three map voxels (plus singles), against the sequential reference
+    ds = 0.15
+    om = oracle_mod.OracleMap(ds, _bk(oracle_mod))
+    base = rng.uniform(-3, 3, (3000, 3)).astype(np.float32)
+    g.map_build(base)
+    om.build(base)
+    cells = [np.array([4, -7, 2]), np.array([-9, 3, 1]), np.array([0, 0, 5])]
+    batch = [((c + rng.uniform(0.05, 0.95, (k, 3))) * ds) for c, k in zip(cells, (40, 12, 3))] + [rng.uniform(-3, 3, (400, 3))]
+    batch = np.concatenate(batch, 0).astype(np.float32)
+    batch = _single_box(np.ascontiguousarray(batch[rng.permutation(len(batch))]), ds)
+    assert g.map_add_points(batch, True) == om.add_points(batch, True)
+    assert g.map_validnum() == om.validnum() and _same_set(g.map_download(), om.flatten())
+    g.close()

@@ -175,6 +175,13 @@ int liinit_comm_mode(liinit_ctx* h, int* peer_memory);
 /* nranks / rank of the context and the slot [shard_lo, shard_lo + shard_n) of the resident frame this rank works on. */
 int liinit_comm_info(liinit_ctx* h, int* nranks, int* rank, int* shard_lo, int* shard_n);
 
+/* A scan is searched more than once (laserMapping.cpp:1102-1106: rematch after convergence / at the last but one iteration). By default
+ * the later search passes of a scan are SEEDED: the five neighbours the previous pass stored still exist in the map (the library tracks
+ * every call that can remove a point), so their largest distance from the moved query bounds the new 5th-neighbour distance -- one shell,
+ * hardly any inserts, same result bit for bit. enabled = 0 makes every search pass start from scratch (what bench.py times as the metric:
+ * the FIRST search pass of a scan). */
+int liinit_set_reseed(liinit_ctx* h, int enabled);
+
 /* instrumentation (the reference has none around this loop) ---- */
 /* Device time in milliseconds of the kernels of the last liinit_icp_iterate* call (CUDA events on the context's
  * stream) and the number of kernel launches it made. */

@@ -37,7 +37,7 @@ SYMBOLS = [
     "liinit_raw_download", "liinit_raw_downsample",
     "liinit_icp_iterate", "liinit_icp_iterate_device", "liinit_scan_download_effect", "liinit_scan_download_state",
     "liinit_map_incremental", "liinit_last_pass_timing", "liinit_last_pass_kernel_times", "liinit_launch_count", "liinit_map_stats", "liinit_knn_index",
-    "liinit_comm_unique_id", "liinit_comm_init", "liinit_comm_info", "liinit_comm_last_local", "liinit_comm_mode", "liinit_debug_esti_plane",
+    "liinit_comm_unique_id", "liinit_comm_init", "liinit_comm_info", "liinit_comm_last_local", "liinit_comm_mode", "liinit_debug_esti_plane", "liinit_set_reseed",
 ]
 
 
@@ -94,6 +94,7 @@ def load():
     L.liinit_debug_esti_plane.argtypes = [vp, vp, C.c_int, vp, vp]
     L.liinit_comm_last_local.argtypes = [vp, _f64]
     L.liinit_comm_mode.argtypes = [vp, C.POINTER(C.c_int)]
+    L.liinit_set_reseed.argtypes = [vp, C.c_int]
     L.liinit_comm_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     for s in SYMBOLS:
         getattr(L, s).restype = getattr(L, s).restype if s == "liinit_last_error" else C.c_int
@@ -331,6 +332,10 @@ class LiInitGpu:
         assert len(unique_id) == 128
         buf = C.create_string_buffer(unique_id, 128)
         self._ck(self.L.liinit_comm_init(self.h, buf, int(nranks), int(rank)))
+
+    def set_reseed(self, enabled: bool):
+        """later search passes of a scan start from the previous pass's neighbours (default on); off = every search from scratch"""
+        self._ck(self.L.liinit_set_reseed(self.h, int(enabled)))
 
     def comm_mode(self) -> str:
         v = C.c_int(0)

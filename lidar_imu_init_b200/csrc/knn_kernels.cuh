@@ -360,7 +360,7 @@ __device__ __forceinline__ void knn5_lockstep(const MapDev& M, float rho2, bool 
 // S.body for the plane kernel and the later passes. No staging copy, no repack launch in front of the search.
 template <int G, bool HOST>
 __global__ void __launch_bounds__(LI_KNN_THREADS, LI_KNN_MIN_BLOCKS)
-k_knn_scan(MapDev M, ScanDev S, PoseD P, float rho2, const float* __restrict__ raw, int stride) {
+k_knn_scan(MapDev M, ScanDev S, PoseD P, float rho2, const float* __restrict__ raw, int stride, int seeded) {
     constexpr int Q = Grp<G>::Q;
     const int lane = threadIdx.x & 31;
     const int gl = lane % G, gid = lane / G, gbase = gid * G;
@@ -390,9 +390,34 @@ k_knn_scan(MapDev M, ScanDev S, PoseD P, float rho2, const float* __restrict__ r
             float4 b = __ldg(&S.body[q]);
             li_body_to_world(P, b.x, b.y, b.z, wx, wy, wz);
         }
+        // A later search pass of the same scan (laserMapping.cpp:1102-1106: rematch after convergence) starts from what the previous one
+        // found: the five stored neighbours still exist in the map (the host only sets `seeded` while no point has been removed since), so
+        // the 5th-neighbour distance at the moved query cannot exceed the largest of THEIR distances from it. That bound is the radius of
+        // the first -- and then only -- shell and the candidate threshold: one shell, a handful of inserts. Exactness is untouched.
+        float rho2q = rho2, thr0 = INFINITY;
+        if (seeded) {   // warp-uniform
+            float bmax = 0.f;
+            bool miss = false;
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                if (k % G == gl && valid) {
+                    const float4 e = S.near_xyz[(size_t)q * 5 + k];
+                    if (e.w == 0.f) miss = true;
+                    else bmax = fmaxf(bmax, li_dist2(wx, wy, wz, e.x, e.y, e.z));
+                }
+            }
+#pragma unroll
+            for (int o = (G > 4 ? 4 : G / 2); o >= 1; o >>= 1) bmax = fmaxf(bmax, __shfl_xor_sync(LI_FULL, bmax, o));   // ranks live in lanes 0..min(G,5)-1 (+ wrap for G < 5)
+            if (G > 4) bmax = __shfl_sync(LI_FULL, bmax, gbase);
+            const bool any_miss = grp_ballot<G>(miss, gbase) != 0u;
+            if (valid && !any_miss && bmax < 5.0f) {
+                rho2q = bmax * (1.0f + 2e-6f) + 1e-12f;
+                thr0 = __uint_as_float(__float_as_uint(bmax) + 1u);   // smallest float above the bound: d <= bmax passes `d < thr0`
+            }
+        }
         float gd[5];
         int gi[5];
-        knn5_lockstep<G>(M, rho2, valid, wx, wy, wz, gd, gi, gl, gbase);
+        knn5_lockstep<G>(M, rho2q, valid, wx, wy, wz, gd, gi, gl, gbase, thr0);
         if (valid) {
             if (gl == 0) S.world[q] = make_float4(wx, wy, wz, 0.f);
             // Nearest_Points as COPIES (ScanDev::near_xyz; w = 1 found, 0 missing rank): the group's lanes share the five gathers --

@@ -142,6 +142,9 @@ struct Ctx {
     void* peer_map[LI_MAX_RANKS] = {nullptr};   // what cudaIpcOpenMemHandle returned (closed in liinit_destroy)
     unsigned xseq = 0;             // pass sequence number (identical on every rank: the passes are collective)
     bool state_gathered = true;    // per-point results of the other ranks' shards are present on this device
+    unsigned map_epoch = 0;        // bumped by everything that can REMOVE a map point (Build, downsample inserts, box delete, compaction)
+    unsigned nbr_epoch = 0;        // map_epoch when the resident scan's Nearest_Points were found
+    bool reseed = true;            // later search passes of a scan start from the previous pass's neighbours (liinit_set_reseed)
     bool have_neighbors = false;   // a search pass has filled near_xyz for the resident scan (point copies: map updates do not invalidate them)
     bool scan_fresh = false;   // new scan whose flags / neighbour lists have not been initialised yet (see init_scan_state)
     const float* attached = nullptr;   // device alias of a page-locked host scan not copied yet (liinit_scan_attach_host)
@@ -382,11 +385,13 @@ void launch_knn_scan(Ctx* c, const PoseD& P) {
     int grid = nblk(threads, LI_KNN_THREADS);
     int cap = c->max_blocks * (256 / LI_KNN_THREADS);
     if (grid > cap) grid = cap;
+    // a later search pass of the same scan, no map point removed in between: seeded by the previous pass's neighbours (knn_kernels.cuh)
+    const int seeded = (c->have_neighbors && !c->scan_fresh && c->nbr_epoch == c->map_epoch && c->reseed) ? 1 : 0;
     if (const float* raw = attached_slot(c)) {
-        k_knn_scan<G, true><<<grid, LI_KNN_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, raw, c->attached_stride);
+        k_knn_scan<G, true><<<grid, LI_KNN_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, raw, c->attached_stride, 0);
         attached_slot_read(c);   // the kernel leaves the packed copy in d_body
     } else {
-        k_knn_scan<G, false><<<grid, LI_KNN_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, nullptr, 0);
+        k_knn_scan<G, false><<<grid, LI_KNN_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, nullptr, 0, seeded);
     }
 }
 
@@ -462,7 +467,8 @@ int run_pass(Ctx* c, const double* R, const double* p, const double* RLI, const 
         CU(cudaEventRecord(c->evm, c->stream));
         if (imu_en) launch_plane<true, true>(c, P, out); else launch_plane<false, true>(c, P, out);
         c->have_neighbors = true;
-        c->scan_fresh = false;   // the two kernels wrote near_ids / selected for every point of the scan
+        c->nbr_epoch = c->map_epoch;
+        c->scan_fresh = false;   // the two kernels wrote the neighbour copies / selected for every point of the scan
         c->launches += 2;
         c->last_launches = 2;
         c->last_was_search = true;
@@ -753,6 +759,7 @@ int liinit_map_build(liinit_ctx* h, const float* xyz, int stride, int n) {
     Ctx* c = &h->c;
     CU(cudaSetDevice(c->device));
     if (n > c->cfg.max_map_points) return fail(c, LIINIT_ERR_CAPACITY, "n exceeds max_map_points");
+    c->map_epoch++;
     // KD_TREE::Build replaces the tree (ikd_Tree.cpp:337-339)
     CU(cudaMemsetAsync(c->d_counters, 0, sizeof(int) * CNT_COUNT, c->stream));
     CU(cudaMemsetAsync(c->M.pool_top, 0, sizeof(unsigned long long), c->stream));
@@ -784,6 +791,7 @@ namespace {
 // (Add_Points ahead, Delete_Point_Boxes behind) would run the pool dry although few points are alive. Compaction = flatten the live
 // points, clear hash + pool, re-insert them (the Build path): every brick gets one tight slab, empty bricks disappear.
 int compact_map(Ctx* c) {
+    c->map_epoch++;
     int r = fetch_counters(c);
     if (r) return r;
     const int live = c->h_counters[CNT_LIVE];
@@ -842,6 +850,7 @@ int liinit_map_add_points(liinit_ctx* h, const float* xyz, int stride, int n, in
     if (!h || (!xyz && n > 0) || n < 0) return LIINIT_ERR_INVALID;
     Ctx* c = &h->c;
     CU(cudaSetDevice(c->device));
+    c->map_epoch++;
     {
         int r = maybe_compact(c, n);
         if (r) return r;
@@ -869,6 +878,7 @@ int liinit_map_delete_boxes(liinit_ctx* h, const float* boxes, int nbox, int* de
     CU(cudaSetDevice(c->device));
     if (deleted) *deleted = 0;
     if (nbox == 0) return LIINIT_OK;
+    c->map_epoch++;
     if ((size_t)nbox * 6 > c->stage_raw_floats) return fail(c, LIINIT_ERR_CAPACITY, "too many boxes");
     CU(cudaMemcpyAsync(c->d_stage_raw, boxes, (size_t)nbox * 6 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemsetAsync(c->d_vg_misc + 6, 0, sizeof(int), c->stream));
@@ -1315,6 +1325,7 @@ int liinit_map_incremental(liinit_ctx* h, const double* R, const double* p, cons
         r = gather_scan_state(c);
         if (r) return r;
     }
+    c->map_epoch++;
     {
         int r = maybe_compact(c, n);
         if (r) return r;
@@ -1537,6 +1548,12 @@ int liinit_comm_info(liinit_ctx* h, int* nranks, int* rank, int* shard_lo, int* 
     if (rank) *rank = h->c.rank;
     if (shard_lo) *shard_lo = h->c.shard_lo;
     if (shard_n) *shard_n = h->c.S.n;
+    return LIINIT_OK;
+}
+
+int liinit_set_reseed(liinit_ctx* h, int enabled) {
+    if (!h) return LIINIT_ERR_INVALID;
+    h->c.reseed = enabled != 0;
     return LIINIT_OK;
 }
 

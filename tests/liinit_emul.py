@@ -61,6 +61,7 @@ def load():
         L.liinit_raw_download.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int)]
         L.liinit_raw_downsample.argtypes = [vp, C.c_float, C.POINTER(C.c_int)]
         L.liinit_debug_esti_plane.argtypes = [vp, vp, C.c_int, vp, vp]
+        L.liinit_set_reseed.argtypes = [vp, C.c_int]
         _L = L
     return _L
 
@@ -151,6 +152,9 @@ class EmulGpu:
         b, sl, pu, pc = C.c_int(0), C.c_int(0), C.c_longlong(0), C.c_longlong(0)
         self._ck(self.L.liinit_map_stats(self.h, C.byref(b), C.byref(sl), C.byref(pu), C.byref(pc)))
         return dict(bricks=b.value, hash_slots=sl.value, pool_used=pu.value, pool_cap=pc.value)
+
+    def set_reseed(self, enabled):
+        self._ck(self.L.liinit_set_reseed(self.h, int(enabled)))
 
     def debug_esti_plane(self, nb):
         a = np.ascontiguousarray(nb, np.float32).reshape(-1, 15)

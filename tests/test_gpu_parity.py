@@ -145,3 +145,40 @@ def test_map_incremental_matches_oracle(gpu_lib, oracle_mod):
     ox, od, oc, _ = om.knn(q)
     assert np.array_equal(gc, oc) and np.array_equal(gd, od) and np.array_equal(gx, ox)
     g.close()
+
+
+@pytest.mark.parametrize("group", [0, 4, 8])
+def test_seeded_later_search_pass_is_identical(gpu_lib, oracle_mod, group):
+    """Later search passes of a scan start from the previous pass's neighbours (liinit_set_reseed, default on): bit-identical per-point state
+    and accumulators to a search from scratch, equal to the oracle; a map update in between switches the seed off."""
+    c = scenes.make_config("C2", N=20000, M=200000, open_air_frac=0.02)
+    p = c["pose_init"]
+    p2 = scenes.perturb_pose(p, 78, dtheta_deg=0.08, dpos=0.02)
+    om = oracle_mod.OracleMap(c["ds"], _best_backend(oracle_mod))
+    om.build(c["map_xyz"])
+    osc = oracle_mod.OracleScan(c["body_xyz"])
+    osc.iterate(om, p.rot_end, p.pos_end, p.R_LI, p.T_LI, False, True)
+    Ho, bo, mo = osc.iterate(om, p2.rot_end, p2.pos_end, p2.R_LI, p2.T_LI, False, True)
+    res = {}
+    for seeded in (True, False):
+        g = gpu_lib.LiInitGpu(c["ds"], max_map_points=400000, max_scan_points=50000, knn_group_lanes=group)
+        g.set_reseed(seeded)
+        g.map_build(c["map_xyz"])
+        g.scan_upload(c["body_xyz"])
+        g.icp_iterate(p.rot_end, p.pos_end, p.R_LI, p.T_LI, False, True)
+        H, b, m, _ = g.icp_iterate(p2.rot_end, p2.pos_end, p2.R_LI, p2.T_LI, False, True)
+        res[seeded] = (H, b, m, g.scan_state(), g.last_pass_kernel_times()[0])
+        assert m == mo and _relerr(H, Ho) <= 1e-9 and _relerr(b, bo) <= 1e-9
+        assert np.array_equal(res[seeded][3]["near_xyz"], osc.get()["near_xyz"])
+        if seeded:
+            extra = _world(c["body_xyz"][:3000], c["pose_gt"]) + np.float32(0.02)
+            assert g.map_add_points(extra, True) == om.add_points(extra, True)
+            H3, b3, m3, _ = g.icp_iterate(p.rot_end, p.pos_end, p.R_LI, p.T_LI, False, True)
+            Ho3, bo3, mo3 = osc.iterate(om, p.rot_end, p.pos_end, p.R_LI, p.T_LI, False, True)
+            assert m3 == mo3 and _relerr(H3, Ho3) <= 1e-9 and np.array_equal(g.scan_state()["near_xyz"], osc.get()["near_xyz"])
+        g.close()
+    (Hs, bs, ms, sts, ts), (Hu, bu, mu, stu, tu) = res[True], res[False]
+    assert ms == mu and np.array_equal(Hs, Hu) and np.array_equal(bs, bu)
+    for k in ("world", "near_xyz", "near_cnt", "selected"):
+        assert np.array_equal(sts[k], stu[k]), k
+    print(f"seeded search kernel {ts:.4f} ms vs {tu:.4f} ms from scratch (G = {group or 'auto'})")

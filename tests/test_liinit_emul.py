@@ -509,3 +509,42 @@ def test_emul_long_index_lists_are_walked_in_input_order(oracle_mod):
     assert g.map_add_points(batch, True) == om.add_points(batch, True)
     assert g.map_validnum() == om.validnum() and _same_set(g.map_download(), om.flatten())
     g.close()
+
+
+@pytest.mark.parametrize("group", [4, 8, 32])
+def test_emul_seeded_second_search_pass(oracle_mod, group):
+    """A later search pass of the same scan starts from the previous pass's neighbours (their largest distance from the moved query bounds
+    the new 5th-neighbour distance): same neighbours, flags, normals and accumulators as a search from scratch and as the oracle; a map
+    update in between (which may remove points) switches the seed off."""
+    c = scenes.make_config("C2", N=2500, M=50000, open_air_frac=0.02)
+    p = c["pose_init"]
+    p2 = scenes.perturb_pose(p, 78, dtheta_deg=0.08, dpos=0.02)
+    om = oracle_mod.OracleMap(c["ds"], _bk(oracle_mod))
+    om.build(c["map_xyz"])
+    osc = oracle_mod.OracleScan(c["body_xyz"])
+    osc.iterate(om, p.rot_end, p.pos_end, p.R_LI, p.T_LI, False, True)
+    Ho, bo, mo = osc.iterate(om, p2.rot_end, p2.pos_end, p2.R_LI, p2.T_LI, False, True)
+    res = {}
+    for seeded in (True, False):
+        g = le.EmulGpu(c["ds"], max_map_points=150000, max_scan_points=5000, knn_group_lanes=group)
+        g.set_reseed(seeded)
+        g.map_build(c["map_xyz"])
+        g.scan_upload(c["body_xyz"])
+        g.icp_iterate(p.rot_end, p.pos_end, p.R_LI, p.T_LI, False, True)
+        H, b, m, _ = g.icp_iterate(p2.rot_end, p2.pos_end, p2.R_LI, p2.T_LI, False, True)
+        res[seeded] = (H, b, m, g.scan_state())
+        assert m == mo and _relerr(H, Ho) <= REL and _relerr(b, bo) <= REL
+        if seeded:   # a downsample insert may remove points: the next search pass must not trust the stored neighbours
+            extra = _world(c["body_xyz"][:600], c["pose_gt"]) + np.float32(0.02)
+            assert g.map_add_points(extra, True) == om.add_points(extra, True)
+            H3, b3, m3, _ = g.icp_iterate(p.rot_end, p.pos_end, p.R_LI, p.T_LI, False, True)
+            Ho3, bo3, mo3 = osc.iterate(om, p.rot_end, p.pos_end, p.R_LI, p.T_LI, False, True)
+            assert m3 == mo3 and _relerr(H3, Ho3) <= REL
+            assert np.array_equal(g.scan_state()["near_xyz"], osc.get()["near_xyz"])
+        g.close()
+    (Hs, bs, ms, sts), (Hu, bu, mu, stu) = res[True], res[False]
+    assert ms == mu and np.array_equal(Hs, Hu) and np.array_equal(bs, bu)
+    for k in ("world", "near_xyz", "near_cnt", "selected"):
+        assert np.array_equal(sts[k], stu[k]), k
+    sel = sts["selected"].astype(bool)
+    assert np.array_equal(sts["normvec"][sel], stu["normvec"][sel])

@@ -358,9 +358,10 @@ __device__ __forceinline__ void knn5_lockstep(const MapDev& M, float rho2, bool 
 // buffer (liinit_scan_attach_host) and the kernel pulls the coordinates over PCIe itself (one contiguous
 // Q*stride*4-byte read per warp batch, hidden behind the other warps' searches), leaving the packed copy in
 // S.body for the plane kernel and the later passes. No staging copy, no repack launch in front of the search.
-template <int G, bool HOST>
+// SEEDED = true (a separate instantiation, so that the first-pass kernel keeps its registers): see below.
+template <int G, bool HOST, bool SEEDED = false>
 __global__ void __launch_bounds__(LI_KNN_THREADS, LI_KNN_MIN_BLOCKS)
-k_knn_scan(MapDev M, ScanDev S, PoseD P, float rho2, const float* __restrict__ raw, int stride, int seeded) {
+k_knn_scan(MapDev M, ScanDev S, PoseD P, float rho2, const float* __restrict__ raw, int stride) {
     constexpr int Q = Grp<G>::Q;
     const int lane = threadIdx.x & 31;
     const int gl = lane % G, gid = lane / G, gbase = gid * G;
@@ -395,7 +396,7 @@ k_knn_scan(MapDev M, ScanDev S, PoseD P, float rho2, const float* __restrict__ r
         // the 5th-neighbour distance at the moved query cannot exceed the largest of THEIR distances from it. That bound is the radius of
         // the first -- and then only -- shell and the candidate threshold: one shell, a handful of inserts. Exactness is untouched.
         float rho2q = rho2, thr0 = INFINITY;
-        if (seeded) {   // warp-uniform
+        if (SEEDED) {
             float bmax = 0.f;
             bool miss = false;
 #pragma unroll

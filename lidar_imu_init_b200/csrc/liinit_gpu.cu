@@ -386,12 +386,14 @@ void launch_knn_scan(Ctx* c, const PoseD& P) {
     int cap = c->max_blocks * (256 / LI_KNN_THREADS);
     if (grid > cap) grid = cap;
     // a later search pass of the same scan, no map point removed in between: seeded by the previous pass's neighbours (knn_kernels.cuh)
-    const int seeded = (c->have_neighbors && !c->scan_fresh && c->nbr_epoch == c->map_epoch && c->reseed) ? 1 : 0;
+    const bool seeded = c->have_neighbors && !c->scan_fresh && c->nbr_epoch == c->map_epoch && c->reseed;
     if (const float* raw = attached_slot(c)) {
-        k_knn_scan<G, true><<<grid, LI_KNN_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, raw, c->attached_stride, 0);
+        k_knn_scan<G, true><<<grid, LI_KNN_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, raw, c->attached_stride);
         attached_slot_read(c);   // the kernel leaves the packed copy in d_body
+    } else if (seeded) {
+        k_knn_scan<G, false, true><<<grid, LI_KNN_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, nullptr, 0);
     } else {
-        k_knn_scan<G, false><<<grid, LI_KNN_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, nullptr, 0, seeded);
+        k_knn_scan<G, false><<<grid, LI_KNN_THREADS, 0, c->stream>>>(c->M, c->S, P, c->rho2, nullptr, 0);
     }
 }
 

@@ -52,8 +52,8 @@ def emit(obj):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the search kernel on C2 (ncu --set full, cold cache), per index
-NCU_DRAM_BYTES_KNN = {1: 117_762_816, 2: 141_602_560}
-NCU_DRAM_SOURCE = {1: "profiles/r01_ncu_full_final_metrics.txt", 2: "profiles/r01_cells/ncu_full_stream_final_metrics.txt"}
+NCU_DRAM_BYTES_KNN = {1: 125_488_896, 2: 141_602_560}   # 1: 110.91 MB read + 14.58 MB written (the kernel now writes the neighbour copies)
+NCU_DRAM_SOURCE = {1: "profiles/r02/ncu_full_final_metrics.txt", 2: "profiles/r01_cells/ncu_full_stream_final_metrics.txt"}
 KNN_KERNEL = {1: "k_knn_scan (5-NN search on whole bricks, lockstep lane groups; dominant kernel of the pass)",
               2: "k_knn_cells_scan (5-NN search on the per-brick cell directory, one scan point per thread; dominant kernel of the pass)"}
 KNN_NAME = {1: "bricks", 2: "cells"}

@@ -15,6 +15,7 @@ ap.add_argument("--index", type=int, default=0)
 a = ap.parse_args()
 c = scenes.make_config("C2", N=a.N, M=a.M)
 g = capi.LiInitGpu(c["ds"], max_map_points=int(a.M * 1.2), max_scan_points=a.N + 10, knn_group_lanes=a.group, brick_cells_log2=a.brick, knn_seed_radius_cells=a.rho, knn_index=a.index)
+g.set_reseed(False)   # every search pass from scratch: the captures show the FIRST search pass of a scan (the bench metric)
 g.map_build(c["map_xyz"])
 g.scan_upload(c["body_xyz"])
 p = c["pose_init"]

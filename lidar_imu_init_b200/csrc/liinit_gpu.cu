@@ -434,7 +434,7 @@ template <bool IMU, bool SEARCH>
 void launch_plane(Ctx* c, const PoseD& P, double* out) {
     // one wave of 256-thread blocks (2 resident per SM at ~100-130 registers), grid-stride over the scan
     int grid = nblk(c->S.n, 256);
-    if (grid > c->num_sms * 2 * LI_PLANE_WAVES) grid = c->num_sms * 2 * LI_PLANE_WAVES;
+    if (grid > c->num_sms * LI_PLANE_MIN_BLOCKS * LI_PLANE_WAVES) grid = c->num_sms * LI_PLANE_MIN_BLOCKS * LI_PLANE_WAVES;
     if (grid < 1) grid = 1;   // (an empty slot of a multi-GPU frame still takes part in the exchange)
     const XchgTable* X = (c->nranks > 1 && c->comm_p2p) ? c->d_xtab : nullptr;
     // the lockstep search leaves the neighbour copies in S.near_xyz itself; the cell-directory search hands pool offsets over, which

@@ -434,7 +434,7 @@ def run_gpu(args, rank, world, local_rank):
                     "parallelism": "1 GPU" if world == 1 else (f"{world} GPUs, map replicated, frame of {NF} points cut into {world} slots by the library, "
                                                                "accumulators summed over the ranks inside liinit_icp_iterate (" + g.comm_mode() + ")"),
                     "l2": "flushed between timed steps (256 MiB memset outside the events)", "knn_index": KNN_NAME[kidx],
-                    "knn_group_lanes": (args.group or "auto (by frame size: 4 lanes beyond 170k points per GPU)") if kidx == 1 else None, "brick_cells_log2": args.brick or 3,
+                    "knn_group_lanes": (args.group or "auto (by frame size: 4 lanes beyond 70k points per GPU)") if kidx == 1 else None, "brick_cells_log2": args.brick or 3,
                     "selected_points": int(m_sel), "map_build_s": build_s, "map_points_live": g.map_validnum()},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(N * 12 + 192), "d2h_bytes_per_step": 160 * 8,
                 "ms_per_step": e2e_ms / args.steps,

@@ -45,7 +45,7 @@ typedef struct liinit_config {
     int brick_cells_log2;    /* voxels per brick edge = 1<<this; 0 -> default (3, i.e. brick edge = 8*ds) */
     int hash_capacity_log2;  /* brick hash slots = 1<<this; 0 -> derived from max_map_points */
     int knn_group_lanes;     /* lanes cooperating on one scan point in the lockstep 5-NN kernel: 2, 4, 8, 16 or 32; 0 -> chosen per pass from the frame
-                                size (32 lanes up to 20k points ... 4 lanes beyond 170k: small frames need the latency, large ones the throughput) */
+                                size (32 lanes up to 14k points, 8 up to 70k, 4 beyond: small frames need the latency, large ones the throughput) */
     float knn_seed_radius_cells; /* first search shell of the 5-NN kernel, in map voxels (radius = this * filter_size_map); 0 -> default (2) */
     int knn_index;           /* how the 5-NN kernel searches the brick hash: LIINIT_KNN_BRICKS (lockstep groups of knn_group_lanes lanes over whole bricks)
                                 or LIINIT_KNN_CELLS (thread per scan point over the per-brick cell directory; needs brick_cells_log2 = 3); 0 -> default */

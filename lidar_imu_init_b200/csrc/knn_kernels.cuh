@@ -226,35 +226,51 @@ struct KnnGeom {
     float ds, margin;   // voxel edge; rounding slack added to every pruning box
 };
 
-// Lockstep scan of the bricks found by the lanes of each group in the current probe round. thr: only candidates with
-// d < thr (and d <= 5) matter. prune: skip bricks whose box distance is not below thr.
-template <int G>
-__device__ __forceinline__ void lockstep_scan_found(const float4* __restrict__ pool, bool found, unsigned first, unsigned count, float dbox,
-                                                    float qx, float qy, float qz, float thr, float (&ld)[5], int (&li)[5], int gl, int gbase) {
-    unsigned fm = grp_ballot<G>(found, gbase);
-    while (__any_sync(LI_FULL, fm != 0u)) {
-        const bool has = fm != 0u;
-        const int src = has ? (__ffs(fm) - 1) : 0;
-        fm &= fm - 1u;
-        const float db = grp_shfl<G>(dbox, src, gbase);
-        const unsigned f = grp_shfl<G>(first, src, gbase);
-        const unsigned c = grp_shfl<G>(count, src, gbase);
-#if LI_GROUP_BOUND
-        // The group's 5th best so far is at most m = min over its lanes of their private 5th best (a lane holding five
-        // entries proves five candidates within its ld[4]). Candidates and whole bricks STRICTLY beyond m can never
-        // enter the final top-5 (ties at m are kept, so the result is the one the private bounds alone would give).
-        unsigned mb = grp_min<G>(__float_as_uint(ld[4]));
-        mb = min(mb + 1u, 0x7f800000u);                      // smallest float above m (inf stays inf)
-        const float thr_g = fminf(thr, __uint_as_float(mb));
-        const unsigned cnt = (has && db < thr_g) ? c : 0u;
-        group_scan_pipelined<G>(pool, f, cnt, qx, qy, qz, thr_g, ld, li, gl);
-#else
-        const unsigned cnt = (has && db < thr) ? c : 0u;
-        group_scan_pipelined<G>(pool, f, cnt, qx, qy, qz, thr, ld, li, gl);
+// ---- a shell: PROBE ALL its bricks first, then scan what was found SLOT-ALIGNED -------------------------------------------------------
+// Round 1 alternated {enumerate G bricks, probe them, scan what was found}: a 27-brick closing shell was seven dependent
+// {hash probe -> slab loads} round trips, and in most of those rounds one or two of the warp's groups scanned while the others waited.
+// Round 2 (profiles/r02/probe_v3_*.log: 0.183 -> 0.161 ms at G = 4 on the same box, bit-identical results):
+//   A  every lane evaluates LI_KNN_PB bricks per round and issues their hash probes back to back (first probe of the open-addressing
+//      lookup split into issue / finish); found bricks go to the GROUP's list in shared memory through a group ballot;
+//   B  the s-th listed brick of every group is scanned at the same time by group_scan_pipelined: the warp's trip count is the sum over
+//      list slots of the longest slab in that slot, and the number of slots is the maximum over the groups of their found bricks --
+//      instead of a sum over enumeration rounds.
+// (Streaming the concatenated slabs through one cursor per group -- no per-brick restart at all -- was measured too and lost to the cursor
+// arithmetic: 0.269 ms, profiles/r02/knn_lockstep_v2_source.cuh.)
+#ifndef LI_KNN_PB
+#define LI_KNN_PB 2          // bricks evaluated (hash probes in flight) per lane and round; 1 / 3 / 4 measured: 0.171 / 0.161 / 0.173 ms
 #endif
+#ifndef LI_KNN_LIST
+#define LI_KNN_LIST 32       // found bricks a group lists before it scans them
+#endif
+__device__ __forceinline__ uint4 li_brick_probe_issue(const uint4* __restrict__ ent, unsigned mask, unsigned long long key, unsigned& h) {
+    h = li_hash(key) & mask;
+    return __ldg(&ent[h]);
+}
+__device__ __forceinline__ bool li_brick_probe_finish(const uint4* __restrict__ ent, unsigned mask, unsigned long long key, unsigned h, uint4 e,
+                                                      unsigned& first, unsigned& count) {
+    for (unsigned i = 0; i <= mask; i++) {
+        const unsigned long long k = (unsigned long long)e.x | ((unsigned long long)e.y << 32);
+        if (k == key) { first = e.z; count = e.w; return true; }
+        if (k == LI_EMPTY_KEY) return false;
+        h = (h + 1) & mask;
+        e = __ldg(&ent[h]);
+    }
+    return false;
+}
+template <int G>
+__device__ __forceinline__ void group_scan_listed(const float4* __restrict__ pool, const uint2* __restrict__ glist, int nl, float qx, float qy, float qz,
+                                                  float thr, float (&ld)[5], int (&li)[5], int gl) {
+    for (int s = 0; __any_sync(LI_FULL, s < nl); s++) {
+        unsigned f = 0, c = 0;
+        if (s < nl) {
+            const uint2 e = glist[s];
+            f = e.x;
+            c = e.y;
+        }
+        group_scan_pipelined<G>(pool, f, c, qx, qy, qz, thr, ld, li, gl);
     }
 }
-
 // Exact 5-NN of Q = 32/G queries by one warp in lockstep. ALL 32 lanes must call; `valid` is group-uniform.
 // gd/gi: ascending distances / pool offsets (-1 = missing), uniform within each group.
 //
@@ -267,9 +283,11 @@ __device__ __forceinline__ void lockstep_scan_found(const float4* __restrict__ p
 // The first shell is a guess (rho = seed radius): with a dense map most queries finish in it, the rest need one closing step.
 // thr0: a bound already known for the 5th best (only candidates below it can matter) -- INFINITY unless an earlier stage
 // (the cell-directory first round of the hybrid search, cells.cuh) handed it over.
+// glist: this GROUP's list of found bricks (LI_KNN_LIST entries of shared memory).
 template <int G>
 __device__ __forceinline__ void knn5_lockstep(const MapDev& M, float rho2, bool valid, float qx, float qy, float qz, float (&gd)[5],
-                                              int (&gi)[5], int gl, int gbase, float thr0 = INFINITY) {
+                                               int (&gi)[5], int gl, int gbase, uint2* __restrict__ glist, float thr0 = INFINITY) {
+    constexpr int PB = LI_KNN_PB;
     float ld[5];
     int li[5];
 #pragma unroll
@@ -289,19 +307,16 @@ __device__ __forceinline__ void knn5_lockstep(const MapDev& M, float rho2, bool 
     if (!act) {
         qx = 0.f; qy = 0.f; qz = 0.f;
     }
-    // slack for float cell assignment / edge products: relative 2^-23 effects, bounded generously
     g.margin = 1e-6f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + 16.0f * B);
-
     const float inv_ds = 1.0f / g.ds;
-    const float slk = 0.02f + 4e-7f * (fabsf(qx) + fabsf(qy) + fabsf(qz)) * inv_ds;   // cells; covers the reciprocal-multiply rounding
+    const float slk = 0.02f + 4e-7f * (fabsf(qx) + fabsf(qy) + fabsf(qz)) * inv_ds;
+    const unsigned ltg = (1u << gl) - 1u;
     bool done = !act;
     float lo2 = 0.f, hi2 = rho2;
     while (__any_sync(LI_FULL, !done)) {
         const bool need = !done;
-        const bool last = hi2 >= 5.0f;   // the radius bound d2 <= 5 is inclusive (ikd_Tree.cpp:842)
+        const bool last = hi2 >= 5.0f;
         const float r = sqrtf(fminf(hi2, 5.0f)) * (1.0f + 1e-6f) + g.margin;
-        // conservative cell range of the ball's bounding box: reciprocal multiply + a small slack (slk) instead of the IEEE
-        // division of li_cell (only the enumeration range, never a point's cell, is computed this way)
         const int lx = (int)floorf((qx - r) * inv_ds - slk) >> g.bs, hx = (int)floorf((qx + r) * inv_ds + slk) >> g.bs;
         const int ly = (int)floorf((qy - r) * inv_ds - slk) >> g.bs, hy = (int)floorf((qy + r) * inv_ds + slk) >> g.bs;
         const int lz = (int)floorf((qz - r) * inv_ds - slk) >> g.bs, hz = (int)floorf((qz + r) * inv_ds + slk) >> g.bs;
@@ -310,34 +325,63 @@ __device__ __forceinline__ void knn5_lockstep(const MapDev& M, float rho2, bool 
         const int total = need ? nxy * nz : 0;
         const float inv_nxy = 1.0f / (float)nxy, inv_nx = 1.0f / (float)nx;
         const float thr = (gi[4] >= 0) ? gd[4] : thr0;
-        for (int base = 0; __any_sync(LI_FULL, base < total); base += G) {
-            const int idx = base + gl;
-            const bool want = idx < total;
-            const int iz = (int)(((float)idx + 0.5f) * inv_nxy);
-            const int rem = idx - iz * nxy;
-            const int iy = (int)(((float)rem + 0.5f) * inv_nx);
-            const int ix = rem - iy * nx;
-            unsigned first = 0, count = 0;
-            float dbox = INFINITY;
-            bool found = false;
-            if (want) {
+        int nl = 0;
+        for (int base = 0; __any_sync(LI_FULL, base < total); base += PB * G) {
+            unsigned long long key[PB];
+            unsigned hs[PB];
+            uint4 ent[PB];
+            bool want[PB];
+#pragma unroll
+            for (int k = 0; k < PB; k++) {
+                const int idx = base + k * G + gl;
+                want[k] = idx < total;
+                const int iz = (int)(((float)idx + 0.5f) * inv_nxy);
+                const int rem = idx - iz * nxy;
+                const int iy = (int)(((float)rem + 0.5f) * inv_nx);
+                const int ix = rem - iy * nx;
                 const int kx = lx + ix, ky = ly + iy, kz = lz + iz;
-                const int bs = g.bs;
-                float lox = (float)(kx << bs) * g.ds - g.margin, hix = (float)((kx + 1) << bs) * g.ds + g.margin;
-                float loy = (float)(ky << bs) * g.ds - g.margin, hiy = (float)((ky + 1) << bs) * g.ds + g.margin;
-                float loz = (float)(kz << bs) * g.ds - g.margin, hiz = (float)((kz + 1) << bs) * g.ds + g.margin;
-                float ex = fmaxf(0.f, fmaxf(lox - qx, qx - hix));
-                float ey = fmaxf(0.f, fmaxf(loy - qy, qy - hiy));
-                float ez = fmaxf(0.f, fmaxf(loz - qz, qz - hiz));
-                dbox = (ex * ex + ey * ey + ez * ez) * (1.0f - 1e-6f);
-                const bool in_shell = dbox >= lo2 && (last ? dbox <= 5.0f : dbox < hi2);
-                if (in_shell && dbox < thr) {
-                    found = li_brick_find(M.ent, M.mask, li_pack_key(kx, ky, kz), first, count);
-                    found = found && count > 0u;
+                key[k] = 0ull;
+                hs[k] = 0u;
+                ent[k] = make_uint4(0u, 0u, 0u, 0u);
+                if (want[k]) {
+                    const int bs = g.bs;
+                    const float lox = (float)(kx << bs) * g.ds - g.margin, hix = (float)((kx + 1) << bs) * g.ds + g.margin;
+                    const float loy = (float)(ky << bs) * g.ds - g.margin, hiy = (float)((ky + 1) << bs) * g.ds + g.margin;
+                    const float loz = (float)(kz << bs) * g.ds - g.margin, hiz = (float)((kz + 1) << bs) * g.ds + g.margin;
+                    const float ex = fmaxf(0.f, fmaxf(lox - qx, qx - hix));
+                    const float ey = fmaxf(0.f, fmaxf(loy - qy, qy - hiy));
+                    const float ez = fmaxf(0.f, fmaxf(loz - qz, qz - hiz));
+                    const float dbox = (ex * ex + ey * ey + ez * ez) * (1.0f - 1e-6f);
+                    const bool in_shell = dbox >= lo2 && (last ? dbox <= 5.0f : dbox < hi2);
+                    want[k] = in_shell && dbox < thr;
+                    if (want[k]) {
+                        key[k] = li_pack_key(kx, ky, kz);
+                        ent[k] = li_brick_probe_issue(M.ent, M.mask, key[k], hs[k]);
+                    }
                 }
             }
-            lockstep_scan_found<G>(M.pool, found, first, count, dbox, qx, qy, qz, thr, ld, li, gl, gbase);
+#pragma unroll
+            for (int k = 0; k < PB; k++) {
+                unsigned first = 0, count = 0;
+                bool found = false;
+                if (want[k]) {
+                    found = li_brick_probe_finish(M.ent, M.mask, key[k], hs[k], ent[k], first, count);
+                    found = found && count > 0u;
+                }
+                const unsigned fm = grp_ballot<G>(found, gbase);
+                if (found) glist[nl + __popc(fm & ltg)] = make_uint2(first, count);
+                nl += __popc(fm);
+            }
+            if (__any_sync(LI_FULL, nl > LI_KNN_LIST - PB * G)) {
+                __syncwarp();
+                group_scan_listed<G>(M.pool, glist, nl, qx, qy, qz, thr, ld, li, gl);
+                nl = 0;
+                __syncwarp();
+            }
         }
+        __syncwarp();
+        group_scan_listed<G>(M.pool, glist, nl, qx, qy, qz, thr, ld, li, gl);
+        __syncwarp();
         group_merge<G>(ld, li, gd, gi, gl, gbase);
         if (need) {
             const bool full = gi[4] >= 0;
@@ -346,12 +390,14 @@ __device__ __forceinline__ void knn5_lockstep(const MapDev& M, float rho2, bool 
             } else {
                 lo2 = hi2;
                 hi2 = full ? fminf(gd[4] * (1.0f + 1e-6f), 5.0f) : fminf(4.0f * hi2, 5.0f);
-                // a closing step at hi2 = g5 scans dbox < g5 only (strict), the final radius step dbox <= 5
                 if (full && hi2 >= 5.0f) hi2 = 5.0f;
             }
         }
     }
 }
+#define LI_KNN_SMEM_DECL(G, W) __shared__ uint2 s_glist[W][32 / (G)][LI_KNN_LIST]
+#define LI_KNN_CALL(G, M, rho2, valid, QX_, QY_, QZ_, gd, gi, gl, gbase, THR0_) \
+    knn5_lockstep<G>(M, rho2, valid, QX_, QY_, QZ_, gd, gi, gl, gbase, s_glist[threadIdx.x >> 5][(threadIdx.x & 31) / (G)], THR0_)
 
 // ---- search kernel of an ICP pass: world transform + 5-NN for every scan point -----------------------
 // HOST = true: the scan has not been copied yet -- `raw` is a device-visible alias of the caller's page-locked host
@@ -363,6 +409,7 @@ template <int G, bool HOST, bool SEEDED = false>
 __global__ void __launch_bounds__(LI_KNN_THREADS, LI_KNN_MIN_BLOCKS)
 k_knn_scan(MapDev M, ScanDev S, PoseD P, float rho2, const float* __restrict__ raw, int stride) {
     constexpr int Q = Grp<G>::Q;
+    LI_KNN_SMEM_DECL(G, LI_KNN_THREADS / 32);
     const int lane = threadIdx.x & 31;
     const int gl = lane % G, gid = lane / G, gbase = gid * G;
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -418,7 +465,7 @@ k_knn_scan(MapDev M, ScanDev S, PoseD P, float rho2, const float* __restrict__ r
         }
         float gd[5];
         int gi[5];
-        knn5_lockstep<G>(M, rho2q, valid, wx, wy, wz, gd, gi, gl, gbase, thr0);
+        LI_KNN_CALL(G, M, rho2q, valid, wx, wy, wz, gd, gi, gl, gbase, thr0);
         if (valid) {
             if (gl == 0) S.world[q] = make_float4(wx, wy, wz, 0.f);
             // Nearest_Points as COPIES (ScanDev::near_xyz; w = 1 found, 0 missing rank): the group's lanes share the five gathers --
@@ -443,6 +490,7 @@ template <int G>
 __global__ void __launch_bounds__(256) k_knn_queries(MapDev M, const float4* __restrict__ qpts, int n, int* __restrict__ ids,
                                                      float* __restrict__ d2, float rho2) {
     constexpr int Q = Grp<G>::Q;
+    LI_KNN_SMEM_DECL(G, 256 / 32);
     const int lane = threadIdx.x & 31;
     const int gl = lane % G, gid = lane / G, gbase = gid * G;
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -454,7 +502,7 @@ __global__ void __launch_bounds__(256) k_knn_queries(MapDev M, const float4* __r
         if (valid) p = __ldg(&qpts[q]);
         float gd[5];
         int gi[5];
-        knn5_lockstep<G>(M, rho2, valid, p.x, p.y, p.z, gd, gi, gl, gbase);
+        LI_KNN_CALL(G, M, rho2, valid, p.x, p.y, p.z, gd, gi, gl, gbase, INFINITY);
         if (valid && gl == 0) {
 #pragma unroll
             for (int k = 0; k < 5; k++) {

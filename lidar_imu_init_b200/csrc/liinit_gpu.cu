@@ -360,12 +360,13 @@ void set_scan(Ctx* c, int n) {
 
 // Lanes per scan point when the caller left knn_group_lanes = 0. A warp works on 32/G points at once and lives as long as its slowest
 // one: 4 lanes give the best throughput once every SM holds several such batches, but a small frame then occupies a fraction of the
-// GPU for a long batch time. Measured on one B200 (C2 scene, both poses, profiles/r02/probe_frame_size_vs_group_lanes.log):
-//   2k points: 0.049 ms at G = 4, 0.015 ms at G = 32;   30k: 0.076 / 0.052 (G = 16);   120k: 0.150 / 0.117 (G = 8);   240k: 0.199 (G = 4).
+// GPU for a long batch time. Measured on one B200 (C2 scene, both poses; profiles/r02/probe_frame_size_vs_group_lanes.log for the first
+// shape of the search, profiles/r02/probe_v3_parameters_and_frame_sizes.log for the present one), search kernel ms at the initial pose:
+//   8k points: 0.044 (G = 4) / 0.029 (8) / 0.023 (16) / 0.023 (32);   20k: 0.044 / 0.033 / 0.036 / 0.040;   45k: 0.058 / 0.049 / 0.062 / 0.082;
+//   60k: 0.067 / 0.068;   90k: 0.084 / 0.088;   130k: 0.109 / 0.111;   170k: 0.129 / 0.147;   240k: 0.161 / 0.190.
 int group_for(int n) {
-    if (n <= 20000) return 32;
-    if (n <= 45000) return 16;
-    if (n <= 170000) return 8;
+    if (n <= 14000) return 32;
+    if (n <= 70000) return 8;
     return 4;
 }
 

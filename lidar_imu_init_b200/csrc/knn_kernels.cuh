@@ -243,6 +243,9 @@ struct KnnGeom {
 #ifndef LI_KNN_LIST
 #define LI_KNN_LIST 32       // found bricks a group lists before it scans them
 #endif
+#ifndef LI_KNN_PREFETCH
+#define LI_KNN_PREFETCH 4    // 128-byte lines of a found slab prefetched to L2 when it is listed: with a cold L2 (bench) 0.1952 -> 0.1898 ms, warm no change
+#endif
 __device__ __forceinline__ uint4 li_brick_probe_issue(const uint4* __restrict__ ent, unsigned mask, unsigned long long key, unsigned& h) {
     h = li_hash(key) & mask;
     return __ldg(&ent[h]);
@@ -371,6 +374,16 @@ __device__ __forceinline__ void knn5_lockstep(const MapDev& M, float rho2, bool 
                 const unsigned fm = grp_ballot<G>(found, gbase);
                 if (found) glist[nl + __popc(fm & ltg)] = make_uint2(first, count);
                 nl += __popc(fm);
+#if LI_KNN_PREFETCH && !defined(LI_SIMT_EMUL)
+                // the slab will be read by the whole group a few hundred cycles from now: start moving its first lines towards L2
+                if (found) {
+                    const char* pf = reinterpret_cast<const char*>(M.pool + first);
+                    const unsigned bytes = count * 16u;
+#pragma unroll
+                    for (int l = 0; l < LI_KNN_PREFETCH; l++)
+                        if ((unsigned)l * 128u < bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + l * 128));
+                }
+#endif
             }
             if (__any_sync(LI_FULL, nl > LI_KNN_LIST - PB * G)) {
                 __syncwarp();

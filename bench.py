@@ -52,7 +52,7 @@ def emit(obj):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the search kernel on C2 (ncu --set full, cold cache), per index
-NCU_DRAM_BYTES_KNN = {1: 125_488_896, 2: 141_602_560}   # 1: 110.91 MB read + 14.58 MB written (the kernel now writes the neighbour copies)
+NCU_DRAM_BYTES_KNN = {1: 124_534_016, 2: 141_602_560}   # 1: 111.01 MB read + 13.53 MB written (the kernel writes the neighbour copies)
 NCU_DRAM_SOURCE = {1: "profiles/r02/ncu_full_final_metrics.txt", 2: "profiles/r01_cells/ncu_full_stream_final_metrics.txt"}
 KNN_KERNEL = {1: "k_knn_scan (5-NN search on whole bricks, lockstep lane groups; dominant kernel of the pass)",
               2: "k_knn_cells_scan (5-NN search on the per-brick cell directory, one scan point per thread; dominant kernel of the pass)"}
@@ -383,11 +383,13 @@ def run_gpu(args, rank, world, local_rank):
             torch.cuda.synchronize()
             l1 = g.launch_count()
         ms = [a.elapsed_time(b) for a, b in ev]
+        timed.last_steps = ms
         return float(np.sum(ms)), (l1 - l0), float(np.mean(knn_ms)), float(np.mean(plane_ms))
 
     sampler = ClockSampler(local_rank)   # samples across all three timed loops (each lasts only a few ms)
     sampler.start()
     tot_ms, launches, knn_ms, plane_ms = timed(step_resident, args.steps, args.warmup, True)
+    step_ms = list(timed.last_steps)
     warm_ms, _, knn_warm, plane_warm = timed(step_resident, args.steps, 1, False)
     e2e_ms, _, _, _ = timed(step_e2e, args.steps, args.warmup, True)
     e2e_staged_ms, _, _, _ = timed(step_e2e_staged, args.steps, args.warmup, True)
@@ -435,7 +437,9 @@ def run_gpu(args, rank, world, local_rank):
                                                                "accumulators summed over the ranks inside liinit_icp_iterate (" + g.comm_mode() + ")"),
                     "l2": "flushed between timed steps (256 MiB memset outside the events)", "knn_index": KNN_NAME[kidx],
                     "knn_group_lanes": (args.group or "auto (by frame size: 4 lanes beyond 70k points per GPU)") if kidx == 1 else None, "brick_cells_log2": args.brick or 3,
-                    "selected_points": int(m_sel), "map_build_s": build_s, "map_points_live": g.map_validnum()},
+                    "selected_points": int(m_sel), "map_build_s": build_s, "map_points_live": g.map_validnum(),
+                    "step_ms": {"min": float(np.min(step_ms)), "median": float(np.median(step_ms)), "max": float(np.max(step_ms)),
+                                "note": "this rank's device time of the timed steps; ms_per_step is their mean, max over ranks"}},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(N * 12 + 192), "d2h_bytes_per_step": 160 * 8,
                 "ms_per_step": e2e_ms / args.steps,
                 "host_input": ("pinned packed xyz, read by the search kernel over PCIe (liinit_scan_attach_host, no staging copy)" if world == 1 else

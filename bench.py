@@ -192,6 +192,38 @@ def _interleave_memory():
         return f"unavailable ({e!r})"
 
 
+def _bind_near_gpu(torch, local_rank):
+    """Run the launching thread, and allocate the pinned frame it hands to the library, on the NUMA node the GPU hangs off: the search
+    kernel reads the frame over PCIe in place, and a frame on the other socket adds an inter-socket hop to every read (the e2e step
+    was 0.268 .. 0.305 ms box to box without this). What a deployment does with numactl. Best effort.
+    -> (affinity to restore for the CPU arm, description)"""
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read())
+        if node < 0:
+            return None, f"not bound (GPU {bdf}: NUMA node unknown)"
+        cpus = set()
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if not use:
+            return None, f"not bound (no allowed CPU on node {node})"
+        os.sched_setaffinity(0, use)
+        import ctypes
+        mask = ctypes.c_ulong(1 << node)
+        libc = ctypes.CDLL(None, use_errno=True)
+        rc = libc.syscall(238, 1, ctypes.byref(mask), ctypes.c_ulong(node + 2))   # SYS_set_mempolicy, MPOL_PREFERRED
+        return allowed, f"launch thread on the {len(use)} CPUs of NUMA node {node} (GPU {bdf}), pinned frame " + \
+            ("preferred on that node" if rc == 0 else f"placement left to first touch (set_mempolicy errno {ctypes.get_errno()})")
+    except Exception as e:
+        return None, f"not bound ({e!r})"
+
+
 def _cpu_env():
     # read by libgomp when the oracle library is loaded: one thread per core, spread over the sockets, no migration
     os.environ.setdefault("OMP_PROC_BIND", "spread")
@@ -312,6 +344,7 @@ def run_gpu(args, rank, world, local_rank):
         raise RuntimeError("bench.py needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    affinity0, host_binding = (None, "off (--no-bind)") if args.no_bind else _bind_near_gpu(torch, local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     cfg = args.config
@@ -391,7 +424,7 @@ def run_gpu(args, rank, world, local_rank):
     tot_ms, launches, knn_ms, plane_ms = timed(step_resident, args.steps, args.warmup, True)
     step_ms = list(timed.last_steps)
     warm_ms, _, knn_warm, plane_warm = timed(step_resident, args.steps, 1, False)
-    e2e_ms, _, _, _ = timed(step_e2e, args.steps, args.warmup, True)
+    e2e_ms, _, e2e_knn_ms, e2e_plane_ms = timed(step_e2e, args.steps, args.warmup, True)
     e2e_staged_ms, _, _, _ = timed(step_e2e_staged, args.steps, args.warmup, True)
     g.scan_upload_ptr(body4.data_ptr(), SCAN_STRIDE, NF)
     clocks = sampler.stop()
@@ -445,7 +478,8 @@ def run_gpu(args, rank, world, local_rank):
                 "host_input": ("pinned packed xyz, read by the search kernel over PCIe (liinit_scan_attach_host, no staging copy)" if world == 1 else
                                "pinned packed xyz of the whole frame; every rank's search kernel reads ITS SLOT over PCIe (liinit_scan_attach_host; the "
                                "other slots would be copied when map_incremental or a download needs the whole frame)"),
-                "ms_per_step_staged_copy": e2e_staged_ms / args.steps},
+                "ms_per_step_staged_copy": e2e_staged_ms / args.steps,
+                "kernel_ms": e2e_knn_ms, "plane_kernel_ms": e2e_plane_ms, "host_binding": host_binding},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": KNN_KERNEL[kidx], "achieved": ach, "peak": peak,
@@ -499,6 +533,8 @@ def run_gpu(args, rank, world, local_rank):
         except Exception as e:
             out["extras"] = {"error": repr(e)}
     if rank == 0 and world == 1 and not args.no_cpu and cfg != "C4":
+        if affinity0:
+            os.sched_setaffinity(0, affinity0)   # the CPU arm gets the whole machine back (its threads inherit this mask)
         _cpu_env()
         numa = _interleave_memory()
         threads = os.cpu_count() or 1
@@ -547,6 +583,7 @@ def main():
     ap.add_argument("--knn-index", type=int, default=0, help="0 = library default, 1 = bricks (lockstep groups), 2 = cells (cell directory)")
     ap.add_argument("--cpu-sample", type=int, default=240_000)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-bind", action="store_true", help="do not bind the launch thread / pinned frame to the GPU's NUMA node")
     args = ap.parse_args()
     args.scan_points = args.scan_points or CONFIGS[args.config][0]
     args.map_points = args.map_points or CONFIGS[args.config][1]

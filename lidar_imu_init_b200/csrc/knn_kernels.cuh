@@ -111,16 +111,9 @@ __device__ __forceinline__ void group_merge(const float (&ld)[5], const int (&li
 //   * out-of-range slots are not padded: the load is predicated (the register keeps an old, finite point) and the
 //     range test is folded into the candidate's single compare;
 //   * the two buffers swap roles by unrolling the loop twice instead of being copied.
-#ifndef LI_SCAN_V2
-#define LI_SCAN_V2 1
-#endif
-#ifndef LI_GROUP_BOUND
-#define LI_GROUP_BOUND 0
-#endif
 #ifndef LI_DIST_PACKED
 #define LI_DIST_PACKED 1
 #endif
-#if LI_SCAN_V2
 // a float the compiler must treat as defined but that costs no instruction (contents: whatever the register held)
 __device__ __forceinline__ float li_stale_float() {
 #ifdef LI_SIMT_EMUL
@@ -187,39 +180,6 @@ __device__ __forceinline__ void group_scan_pipelined(const float4* __restrict__ 
         rem -= 2 * U * G;
     }
 }
-#else
-template <int G, int U = LI_KNN_U>
-__device__ __forceinline__ void group_scan_pipelined(const float4* __restrict__ pool, unsigned f, unsigned cnt, float qx, float qy, float qz,
-                                                     float thr, float (&ld)[5], int (&li)[5], int gl) {
-    const float4* __restrict__ sp = pool + f;
-    const float cap5 = __uint_as_float(0x40a00001u);   // smallest float above 5: d <= 5 <=> d < cap5
-    const float thr5 = fminf(thr, cap5);
-    float tau = fminf(thr5, ld[4]);
-    float4 p[U], pn[U];
-#pragma unroll
-    for (int u = 0; u < U; u++) {
-        unsigned j = gl + u * G;
-        p[u] = (j < cnt) ? __ldg(sp + j) : make_float4(1e18f, 1e18f, 1e18f, 0.f);
-    }
-    for (unsigned j0 = gl; __any_sync(LI_FULL, j0 < cnt); j0 += U * G) {
-#pragma unroll
-        for (int u = 0; u < U; u++) {   // prefetch the next batch
-            unsigned j = j0 + (U + u) * G;
-            pn[u] = (j < cnt) ? __ldg(sp + j) : make_float4(1e18f, 1e18f, 1e18f, 0.f);
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            float d = li_dist2(qx, qy, qz, p[u].x, p[u].y, p[u].z);   // padding gives d = +inf
-            if (d < tau) {
-                local_insert(ld, li, d, (int)(f + j0 + u * G));
-                tau = fminf(thr5, ld[4]);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) p[u] = pn[u];
-    }
-}
-#endif
 
 struct KnnGeom {
     int bs;             // log2(voxels per brick edge)

@@ -86,3 +86,31 @@ def test_attach_rejects_pageable_memory():
     g.scan_upload(body)                                          # the context stays usable
     p = c["pose_init"]
     g.icp_iterate(p.rot_end, p.pos_end, p.R_LI, p.T_LI, False, True)
+
+
+def test_attach_frame_after_frame():
+    """The in-place host read gives the results of the copy path frame after frame through the same buffers (shrinking frames: the tails
+    of the device arrays hold older frames), a NaN coordinate included."""
+    import torch
+    from lidar_imu_init_b200 import scenes
+    c = scenes.make_config("C1")
+    p = c["pose_init"]
+    base = c["body_xyz"]
+    n = len(base)
+    g = _ctx(c, n)
+    ref_ctx = _ctx(c, n)
+    host = torch.empty((n, 3), dtype=torch.float32).pin_memory()
+    rng = np.random.default_rng(5)
+    for it in range(12):
+        m = n - 37 * it                                          # the frames shrink: the tail of the buffers holds older frames
+        body = (base[rng.permutation(n)[:m]] * np.float32(1.0 - 1e-3 * it)).astype(np.float32)
+        if it % 3 == 1:
+            body.view(np.uint32)[m // 2, 1] = 0xFFFFFFFF         # a NaN: the point is dropped like any non-finite one
+        host[:m] = torch.from_numpy(body)
+        g.scan_attach_ptr(host.data_ptr(), 3, m)
+        got = g.icp_iterate(p.rot_end, p.pos_end, p.R_LI, p.T_LI, False, True)
+        ref_ctx.scan_upload(body)
+        ref = ref_ctx.icp_iterate(p.rot_end, p.pos_end, p.R_LI, p.T_LI, False, True)
+        for a, b in zip(ref, got):
+            assert np.array_equal(np.asarray(a), np.asarray(b)), it
+        assert np.array_equal(g.scan_body().view(np.uint32), body.view(np.uint32)), it

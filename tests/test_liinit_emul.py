@@ -242,6 +242,7 @@ def test_emul_attach_voxelgrid_layouts_and_errors(oracle_mod, case):
     body = c["body_xyz"][:1000]
     g.scan_upload(body)
     ref = g.icp_iterate(p.rot_end, p.pos_end, p.R_LI, p.T_LI, False, True)
+    g_selected_17 = bool(g.scan_state()["selected"][17])
     for stride in (3, 4, 12):                                                   # point layouts + the in-place host read of the search kernel
         wide = np.full((len(body), stride), 7.0, np.float32)
         wide[:, :3] = body
@@ -249,6 +250,15 @@ def test_emul_attach_voxelgrid_layouts_and_errors(oracle_mod, case):
         got = g.icp_iterate(p.rot_end, p.pos_end, p.R_LI, p.T_LI, False, True)
         assert got[2] == ref[2] and np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1])
         assert np.array_equal(g.scan_body(), body)
+    # a NaN coordinate travels through the in-place read like through the copy path (the point is dropped)
+    odd = body.copy()
+    odd.view(np.uint32)[17, 2] = 0xFFFFFFFF
+    g.scan_upload(odd)
+    ref2 = g.icp_iterate(p.rot_end, p.pos_end, p.R_LI, p.T_LI, False, True)
+    g.scan_attach(odd)
+    got2 = g.icp_iterate(p.rot_end, p.pos_end, p.R_LI, p.T_LI, False, True)
+    assert got2[2] == ref2[2] == ref[2] - int(g_selected_17) and np.array_equal(got2[0], ref2[0]) and np.array_equal(got2[1], ref2[1])
+    assert np.array_equal(g.scan_body().view(np.uint32), odd.view(np.uint32))
     # scan voxel grid (PCL VoxelGrid semantics, row N2) against the oracle restatement
     raw = (body[:, None, :] + np.random.default_rng(3).normal(0, 0.05, (len(body), 4, 3)).astype(np.float32)).reshape(-1, 3)
     n = g.scan_upload_raw(raw, 0.5)

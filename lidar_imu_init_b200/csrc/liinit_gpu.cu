@@ -811,8 +811,8 @@ int compact_map(Ctx* c) {
         k_map_flatten4<<<nblk((long long)c->h_counters[CNT_BRICKS] * 32, 256), 256, 0, c->stream>>>(c->M, c->hash_slots, d_tmp, live, d_n);
         c->launches++;
     }
-    cudaMemsetAsync(c->d_counters, 0, sizeof(int) * CNT_COUNT, c->stream);
-    cudaMemsetAsync(c->M.pool_top, 0, sizeof(unsigned long long), c->stream);
+    CU(cudaMemsetAsync(c->d_counters, 0, sizeof(int) * CNT_COUNT, c->stream));
+    CU(cudaMemsetAsync(c->M.pool_top, 0, sizeof(unsigned long long), c->stream));
     k_map_clear<<<nblk(c->hash_slots, 256), 256, 0, c->stream>>>(c->M.ent, c->M.aux, c->hash_slots);
     c->launches++;
     if (c->cells) {

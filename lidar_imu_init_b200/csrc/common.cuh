@@ -8,6 +8,21 @@
 //   * pool: float4 points; every brick owns one contiguous, 128-byte aligned slab
 //     [first, first+cap) of which [first, first+count) are live. w carries the voxel-in-brick id.
 #pragma once
+
+// Invariants that only the CPU build of the library checks (tests/emul: every kernel compiled for the host): no instruction on the device.
+#ifdef LI_SIMT_EMUL
+#include <cstdio>
+#include <cstdlib>
+#define LI_EMUL_ASSERT(cond)                                                              \
+    do {                                                                                  \
+        if (!(cond)) {                                                                    \
+            fprintf(stderr, "LI_EMUL_ASSERT failed: %s (%s:%d)\n", #cond, __FILE__, __LINE__); \
+            abort();                                                                      \
+        }                                                                                 \
+    } while (0)
+#else
+#define LI_EMUL_ASSERT(cond) ((void)0)
+#endif
 #ifdef __CUDACC__
 #include <cuda_runtime.h>
 #elif defined(LI_SIMT_EMUL)   // tests/emul/simt_shim.h brings the vector types and constructors (and no CUDA API header)

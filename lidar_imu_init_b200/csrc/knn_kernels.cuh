@@ -201,8 +201,10 @@ struct KnnGeom {
 #define LI_KNN_PB 2          // bricks evaluated (hash probes in flight) per lane and round; 1 / 3 / 4 measured: 0.171 / 0.161 / 0.173 ms
 #endif
 #ifndef LI_KNN_LIST
-#define LI_KNN_LIST 32       // found bricks a group lists before it scans them
+#define LI_KNN_LIST 32       // found bricks a group lists before it scans them ...
 #endif
+// ... and never fewer than one round can find: LI_KNN_PB * G bricks are probed between two looks at the fill level (G = 32: 64)
+#define LI_KNN_LISTG(G) ((LI_KNN_LIST) > (LI_KNN_PB) * (G) ? (LI_KNN_LIST) : (LI_KNN_PB) * (G))
 #ifndef LI_KNN_PREFETCH
 #define LI_KNN_PREFETCH 4    // 128-byte lines of a found slab prefetched to L2 when it is listed: with a cold L2 (bench) 0.1952 -> 0.1898 ms, warm no change
 #endif
@@ -246,11 +248,12 @@ __device__ __forceinline__ void group_scan_listed(const float4* __restrict__ poo
 // The first shell is a guess (rho = seed radius): with a dense map most queries finish in it, the rest need one closing step.
 // thr0: a bound already known for the 5th best (only candidates below it can matter) -- INFINITY unless an earlier stage
 // (the cell-directory first round of the hybrid search, cells.cuh) handed it over.
-// glist: this GROUP's list of found bricks (LI_KNN_LIST entries of shared memory).
+// glist: this GROUP's list of found bricks (LI_KNN_LISTG(G) entries of shared memory).
 template <int G>
 __device__ __forceinline__ void knn5_lockstep(const MapDev& M, float rho2, bool valid, float qx, float qy, float qz, float (&gd)[5],
                                                int (&gi)[5], int gl, int gbase, uint2* __restrict__ glist, float thr0 = INFINITY) {
     constexpr int PB = LI_KNN_PB;
+    constexpr int LIST = LI_KNN_LISTG(G);
     float ld[5];
     int li[5];
 #pragma unroll
@@ -332,6 +335,7 @@ __device__ __forceinline__ void knn5_lockstep(const MapDev& M, float rho2, bool 
                     found = found && count > 0u;
                 }
                 const unsigned fm = grp_ballot<G>(found, gbase);
+                LI_EMUL_ASSERT(nl + __popc(fm) <= LIST);
                 if (found) glist[nl + __popc(fm & ltg)] = make_uint2(first, count);
                 nl += __popc(fm);
 #if LI_KNN_PREFETCH && !defined(LI_SIMT_EMUL)
@@ -345,7 +349,7 @@ __device__ __forceinline__ void knn5_lockstep(const MapDev& M, float rho2, bool 
                 }
 #endif
             }
-            if (__any_sync(LI_FULL, nl > LI_KNN_LIST - PB * G)) {
+            if (__any_sync(LI_FULL, nl > LIST - PB * G)) {   // the next round could find PB * G more
                 __syncwarp();
                 group_scan_listed<G>(M.pool, glist, nl, qx, qy, qz, thr, ld, li, gl);
                 nl = 0;
@@ -368,7 +372,7 @@ __device__ __forceinline__ void knn5_lockstep(const MapDev& M, float rho2, bool 
         }
     }
 }
-#define LI_KNN_SMEM_DECL(G, W) __shared__ uint2 s_glist[W][32 / (G)][LI_KNN_LIST]
+#define LI_KNN_SMEM_DECL(G, W) __shared__ uint2 s_glist[W][32 / (G)][LI_KNN_LISTG(G)]
 #define LI_KNN_CALL(G, M, rho2, valid, QX_, QY_, QZ_, gd, gi, gl, gbase, THR0_) \
     knn5_lockstep<G>(M, rho2, valid, QX_, QY_, QZ_, gd, gi, gl, gbase, s_glist[threadIdx.x >> 5][(threadIdx.x & 31) / (G)], THR0_)
 

@@ -251,3 +251,26 @@ def test_downsample_box_membership_is_geometric(gpu_lib, oracle_mod):
             assert g.map_validnum() == om.validnum()
         assert set(map(bytes, g.map_download())) == set(map(bytes, om.flatten()))
         g.close()
+
+
+@pytest.mark.parametrize("group", [0, 4, 16, 32])
+def test_hollow_with_dense_surroundings(gpu_lib, group):
+    """tests/hollow_case.py: a shell that finds 44 non-empty bricks in one probing round (more than the 32 entries a 32-lane group's
+    list once had: the surplus went into the next warp's list). 4000 queries so that every warp of a block is at work at the same time."""
+    import hollow_case as hc
+    mp, qs = hc.hollow_map_and_queries(4000)
+    g = gpu_lib.LiInitGpu(hc.DS, max_map_points=80000, max_scan_points=len(qs) + 16, knn_group_lanes=group)
+    g.map_build(mp)
+    live = g.map_download()
+    g.scan_upload(qs)
+    I, z = np.eye(3), np.zeros(3)
+    g.icp_iterate(I, z, I, z, False, True)
+    st = g.scan_state()
+    want = hc.brute_force_sets(live, qs[:400])
+    for i in range(400):
+        assert st["near_cnt"][i] == 5 and set(map(bytes, st["near_xyz"][i])) == want[i], (group, i)
+    # every query, cheaply: the five distances against a brute-force 5th-neighbour distance
+    d5 = np.array([np.sort(((live - q) ** 2).astype(np.float32).sum(1))[4] for q in qs[::10]])
+    got = ((st["near_xyz"][::10] - qs[::10, None, :]) ** 2).astype(np.float32).sum(2).max(1)
+    assert np.allclose(got, d5, rtol=1e-5)
+    g.close()

@@ -558,3 +558,21 @@ def test_emul_seeded_second_search_pass(oracle_mod, group):
         assert np.array_equal(sts[k], stu[k]), k
     sel = sts["selected"].astype(bool)
     assert np.array_equal(sts["normvec"][sel], stu["normvec"][sel])
+
+
+@pytest.mark.parametrize("group", [0, 2, 4, 8, 16, 32])
+def test_emul_hollow_with_dense_surroundings(group):
+    """tests/hollow_case.py: 44 bricks found in one probing round. The CPU build checks the list capacity itself (LI_EMUL_ASSERT)."""
+    import hollow_case as hc
+    mp, qs = hc.hollow_map_and_queries(2)
+    g = le.EmulGpu(hc.DS, max_map_points=80000, max_scan_points=100, knn_group_lanes=group)
+    g.map_build(mp)
+    live = g.map_download()
+    g.scan_upload(qs)
+    I, z = np.eye(3), np.zeros(3)
+    g.icp_iterate(I, z, I, z, False, True)
+    st = g.scan_state()
+    want = hc.brute_force_sets(live, qs)
+    for i in range(len(qs)):
+        assert st["near_cnt"][i] == 5 and set(map(bytes, st["near_xyz"][i])) == want[i], (group, i)
+    g.close()

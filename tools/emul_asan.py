@@ -41,4 +41,26 @@ for index in (1, 2):
         live = g.map_download()
         print(f"index {index} search {search}: m={m} map_incremental={na},{nn} voxel-grid leaves={n} live={len(live)}", flush=True)
         g.close()
+# the lockstep search at every group width: first pass, seeded later pass, in-place host read, compaction, and the hollow scene whose
+# last shell lists 44 bricks in one probing round (tests/hollow_case.py)
+import hollow_case as hc
+hmap, hq = hc.hollow_map_and_queries(40)
+I3, z3 = np.eye(3), np.zeros(3)
+for group in (0, 2, 4, 8, 16, 32):
+    g = le.EmulGpu(c["ds"], max_map_points=100000, max_scan_points=3000, knn_group_lanes=group, hash_capacity_log2=14)
+    g.map_build(c["map_xyz"])
+    g.scan_attach(c["body_xyz"][:1200])
+    g.icp_iterate(p.rot_end, p.pos_end, p.R_LI, p.T_LI, False, True)
+    _, _, m2, _ = g.icp_iterate(gt.rot_end, gt.pos_end, gt.R_LI, gt.T_LI, False, True)     # seeded by the first pass's neighbours
+    g.map_delete_boxes(np.array([[-1, -1, -1, 30, 30, 30]], np.float32))
+    g.map_compact()
+    g.icp_iterate(gt.rot_end, gt.pos_end, gt.R_LI, gt.T_LI, False, True)
+    g.close()
+    g = le.EmulGpu(hc.DS, max_map_points=80000, max_scan_points=100, knn_group_lanes=group)
+    g.map_build(hmap)
+    g.scan_upload(hq)
+    g.icp_iterate(I3, z3, I3, z3, False, True)
+    cnt = g.scan_state()["near_cnt"]
+    print(f"group {group}: seeded pass m={m2}, hollow scene neighbours found {int(cnt.min())}..{int(cnt.max())}", flush=True)
+    g.close()
 print("emul_asan: no AddressSanitizer report")

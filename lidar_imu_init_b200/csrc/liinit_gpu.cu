@@ -231,6 +231,17 @@ int check_map_err(Ctx* c) {
         cudaMemsetAsync(c->d_counters + CNT_ERR, 0, sizeof(int), c->stream);
         c->h_counters[CNT_ERR] = 0;
     }
+    if (e & ERR_POOL_FULL) {
+        // the failed reservations left the bump allocator beyond the capacity (k_ins_reserve): back to the end of the last slab in use
+        const int nb = c->h_counters[CNT_BRICKS];
+        cudaMemsetAsync(c->M.pool_top, 0, sizeof(unsigned long long), c->stream);
+        if (nb > 0) {
+            k_pool_top_recompute<<<nblk(nb, 256), 256, 0, c->stream>>>(c->M, nb);
+            c->launches++;
+        }
+        cudaMemcpyAsync(c->h_pool_top, c->M.pool_top, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream);
+        cudaStreamSynchronize(c->stream);
+    }
     if (e & ERR_HASH_FULL) return fail(c, LIINIT_ERR_CAPACITY, "brick hash table full (raise hash_capacity_log2 / max_map_points)");
     if (e & ERR_POOL_FULL) return fail(c, LIINIT_ERR_CAPACITY, "map point pool full (raise max_map_points, or liinit_map_compact after deletes)");
     return LIINIT_OK;

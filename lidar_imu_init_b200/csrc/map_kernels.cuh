@@ -142,7 +142,10 @@ __global__ void k_ins_reserve(MapDev M) {
             if (lane == 0) {
                 atomicOr(&M.counters[CNT_ERR], ERR_POOL_FULL);
                 M.aux[s].y = 0u;   // nothing will be appended to this brick
-                atomicAdd(M.pool_top, (unsigned long long)(-(long long)ncap));   // give the failed reservation back: later, smaller ones may still fit
+                // pool_top is NOT rolled back here: between this warp's add and a subtraction other warps reserve, and one of them may fit
+                // and keep a slab ABOVE the value the subtractions end on -- the next reservation would be handed the same slots. The
+                // allocator stays beyond the capacity for the rest of the call (every later reservation of this batch fails, the call
+                // returns LIINIT_ERR_CAPACITY), and the host then has k_pool_top_recompute put it back on the end of the last slab in use.
             }
             continue;
         }
@@ -154,6 +157,15 @@ __global__ void k_ins_reserve(MapDev M) {
     }
     if (lane == 0) M.aux[s].z = 0u;
     }
+}
+
+// After a failed reservation (host side, check_map_err): pool_top := end of the highest slab any brick owns (pool_top zeroed first).
+__global__ void k_pool_top_recompute(MapDev M, int nbricks) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nbricks) return;
+    const int s = M.brick_slots[i];
+    const unsigned cap = M.aux[s].x;
+    if (cap) atomicMax(M.pool_top, (unsigned long long)M.ent[s].z + cap);
 }
 
 // pass 3: append. ent.count is not modified until the commit, so first+count is the append base.

@@ -274,3 +274,37 @@ def test_hollow_with_dense_surroundings(gpu_lib, group):
     got = ((st["near_xyz"][::10] - qs[::10, None, :]) ** 2).astype(np.float32).sum(2).max(1)
     assert np.allclose(got, d5, rtol=1e-5)
     g.close()
+
+
+def test_pool_full_leaves_a_consistent_map(gpu_lib):
+    """A batch that exhausts the point pool fails once with LIINIT_ERR_CAPACITY; what is stored stays intact under the concurrent
+    reservations of the failing batch (no slab handed out twice), the allocator is back inside the pool, later batches fit again.
+    (Same scenario as tests/test_liinit_emul.py::test_emul_pool_full_leaves_a_consistent_map, here with thousands of warps reserving at once.)"""
+    from lidar_imu_init_b200.capi import LiInitError
+    ds = 0.15
+    rng = np.random.default_rng(11)
+    g = gpu_lib.LiInitGpu(ds, max_map_points=20000, max_scan_points=100, hash_capacity_log2=19)   # hash large enough: the POOL runs out
+    cap = g.map_stats()["pool_cap"]
+    first = rng.uniform(-20, 20, (15000, 3)).astype(np.float32)
+    g.map_build(first)
+    assert g.map_validnum() == 15000
+    used0 = g.map_stats()["pool_used"]
+    far = rng.uniform(-2000, 2000, (cap // 8, 3)).astype(np.float32)      # one new brick (a 16-point slab) per point: twice the pool
+    with pytest.raises(LiInitError) as e:
+        g.map_add_points(far, False)
+    assert e.value.code == -3
+    st = g.map_stats()
+    assert used0 <= st["pool_used"] <= cap
+    live = g.map_download()
+    have = set(map(bytes, live))
+    assert len(live) == g.map_validnum() == len(have)
+    assert set(map(bytes, first)) <= have and have <= set(map(bytes, first)) | set(map(bytes, far))
+    g.map_delete_boxes(np.array([[-3000, -3000, -3000, -21, 3000, 3000], [21, -3000, -3000, 3000, 3000, 3000]], np.float32))
+    g.map_compact()
+    more = rng.uniform(-20, 20, (2000, 3)).astype(np.float32)
+    assert g.map_add_points(more, False) == 2000
+    live2 = set(map(bytes, g.map_download()))
+    assert set(map(bytes, first)) | set(map(bytes, more)) <= live2 and len(live2) == g.map_validnum()
+    x, d, cnt = g.nearest_search(first[:500])
+    assert np.all(d[:, 0] == 0) and np.array_equal(x[:, 0], first[:500])
+    g.close()

@@ -576,3 +576,38 @@ def test_emul_hollow_with_dense_surroundings(group):
     for i in range(len(qs)):
         assert st["near_cnt"][i] == 5 and set(map(bytes, st["near_xyz"][i])) == want[i], (group, i)
     g.close()
+
+
+def test_emul_pool_full_leaves_a_consistent_map():
+    """A batch that exhausts the point pool fails with LIINIT_ERR_CAPACITY once; the bricks whose slabs had been reserved before keep
+    their points, the allocator is put back on the end of the last slab in use (not left beyond the capacity, not rolled back under
+    concurrent reservations), and later, smaller batches fit again without touching what is stored."""
+    ds = 0.15
+    rng = np.random.default_rng(11)
+    g = le.EmulGpu(ds, max_map_points=2000, max_scan_points=100, hash_capacity_log2=18)   # hash large enough: the POOL runs out
+    cap = g.map_stats()["pool_cap"]
+    first = rng.uniform(-6, 6, (1500, 3)).astype(np.float32)
+    g.map_build(first)
+    assert g.map_validnum() == 1500
+    used0 = g.map_stats()["pool_used"]
+    # many new bricks, 16-point slabs each: far more than the pool has left
+    far = (rng.uniform(-400, 400, (cap // 8, 3))).astype(np.float32)
+    with pytest.raises(le.EmulError) as e:
+        g.map_add_points(far, False)
+    assert e.value.code == -3
+    st = g.map_stats()
+    assert used0 <= st["pool_used"] <= cap                       # back inside the pool, nothing that is in use was given away
+    live = g.map_download()
+    assert len(live) == g.map_validnum() and len(set(map(bytes, live))) == len(live)
+    have = set(map(bytes, live))
+    assert set(map(bytes, first)) <= have and have <= set(map(bytes, first)) | set(map(bytes, far))
+    # the next batches are judged on their own; what is stored stays
+    g.map_delete_boxes(np.array([[-500, -500, -500, -7, 500, 500], [7, -500, -500, 500, 500, 500]], np.float32))
+    g.map_compact()
+    more = rng.uniform(-6, 6, (200, 3)).astype(np.float32)
+    assert g.map_add_points(more, False) == 200
+    live2 = set(map(bytes, g.map_download()))
+    assert set(map(bytes, first)) | set(map(bytes, more)) <= live2 and len(live2) == g.map_validnum()
+    x, d, cnt = g.nearest_search(first[:50])
+    assert np.all(d[:, 0] == 0) and np.array_equal(x[:, 0], first[:50])
+    g.close()

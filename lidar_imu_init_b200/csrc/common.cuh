@@ -61,7 +61,7 @@ struct MapDev {
     unsigned sb_mask;              // slots - 1
 };
 
-enum { CNT_TOUCHED = 0, CNT_ERR = 1, CNT_LIVE = 2, CNT_BRICKS = 3, CNT_CHANGED = 4, CNT_DROPPED = 5, CNT_NADD = 6, CNT_NNOD = 7, CNT_COUNT = 16 };
+enum { CNT_TOUCHED = 0, CNT_ERR = 1, CNT_LIVE = 2, CNT_BRICKS = 3, CNT_CHANGED = 4, CNT_DROPPED = 5, CNT_NADD = 6, CNT_NNOD = 7, CNT_COUPLED = 8, CNT_COUNT = 16 };
 enum { ERR_HASH_FULL = 1, ERR_POOL_FULL = 2, ERR_RANGE = 4 };
 
 // Pose part of StatesGroup (common_lib.h:160-163), row-major doubles.

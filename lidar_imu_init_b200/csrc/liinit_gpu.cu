@@ -252,6 +252,7 @@ int reset_batch_counters(Ctx* c) {
     static const int zeros[CNT_COUNT] = {0};
     CU(cudaMemcpyAsync(c->d_counters + CNT_TOUCHED, zeros, sizeof(int), cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->d_counters + CNT_CHANGED, zeros, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_counters + CNT_COUPLED, zeros, sizeof(int), cudaMemcpyHostToDevice, c->stream));
     return LIINIT_OK;
 }
 
@@ -297,11 +298,14 @@ int downsample_insert(Ctx* c, const float4* pts, int n, const int* sel, int want
     k_vox_clear<<<nblk((long long)V.mask + 1, 256), 256, 0, c->stream>>>(V);
     k_ds_link<<<nblk(n, 256), 256, 0, c->stream>>>(c->M, V, pts, n, sel, want, c->d_vslot_of, c->d_slot_of, c->d_ins);
     k_ins_reserve<<<c->num_sms * 8, 256, 0, c->stream>>>(c->M);
+    k_ds_scan<<<nblk((long long)V.mask + 1, 128), 128, 0, c->stream>>>(c->M, V, pts, c->d_vslot_of);
     k_ds_replay<<<nblk((long long)V.mask + 1, 128), 128, 0, c->stream>>>(c->M, V, pts, c->d_vslot_of, c->d_ins);
+    // boxes that share a point with another box of the batch (one-ulp overlaps of the float boxes): one warp, batch order (returns at once when there are none)
+    k_ds_coupled<<<1, 32, 0, c->stream>>>(c->M, V, pts, c->d_vslot_of, c->d_ins, reinterpret_cast<int*>(c->d_rs_keys), reinterpret_cast<int*>(c->d_rs_vals));
     k_ds_append<<<nblk(n, 256), 256, 0, c->stream>>>(c->M, pts, n, c->d_slot_of, c->d_ins);
     // tombstoned bricks were added to the touched list by the replay (worst case n + n bricks): grid-stride inside
     k_ds_compact<<<c->num_sms * 8, 256, 0, c->stream>>>(c->M);
-    c->launches += 6;
+    c->launches += 8;
     refresh_cells_touched(c);
     CU(cudaGetLastError());
     return LIINIT_OK;
@@ -686,6 +690,9 @@ int liinit_create(const liinit_config* cfg, liinit_ctx** out) {
         c->V.mask = (1u << vl) - 1;
         CUC(cudaMalloc(&c->V.keys, ((size_t)c->V.mask + 1) * 8));
         CUC(cudaMalloc(&c->V.head, ((size_t)c->V.mask + 1) * 4));
+        CUC(cudaMalloc(&c->V.coupled, ((size_t)c->V.mask + 1) * 4));
+        CUC(cudaMalloc(&c->V.sum, ((size_t)c->V.mask + 1) * sizeof(int4)));
+        CUC(cudaMalloc(&c->V.clist, ((size_t)c->V.mask + 1) * 4));
         CUC(cudaMalloc(&c->d_vg_imin, ((size_t)c->V.mask + 1) * 4));
         CUC(cudaMalloc(&c->d_vg_block, ((size_t)batch / 1024 + 2) * 4));
         CUC(cudaMalloc(&c->d_vg_misc, 8 * 4));
@@ -740,7 +747,7 @@ int liinit_destroy(liinit_ctx* h) {
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     cudaFree(c->M.ent); cudaFree(c->M.brick_slots); cudaFree(c->M.aux); cudaFree(c->M.pool); cudaFree(c->M.pool_top); cudaFree(c->M.touched_list); cudaFree(c->M.cocc); cudaFree(c->M.cdir); cudaFree(c->M.sb_keys); cudaFree(c->M.sb_occ); cudaFree(c->d_ticket);
     cudaFree(c->d_counters); cudaFreeHost(c->h_counters); cudaFreeHost(c->h_pool_top); cudaFree(c->d_stage_raw); cudaFree(c->d_stage_pts);
-    cudaFree(c->d_slot_of); cudaFree(c->d_vslot_of); cudaFree(c->d_flag); cudaFree(c->d_ins); cudaFree(c->V.keys); cudaFree(c->V.head); cudaFree(c->d_vg_imin); cudaFree(c->d_vg_block); cudaFree(c->d_vg_misc); cudaFree(c->d_rs_keys); cudaFree(c->d_rs_vals); cudaFree(c->d_rs_hist); cudaFree(c->d_vg_params); cudaFree(c->d_tmin_idx); cudaFree(c->d_poses);
+    cudaFree(c->d_slot_of); cudaFree(c->d_vslot_of); cudaFree(c->d_flag); cudaFree(c->d_ins); cudaFree(c->V.keys); cudaFree(c->V.head); cudaFree(c->V.coupled); cudaFree(c->V.sum); cudaFree(c->V.clist); cudaFree(c->d_vg_imin); cudaFree(c->d_vg_block); cudaFree(c->d_vg_misc); cudaFree(c->d_rs_keys); cudaFree(c->d_rs_vals); cudaFree(c->d_rs_hist); cudaFree(c->d_vg_params); cudaFree(c->d_tmin_idx); cudaFree(c->d_poses);
     cudaFree(c->d_body); cudaFree(c->d_world); cudaFree(c->d_near_ids); cudaFree(c->d_near_xyz); cudaFree(c->d_selected); cudaFree(c->d_normvec);
     cudaFree(c->d_acc); cudaFree(c->d_red);
 #ifndef LI_SIMT_EMUL

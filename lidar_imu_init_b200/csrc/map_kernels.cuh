@@ -87,7 +87,11 @@ __device__ __forceinline__ void li_storage(const MapDev& M, float4 p, int cx, in
 
 // add a hash slot to the batch's touched list exactly once (aux.w is the membership flag)
 __device__ __forceinline__ void li_touch(const MapDev& M, int s) {
-    if (atomicExch(&M.aux[s].w, 1u) == 0u) M.touched_list[atomicAdd(&M.counters[CNT_TOUCHED], 1)] = s;
+    if (atomicExch(&M.aux[s].w, 1u) == 0u) {
+        const int t = atomicAdd(&M.counters[CNT_TOUCHED], 1);
+        LI_EMUL_ASSERT(t >= 0 && (unsigned)t <= M.mask);   // every hash slot is listed at most once per batch
+        M.touched_list[t] = s;
+    }
 }
 
 // ---- plain insert (Build, Add_Points(.., false)) -------------------------------------------------
@@ -115,7 +119,9 @@ __global__ void k_ins_count(MapDev M, const float4* __restrict__ pts, int n, con
     }
     slot_of[i] = s;
     if (created) {
-        M.brick_slots[atomicAdd(&M.counters[CNT_BRICKS], 1)] = s;
+        const int nb = atomicAdd(&M.counters[CNT_BRICKS], 1);
+        LI_EMUL_ASSERT(nb >= 0 && (unsigned)nb <= M.mask);
+        M.brick_slots[nb] = s;
         li_sb_mark(M, key);
     }
     atomicAdd(&M.aux[s].y, 1u);
@@ -184,6 +190,7 @@ __global__ void k_ins_append(MapDev M, const float4* __restrict__ pts, int n, co
     unsigned vib;
     li_storage(M, p, cx, cy, cz, key, vib);
     p.w = __uint_as_float(vib);
+    LI_EMUL_ASSERT(e.w + j < a.x && (unsigned long long)e.z + a.x <= M.pool_cap);   // inside the brick's slab, the slab inside the pool
     M.pool[(size_t)e.z + e.w + j] = p;
 }
 
@@ -214,6 +221,10 @@ struct VoxTmp {
     unsigned long long* keys;   // box key (division cell of the new points)
     int* head;                  // newest batch index linked into this box (-1 = none)
     unsigned mask;
+    // Add_Points(downsample) only (nullptr for the scan voxel grid, which shares the hash):
+    int* coupled;               // 1: the box shares a point with another box that also receives new points -> replayed by k_ds_coupled
+    int4* sum;                  // what k_ds_scan found in the box: {count, best distance (float bits), pool offset of the best point, any brick}
+    int* clist;                 // slots of the coupled boxes [counters[CNT_COUPLED]]
 };
 
 __global__ void k_vox_clear(VoxTmp V) {
@@ -221,6 +232,7 @@ __global__ void k_vox_clear(VoxTmp V) {
     if (i > V.mask) return;
     V.keys[i] = LI_EMPTY_KEY;
     V.head[i] = -1;
+    if (V.coupled) V.coupled[i] = 0;
 }
 
 // Distance of p to the centre of its downsample box, float arithmetic of ikd_Tree.cpp:389-401.
@@ -260,7 +272,9 @@ __global__ void k_ds_link(MapDev M, VoxTmp V, const float4* __restrict__ pts, in
         return;
     }
     if (created) {
-        M.brick_slots[atomicAdd(&M.counters[CNT_BRICKS], 1)] = s;
+        const int nb = atomicAdd(&M.counters[CNT_BRICKS], 1);
+        LI_EMUL_ASSERT(nb >= 0 && (unsigned)nb <= M.mask);
+        M.brick_slots[nb] = s;
         li_sb_mark(M, skey);
     }
     slot_of[i] = s;
@@ -298,56 +312,152 @@ __global__ void k_ds_link(MapDev M, VoxTmp V, const float4* __restrict__ pts, in
 // is order dependent in the reference's sequential walk; here the two box threads are not ordered. Documented)
 struct DsBox {
     float mn[3], mx[3];
+    float mx_prev[3], mn_next[3];   // upper end of the box below / lower end of the box above, per axis
+    int c[3];                       // division cell
+    int blo[3], bhi[3];             // range of brick coordinates per axis that can store a point of this box
 };
 __device__ __forceinline__ bool li_in_box(const DsBox& B, const float4& q) {
     return q.x >= B.mn[0] && q.x < B.mx[0] && q.y >= B.mn[1] && q.y < B.mx[1] && q.z >= B.mn[2] && q.z < B.mx[2];
 }
+__device__ __forceinline__ void li_ds_box(const MapDev& M, const float4& ph, DsBox& B) {
+    B.c[0] = li_cell(ph.x, M.ds); B.c[1] = li_cell(ph.y, M.ds); B.c[2] = li_cell(ph.z, M.ds);
+    const int bm = (1 << M.bshift) - 1;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const float cf = (float)B.c[a];
+        B.mn[a] = __fmul_rn(cf, M.ds);
+        B.mx[a] = __fadd_rn(B.mn[a], M.ds);
+        B.mx_prev[a] = __fadd_rn(__fmul_rn(cf - 1.0f, M.ds), M.ds);
+        B.mn_next[a] = __fmul_rn(cf + 1.0f, M.ds);
+        const int b0 = B.c[a] >> M.bshift;
+        B.blo[a] = (B.mn[a] < B.mx_prev[a] && (B.c[a] & bm) == 0) ? b0 - 1 : b0;      // overlap with box c-1, which lives in the brick below
+        B.bhi[a] = (B.mx[a] > B.mn_next[a] && (B.c[a] & bm) == bm) ? b0 + 1 : b0;     // overlap with box c+1, which lives in the brick above
+    }
+}
+// slot of a box in the batch's temporary hash, -1 when the batch has no new point for that cell
+__device__ __forceinline__ int li_vox_find(const VoxTmp& V, unsigned long long key) {
+    unsigned h = li_hash(key) & V.mask;
+    for (unsigned t = 0; t <= V.mask; t++) {
+        const unsigned long long k = V.keys[h];
+        if (k == key) return V.head[h] >= 0 ? (int)h : -1;
+        if (k == LI_EMPTY_KEY) return -1;
+        h = (h + 1) & V.mask;
+    }
+    return -1;
+}
+__device__ __forceinline__ void li_couple(const MapDev& M, const VoxTmp& V, int v) {
+    if (atomicExch(&V.coupled[v], 1) == 0) V.clist[atomicAdd(&M.counters[CNT_COUPLED], 1)] = v;
+}
+// x lies in box B.c (or is a new point filed under it). Per axis lo[a]..hi[a] is the range of cell offsets (-1, 0, +1) whose float
+// interval contains x[a] (empty when lo > hi: a one-ulp gap). Every OTHER box that contains x and receives new points in this batch is
+// coupled with box v: the reference's sequential walk lets such boxes see each other's deletions and insertions.
+__device__ __forceinline__ void li_couple_neighbours(const MapDev& M, const VoxTmp& V, const DsBox& B, int v, const int (&lo)[3], const int (&hi)[3]) {
+    for (int oz = lo[2]; oz <= hi[2]; oz++)
+        for (int oy = lo[1]; oy <= hi[1]; oy++)
+            for (int ox = lo[0]; ox <= hi[0]; ox++) {
+                if ((ox | oy | oz) == 0) continue;
+                const int w = li_vox_find(V, li_pack_key(B.c[0] + ox, B.c[1] + oy, B.c[2] + oz));
+                if (w >= 0) {
+                    li_couple(M, V, v);
+                    li_couple(M, V, w);
+                }
+            }
+}
 
+// pass D3a: one thread per box -- what the box holds before the batch (count, the point closest to the box centre: first minimum in
+// visiting order), and which boxes are COUPLED. The float boxes of neighbouring cells overlap by one ulp here and there; a point inside
+// an overlap belongs to two boxes. When both receive new points in one batch the reference's walk is order dependent ACROSS the boxes
+// (the first one may delete the shared point before the second one looks), so such boxes -- through a shared existing point or through
+// a new point that lies in the other box -- are taken out of the parallel replay and walked in batch order by k_ds_coupled.
+// (Found by tools/emul_fuzz.py on lattice clouds 5 km from the origin: one changed-box count off by one, same live set.)
+__global__ void k_ds_scan(MapDev M, VoxTmp V, const float4* __restrict__ pts, const int* __restrict__ next_of) {
+    unsigned v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v > V.mask) return;
+    const int head = V.head[v];
+    if (head < 0) return;
+    DsBox B;
+    li_ds_box(M, pts[head], B);
+    int nE = 0;
+    float bd = INFINITY;
+    int bref = -1;
+    bool have = false;
+    for (int kz = B.blo[2]; kz <= B.bhi[2]; kz++)
+        for (int ky = B.blo[1]; ky <= B.bhi[1]; ky++)
+            for (int kx = B.blo[0]; kx <= B.bhi[0]; kx++) {
+                unsigned first = 0, count = 0;
+                // (li_brick_find uses the read-only path; ent is not modified between D2's reserve and this kernel)
+                if (!li_brick_find(M.ent, M.mask, li_pack_key(kx, ky, kz), first, count)) continue;
+                have = true;
+                for (unsigned j = 0; j < count; j++) {
+                    const float4 q = M.pool[(size_t)first + j];
+                    if (__float_as_uint(q.w) == 0xffffffffu || !li_in_box(B, q)) continue;
+                    nE++;
+                    const float d = li_center_dist_cell(q.x, q.y, q.z, B.c[0], B.c[1], B.c[2], M.ds);
+                    if (d < bd) { bd = d; bref = (int)(first + j); }
+                    const float qa[3] = {q.x, q.y, q.z};
+                    int lo[3], hi[3];
+                    bool shared = false;
+#pragma unroll
+                    for (int a = 0; a < 3; a++) {
+                        lo[a] = qa[a] < B.mx_prev[a] ? -1 : 0;
+                        hi[a] = qa[a] >= B.mn_next[a] ? 1 : 0;
+                        shared = shared || lo[a] != 0 || hi[a] != 0;
+                    }
+                    if (shared) li_couple_neighbours(M, V, B, (int)v, lo, hi);
+                }
+            }
+    // new points filed under this cell that lie in another box too (or only there)
+    for (int t = head; t >= 0; t = next_of[t]) {
+        const float4 p = pts[t];
+        const float pa[3] = {p.x, p.y, p.z};
+        int lo[3], hi[3];
+        bool plain = true;
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            const float cf = (float)B.c[a];
+            const float mn_prev = __fmul_rn(cf - 1.0f, M.ds), mx_next = __fadd_rn(B.mn_next[a], M.ds);
+            const bool in_prev = pa[a] >= mn_prev && pa[a] < B.mx_prev[a];
+            const bool in_own = pa[a] >= B.mn[a] && pa[a] < B.mx[a];
+            const bool in_next = pa[a] >= B.mn_next[a] && pa[a] < mx_next;
+            lo[a] = in_prev ? -1 : (in_own ? 0 : (in_next ? 1 : 2));       // the intervals are consecutive: the offsets that hold form a range
+            hi[a] = in_next ? 1 : (in_own ? 0 : (in_prev ? -1 : -2));      // (lo > hi: a one-ulp gap -- the point is in no box at all)
+            plain = plain && lo[a] == 0 && hi[a] == 0;
+        }
+        if (!plain) li_couple_neighbours(M, V, B, (int)v, lo, hi);
+    }
+    V.sum[v] = make_int4(nE, __float_as_int(bd), bref, have ? 1 : 0);
+}
+
+// pass D3: one thread per box that is not coupled -- replay the box's new points in batch order (see the state machine above).
+// Existing losers are tombstoned (w = 0xffffffff), ins[i] = 1 marks the new points that end up in the map.
+//
+// Which existing points are "in the box" is decided GEOMETRICALLY, as Search_by_range / Delete_by_range decide it
+// (vertex_min <= x && x < vertex_max per axis, ikd_Tree.cpp:633,980), not by the voxel id a point was filed under: the float boxes
+// [fl(k ds), fl(fl(k ds) + ds)) of neighbouring k do not tile the axis -- they leave one-ulp gaps AND one-ulp overlaps, and a
+// point inside an overlap belongs to both boxes although it is stored under one index only (found by tools/emul_fuzz.py: lattice
+// points 900 m from the origin). Such a point can sit in the adjacent brick when the box touches a brick face, so up to two bricks
+// per axis are looked at -- one in all but ulp cases.
 __global__ void k_ds_replay(MapDev M, VoxTmp V, const float4* __restrict__ pts, int* __restrict__ next_of,
                             int* __restrict__ ins) {
     unsigned v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v > V.mask) return;
     int head = V.head[v];
     if (head < 0) return;
-    // the box
-    float4 ph = pts[head];
-    const int c[3] = {li_cell(ph.x, M.ds), li_cell(ph.y, M.ds), li_cell(ph.z, M.ds)};
-    const int cx = c[0], cy = c[1], cz = c[2];
+    if (V.coupled[v]) return;   // k_ds_coupled walks it
     DsBox B;
-    int blo[3], bhi[3];   // range of brick coordinates per axis that can store a point of this box
-    const int bm = (1 << M.bshift) - 1;
-#pragma unroll
-    for (int a = 0; a < 3; a++) {
-        const float cf = (float)c[a];
-        B.mn[a] = __fmul_rn(cf, M.ds);
-        B.mx[a] = __fadd_rn(B.mn[a], M.ds);
-        const float mx_prev = __fadd_rn(__fmul_rn(cf - 1.0f, M.ds), M.ds);   // upper end of box c-1
-        const float mn_next = __fmul_rn(cf + 1.0f, M.ds);                    // lower end of box c+1
-        const int b0 = c[a] >> M.bshift;
-        blo[a] = (B.mn[a] < mx_prev && (c[a] & bm) == 0) ? b0 - 1 : b0;      // overlap with box c-1, which lives in the brick below
-        bhi[a] = (B.mx[a] > mn_next && (c[a] & bm) == bm) ? b0 + 1 : b0;     // overlap with box c+1, which lives in the brick above
-    }
-    // existing content of the box: count, the point closest to the box centre (first minimum in visiting order)
-    int nE = 0;
-    float bd = INFINITY;
-    long long bref = -1;    // >= 0: pool offset of an existing point; <= -2: new point index -(bref+2)
+    li_ds_box(M, pts[head], B);
+    const int cx = B.c[0], cy = B.c[1], cz = B.c[2];
+    // existing content of the box (k_ds_scan)
+    const int4 sm = V.sum[v];
+    int nE = sm.x;
+    float bd = __int_as_float(sm.y);
+    long long bref = sm.z;    // >= 0: pool offset of an existing point; <= -2: new point index -(bref+2)
     float bxx = 0, byy = 0, bzz = 0;
-    bool have = false;
-    for (int kz = blo[2]; kz <= bhi[2]; kz++)
-        for (int ky = blo[1]; ky <= bhi[1]; ky++)
-            for (int kx = blo[0]; kx <= bhi[0]; kx++) {
-                unsigned first = 0, count = 0;
-                // (li_brick_find uses the read-only path; ent is not modified between D2's reserve and this kernel)
-                if (!li_brick_find(M.ent, M.mask, li_pack_key(kx, ky, kz), first, count)) continue;
-                have = true;
-                for (unsigned j = 0; j < count; j++) {
-                    float4 q = M.pool[(size_t)first + j];
-                    if (__float_as_uint(q.w) == 0xffffffffu || !li_in_box(B, q)) continue;
-                    nE++;
-                    float d = li_center_dist_cell(q.x, q.y, q.z, cx, cy, cz, M.ds);
-                    if (d < bd) { bd = d; bref = (long long)first + j; bxx = q.x; byy = q.y; bzz = q.z; }
-                }
-            }
+    if (bref >= 0) {
+        const float4 q = M.pool[bref];
+        bxx = q.x; byy = q.y; bzz = q.z;
+    }
+    const bool have = sm.w != 0;
     bool modified = false;
     int changed = 0;
     // batch order = ascending index. Short lists (the usual box: one to three new points): repeatedly take the smallest index greater than
@@ -393,9 +503,9 @@ __global__ void k_ds_replay(MapDev M, VoxTmp V, const float4* __restrict__ pts, 
     if (!(modified && have)) return;
     // the box was deleted at least once: every existing point in it except a surviving best one goes; the bricks that hold tombstones are
     // put on the touched list so that the compaction squeezes them out
-    for (int kz = blo[2]; kz <= bhi[2]; kz++)
-        for (int ky = blo[1]; ky <= bhi[1]; ky++)
-            for (int kx = blo[0]; kx <= bhi[0]; kx++) {
+    for (int kz = B.blo[2]; kz <= B.bhi[2]; kz++)
+        for (int ky = B.blo[1]; ky <= B.bhi[1]; ky++)
+            for (int kx = B.blo[0]; kx <= B.bhi[0]; kx++) {
                 const unsigned long long key = li_pack_key(kx, ky, kz);
                 unsigned first = 0, count = 0;
                 if (!li_brick_find(M.ent, M.mask, key, first, count)) continue;
@@ -418,6 +528,118 @@ __global__ void k_ds_replay(MapDev M, VoxTmp V, const float4* __restrict__ pts, 
             }
 }
 
+// pass D3c: the coupled boxes (k_ds_scan), by ONE warp: their new points are gathered, put in batch order, and lane 0 walks them the
+// way the reference walks a batch -- for every point the box is looked up afresh (existing points that are still alive + the new points
+// accepted so far that lie in it, both geometrically), so what one box deletes or inserts is seen by the next. An ulp-rare path: a
+// handful of points per batch on sensor data, thousands only on lattice-aligned synthetic clouds.
+__global__ void k_ds_coupled(MapDev M, VoxTmp V, const float4* __restrict__ pts, const int* __restrict__ next_of, int* __restrict__ ins,
+                             int* __restrict__ cidx, int* __restrict__ csorted) {
+    const int nc = M.counters[CNT_COUPLED];
+    if (nc == 0) return;
+    const int lane = threadIdx.x & 31;
+    __shared__ int s_n;
+    if (lane == 0) s_n = 0;
+    __syncwarp();
+    for (int b = lane; b < nc; b += 32)
+        for (int t = V.head[V.clist[b]]; t >= 0; t = next_of[t]) cidx[atomicAdd(&s_n, 1)] = t;
+    __syncwarp();
+    const int n = s_n;
+    for (int a = lane; a < n; a += 32) {   // rank sort: the indices are distinct
+        const int x = cidx[a];
+        int r = 0;
+        for (int b = 0; b < n; b++) r += cidx[b] < x;
+        csorted[r] = x;
+    }
+    __syncwarp();
+    // the walk itself: one point after the other, the warp shares the work INSIDE a step (lane-strided scans, a lexicographic minimum
+    // over (distance, visiting order) so that "first minimum in visiting order" is what a single thread would have found)
+    int changed = 0;
+    for (int pos = 0; pos < n; pos++) {
+        const int cur = csorted[pos];
+        const float4 p = pts[cur];
+        DsBox B;
+        li_ds_box(M, p, B);
+        const float dp = li_center_dist_cell(p.x, p.y, p.z, B.c[0], B.c[1], B.c[2], M.ds);
+        // Downsample_Storage = Search_by_range(box): live existing points, then the new points accepted so far
+        int nE = 0;
+        float bd = INFINITY;
+        unsigned long long ord = ~0ull;   // visiting order of the best candidate: (brick sequence number << 32 | slot), new points after all bricks
+        long long bref = -1;              // >= 0: pool offset of an existing point; <= -2: new point index -(bref+2); -1: none
+        unsigned seq = 0;
+        for (int kz = B.blo[2]; kz <= B.bhi[2]; kz++)
+            for (int ky = B.blo[1]; ky <= B.bhi[1]; ky++)
+                for (int kx = B.blo[0]; kx <= B.bhi[0]; kx++, seq++) {
+                    unsigned first = 0, count = 0;
+                    if (!li_brick_find(M.ent, M.mask, li_pack_key(kx, ky, kz), first, count)) continue;
+                    for (unsigned jj = lane; jj < count; jj += 32) {
+                        const float4 q = M.pool[(size_t)first + jj];
+                        if (__float_as_uint(q.w) == 0xffffffffu || !li_in_box(B, q)) continue;
+                        nE++;
+                        const float d = li_center_dist_cell(q.x, q.y, q.z, B.c[0], B.c[1], B.c[2], M.ds);
+                        if (d < bd) { bd = d; ord = ((unsigned long long)seq << 32) | jj; bref = (long long)first + jj; }
+                    }
+                }
+        for (int e = lane; e < pos; e += 32) {
+            const int k = csorted[e];
+            if (!ins[k]) continue;
+            const float4 q = pts[k];
+            if (!li_in_box(B, q)) continue;
+            nE++;
+            const float d = li_center_dist_cell(q.x, q.y, q.z, B.c[0], B.c[1], B.c[2], M.ds);
+            if (d < bd) { bd = d; ord = (1ull << 60) | (unsigned)e; bref = -((long long)k + 2); }
+        }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            nE += __shfl_xor_sync(LI_FULL, nE, o);
+            const float d2 = __shfl_xor_sync(LI_FULL, bd, o);
+            const unsigned long long o2 = __shfl_xor_sync(LI_FULL, ord, o);
+            const long long b2 = __shfl_xor_sync(LI_FULL, bref, o);
+            if (d2 < bd || (d2 == bd && o2 < ord)) { bd = d2; ord = o2; bref = b2; }
+        }
+        float bxx = 0, byy = 0, bzz = 0;
+        if (bref >= 0) { const float4 q = M.pool[bref]; bxx = q.x; byy = q.y; bzz = q.z; }
+        else if (bref <= -2) { const float4 q = pts[-(bref + 2)]; bxx = q.x; byy = q.y; bzz = q.z; }
+        const bool newwins = !(nE > 0 && bd < dp);
+        const bool same = newwins || (nE > 0 && fabsf(__fsub_rn(p.x, bxx)) < 1e-6f && fabsf(__fsub_rn(p.y, byy)) < 1e-6f &&
+                                      fabsf(__fsub_rn(p.z, bzz)) < 1e-6f);
+        if (!(nE > 1 || same)) continue;   // (uniform: every lane holds the same reduced values)
+        changed++;
+        // Delete_by_range(box), then the winner is (re)inserted
+        if (nE > 0) {
+            for (int kz = B.blo[2]; kz <= B.bhi[2]; kz++)
+                for (int ky = B.blo[1]; ky <= B.bhi[1]; ky++)
+                    for (int kx = B.blo[0]; kx <= B.bhi[0]; kx++) {
+                        const unsigned long long key = li_pack_key(kx, ky, kz);
+                        unsigned first = 0, count = 0;
+                        if (!li_brick_find(M.ent, M.mask, key, first, count)) continue;
+                        bool any = false;
+                        for (unsigned jj = lane; jj < count; jj += 32) {
+                            float4* qp = &M.pool[(size_t)first + jj];
+                            if (__float_as_uint(qp->w) == 0xffffffffu || !li_in_box(B, *qp)) continue;
+                            if (!newwins && bref == (long long)first + jj) continue;
+                            qp->w = __uint_as_float(0xffffffffu);
+                            any = true;
+                        }
+                        if (!__any_sync(LI_FULL, any) || lane != 0) continue;
+                        unsigned h = li_hash(key) & M.mask;
+                        for (unsigned t = 0; t <= M.mask; t++) {
+                            unsigned long long k = *reinterpret_cast<volatile unsigned long long*>(&M.ent[h]);
+                            if (k == key) { li_touch(M, (int)h); break; }
+                            if (k == LI_EMPTY_KEY) break;
+                            h = (h + 1) & M.mask;
+                        }
+                    }
+            for (int e = lane; e < pos; e += 32) {
+                const int k = csorted[e];
+                if (ins[k] && li_in_box(B, pts[k]) && !(!newwins && bref == -((long long)k + 2))) ins[k] = 0;
+            }
+        }
+        if (newwins && lane == 0) ins[cur] = 1;
+        __syncwarp();   // the next step reads the tombstones and ins[] this one wrote
+    }
+    if (changed && lane == 0) atomicAdd(&M.counters[CNT_CHANGED], changed);
+}
+
 // pass D3b: append the new points that survived the replay.
 __global__ void k_ds_append(MapDev M, const float4* __restrict__ pts, int n, const int* __restrict__ slot_of,
                             const int* __restrict__ ins) {
@@ -435,6 +657,7 @@ __global__ void k_ds_append(MapDev M, const float4* __restrict__ pts, int n, con
     unsigned vib;
     li_storage(M, p, cx, cy, cz, key, vib);
     p.w = __uint_as_float(vib);
+    LI_EMUL_ASSERT(e.w + j < M.aux[s].x && (unsigned long long)e.z + M.aux[s].x <= M.pool_cap);
     M.pool[(size_t)e.z + e.w + j] = p;
 }
 

@@ -308,3 +308,27 @@ def test_pool_full_leaves_a_consistent_map(gpu_lib):
     x, d, cnt = g.nearest_search(first[:500])
     assert np.all(d[:, 0] == 0) and np.array_equal(x[:, 0], first[:500])
     g.close()
+
+
+def test_coupled_boxes_are_walked_in_batch_order(gpu_lib, oracle_mod):
+    """tests/coupled_case.py: downsample boxes that share an existing point (one-ulp overlap of their float boxes) and both receive new
+    points in one batch -- changed-box count and live set equal the reference's sequential walk for every batch order."""
+    import coupled_case as cc
+    f = np.float32
+    base, batches = cc.scene()
+    counts = []
+    for order, batch in enumerate(batches):
+        g = gpu_lib.LiInitGpu(cc.DS, max_map_points=20000, max_scan_points=100, hash_capacity_log2=12)
+        om = oracle_mod.OracleMap(cc.DS, 0)            # the restated tree: deterministic counters
+        g.map_build(base)
+        om.build(base)
+        a, b = g.map_add_points(batch, True), om.add_points(batch, True)
+        assert a == b, (order, a, b)
+        counts.append(a)
+        live, want = g.map_download(), om.flatten()
+        assert g.map_validnum() == om.validnum() and set(map(bytes, live)) == set(map(bytes, np.ascontiguousarray(want, np.float32))), order
+        more = (batch + f(0.004)).astype(f)
+        assert g.map_add_points(more, True) == om.add_points(more, True)
+        assert set(map(bytes, g.map_download())) == set(map(bytes, np.ascontiguousarray(om.flatten(), np.float32))), order
+        g.close()
+    assert counts[0] != counts[1]

@@ -611,3 +611,27 @@ def test_emul_pool_full_leaves_a_consistent_map():
     x, d, cnt = g.nearest_search(first[:50])
     assert np.all(d[:, 0] == 0) and np.array_equal(x[:, 0], first[:50])
     g.close()
+
+
+@pytest.mark.parametrize("index", [BRICKS, CELLS])
+def test_emul_coupled_boxes_are_walked_in_batch_order(oracle_mod, index):
+    """tests/coupled_case.py: two downsample boxes that share an existing point and BOTH receive new points in one batch. The device takes
+    such boxes out of the parallel replay and walks them in batch order (k_ds_scan / k_ds_coupled); found by tools/emul_fuzz.py."""
+    import coupled_case as cc
+    f = np.float32
+    base, batches = cc.scene()
+    counts = []
+    for order, batch in enumerate(batches):
+        g = le.EmulGpu(cc.DS, max_map_points=20000, max_scan_points=100, knn_index=index, hash_capacity_log2=12)
+        om = oracle_mod.OracleMap(cc.DS, 0)            # the restated tree: deterministic counters
+        g.map_build(base)
+        om.build(base)
+        a, b = g.map_add_points(batch, True), om.add_points(batch, True)
+        assert a == b, (order, a, b)
+        counts.append(a)
+        assert g.map_validnum() == om.validnum() and _same_set(g.map_download(), om.flatten()), order
+        more = (batch + f(0.004)).astype(f)            # and once more on top of the result
+        assert g.map_add_points(more, True) == om.add_points(more, True)
+        assert _same_set(g.map_download(), om.flatten()), order
+        g.close()
+    assert counts[0] != counts[1]                      # the scene IS order dependent

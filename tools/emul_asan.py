@@ -41,6 +41,22 @@ for index in (1, 2):
         live = g.map_download()
         print(f"index {index} search {search}: m={m} map_incremental={na},{nn} voxel-grid leaves={n} live={len(live)}", flush=True)
         g.close()
+# Add_Points(downsample) on lattice-aligned clouds far from the origin: nearly every box is coupled with a neighbour (one-ulp overlaps of
+# the float boxes), the batch is walked by k_ds_coupled
+def lattice(rng, n, ds, off):
+    k = rng.integers(-40, 40, (n, 3)).astype(np.float32)
+    a = (k * np.float32(ds)).astype(np.float32)
+    j = rng.integers(0, 3, n)
+    a = np.where(j[:, None] == 0, a, np.where(j[:, None] == 1, np.nextafter(a, np.float32(1e9)), np.nextafter(a, np.float32(-1e9))))
+    return (a.astype(np.float64) + off).astype(np.float32)
+rng = np.random.default_rng(5)
+off = np.array([-5200.0, 3640.0, -520.0])
+for index in (1, 2):
+    g = le.EmulGpu(0.2, max_map_points=60000, max_scan_points=100, knn_index=index, hash_capacity_log2=13)
+    g.map_build(lattice(rng, 3000, 0.2, off))
+    ch = [g.map_add_points(lattice(rng, 1500, 0.2, off), True) for _ in range(3)]
+    print(f"index {index}: lattice downsample batches changed {ch}, live {g.map_validnum()}", flush=True)
+    g.close()
 # the lockstep search at every group width: first pass, seeded later pass, in-place host read, compaction, and the hollow scene whose
 # last shell lists 44 bricks in one probing round (tests/hollow_case.py)
 import hollow_case as hc

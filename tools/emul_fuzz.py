@@ -9,6 +9,9 @@ import numpy as np
 import liinit_emul as le
 from oracle import oracle as orc
 
+# EMUL_FUZZ_COUPLED=0: keep new points that lie in two float boxes (one-ulp overlaps) out of downsample batches, as before the coupled
+# boxes were walked in batch order (k_ds_coupled); default: let them in -- the lattice clouds then couple nearly every box
+COUPLED = os.environ.get("EMUL_FUZZ_COUPLED", "1") != "0"
 n_sc = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 seed0 = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 bk = 1 if orc.has_ikd() else 0
@@ -91,7 +94,7 @@ for sc in range(n_sc):
         if op < 2:
             pts = cloud(rng, int(rng.integers(50, 2500)), ds, int(rng.integers(0, 4)), off)
             down = bool(rng.integers(0, 2))
-            if down:
+            if down and not COUPLED:
                 pts = np.ascontiguousarray(pts[~multi_box(pts, ds)])
                 if len(pts) == 0:
                     continue

@@ -300,16 +300,6 @@ __global__ void k_ds_link(MapDev M, VoxTmp V, const float4* __restrict__ pts, in
     next_of[i] = atomicExch(&V.head[slot], i);
 }
 
-// pass D3: one thread per box -- replay the box's new points in batch order (see the state machine above).
-// Existing losers are tombstoned (w = 0xffffffff), ins[i] = 1 marks the new points that end up in the map.
-//
-// Which existing points are "in the box" is decided GEOMETRICALLY, as Search_by_range / Delete_by_range decide it
-// (vertex_min <= x && x < vertex_max per axis, ikd_Tree.cpp:633,980), not by the voxel id a point was filed under: the float boxes
-// [fl(k ds), fl(fl(k ds) + ds)) of neighbouring k do not tile the axis -- they leave one-ulp gaps AND one-ulp overlaps, and a
-// point inside an overlap belongs to both boxes although it is stored under one index only (found by tools/emul_fuzz.py: lattice
-// points 900 m from the origin). Such a point can sit in the adjacent brick when the box touches a brick face, so up to two bricks
-// per axis are looked at -- one in all but ulp cases. (A point shared by two boxes that BOTH receive new points in the same batch
-// is order dependent in the reference's sequential walk; here the two box threads are not ordered. Documented)
 struct DsBox {
     float mn[3], mx[3];
     float mx_prev[3], mn_next[3];   // upper end of the box below / lower end of the box above, per axis
@@ -528,10 +518,10 @@ __global__ void k_ds_replay(MapDev M, VoxTmp V, const float4* __restrict__ pts, 
             }
 }
 
-// pass D3c: the coupled boxes (k_ds_scan), by ONE warp: their new points are gathered, put in batch order, and lane 0 walks them the
-// way the reference walks a batch -- for every point the box is looked up afresh (existing points that are still alive + the new points
-// accepted so far that lie in it, both geometrically), so what one box deletes or inserts is seen by the next. An ulp-rare path: a
-// handful of points per batch on sensor data, thousands only on lattice-aligned synthetic clouds.
+// pass D3c: the coupled boxes (k_ds_scan), by ONE warp: their new points are gathered, put in batch order and walked the way the
+// reference walks a batch -- for every point the box is looked up afresh (existing points that are still alive + the new points
+// accepted so far that lie in it, both geometrically), so what one box deletes or inserts is seen by the next. The lanes share the
+// work inside a step. An ulp-rare path: a handful of points per batch on sensor data, thousands only on lattice-aligned synthetic clouds.
 __global__ void k_ds_coupled(MapDev M, VoxTmp V, const float4* __restrict__ pts, const int* __restrict__ next_of, int* __restrict__ ins,
                              int* __restrict__ cidx, int* __restrict__ csorted) {
     const int nc = M.counters[CNT_COUPLED];

@@ -40,7 +40,7 @@ def _lattice_cloud(rng, n, ds, off):
 
 
 def _single_box(pts, ds):
-    """keeps the points that lie in the float box of their division cell and in no neighbouring one (deviations)"""
+    """keeps the points that lie in the float box of their division cell and in no neighbouring one (coupled boxes)"""
     f, d = np.float32, np.float32(ds)
     c = np.floor(pts / d).astype(np.float32)
     bad = np.zeros(len(pts), bool)
@@ -398,21 +398,26 @@ def test_emul_raw_front_end(oracle_mod):
     g.close()
 
 
+@pytest.mark.parametrize("multi", [False, True])
 @pytest.mark.parametrize("off", [0.0, 900.0])
-def test_emul_downsample_box_membership_is_geometric(oracle_mod, off):
+def test_emul_downsample_box_membership_is_geometric(oracle_mod, off, multi):
     """Regression for a mismatch found by tools/emul_fuzz.py: the float boxes [fl(k ds), fl(fl(k ds) + ds)) of neighbouring k overlap by one
     ulp, so an EXISTING point on the lattice belongs to two boxes although it is filed under one voxel id; Add_Points(downsample) must find
-    it from either box (Search_by_range / Delete_by_range test coordinates, ikd_Tree.cpp:633,980)."""
+    it from either box (Search_by_range / Delete_by_range test coordinates, ikd_Tree.cpp:633,980).
+    multi: the NEW points may lie in two boxes as well -- nearly every box of a batch is then coupled with a neighbour and the batch is
+    walked in order (k_ds_coupled); compared with the restated tree, whose counters do not depend on a rebuild thread's timing."""
     rng = np.random.default_rng(1011)
     ds = 0.15
     o = off * np.array([1.0, -0.7, 0.1])
     first = _lattice_cloud(rng, 3500, ds, o)
     g = le.EmulGpu(ds, max_map_points=60000, max_scan_points=4000, hash_capacity_log2=13)
-    om = oracle_mod.OracleMap(ds, _bk(oracle_mod))
+    om = oracle_mod.OracleMap(ds, 0 if multi else _bk(oracle_mod))
     g.map_build(first)
     om.build(first)
     for k in range(3):
-        pts = _single_box(_lattice_cloud(rng, 1500, ds, o), ds)
+        pts = _lattice_cloud(rng, 1500, ds, o)
+        if not multi:
+            pts = _single_box(pts, ds)
         assert g.map_add_points(pts, True) == om.add_points(pts, True)
         assert g.map_validnum() == om.validnum()
     assert _same_set(g.map_download(), om.flatten())

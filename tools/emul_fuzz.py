@@ -37,8 +37,8 @@ def cloud(rng, n, ds, kind, off):
 def multi_box(pts, ds):
     """new points that lie in a float box other than (or besides) the one of their division cell: [fl(k ds), fl(fl(k ds) + ds)) boxes of
     neighbouring k overlap or leave gaps by one ulp. Within ONE downsample batch such a point also competes in the neighbouring box in the
-    reference's sequential walk; the device replays boxes independently (deviations) -- the fuzz keeps them out of
-    downsample batches and lets them in everywhere else (Build, plain adds, as existing points of later batches)."""
+    reference's sequential walk; the device couples such boxes and walks them in batch order (coupled boxes). With
+    EMUL_FUZZ_COUPLED=0 the fuzz keeps these points out of downsample batches, as it had to before that."""
     f = np.float32
     d = f(ds)
     c = np.floor(pts / d).astype(np.float32)

@@ -40,6 +40,17 @@ for sc in range(n_sc):
         assert np.array_equal(st["normvec"][sel], so["normvec"][sel]), (tag, "normvec")
         if mo > 0:
             assert rel(H, Ho) <= 1e-9 and rel(b, bo) <= 1e-9, (tag, "H")
+        # a later search pass of the same scan, map untouched: started from the stored neighbours (seeded), must equal a search from scratch
+        p1 = scenes.perturb_pose(p, int(rng.integers(0, 10**6)), dtheta_deg=float(rng.choice([0.02, 0.3])), dpos=float(rng.choice([0.005, 0.08])))
+        H1, b1, m1, _ = g.icp_iterate(p1.rot_end, p1.pos_end, p1.R_LI, p1.T_LI, imu_en, True)
+        Ho1, bo1, mo1 = osc.iterate(om, p1.rot_end, p1.pos_end, p1.R_LI, p1.T_LI, imu_en, True)
+        st, so = g.scan_state(), osc.get()
+        assert m1 == mo1 and (mo1 == 0 or (rel(H1, Ho1) <= 1e-9 and rel(b1, bo1) <= 1e-9)), (tag, "seeded pass")
+        for k in ("world", "near_cnt", "selected"):
+            assert np.array_equal(st[k], so[k]), (tag, "seeded pass", k)
+        found = np.arange(5)[None, :] < so["near_cnt"][:, None]      # (ranks beyond the count hold whatever an earlier pass left there)
+        assert np.array_equal(st["near_xyz"][found], so["near_xyz"][found]), (tag, "seeded pass", "near_xyz")
+        p = p1
         p2 = scenes.perturb_pose(p, int(rng.integers(0, 10**6)), dtheta_deg=0.05, dpos=0.01)
         H2, b2, m2, _ = g.icp_iterate(p2.rot_end, p2.pos_end, p2.R_LI, p2.T_LI, imu_en, False)
         Ho2, bo2, mo2 = osc.iterate(om, p2.rot_end, p2.pos_end, p2.R_LI, p2.T_LI, imu_en, False)

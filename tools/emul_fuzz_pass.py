@@ -21,6 +21,19 @@ for sc in range(n_sc):
     N, M = int(rng.integers(300, 2500)), int(rng.integers(8000, 50000))
     c = scenes.make_config("C2", seed=int(rng.integers(1, 1000)), N=N, M=M, open_air_frac=float(rng.choice([0.0, 0.02, 0.2])), imu_en=imu_en,
                            order=str(rng.choice(["voxel", "shuffle", "morton"])))
+    if rng.integers(0, 4) == 0:
+        # a volumetric map with hollows instead of surfaces (dense surroundings, empty neighbourhoods: the shells of the search grow to
+        # their last size and find many bricks at once), scan points inside and around the hollows
+        vol = rng.uniform(-4.5, 4.5, (M, 3))
+        centres = rng.uniform(-3, 3, (int(rng.integers(2, 8)), 3))
+        for cc in centres:
+            vol = vol[((vol - cc) ** 2).sum(1) > rng.uniform(0.6, 1.6) ** 2]
+        c = dict(c)
+        gt = c["pose_gt"]
+        c["map_xyz"] = np.ascontiguousarray(vol, np.float32)
+        w = np.concatenate([centres[rng.integers(0, len(centres), N // 2)] + rng.normal(0, 0.25, (N // 2, 3)), rng.uniform(-4, 4, (N - N // 2, 3))])
+        # body points such that the ground-truth pose maps them onto w
+        c["body_xyz"] = np.ascontiguousarray((gt.R_LI.T @ (gt.rot_end.T @ (w - gt.pos_end).T - gt.T_LI[:, None])).T, np.float32)
     p = scenes.perturb_pose(c["pose_gt"], int(rng.integers(0, 10**6)), dtheta_deg=float(rng.choice([0.0, 0.1, 0.5, 3.0])), dpos=float(rng.choice([0.0, 0.05, 0.5])))
     g = le.EmulGpu(c["ds"], max_map_points=3 * M + 20000, max_scan_points=N + 10, knn_index=index, knn_group_lanes=int(rng.choice([0, 2, 4, 8, 16, 32])),
                    knn_seed_radius_cells=float(rng.choice([0.0, 1.0, 4.0])), hash_capacity_log2=14)

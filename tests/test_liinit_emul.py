@@ -484,7 +484,14 @@ def test_emul_map_compact_gives_dead_storage_back(oracle_mod):
     ox, od, oc, _ = om.knn(q)
     assert np.array_equal(gc, oc) and np.array_equal(gd, od) and np.array_equal(gx, ox)
     new = q[:1500] + np.float32(0.017)
-    assert g.map_add_points(new, True) == om.add_points(new, True) and g.map_validnum() == om.validnum()
+    # (the changed-box COUNT is compared with the restated tree rebuilt from the same live set: the verbatim tree's own count depends, once
+    # in a long while, on where its rebuild thread is -- seen once under load; everything up to here was compared with the verbatim tree)
+    om0 = oracle_mod.OracleMap(c["ds"], 0)
+    om0.build(om.flatten())
+    changed = g.map_add_points(new, True)
+    om.add_points(new, True)
+    assert changed == om0.add_points(new, True) and g.map_validnum() == om0.validnum()
+    assert _same_set(g.map_download(), om0.flatten())
     g.close()
     # a capacity error is reported to the call that hit it and does not stick
     g = le.EmulGpu(c["ds"], max_map_points=3000, max_scan_points=100, hash_capacity_log2=10)   # 1024 hash slots

@@ -19,7 +19,10 @@ inline void mulT33(const double* A, const double* B, double* C) {   // A^T * B
 }
 
 // Dense inverse by LU with partial pivoting (what Eigen's .inverse() does for a 24x24, laserMapping.cpp:1081).
-bool invert(const double* A, double* X, int n) {
+// ncols < n: only the first ncols columns of the inverse are solved for (the others of X are left untouched) -- the gain K_1 enters
+// the update through its first 12 columns only; a column of the inverse does not depend on which other columns are computed.
+bool invert(const double* A, double* X, int n, int ncols = -1) {
+    if (ncols < 0) ncols = n;
     double lu[D * D];
     int perm[D];
     std::memcpy(lu, A, sizeof(double) * n * n);
@@ -50,7 +53,7 @@ bool invert(const double* A, double* X, int n) {
             for (int j = k + 1; j < n; j++) lu[i * n + j] -= f * lu[k * n + j];
         }
     }
-    for (int c = 0; c < n; c++) {
+    for (int c = 0; c < ncols; c++) {
         double y[D];
         for (int i = 0; i < n; i++) {
             double s = (perm[i] == c) ? 1.0 : 0.0;
@@ -135,12 +138,16 @@ void liinit_state_boxminus(const liinit_state* a, const liinit_state* b, double*
     }
 }
 
-int liinit_ieskf_update(liinit_state* st, const liinit_state* prop, const double* HtH, const double* Htr, double* sol, double* KH) {
+// cov_inv: state.cov^-1 when the caller already has it (the covariance does not change between the iterations of a scan,
+// laserMapping.cpp:1081 vs :1127: liinit_scan_update inverts it once), else nullptr.
+static int ieskf_update(liinit_state* st, const liinit_state* prop, const double* HtH, const double* Htr, double* sol, double* KH,
+                        const double* cov_inv) {
     double S[D * D], K1[D * D];
-    if (!invert(st->cov, S, D)) return LIINIT_ERR_INVALID;      // cov^-1
+    if (cov_inv) std::memcpy(S, cov_inv, sizeof(S));
+    else if (!invert(st->cov, S, D)) return LIINIT_ERR_INVALID;      // cov^-1
     for (int a = 0; a < 12; a++)
         for (int b = 0; b < 12; b++) S[a * D + b] += 1000.0 * HtH[a * 12 + b];   // R_inv = 1000 (laserMapping.cpp:1050)
-    if (!invert(S, K1, D)) return LIINIT_ERR_INVALID;
+    if (!invert(S, K1, D, 12)) return LIINIT_ERR_INVALID;            // (columns 0..11 of K_1 are all the update reads)
     double vec[D];
     liinit_state_boxminus(prop, st, vec);
     double G[D * 12];   // K*Hsub
@@ -163,12 +170,18 @@ int liinit_ieskf_update(liinit_state* st, const liinit_state* prop, const double
     return LIINIT_OK;
 }
 
+int liinit_ieskf_update(liinit_state* st, const liinit_state* prop, const double* HtH, const double* Htr, double* sol, double* KH) {
+    return ieskf_update(st, prop, HtH, Htr, sol, KH, nullptr);
+}
+
 int liinit_scan_update(liinit_ctx* h, liinit_state* state, int max_iter, int imu_en, liinit_scan_stats* stats) {
     if (!h || !state || max_iter < 1) return LIINIT_ERR_INVALID;
     liinit_state prop = *state;            // state_propagat = state (laserMapping.cpp:910)
     int rematch_num = 0, nearest_search_en = 1;
     liinit_scan_stats st{};
     double HtH[144], Htr[12], sol[D], KH[D * 12];
+    double cov_inv[D * D];                 // state.cov is only replaced at the end of the scan (:1127): one inversion for all iterations
+    if (!invert(state->cov, cov_inv, D)) return LIINIT_ERR_INVALID;
     for (int it = 0; it < max_iter; it++) {
         int m = 0;
         double rs = 0;
@@ -176,7 +189,7 @@ int liinit_scan_update(liinit_ctx* h, liinit_state* state, int max_iter, int imu
         int rc = liinit_icp_iterate(h, state->rot_end, state->pos_end, state->offset_R_L_I, state->offset_T_L_I, imu_en,
                                     nearest_search_en, HtH, Htr, &m, &rs);
         if (rc != LIINIT_OK) return rc;
-        rc = liinit_ieskf_update(state, &prop, HtH, Htr, sol, KH);
+        rc = ieskf_update(state, &prop, HtH, Htr, sol, KH, cov_inv);
         if (rc != LIINIT_OK) return rc;
         st.iterations++;
         st.effect_feat_num = m;

@@ -254,3 +254,55 @@ class EmulGpu:
         self._ck(self.L.liinit_map_incremental(self.h, _c64(rot_end), _c64(pos_end), _c64(R_LI), _c64(T_LI), float(ds), int(flg_EKF_inited), C.byref(a),
                                                C.byref(b)))
         return a.value, b.value
+
+
+# ---- the product's host-side C++ (csrc/host/liinit_host.cpp: IESKF, per-scan driver) linked against the emulated library ----------------
+_H = None
+
+
+class ScanStats(C.Structure):   # csrc/host/liinit_host.h: liinit_scan_stats
+    _fields_ = [("iterations", C.c_int), ("search_passes", C.c_int), ("effect_feat_num", C.c_int), ("converged", C.c_int),
+                ("last_rot_deg", C.c_double), ("last_trans_cm", C.c_double), ("res_sq", C.c_double)]
+
+
+def host_lib():
+    """liinit_host.cpp compiled as it is and linked against libliinit_emul.so instead of libliinit_gpu.so: liinit_scan_update then drives
+    the emulated kernels through the same C-ABI calls -- the per-scan driver on the CPU, for -m "not gpu" runs"""
+    global _H
+    if _H is not None:
+        return _H
+    import subprocess
+    emul = _mk.build()
+    src = os.path.join(_mk.CSRC, "host", "liinit_host.cpp")
+    out = os.path.join(_mk.GEN, "libliinit_host_emul.so")
+    deps = [src, os.path.join(_mk.CSRC, "host", "liinit_host.h"), emul]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", os.path.normpath(os.path.join(_mk.CSRC, "..", "..", "include")),
+                               "-o", out, src, "-L", os.path.dirname(emul), "-lliinit_emul", "-Wl,-rpath," + os.path.dirname(emul)])
+    load()
+    H = C.CDLL(out)
+    H.liinit_scan_update.restype = C.c_int
+    H.liinit_scan_update.argtypes = [vp, _f64, C.c_int, C.c_int, C.POINTER(ScanStats)]
+    H.liinit_state_init.argtypes = [_f64]
+    _H = H
+    return H
+
+
+def scan_update(g: "EmulGpu", state, max_iteration=5, imu_en=False):
+    s = np.ascontiguousarray(state, np.float64).copy()
+    st = ScanStats()
+    rc = host_lib().liinit_scan_update(g.h, s, int(max_iteration), int(imu_en), C.byref(st))
+    if rc != 0:
+        raise EmulError(rc, (g.L.liinit_last_error(g.h) or b"").decode())
+    return s, {k: getattr(st, k) for k, _ in ScanStats._fields_}
+
+
+def state_from_pose(rot_end, pos_end, R_LI, T_LI):
+    """liinit_state (csrc/host/liinit_host.h): rot_end 9 | pos_end 3 | offset_R_L_I 9 | offset_T_L_I 3 | vel 3 | bias_g 3 | bias_a 3 | gravity 3 | cov 24x24"""
+    s = np.zeros(36 + 576)
+    host_lib().liinit_state_init(s)
+    s[0:9] = np.asarray(rot_end, float).reshape(9)
+    s[9:12] = pos_end
+    s[12:21] = np.asarray(R_LI, float).reshape(9)
+    s[21:24] = T_LI
+    return s

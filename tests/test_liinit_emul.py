@@ -647,3 +647,62 @@ def test_emul_coupled_boxes_are_walked_in_batch_order(oracle_mod, index):
         assert _same_set(g.map_download(), om.flatten()), order
         g.close()
     assert counts[0] != counts[1]                      # the scene IS order dependent
+
+
+def _angle(Ra, Rb):
+    return float(np.arccos(np.clip((np.trace(Ra.T @ Rb) - 1) / 2, -1, 1)))
+
+
+@pytest.mark.parametrize("imu_en", [False, True])
+def test_emul_scan_update_driver_over_a_trajectory(oracle_mod, imu_en):
+    """The product's C++ per-scan driver (csrc/host/liinit_host.cpp: liinit_scan_update -- IESKF in information form, rematch policy,
+    covariance update; laserMapping.cpp:936-1134) linked against the CPU build of the library, scan after scan with map_incremental in
+    between, against the oracle's restatement: same iteration / search-pass / effective-point counts at every scan, poses within 1e-6.
+    The same loop as tests/test_gpu_trajectory.py, smaller."""
+    ds = 0.15
+    scene = scenes.box_scene(30.0, 20.0, 5.0, n_slabs_x=1, n_slabs_y=1)
+    R_LI, T_LI = scenes.sample_extrinsic() if imu_en else scenes.identity_extrinsic()
+    poses, pos, yaw = [], np.array([10.0, 8.0, 1.4]), 0.3
+    for k in range(4):
+        poses.append(scenes.Pose(scenes.rot_from_rpy(0.02 * np.sin(k), 0.015 * np.cos(k), yaw), pos.copy(), R_LI, T_LI))
+        pos = pos + np.array([0.22, 0.11, 0.01])
+        yaw += np.deg2rad(1.5)
+    scans = [scenes.scan_points(scene, p, 1000, seed=100 + k, det_range=60.0, sigma=0.01, open_air_frac=0.01) for k, p in enumerate(poses)]
+    g = le.EmulGpu(ds, max_map_points=100000, max_scan_points=3000)
+    om = oracle_mod.OracleMap(ds, _bk(oracle_mod))
+    w0 = _world(scans[0], poses[0])
+    g.map_build(w0)
+    om.build(w0)
+
+    st_g = le.state_from_pose(poses[0].rot_end, poses[0].pos_end, R_LI, T_LI)
+    cov = np.eye(24) * 1e-5
+    cov[0:3, 0:3] = np.eye(3) * 1e-3
+    cov[3:6, 3:6] = np.eye(3) * 1e-2
+    cov[6:9, 6:9] = np.eye(3) * 5e-5
+    cov[9:12, 9:12] = np.eye(3) * 1e-5
+    st_g[36:] = cov.reshape(-1)
+    st_o = st_g.copy()
+    max_dp = max_dr = 0.0
+    for k in range(1, len(poses)):
+        prior = scenes.perturb_pose(poses[k], 500 + k, dtheta_deg=0.2, dpos=0.03)
+        for st in (st_g, st_o):
+            st[0:9] = prior.rot_end.reshape(9)
+            st[9:12] = prior.pos_end
+            c = st[36:].reshape(24, 24)
+            c[0:3, 0:3] += np.eye(3) * 1e-4
+            c[3:6, 3:6] += np.eye(3) * 1e-3
+        g.scan_upload(scans[k])
+        st_g, stats = le.scan_update(g, st_g, 5, imu_en)
+        sc = oracle_mod.OracleScan(scans[k])
+        st_o, iters, searches, m = sc.scan_update(om, st_o, 5, imu_en)
+        assert stats["iterations"] == iters and stats["search_passes"] == searches and stats["effect_feat_num"] == m, k
+        Rg, pg, RLg, TLg = st_g[0:9].reshape(3, 3), st_g[9:12], st_g[12:21].reshape(3, 3), st_g[21:24]
+        Ro, po, RLo, TLo = st_o[0:9].reshape(3, 3), st_o[9:12], st_o[12:21].reshape(3, 3), st_o[21:24]
+        max_dp = max(max_dp, float(np.abs(pg - po).max()), float(np.abs(TLg - TLo).max()))
+        max_dr = max(max_dr, _angle(Rg, Ro), _angle(RLg, RLo))
+        na, nn = g.map_incremental(Rg, pg, RLg, TLg, ds)
+        _, oa, on, _ = sc.map_incremental(om, Ro, po, RLo, TLo, ds)
+        assert (na, nn) == (oa, on) and g.map_validnum() == om.validnum(), k
+    assert max_dp < 1e-6 and max_dr < 1e-6, (max_dp, max_dr)
+    assert np.allclose(st_g[36:], st_o[36:], rtol=1e-3, atol=1e-7)
+    g.close()

@@ -1,7 +1,7 @@
 // knn_kernels.cuh -- exact bounded 5-NN on the brick hash (replaces KD_TREE::Nearest_Search,
 // ikd_Tree.cpp:349-379, Search :825-968).
 //
-// G lanes (G = 8, 16 or 32) cooperate on one query, so a warp works on Q = 32/G queries AT ONCE and IN LOCKSTEP:
+// G lanes (G = 2, 4, 8, 16 or 32; chosen per pass from the frame size, group_for() in liinit_gpu.cu) cooperate on one query, so a warp works on Q = 32/G queries AT ONCE and IN LOCKSTEP:
 // every loop is warp-uniform (its trip count is the maximum over the warp's groups, idle groups are predicated
 // off) and every shuffle / ballot uses the full mask. Sub-mask *_sync intrinsics make the hardware run the groups
 // one after the other (measured in round 1: 11 of 32 lanes active); lockstep keeps all 32 lanes issuing together.
@@ -9,6 +9,8 @@
 //   Shell iteration on the brick-box distance (see knn5_lockstep): the first shell is a guessed radius rho around the
 //   query, then one closing shell [rho^2, g5) once 5 neighbours are known (or growing shells while fewer are known).
 //   The search is exact: it stops only when no unscanned brick can hold a point closer than the current 5th.
+//   Inside a shell every brick is probed first (two hash probes in flight per lane, found bricks listed per group in shared memory),
+//   then the listed slabs are scanned slot-aligned: the s-th brick of every group at the same time.
 //
 // A brick's slab is read by G consecutive lanes -> contiguous 16*G-byte segments; every lane keeps a private sorted
 // top-5 of the candidates IT saw; the group's top-5 is merged at phase boundaries.

@@ -183,6 +183,8 @@ __device__ __forceinline__ void group_scan_pipelined(const float4* __restrict__ 
     }
 }
 
+__device__ __forceinline__ int li_shl(int v, int s) { return (int)((unsigned)v << s); }   // v * 2^s for either sign
+
 struct KnnGeom {
     int bs;             // log2(voxels per brick edge)
     float ds, margin;   // voxel edge; rounding slack added to every pruning box
@@ -313,9 +315,10 @@ __device__ __forceinline__ void knn5_lockstep(const MapDev& M, float rho2, bool 
                 ent[k] = make_uint4(0u, 0u, 0u, 0u);
                 if (want[k]) {
                     const int bs = g.bs;
-                    const float lox = (float)(kx << bs) * g.ds - g.margin, hix = (float)((kx + 1) << bs) * g.ds + g.margin;
-                    const float loy = (float)(ky << bs) * g.ds - g.margin, hiy = (float)((ky + 1) << bs) * g.ds + g.margin;
-                    const float loz = (float)(kz << bs) * g.ds - g.margin, hiz = (float)((kz + 1) << bs) * g.ds + g.margin;
+                    // (brick coordinate -> first cell: the shift is done on the unsigned image, a negative int may not be shifted before C++20)
+                    const float lox = (float)li_shl(kx, bs) * g.ds - g.margin, hix = (float)li_shl(kx + 1, bs) * g.ds + g.margin;
+                    const float loy = (float)li_shl(ky, bs) * g.ds - g.margin, hiy = (float)li_shl(ky + 1, bs) * g.ds + g.margin;
+                    const float loz = (float)li_shl(kz, bs) * g.ds - g.margin, hiz = (float)li_shl(kz + 1, bs) * g.ds + g.margin;
                     const float ex = fmaxf(0.f, fmaxf(lox - qx, qx - hix));
                     const float ey = fmaxf(0.f, fmaxf(loy - qy, qy - hiy));
                     const float ez = fmaxf(0.f, fmaxf(loz - qz, qz - hiz));

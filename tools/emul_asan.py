@@ -1,5 +1,5 @@
 """AddressSanitizer over EVERY kernel and entry point, on the CPU: builds the emulated library (tests/emul/make_liinit_emul.py) with
--fsanitize=address and drives build / search + reuse pass / map_incremental / Add_Points / box delete / nearest search / voxel grid /
+-fsanitize=address,undefined and drives build / search + reuse pass / map_incremental / Add_Points / box delete / nearest search / voxel grid /
 download through it for both spatial indexes. Complements compute-sanitizer on the GPU (profiles/r01_sanitizer.txt).
 usage:  python tools/emul_asan.py          (re-executes itself with libasan preloaded)"""
 import os, subprocess, sys
@@ -12,7 +12,7 @@ if os.environ.get("LI_EMUL_ASAN_CHILD") != "1":
     import liinit_emul as le
     le._mk.build(force=False)            # generates tests/emul/_gen/liinit_gpu_emul.cpp
     gen = os.path.join(le._mk.GEN, "liinit_gpu_emul.cpp")
-    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-fsanitize=address", "-fno-omit-frame-pointer",
+    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-fno-omit-frame-pointer",
                            "-Wno-attributes", "-Wno-unknown-pragmas", "-DLI_SIMT_EMUL=1", "-I", le._mk.HERE, "-I", le._mk.CSRC,
                            "-I", os.path.join(ROOT, "include"), "-I", le._mk.CUDA_INC, gen, "-o", OUT])
     env = dict(os.environ, LD_PRELOAD=ASAN_LIB, ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0", LI_EMUL_ASAN_CHILD="1")
@@ -79,4 +79,4 @@ for group in (0, 2, 4, 8, 16, 32):
     cnt = g.scan_state()["near_cnt"]
     print(f"group {group}: seeded pass m={m2}, hollow scene neighbours found {int(cnt.min())}..{int(cnt.max())}", flush=True)
     g.close()
-print("emul_asan: no AddressSanitizer report")
+print("emul_asan: no AddressSanitizer / UndefinedBehaviorSanitizer report")

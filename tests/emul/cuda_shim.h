@@ -22,12 +22,30 @@ inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { p->multiProcessorCount = 2; return cudaSuccess; }   // small fixed grids
+// cudaMalloc does not zero device memory. LIINIT_EMUL_POISON=1: every allocation is filled with 0xCD, so that code which leans on fresh
+// pages being zero shows up as a failing test here instead of as a rare failure on a GPU whose memory was used before.
+inline bool li_emul_poison() {
+    static const bool on = [] { const char* e = getenv("LIINIT_EMUL_POISON"); return e && e[0] == '1'; }();
+    return on;
+}
 template <class T>
-inline cudaError_t cudaMalloc(T** p, size_t n) { *p = (T*)malloc(n ? n : 1); return *p ? cudaSuccess : 2; }
+inline cudaError_t cudaMalloc(T** p, size_t n) {
+    *p = (T*)malloc(n ? n : 1);
+    if (*p && li_emul_poison()) memset((void*)*p, 0xCD, n ? n : 1);
+    return *p ? cudaSuccess : 2;
+}
 template <class T>
-inline cudaError_t cudaMallocHost(T** p, size_t n) { *p = (T*)calloc(n ? n : 1, 1); return *p ? cudaSuccess : 2; }
+inline cudaError_t cudaMallocHost(T** p, size_t n) {
+    *p = (T*)calloc(n ? n : 1, 1);
+    if (*p && li_emul_poison()) memset((void*)*p, 0xCD, n ? n : 1);
+    return *p ? cudaSuccess : 2;
+}
 template <class T>
-inline cudaError_t cudaHostAlloc(T** p, size_t n, unsigned) { *p = (T*)calloc(n ? n : 1, 1); return *p ? cudaSuccess : 2; }
+inline cudaError_t cudaHostAlloc(T** p, size_t n, unsigned) {
+    *p = (T*)calloc(n ? n : 1, 1);
+    if (*p && li_emul_poison()) memset((void*)*p, 0xCD, n ? n : 1);
+    return *p ? cudaSuccess : 2;
+}
 inline cudaError_t cudaHostGetDevicePointer(void** d, void* h, unsigned) { *d = h; return cudaSuccess; }
 inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
 inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }

@@ -23,6 +23,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <type_traits>
+#include <vector>
 
 using std::isfinite;
 
@@ -239,7 +240,22 @@ inline void simt_launch(unsigned grid, unsigned block, void (*fn)(void*), void* 
     blockDim = SimtDim{block, 1, 1};
     gridDim = SimtDim{grid, 1, 1};
     g_b.nthreads = (int)block;
-    for (unsigned b = 0; b < grid; b++) {
+    // LIINIT_EMUL_SHUFFLE=<seed>: the blocks of every launch run in a pseudo-random order and the threads of every other block are
+    // scheduled last-to-first -- the device promises no order either; a result that depends on it fails the oracle comparisons here
+    static const unsigned shuffle_seed = [] { const char* e = getenv("LIINIT_EMUL_SHUFFLE"); return e ? (unsigned)atoi(e) * 2654435761u + 1u : 0u; }();
+    static unsigned shuffle_state = shuffle_seed;
+    static std::vector<unsigned> order;
+    order.resize(grid);
+    for (unsigned b = 0; b < grid; b++) order[b] = b;
+    if (shuffle_seed)
+        for (unsigned b = grid; b > 1; b--) {
+            shuffle_state = shuffle_state * 1664525u + 1013904223u;
+            const unsigned j = (shuffle_state >> 8) % b;
+            const unsigned t = order[b - 1]; order[b - 1] = order[j]; order[j] = t;
+        }
+    for (unsigned bi = 0; bi < grid; bi++) {
+        const unsigned b = order[bi];
+        const bool reverse = shuffle_seed && (bi & 1u);
         blockIdx = SimtDim{b, 0, 0};
         g_b.barr = 0; g_b.bgen = 0; g_b.blive = (int)block;
         for (unsigned w = 0; w < block / 32; w++) { g_b.warr[w] = 0; g_b.wgen[w] = 0; g_b.wlive[w] = 32; }
@@ -254,7 +270,8 @@ inline void simt_launch(unsigned grid, unsigned block, void (*fn)(void*), void* 
         }
         for (bool alive = true; alive;) {
             alive = false;
-            for (unsigned t = 0; t < block; t++) {
+            for (unsigned tt = 0; tt < block; tt++) {
+                const unsigned t = reverse ? block - 1 - tt : tt;
                 if (g_b.fin[t]) continue;
                 g_b.cur = (int)t;
                 threadIdx = SimtDim{t, 0, 0};

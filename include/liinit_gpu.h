@@ -161,7 +161,9 @@ int liinit_debug_esti_plane(liinit_ctx* h, const float* nb_xyz, int n, double* p
  * process (CUDA IPC) and the LAST BLOCK of the plane kernel does the collective itself -- peer stores of its 160 doubles into every rank's
  * buffer, a system-scope flag, a spin on the other ranks' flags, a rank-ordered sum (bit-identical on every rank): no extra launch, no
  * NCCL kernel. If any rank cannot map its peers (ranks as threads of one process, no peer access) or LIINIT_COMM_MODE=nccl is set, all
- * ranks use ncclAllReduce on the context's stream instead. NCCL always carries the set-up and the all-gathers of per-point results. */
+ * ranks use ncclAllReduce on the context's stream instead. NCCL always carries the set-up and the all-gathers of per-point results.
+ * As with any collective: a rank that does not make the call (it returned an error earlier, or died) leaves the others waiting -- the
+ * spin in the plane kernel has no time-out, exactly like a pending ncclAllReduce; supervise the ranks from outside. */
 #define LIINIT_COMM_ID_BYTES 128
 /* ncclGetUniqueId: call on ONE rank, hand the 128 bytes to the others through whatever channel the application has. */
 int liinit_comm_unique_id(void* id128);

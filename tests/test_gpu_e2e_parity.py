@@ -50,7 +50,7 @@ def make_oracle_odometry(orc, ds, nthreads, **kw):
     return OracleOdometry()
 
 
-def run_lockstep(gpu_lib, orc, seconds=60.0, points=4000, seed=0, t_off=0.013, ds=0.15, lio_scans=None, verbose=False):
+def run_lockstep(gpu_lib, orc, seconds=60.0, points=4000, seed=0, t_off=0.013, ds=0.15, lio_scans=None, verbose=False, odometry_cls=None):
     import calib_sim
     from lidar_imu_init_b200 import host, scenes
     from lidar_imu_init_b200.odometry import LidarOdometry
@@ -62,7 +62,7 @@ def run_lockstep(gpu_lib, orc, seconds=60.0, points=4000, seed=0, t_off=0.013, d
     eye, zero = np.eye(3), np.zeros(3)
     kw = dict(max_iteration=4, orig_odom_freq=10, cut_frame_num=5)
     g = gpu_lib.LiInitGpu(ds, max_map_points=3_000_000, max_scan_points=points + 16) if gpu_lib is not None else None
-    lo_g = LidarOdometry(g, ds, **kw) if g is not None else None
+    lo_g = (odometry_cls or LidarOdometry)(g, ds, **kw) if g is not None else None
     lo_o = make_oracle_odometry(orc, ds, min(16, os.cpu_count() or 1), **kw)
     ti, wi, ai = S["imu"]
     tl = S["lidar"][0]
@@ -184,3 +184,33 @@ def test_oracle_side_of_the_loop_runs_on_cpu(oracle_mod):
     _build.build_calib()
     out = run_lockstep(None, oracle_mod, seconds=12.0, points=1500, lio_scans=20)
     assert out["init_scan"] is not None and out["lio"]["scans"] == 20
+
+
+def test_product_side_of_the_loop_on_the_cpu_build(oracle_mod):
+    """The PRODUCT half of the lockstep harness without a GPU: LidarOdometry (constant-velocity propagation, liinit_scan_update -- the C++
+    IESKF loop --, map_incremental) on the CPU build of the library (tests/emul: the same kernels and host code compiled for the host,
+    liinit_host.cpp linked against it) against the oracle-driven loop, scan after scan. A checker of logic for -m "not gpu" runs; short
+    (the emulated kernels are 10^3 times slower), so it stays in the LiDAR-only leg."""
+    import liinit_emul as le
+    if not le.available():
+        pytest.skip("g++ or the CUDA vector-type headers are missing")
+    from lidar_imu_init_b200 import _build
+    from lidar_imu_init_b200.odometry import LidarOdometry
+    _build.build_gpu()
+    _build.build_host()
+    _build.build_calib()
+
+    class EmulOdometry(LidarOdometry):
+        def _scan_update(self, body_xyz, state):
+            self.g.scan_upload(body_xyz)
+            return le.scan_update(self.g, state, self.max_iteration, self.imu_en)
+
+    class Lib:
+        @staticmethod
+        def LiInitGpu(ds, max_map_points, max_scan_points):
+            return le.EmulGpu(ds, max_map_points=200000, max_scan_points=max_scan_points)
+
+    out = run_lockstep(Lib, oracle_mod, seconds=0.8, points=300, odometry_cls=EmulOdometry)
+    assert out["scans"] >= 35 and out["init_scan"] is None
+    assert out["max_dp"] <= 1e-6 and out["max_dr"] <= 1e-6, out
+    assert out.get("dm_max", 0) <= 1 and out["map_points_gpu"] == out["map_points_oracle"]

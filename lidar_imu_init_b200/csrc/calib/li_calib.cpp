@@ -37,7 +37,6 @@ struct V3 {
     double norm() const { return std::sqrt(x * x + y * y + z * z); }
     double operator[](int i) const { return i == 0 ? x : (i == 1 ? y : z); }
 };
-V3 cross(const V3& a, const V3& b) { return V3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 
 struct M3 {
     double m[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};

@@ -22,7 +22,17 @@ def oracle_mod():
 
 @pytest.fixture(scope="session")
 def gpu_lib():
-    """The product's CUDA library through its C-ABI binding; built if missing (nvcc, no GPU needed to build)."""
+    """The product's CUDA library through its C-ABI binding; built if missing (nvcc, no GPU needed to build).
+    LIINIT_GPU_TESTS_ON_EMUL=1 (developer pre-flight, never set by the suite): the bodies of `-m gpu` tests that only use the map / scan
+    entry points run against the CPU build of the library (tests/emul) instead -- a dry run of a GPU test before GPU time is spent on it."""
+    if os.environ.get("LIINIT_GPU_TESTS_ON_EMUL") == "1":
+        import types
+        import liinit_emul as le
+
+        def make(ds, **kw):
+            kw.pop("device_id", None)
+            return le.EmulGpu(ds, **kw)
+        return types.SimpleNamespace(LiInitGpu=make, LiInitError=le.EmulError, load=le.load)
     from lidar_imu_init_b200 import _build, capi
     _build.build_gpu()
     capi.load()

@@ -280,7 +280,6 @@ def test_pool_full_leaves_a_consistent_map(gpu_lib):
     """A batch that exhausts the point pool fails once with LIINIT_ERR_CAPACITY; what is stored stays intact under the concurrent
     reservations of the failing batch (no slab handed out twice), the allocator is back inside the pool, later batches fit again.
     (Same scenario as tests/test_liinit_emul.py::test_emul_pool_full_leaves_a_consistent_map, here with thousands of warps reserving at once.)"""
-    from lidar_imu_init_b200.capi import LiInitError
     ds = 0.15
     rng = np.random.default_rng(11)
     g = gpu_lib.LiInitGpu(ds, max_map_points=20000, max_scan_points=100, hash_capacity_log2=19)   # hash large enough: the POOL runs out
@@ -290,7 +289,7 @@ def test_pool_full_leaves_a_consistent_map(gpu_lib):
     assert g.map_validnum() == 15000
     used0 = g.map_stats()["pool_used"]
     far = rng.uniform(-2000, 2000, (cap // 8, 3)).astype(np.float32)      # one new brick (a 16-point slab) per point: twice the pool
-    with pytest.raises(LiInitError) as e:
+    with pytest.raises(gpu_lib.LiInitError) as e:
         g.map_add_points(far, False)
     assert e.value.code == -3
     st = g.map_stats()
